@@ -1,0 +1,195 @@
+/* ceed_b200.h -- C ABI of the B200-native libCEED operator-apply path ("/gpu/cuda/b200").
+ *
+ * This is the drop-in boundary: a plain C interface (opaque handles, raw pointers, sizes, int error
+ * codes; no C++/torch types) that a libCEED backend binds into the reference's per-object function
+ * pointer slots (CeedSetBackendFunction, /root/reference/include/ceed/backend.h:246-261,
+ * slot table /root/reference/include/ceed-impl.h:101-399).  `libceed_b200/backend/` contains that binding
+ * (INTEGRATION.md shows how it is registered); everything below is what it calls.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to /root/reference).
+ * Enumerations use the reference's numeric values (include/ceed/types.h:186-252) so they can be passed through.
+ *
+ * Error convention (include/ceed/types.h:162-181): 0 = success, >0 recoverable, <0 fatal.  The message
+ * of the last failure on a context is available from ceedb200_last_error().
+ *
+ * Threading: like the reference (README.md:74-80) a context and its objects are single-threaded;
+ * use one context per GPU / thread.  All work is enqueued on one CUDA stream per context.
+ */
+#ifndef CEED_B200_H
+#define CEED_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CEEDB200_EXPORT __attribute__((visibility("default")))
+
+typedef double  b200_scalar; /* CeedScalar (include/ceed/ceed-f64.h:17) */
+typedef int32_t b200_int;    /* CeedInt    (include/ceed/types.h:131)   */
+typedef int64_t b200_size;   /* CeedSize   (include/ceed/types.h:136)   */
+
+typedef struct B200Ceed_        *B200Ceed;
+typedef struct B200Vector_      *B200Vector;
+typedef struct B200Restriction_ *B200Restriction;
+typedef struct B200Basis_       *B200Basis;
+typedef struct B200QFContext_   *B200QFContext;
+typedef struct B200QFunction_   *B200QFunction;
+typedef struct B200Operator_    *B200Operator;
+
+enum { B200_MEM_HOST = 0, B200_MEM_DEVICE = 1 };                               /* CeedMemType       */
+enum { B200_COPY_VALUES = 0, B200_USE_POINTER = 1, B200_OWN_POINTER = 2 };      /* CeedCopyMode      */
+enum { B200_NORM_1 = 0, B200_NORM_2 = 1, B200_NORM_MAX = 2 };                   /* CeedNormType      */
+enum { B200_NOTRANSPOSE = 0, B200_TRANSPOSE = 1 };                              /* CeedTransposeMode */
+enum { B200_EVAL_NONE = 0, B200_EVAL_INTERP = 1, B200_EVAL_GRAD = 2, B200_EVAL_WEIGHT = 16 }; /* CeedEvalMode */
+enum { B200_GAUSS = 0, B200_GAUSS_LOBATTO = 1 };                                /* CeedQuadMode      */
+enum {
+  B200_SUCCESS = 0, B200_ERROR_MINOR = 1, B200_ERROR_DIMENSION = 2, B200_ERROR_INCOMPLETE = 3, B200_ERROR_INCOMPATIBLE = 4,
+  B200_ERROR_ACCESS = 5, B200_ERROR_MAJOR = -1, B200_ERROR_BACKEND = -2, B200_ERROR_UNSUPPORTED = -3
+};
+/* How the fused operator kernel adds element contributions into the output L-vector. */
+enum {
+  B200_SCATTER_DETERMINISTIC = 0, /* owner-store + ordered halo sum; bitwise reproducible, no atomics (default) */
+  B200_SCATTER_ATOMIC        = 1, /* red.global.add.f64, like /gpu/cuda/gen (cuda-gen-templates.h:385-396)   */
+  B200_SCATTER_EVECTOR       = 2  /* E-vector to HBM + CSR transpose kernel, like /gpu/cuda/ref               */
+};
+
+/* ---------------------------------------------------------------- context (Ceed)
+ * replaces CeedInit_Cuda / Ceed_Cuda: backends/cuda/ceed-cuda-common.c:19-35, ceed-cuda-common.h:67-72 */
+CEEDB200_EXPORT int         ceedb200_init(int device_id, B200Ceed *ceed);
+CEEDB200_EXPORT int         ceedb200_destroy(B200Ceed ceed);
+CEEDB200_EXPORT const char *ceedb200_last_error(B200Ceed ceed);
+CEEDB200_EXPORT const char *ceedb200_version(void);
+/* CeedAddJitSourceRoot / CeedAddJitDefine: interface/ceed.c:1515,1579; consumed by NVRTC as -I / -D
+ * (backends/cuda/ceed-cuda-compile.cpp:99-131) */
+CEEDB200_EXPORT int ceedb200_add_jit_source_root(B200Ceed ceed, const char *path);
+CEEDB200_EXPORT int ceedb200_add_jit_define(B200Ceed ceed, const char *define);
+/* CeedSetStream (interface/ceed.c:1408): `stream` is a cudaStream_t; NULL = legacy default stream */
+CEEDB200_EXPORT int ceedb200_set_stream(B200Ceed ceed, void *stream);
+CEEDB200_EXPORT int ceedb200_get_stream(B200Ceed ceed, void **stream);
+CEEDB200_EXPORT int ceedb200_synchronize(B200Ceed ceed);
+CEEDB200_EXPORT int ceedb200_set_scatter_mode(B200Ceed ceed, int mode);
+/* number of kernels launched by this context so far (bench.py's gpu_launches) */
+CEEDB200_EXPORT int64_t ceedb200_launch_count(B200Ceed ceed);
+
+/* ---------------------------------------------------------------- vector (CeedVector)
+ * replaces CeedVector_Cuda: backends/cuda-ref/ceed-cuda-ref.h:15-22, ceed-cuda-ref-vector.c:21-130,177-228,307-485,
+ * kernels backends/cuda-ref/kernels/cuda-ref-vector.cu:14-215 */
+CEEDB200_EXPORT int ceedb200_vector_create(B200Ceed ceed, b200_size length, B200Vector *vec);
+CEEDB200_EXPORT int ceedb200_vector_destroy(B200Vector vec);
+CEEDB200_EXPORT int ceedb200_vector_length(B200Vector vec, b200_size *length);
+CEEDB200_EXPORT int ceedb200_vector_has_valid_array(B200Vector vec, int *has_valid);
+CEEDB200_EXPORT int ceedb200_vector_has_borrowed_array_of_type(B200Vector vec, int mem_type, int *has_borrowed);
+CEEDB200_EXPORT int ceedb200_vector_set_array(B200Vector vec, int mem_type, int copy_mode, b200_scalar *array);
+CEEDB200_EXPORT int ceedb200_vector_take_array(B200Vector vec, int mem_type, b200_scalar **array);
+CEEDB200_EXPORT int ceedb200_vector_set_value(B200Vector vec, b200_scalar value);
+CEEDB200_EXPORT int ceedb200_vector_set_value_strided(B200Vector vec, b200_size start, b200_size stop, b200_size step, b200_scalar value);
+CEEDB200_EXPORT int ceedb200_vector_sync_array(B200Vector vec, int mem_type);
+CEEDB200_EXPORT int ceedb200_vector_get_array(B200Vector vec, int mem_type, b200_scalar **array);             /* read-write */
+CEEDB200_EXPORT int ceedb200_vector_get_array_read(B200Vector vec, int mem_type, const b200_scalar **array);  /* read-only  */
+CEEDB200_EXPORT int ceedb200_vector_get_array_write(B200Vector vec, int mem_type, b200_scalar **array);       /* write-only */
+CEEDB200_EXPORT int ceedb200_vector_copy_strided(B200Vector src, b200_size start, b200_size stop, b200_size step, B200Vector dst);
+CEEDB200_EXPORT int ceedb200_vector_norm(B200Vector vec, int norm_type, b200_scalar *norm);
+CEEDB200_EXPORT int ceedb200_vector_scale(B200Vector x, b200_scalar alpha);
+CEEDB200_EXPORT int ceedb200_vector_reciprocal(B200Vector x);
+CEEDB200_EXPORT int ceedb200_vector_filter(B200Vector x, b200_scalar epsilon);
+CEEDB200_EXPORT int ceedb200_vector_axpy(B200Vector y, b200_scalar alpha, B200Vector x);                       /* y = alpha x + y        */
+CEEDB200_EXPORT int ceedb200_vector_axpby(B200Vector y, b200_scalar alpha, b200_scalar beta, B200Vector x);    /* y = alpha x + beta y   */
+CEEDB200_EXPORT int ceedb200_vector_pointwise_mult(B200Vector w, B200Vector x, B200Vector y);                  /* w = x .* y             */
+
+/* ---------------------------------------------------------------- element restriction (CeedElemRestriction)
+ * replaces CeedElemRestrictionCreate_Cuda / Apply: backends/cuda-ref/ceed-cuda-ref-restriction.c:24-291,416-661,
+ * kernels include/ceed/jit-source/cuda/cuda-ref-restriction-offset.h:15-66, -strided.h:15-39.
+ * E-vector layout is {1, num_elem*elem_size, elem_size} = [comp][elem][node] (cuda-ref-restriction.c:532-534). */
+CEEDB200_EXPORT int ceedb200_restriction_create(B200Ceed ceed, b200_int num_elem, b200_int elem_size, b200_int num_comp, b200_int comp_stride,
+                                                b200_size l_size, int mem_type, int copy_mode, const b200_int *offsets, B200Restriction *rstr);
+/* strides = NULL selects CEED_STRIDES_BACKEND (interface/ceed-elemrestriction.c:630): {1, elem_size*num_elem, elem_size} */
+CEEDB200_EXPORT int ceedb200_restriction_create_strided(B200Ceed ceed, b200_int num_elem, b200_int elem_size, b200_int num_comp, b200_size l_size,
+                                                        const b200_int strides[3], B200Restriction *rstr);
+CEEDB200_EXPORT int ceedb200_restriction_destroy(B200Restriction rstr);
+CEEDB200_EXPORT int ceedb200_restriction_apply(B200Restriction rstr, int t_mode, B200Vector u, B200Vector v);
+CEEDB200_EXPORT int ceedb200_restriction_get_offsets(B200Restriction rstr, int mem_type, const b200_int **offsets);
+CEEDB200_EXPORT int ceedb200_restriction_get_e_layout(B200Restriction rstr, b200_int layout[3]);
+CEEDB200_EXPORT int ceedb200_restriction_get_info(B200Restriction rstr, b200_int *num_elem, b200_int *elem_size, b200_int *num_comp,
+                                                  b200_size *l_size, b200_size *e_size);
+
+/* ---------------------------------------------------------------- basis (CeedBasis, tensor H1)
+ * replaces CeedBasisCreateTensorH1_Cuda_shared / CeedBasisApply: backends/cuda-shared/ceed-cuda-shared-basis.c:24-196,603-666,
+ * device code include/ceed/jit-source/cuda/cuda-shared-basis-tensor.h:18-514.
+ * Matrices are row-major interp_1d[q*P+p], grad_1d[q*P+p] (include/ceed-impl.h:224-228).
+ * Q-vector layout [dim][comp][elem][qpt]; E-vector layout [comp][elem][node]. */
+CEEDB200_EXPORT int ceedb200_basis_create_tensor_h1(B200Ceed ceed, b200_int dim, b200_int num_comp, b200_int P_1d, b200_int Q_1d,
+                                                    const b200_scalar *interp_1d, const b200_scalar *grad_1d, const b200_scalar *q_ref_1d,
+                                                    const b200_scalar *q_weight_1d, B200Basis *basis);
+/* host construction of Lagrange matrices: restates interface/ceed-basis.c:1617-1680 (Fornberg), :2529 (Gauss), :2581 (Lobatto) */
+CEEDB200_EXPORT int ceedb200_basis_create_tensor_h1_lagrange(B200Ceed ceed, b200_int dim, b200_int num_comp, b200_int P, b200_int Q, int quad_mode,
+                                                             B200Basis *basis);
+CEEDB200_EXPORT int ceedb200_basis_destroy(B200Basis basis);
+CEEDB200_EXPORT int ceedb200_basis_apply(B200Basis basis, b200_int num_elem, int t_mode, int eval_mode, B200Vector u, B200Vector v);
+CEEDB200_EXPORT int ceedb200_basis_apply_add(B200Basis basis, b200_int num_elem, int t_mode, int eval_mode, B200Vector u, B200Vector v);
+/* which = 0 interp_1d [Q*P], 1 grad_1d [Q*P], 2 q_ref_1d [Q], 3 q_weight_1d [Q], 4 collocated grad [Q*Q] (interface/ceed-basis.c:750-773) */
+CEEDB200_EXPORT int ceedb200_basis_get_matrix(B200Basis basis, int which, b200_scalar *out);
+/* host utilities, no GPU needed (used by host-side tests): */
+CEEDB200_EXPORT int ceedb200_host_gauss_quadrature(b200_int Q, b200_scalar *q_ref_1d, b200_scalar *q_weight_1d);
+CEEDB200_EXPORT int ceedb200_host_lobatto_quadrature(b200_int Q, b200_scalar *q_ref_1d, b200_scalar *q_weight_1d);
+CEEDB200_EXPORT int ceedb200_host_lagrange_1d(b200_int P, b200_int Q, int quad_mode, b200_scalar *interp_1d, b200_scalar *grad_1d,
+                                              b200_scalar *q_ref_1d, b200_scalar *q_weight_1d);
+CEEDB200_EXPORT int ceedb200_host_collocated_grad_1d(b200_int P, b200_int Q, const b200_scalar *interp_1d, const b200_scalar *grad_1d,
+                                                     b200_scalar *collo_grad_1d);
+
+/* ---------------------------------------------------------------- QFunction context (CeedQFunctionContext)
+ * replaces CeedQFunctionContext_Cuda: backends/cuda-ref/ceed-cuda-ref.h:107-114, ceed-cuda-ref-qfunctioncontext.c:152-333 */
+CEEDB200_EXPORT int ceedb200_qfcontext_create(B200Ceed ceed, B200QFContext *ctx);
+CEEDB200_EXPORT int ceedb200_qfcontext_destroy(B200QFContext ctx);
+CEEDB200_EXPORT int ceedb200_qfcontext_set_data(B200QFContext ctx, int mem_type, int copy_mode, size_t size, void *data);
+CEEDB200_EXPORT int ceedb200_qfcontext_take_data(B200QFContext ctx, int mem_type, void **data);
+CEEDB200_EXPORT int ceedb200_qfcontext_get_data(B200QFContext ctx, int mem_type, void **data);       /* read-write: invalidates the other copy */
+CEEDB200_EXPORT int ceedb200_qfcontext_get_data_read(B200QFContext ctx, int mem_type, void **data);
+CEEDB200_EXPORT int ceedb200_qfcontext_has_valid_data(B200QFContext ctx, int *has_valid);
+CEEDB200_EXPORT int ceedb200_qfcontext_has_borrowed_data_of_type(B200QFContext ctx, int mem_type, int *has_borrowed);
+
+/* ---------------------------------------------------------------- QFunction (CeedQFunction)
+ * replaces CeedQFunctionCreate_Cuda / Apply: backends/cuda-ref/ceed-cuda-ref-qfunction.c:21-63, -qfunction-load.cpp:22-113.
+ * `source_path` is the user's header (resolved absolute path or relative to a JIT source root), `kernel_name` the function
+ * defined there with CEED_QFUNCTION(name) (interface/ceed-qfunction.c:259-320).  The source is JIT-compiled with NVRTC. */
+CEEDB200_EXPORT int ceedb200_qfunction_create(B200Ceed ceed, const char *source_path, const char *kernel_name, B200QFunction *qf);
+CEEDB200_EXPORT int ceedb200_qfunction_destroy(B200QFunction qf);
+CEEDB200_EXPORT int ceedb200_qfunction_add_input(B200QFunction qf, const char *field_name, b200_int size, int eval_mode);
+CEEDB200_EXPORT int ceedb200_qfunction_add_output(B200QFunction qf, const char *field_name, b200_int size, int eval_mode);
+CEEDB200_EXPORT int ceedb200_qfunction_set_context(B200QFunction qf, B200QFContext ctx);
+/* standalone apply over Q points: U[i]/V[i] hold field i as [size_i][Q] (doc/sphinx/source/libCEEDdev.md:113-118) */
+CEEDB200_EXPORT int ceedb200_qfunction_apply(B200QFunction qf, b200_int Q, const B200Vector *U, const B200Vector *V);
+
+/* ---------------------------------------------------------------- operator (CeedOperator)
+ * replaces CeedOperatorCreate_Cuda_gen / ApplyAdd: backends/cuda-gen/ceed-cuda-gen-operator.c:105-300,879-908 and the kernel
+ * generator backends/cuda-gen/ceed-cuda-gen-operator-build.cpp:1158-1681.
+ * Field wiring follows CeedOperatorSetField (interface/ceed-operator.c:931-1038):
+ *   rstr == NULL   <=> CEED_ELEMRESTRICTION_NONE (only with EVAL_WEIGHT)
+ *   basis == NULL  <=> CEED_BASIS_NONE (EVAL_NONE fields)
+ *   vec == B200_VECTOR_ACTIVE (the apply arguments) / B200_VECTOR_NONE (EVAL_WEIGHT) / a passive vector */
+#define B200_VECTOR_ACTIVE ((B200Vector)(uintptr_t)1)
+#define B200_VECTOR_NONE ((B200Vector)(uintptr_t)0)
+CEEDB200_EXPORT int ceedb200_operator_create(B200Ceed ceed, B200QFunction qf, B200Operator *op);
+CEEDB200_EXPORT int ceedb200_operator_destroy(B200Operator op);
+CEEDB200_EXPORT int ceedb200_operator_set_field(B200Operator op, const char *field_name, B200Restriction rstr, B200Basis basis, B200Vector vec);
+/* v = A u (overwrite; CeedOperatorApply, interface/ceed-operator.c:2271-2292) */
+CEEDB200_EXPORT int ceedb200_operator_apply(B200Operator op, B200Vector u, B200Vector v);
+/* v += A u (CeedOperatorApplyAdd, interface/ceed-operator.c:2313-2338) */
+CEEDB200_EXPORT int ceedb200_operator_apply_add(B200Operator op, B200Vector u, B200Vector v);
+/* introspection for tests / benchmarks */
+CEEDB200_EXPORT int         ceedb200_operator_is_fused(B200Operator op, int *is_fused);
+CEEDB200_EXPORT const char *ceedb200_operator_kernel_source(B200Operator op);
+CEEDB200_EXPORT int         ceedb200_operator_kernel_info(B200Operator op, int *regs, int *smem_bytes, int *threads, int *elems_per_block,
+                                                          int *grid, int *local_bytes);
+/* device time (ms) of the most recent apply's kernels, measured with CUDA events on the context stream when enabled */
+CEEDB200_EXPORT int ceedb200_operator_set_timing(B200Operator op, int enabled);
+CEEDB200_EXPORT int ceedb200_operator_last_kernel_ms(B200Operator op, float *fused_ms, float *aux_ms);
+/* tuning override: elems_per_block (0 = heuristic), blocks_per_sm (0 = heuristic) */
+CEEDB200_EXPORT int ceedb200_operator_set_tuning(B200Operator op, int elems_per_block, int blocks_per_sm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CEED_B200_H */

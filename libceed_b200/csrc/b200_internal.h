@@ -1,0 +1,176 @@
+// b200_internal.h -- private object model behind include/ceed_b200.h
+#pragma once
+
+#include "b200_driver.h"
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ceed_b200.h"
+
+struct B200Module {
+  CUmodule    module = nullptr;
+  std::string source;
+  std::string log;
+};
+
+struct B200Ceed_ {
+  int          device_id  = 0;
+  cudaStream_t stream     = nullptr;
+  int          num_sms    = 148;
+  size_t       smem_optin = 0;  // max dynamic smem per block (opt-in)
+  size_t       smem_sm    = 0;  // smem per SM
+  int          cc_major = 0, cc_minor = 0;
+  int          scatter_mode = B200_SCATTER_DETERMINISTIC;
+  int64_t      launch_count = 0;
+  std::string  last_error;
+  std::vector<std::string>           jit_roots;
+  std::vector<std::string>           jit_defines;
+  std::map<std::string, B200Module *> module_cache;  // keyed on full source + options
+  // scratch for norms
+  double *d_scratch = nullptr;
+  size_t  scratch_len = 0;
+};
+
+int b200_error(B200Ceed ceed, int code, const char *fmt, ...) __attribute__((format(printf, 3, 4)));
+
+#define B200_CHECK(cond, ceed, code, ...)                      \
+  do {                                                         \
+    if (!(cond)) return b200_error(ceed, code, __VA_ARGS__);   \
+  } while (0)
+#define B200_CALL(...)         \
+  do {                         \
+    int ierr_ = (__VA_ARGS__); \
+    if (ierr_) return ierr_;   \
+  } while (0)
+#define B200_CUDA(ceed, ...)                                                                                             \
+  do {                                                                                                                   \
+    cudaError_t cerr_ = (__VA_ARGS__);                                                                                   \
+    if (cerr_ != cudaSuccess)                                                                                            \
+      return b200_error(ceed, B200_ERROR_BACKEND, "%s:%d CUDA error: %s", __FILE__, __LINE__, cudaGetErrorString(cerr_)); \
+  } while (0)
+#define B200_CU(ceed, ...)                                                                             \
+  do {                                                                                                 \
+    CUresult cres_ = (__VA_ARGS__);                                                                    \
+    if (cres_ != CUDA_SUCCESS) {                                                                       \
+      const char *msg_ = nullptr;                                                                      \
+      cuGetErrorString(cres_, &msg_);                                                                  \
+      return b200_error(ceed, B200_ERROR_BACKEND, "%s:%d CUDA driver error: %s", __FILE__, __LINE__, msg_ ? msg_ : "?"); \
+    }                                                                                                  \
+  } while (0)
+
+// NVRTC compile (cached).  `defines` are extra -D options.
+int b200_jit_compile(B200Ceed ceed, const std::string &source, const std::vector<std::string> &defines, B200Module **module);
+int b200_jit_get_kernel(B200Ceed ceed, B200Module *module, const char *name, CUfunction *kernel);
+int b200_launch(B200Ceed ceed, CUfunction kernel, unsigned grid, unsigned block, unsigned smem_bytes, void **args);
+std::string b200_jit_dir();
+bool b200_compile_only();
+int  b200_dmalloc(B200Ceed ceed, void **p, size_t bytes);
+int  b200_dfree(B200Ceed ceed, void *p);
+int  b200_h2d(B200Ceed ceed, void *d, const void *h, size_t bytes);
+int  b200_d2h(B200Ceed ceed, void *h, const void *d, size_t bytes);
+int  b200_d2d(B200Ceed ceed, void *dst, const void *src, size_t bytes);
+
+// ---------------------------------------------------------------- objects
+enum B200Valid { B200_VALID_NONE = 0, B200_VALID_HOST = 1, B200_VALID_DEVICE = 2, B200_VALID_BOTH = 3 };
+
+struct B200Vector_ {
+  B200Ceed ceed   = nullptr;
+  int64_t  length = 0;
+  double  *h_owned = nullptr, *h_borrowed = nullptr;
+  double  *d_owned = nullptr, *d_borrowed = nullptr;
+  double  *h_array = nullptr, *d_array = nullptr;  // the *valid* pointers (NULL when that side is stale)
+};
+
+struct B200Restriction_ {
+  B200Ceed ceed = nullptr;
+  int      num_elem = 0, elem_size = 0, num_comp = 0;
+  int64_t  comp_stride = 0;  // offset restrictions
+  int64_t  l_size = 0;
+  bool     is_strided = false, backend_strides = false;
+  int64_t  strides[3] = {0, 0, 0};  // node, comp, elem strides in the L-vector
+  // offsets
+  const int32_t *h_offsets = nullptr;        // valid host pointer
+  int32_t       *h_offsets_owned = nullptr;  // allocated by us
+  const int32_t *h_offsets_borrowed = nullptr;
+  int32_t       *d_offsets = nullptr;
+  bool           d_offsets_owned = false;
+  // transpose CSR over referenced L-nodes, entries ordered by ascending E-index (elem, node)
+  //   == summation order of backends/ref/ceed-ref-restriction.c:220-242
+  int64_t  num_nodes = 0;  // distinct L-nodes referenced
+  int32_t *d_lvec_indices = nullptr, *d_t_offsets = nullptr, *d_t_indices = nullptr;
+  // owner/halo decomposition for the fused deterministic scatter (see b200_restriction.cu)
+  int32_t *d_tgt = nullptr;         // per E-entry: >=0 L-index to store into (owner), <0: ~slot in halo buffer
+  int32_t *d_halo_node = nullptr;   // per shared node: L-index
+  int32_t *d_halo_ptr = nullptr;    // per shared node: start slot (CSR), size num_shared+1
+  int64_t  num_shared = 0, num_halo = 0;
+  bool     transpose_built = false, owner_built = false;
+};
+
+struct B200Basis_ {
+  B200Ceed ceed = nullptr;
+  int      dim = 0, num_comp = 0, P = 0, Q = 0;
+  std::vector<double> interp, grad, q_ref, q_weight, collo_grad;  // host copies (1-D)
+  bool     has_collo_grad = false;  // Q >= P
+  bool     is_collocated  = false;  // interp_1d == identity
+  double  *d_interp = nullptr, *d_grad = nullptr, *d_q_weight = nullptr, *d_collo_grad = nullptr;
+};
+
+struct B200QFContext_ {
+  B200Ceed ceed = nullptr;
+  size_t   size = 0;
+  void    *h_owned = nullptr, *h_borrowed = nullptr, *d_owned = nullptr, *d_borrowed = nullptr;
+  void    *h_data = nullptr, *d_data = nullptr;  // valid pointers
+};
+
+struct B200QFField {
+  std::string name;
+  int         size = 0;
+  int         eval_mode = 0;
+};
+
+struct B200QFunction_ {
+  B200Ceed                 ceed = nullptr;
+  std::string              source_path, kernel_name;
+  std::vector<B200QFField> inputs, outputs;
+  B200QFContext            ctx = nullptr;
+  B200Module              *module = nullptr;  // standalone apply kernel
+  CUfunction               kernel = nullptr;
+};
+
+struct B200OpField {
+  B200Restriction rstr = nullptr;
+  B200Basis       basis = nullptr;
+  B200Vector      vec = nullptr;
+  bool            is_active = false, is_set = false;
+};
+
+struct B200OpPlan;  // generated-kernel plan (b200_opgen.cpp)
+
+struct B200Operator_ {
+  B200Ceed                 ceed = nullptr;
+  B200QFunction            qf = nullptr;
+  std::vector<B200OpField> in_fields, out_fields;
+  bool                     is_setup = false;
+  B200OpPlan              *plan = nullptr;
+  int                      tune_epb = 0, tune_bpsm = 0;
+  bool                     timing = false;
+  float                    last_fused_ms = 0.f, last_aux_ms = 0.f;
+  cudaEvent_t              ev[3] = {nullptr, nullptr, nullptr};
+};
+
+// internal helpers shared between translation units
+int b200_vector_device_read(B200Vector vec, const double **d);
+int b200_vector_device_write(B200Vector vec, double **d, bool discard);
+int b200_restriction_build_transpose(B200Restriction rstr);
+int b200_restriction_build_owner(B200Restriction rstr);
+int b200_restriction_e_size(B200Restriction rstr, int64_t *e_size);
+// raw device-pointer restriction kernels (used by the unfused operator path and EVECTOR scatter mode)
+int b200_restriction_apply_raw(B200Restriction rstr, int t_mode, const double *d_u, double *d_v);
+int b200_halo_finalize(B200Restriction rstr, const double *d_halo, double *d_v);
+int b200_memset_async(B200Ceed ceed, void *d, size_t bytes);

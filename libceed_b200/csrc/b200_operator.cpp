@@ -1,0 +1,351 @@
+// b200_operator.cpp -- CeedOperator for the b200 backend: field wiring, lazy setup, fused apply, unfused fallback.
+//
+// Mirrors the host side of the reference's generated-kernel operator (backends/cuda-gen/ceed-cuda-gen-operator.c:105-300):
+// on the first apply the operator is analysed and a fused kernel is generated + JIT-compiled (b200_opgen.cpp); every
+// apply then packs device pointers (:131-171) and launches ONE kernel (+ a small halo-finalize kernel in deterministic
+// scatter mode).  Operators the generator does not cover (1-D/2-D, mixed Q, Q < P gradients) run through an unfused
+// sequence of this backend's own restriction / basis / QFunction kernels, like /gpu/cuda/ref does
+// (backends/cuda-ref/ceed-cuda-ref-operator.c:519-638) -- never through the CPU.
+#include <cstdlib>
+#include <cstring>
+
+#include "b200_opgen.h"
+
+extern "C" int ceedb200_operator_create(B200Ceed ceed, B200QFunction qf, B200Operator *op_out) {
+  B200_CHECK(qf, ceed, B200_ERROR_INCOMPLETE, "operator needs a QFunction");
+  B200Operator op = new B200Operator_();
+  op->ceed        = ceed;
+  op->qf          = qf;
+  op->in_fields.resize(qf->inputs.size());
+  op->out_fields.resize(qf->outputs.size());
+  *op_out = op;
+  return B200_SUCCESS;
+}
+
+static void plan_free(B200Operator op) {
+  B200OpPlan *plan = op->plan;
+  if (!plan) return;
+  for (int i = 0; i < 16; i++) b200_dfree(op->ceed, plan->aux[i]);
+  for (auto *vecs : {&plan->e_in, &plan->q_in, &plan->e_out, &plan->q_out})
+    for (auto v : *vecs) ceedb200_vector_destroy(v);
+  delete plan;
+  op->plan = nullptr;
+}
+
+extern "C" int ceedb200_operator_destroy(B200Operator op) {
+  if (!op) return B200_SUCCESS;
+  plan_free(op);
+  for (int i = 0; i < 3; i++)
+    if (op->ev[i]) cudaEventDestroy(op->ev[i]);
+  delete op;
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_operator_set_field(B200Operator op, const char *field_name, B200Restriction rstr, B200Basis basis, B200Vector vec) {
+  B200Ceed      ceed = op->ceed;
+  B200QFunction qf   = op->qf;
+  B200_CHECK(!op->is_setup, ceed, B200_ERROR_MAJOR, "Operator cannot be changed after set as immutable");
+  for (int io = 0; io < 2; io++) {
+    auto &qfields = io ? qf->outputs : qf->inputs;
+    auto &fields  = io ? op->out_fields : op->in_fields;
+    for (size_t i = 0; i < qfields.size(); i++) {
+      if (qfields[i].name != field_name) continue;
+      const int emode = qfields[i].eval_mode;
+      // same consistency rules as CeedOperatorCheckField (interface/ceed-operator.c:36-82)
+      B200_CHECK((rstr == nullptr) == (emode == B200_EVAL_WEIGHT), ceed, B200_ERROR_INCOMPATIBLE,
+                 "CEED_ELEMRESTRICTION_NONE and CEED_EVAL_WEIGHT must be used together (field %s)", field_name);
+      B200_CHECK((basis == nullptr) == (emode == B200_EVAL_NONE), ceed, B200_ERROR_INCOMPATIBLE,
+                 "CEED_BASIS_NONE and CEED_EVAL_NONE must be used together (field %s)", field_name);
+      if (rstr && basis)
+        B200_CHECK(rstr->num_comp == basis->num_comp, ceed, B200_ERROR_DIMENSION, "Field '%s': restriction has %d components, basis has %d", field_name,
+                   rstr->num_comp, basis->num_comp);
+      fields[i].rstr      = rstr;
+      fields[i].basis     = basis;
+      fields[i].is_active = vec == B200_VECTOR_ACTIVE;
+      fields[i].vec       = (vec == B200_VECTOR_ACTIVE || vec == B200_VECTOR_NONE) ? nullptr : vec;
+      fields[i].is_set    = true;
+      return B200_SUCCESS;
+    }
+  }
+  return b200_error(ceed, B200_ERROR_INCOMPLETE, "QFunction has no field named '%s'", field_name);
+}
+
+extern "C" int ceedb200_operator_set_tuning(B200Operator op, int elems_per_block, int blocks_per_sm) {
+  op->tune_epb  = elems_per_block;
+  op->tune_bpsm = blocks_per_sm;
+  if (op->is_setup) {
+    plan_free(op);
+    op->is_setup = false;
+  }
+  return B200_SUCCESS;
+}
+
+static int operator_setup(B200Operator op) {
+  if (op->is_setup) return B200_SUCCESS;
+  B200Ceed ceed = op->ceed;
+  for (auto *fields : {&op->in_fields, &op->out_fields})
+    for (size_t i = 0; i < fields->size(); i++) B200_CHECK((*fields)[i].is_set, ceed, B200_ERROR_INCOMPLETE, "Not all operator fields set");
+  B200OpPlan *plan = new B200OpPlan();
+  op->plan         = plan;
+  B200_CALL(b200_opgen_plan(op, plan));
+  if (getenv("CEED_B200_NO_FUSE")) {
+    plan->fused         = false;
+    plan->why_not_fused = "CEED_B200_NO_FUSE set";
+  }
+  if (plan->fused) {
+    // auxiliary buffers of offset-restricted outputs
+    auto prepare = [&](B200Restriction r, int slot) -> int {
+      if (!r || r->is_strided) return B200_SUCCESS;
+      if (plan->scatter_mode == B200_SCATTER_DETERMINISTIC) {
+        B200_CALL(b200_restriction_build_owner(r));
+        plan->aux_bytes[slot] = (size_t)r->num_halo * r->num_comp * sizeof(double);
+      } else if (plan->scatter_mode == B200_SCATTER_EVECTOR) {
+        B200_CALL(b200_restriction_build_transpose(r));
+        plan->aux_bytes[slot] = (size_t)r->num_elem * r->elem_size * r->num_comp * sizeof(double);
+      }
+      if (plan->aux_bytes[slot]) B200_CALL(b200_dmalloc(ceed, (void **)&plan->aux[slot], plan->aux_bytes[slot]));
+      return B200_SUCCESS;
+    };
+    for (auto &g : plan->out_groups) B200_CALL(prepare(g.rstr, g.slot));
+    for (auto &f : plan->out_fields)
+      if (f.emode == B200_EVAL_NONE) B200_CALL(prepare(f.rstr, f.slot));
+  } else {
+    if (getenv("CEED_B200_DEBUG")) fprintf(stderr, "[ceed-b200] operator not fused: %s\n", plan->why_not_fused.c_str());
+  }
+  op->is_setup = true;
+  return B200_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------ fused apply
+static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add) {
+  B200Ceed    ceed = op->ceed;
+  B200OpPlan *plan = op->plan;
+  B200OpArgs  args;
+  memset(&args, 0, sizeof(args));
+  args.num_elem = plan->num_elem;
+  if (op->qf->ctx) B200_CALL(ceedb200_qfcontext_get_data(op->qf->ctx, B200_MEM_DEVICE, &args.ctx));
+
+  // inputs
+  for (size_t i = 0; i < op->in_fields.size(); i++) {
+    const B200OpField &f = op->in_fields[i];
+    if (!f.rstr) continue;
+    B200Vector vec = f.is_active ? u : f.vec;
+    B200_CHECK(vec && vec != B200_VECTOR_NONE, ceed, B200_ERROR_INCOMPLETE, "missing input vector for field %zu", i);
+    B200_CHECK(vec->length >= f.rstr->l_size, ceed, B200_ERROR_DIMENSION, "input vector of field %zu shorter than restriction L-size", i);
+    B200_CALL(b200_vector_device_read(vec, &args.in_ptr[i]));
+    args.in_idx[i] = f.rstr->is_strided ? nullptr : f.rstr->d_offsets;
+  }
+  // outputs.  Decide per distinct output vector whether the kernel can store (overwrite) or must accumulate.
+  struct OutVec {
+    B200Vector vec;
+    int        writers;
+    bool       covers;
+  };
+  std::vector<OutVec> outs;
+  for (size_t i = 0; i < op->out_fields.size(); i++) {
+    const B200OpField &f   = op->out_fields[i];
+    B200Vector         vec = f.is_active ? v : f.vec;
+    B200_CHECK(vec && vec != B200_VECTOR_NONE, ceed, B200_ERROR_INCOMPLETE, "missing output vector for field %zu", i);
+    B200_CHECK(vec->length >= f.rstr->l_size, ceed, B200_ERROR_DIMENSION, "output vector of field %zu shorter than restriction L-size", i);
+    // a field that is the first of its group (or EVAL_NONE) is a distinct writer
+    bool is_writer = plan->out_fields[i].emode == B200_EVAL_NONE || plan->out_groups[plan->out_fields[i].group].slot == (int)i;
+    if (!is_writer) continue;
+    bool covers;
+    if (f.rstr->is_strided) {
+      covers = (int64_t)f.rstr->num_elem * f.rstr->elem_size * f.rstr->num_comp == vec->length;
+    } else {
+      B200_CALL(b200_restriction_build_owner(f.rstr));
+      covers = f.rstr->num_nodes * f.rstr->num_comp == vec->length;
+    }
+    bool found = false;
+    for (auto &o : outs)
+      if (o.vec == vec) {
+        o.writers++;
+        found = true;
+      }
+    if (!found) outs.push_back({vec, 1, covers});
+  }
+  // kernel variant: stores are only safe when every output vector has one writer that covers it and the scatter is the
+  // owner/halo scheme (or strided); otherwise zero first and accumulate.
+  int kernel_add = add;
+  if (!add) {
+    bool need_zero = false;
+    for (auto &o : outs) need_zero = need_zero || o.writers > 1 || !o.covers;
+    bool offset_non_det = false;
+    for (size_t i = 0; i < op->out_fields.size(); i++)
+      if (!op->out_fields[i].rstr->is_strided && plan->scatter_mode != B200_SCATTER_DETERMINISTIC) offset_non_det = true;
+    if (need_zero || offset_non_det) {
+      for (auto &o : outs) B200_CALL(ceedb200_vector_set_value(o.vec, 0.0));
+      kernel_add = 1;
+    }
+  }
+  for (size_t i = 0; i < op->out_fields.size(); i++) {
+    const B200OpField &f   = op->out_fields[i];
+    B200Vector         vec = f.is_active ? v : f.vec;
+    // discard previous contents only when the kernel overwrites everything
+    B200_CALL(b200_vector_device_write(vec, &args.out_ptr[i], !kernel_add));
+    if (!f.rstr->is_strided) args.out_idx[i] = plan->scatter_mode == B200_SCATTER_DETERMINISTIC ? f.rstr->d_tgt : f.rstr->d_offsets;
+    args.out_aux[i] = plan->aux[i];
+  }
+  B200_CALL(b200_opgen_build(op, plan, kernel_add));
+  B200KernelVariant &var = plan->variant[kernel_add ? 1 : 0];
+
+  if (op->timing && !op->ev[0])
+    for (int i = 0; i < 3; i++) B200_CUDA(ceed, cudaEventCreate(&op->ev[i]));
+  if (op->timing) B200_CUDA(ceed, cudaEventRecord(op->ev[0], ceed->stream));
+  if (plan->num_elem > 0) {
+    void *kargs[] = {&args};
+    B200_CALL(b200_launch(ceed, var.kernel, plan->grid, plan->threads, plan->smem_bytes, kargs));
+  }
+  if (op->timing) B200_CUDA(ceed, cudaEventRecord(op->ev[1], ceed->stream));
+  // second phase of the scatter
+  for (size_t i = 0; i < op->out_fields.size() && plan->num_elem > 0; i++) {
+    const B200OpField &f = op->out_fields[i];
+    if (f.rstr->is_strided || !plan->aux[i]) continue;
+    bool is_writer = plan->out_fields[i].emode == B200_EVAL_NONE || plan->out_groups[plan->out_fields[i].group].slot == (int)i;
+    if (!is_writer) continue;
+    if (plan->scatter_mode == B200_SCATTER_DETERMINISTIC) B200_CALL(b200_halo_finalize(f.rstr, plan->aux[i], args.out_ptr[i]));
+    else if (plan->scatter_mode == B200_SCATTER_EVECTOR) B200_CALL(b200_restriction_apply_raw(f.rstr, B200_TRANSPOSE, plan->aux[i], args.out_ptr[i]));
+  }
+  if (op->timing) {
+    B200_CUDA(ceed, cudaEventRecord(op->ev[2], ceed->stream));
+    B200_CUDA(ceed, cudaEventSynchronize(op->ev[2]));
+    cudaEventElapsedTime(&op->last_fused_ms, op->ev[0], op->ev[1]);
+    cudaEventElapsedTime(&op->last_aux_ms, op->ev[1], op->ev[2]);
+  }
+  return B200_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------ unfused apply
+static int apply_unfused(B200Operator op, B200Vector u, B200Vector v, int add) {
+  B200Ceed      ceed = op->ceed;
+  B200QFunction qf   = op->qf;
+  B200OpPlan   *plan = op->plan;
+  int           num_elem = -1, nqpts = -1;
+  auto          ipow     = [](int b, int e) {
+    int r = 1;
+    for (int i = 0; i < e; i++) r *= b;
+    return r;
+  };
+  for (auto *fields : {&op->in_fields, &op->out_fields})
+    for (auto &f : *fields) {
+      if (f.rstr && num_elem < 0) num_elem = f.rstr->num_elem;
+      if (f.basis && nqpts < 0) nqpts = ipow(f.basis->Q, f.basis->dim);
+    }
+  if (nqpts < 0)
+    for (auto *fields : {&op->in_fields, &op->out_fields})
+      for (auto &f : *fields)
+        if (f.rstr && nqpts < 0) nqpts = f.rstr->elem_size;
+  B200_CHECK(num_elem >= 0 && nqpts > 0, ceed, B200_ERROR_INCOMPLETE, "operator has no restriction / quadrature space");
+  const int64_t Qtot = (int64_t)num_elem * nqpts;
+  B200_CHECK(Qtot < (1LL << 31), ceed, B200_ERROR_UNSUPPORTED, "Backend does not implement unfused operators with more than 2^31 quadrature points");
+  // work vectors
+  if (plan->q_in.empty() && plan->q_out.empty()) {
+    plan->e_in.assign(op->in_fields.size(), nullptr);
+    plan->q_in.assign(op->in_fields.size(), nullptr);
+    plan->e_out.assign(op->out_fields.size(), nullptr);
+    plan->q_out.assign(op->out_fields.size(), nullptr);
+    for (size_t i = 0; i < op->in_fields.size(); i++) {
+      const B200OpField &f = op->in_fields[i];
+      if (f.rstr) B200_CALL(ceedb200_vector_create(ceed, (int64_t)f.rstr->num_elem * f.rstr->elem_size * f.rstr->num_comp, &plan->e_in[i]));
+      if (qf->inputs[i].eval_mode != B200_EVAL_NONE) B200_CALL(ceedb200_vector_create(ceed, Qtot * qf->inputs[i].size, &plan->q_in[i]));
+    }
+    for (size_t i = 0; i < op->out_fields.size(); i++) {
+      const B200OpField &f = op->out_fields[i];
+      B200_CALL(ceedb200_vector_create(ceed, (int64_t)f.rstr->num_elem * f.rstr->elem_size * f.rstr->num_comp, &plan->e_out[i]));
+      if (qf->outputs[i].eval_mode != B200_EVAL_NONE) B200_CALL(ceedb200_vector_create(ceed, Qtot * qf->outputs[i].size, &plan->q_out[i]));
+    }
+  }
+  std::vector<B200Vector> U(op->in_fields.size()), V(op->out_fields.size());
+  for (size_t i = 0; i < op->in_fields.size(); i++) {
+    const B200OpField &f     = op->in_fields[i];
+    const int          emode = qf->inputs[i].eval_mode;
+    if (emode == B200_EVAL_WEIGHT) {
+      B200_CALL(ceedb200_basis_apply(f.basis, num_elem, B200_NOTRANSPOSE, B200_EVAL_WEIGHT, B200_VECTOR_NONE, plan->q_in[i]));
+      U[i] = plan->q_in[i];
+      continue;
+    }
+    B200Vector vec = f.is_active ? u : f.vec;
+    B200_CHECK(vec && vec != B200_VECTOR_NONE, ceed, B200_ERROR_INCOMPLETE, "missing input vector for field %zu", i);
+    B200_CALL(ceedb200_restriction_apply(f.rstr, B200_NOTRANSPOSE, vec, plan->e_in[i]));
+    if (emode == B200_EVAL_NONE) U[i] = plan->e_in[i];
+    else {
+      B200_CALL(ceedb200_basis_apply(f.basis, num_elem, B200_NOTRANSPOSE, emode, plan->e_in[i], plan->q_in[i]));
+      U[i] = plan->q_in[i];
+    }
+  }
+  for (size_t i = 0; i < op->out_fields.size(); i++) V[i] = qf->outputs[i].eval_mode == B200_EVAL_NONE ? plan->e_out[i] : plan->q_out[i];
+  if (Qtot > 0) B200_CALL(ceedb200_qfunction_apply(qf, (b200_int)Qtot, U.data(), V.data()));
+  // zero distinct output vectors for overwrite semantics
+  if (!add) {
+    std::vector<B200Vector> done;
+    for (size_t i = 0; i < op->out_fields.size(); i++) {
+      B200Vector vec = op->out_fields[i].is_active ? v : op->out_fields[i].vec;
+      bool       seen = false;
+      for (auto d : done) seen = seen || d == vec;
+      if (!seen) {
+        B200_CALL(ceedb200_vector_set_value(vec, 0.0));
+        done.push_back(vec);
+      }
+    }
+  }
+  for (size_t i = 0; i < op->out_fields.size(); i++) {
+    const B200OpField &f     = op->out_fields[i];
+    const int          emode = qf->outputs[i].eval_mode;
+    B200Vector         vec   = f.is_active ? v : f.vec;
+    B200_CHECK(vec && vec != B200_VECTOR_NONE, ceed, B200_ERROR_INCOMPLETE, "missing output vector for field %zu", i);
+    if (emode != B200_EVAL_NONE) B200_CALL(ceedb200_basis_apply(f.basis, num_elem, B200_TRANSPOSE, emode, plan->q_out[i], plan->e_out[i]));
+    B200_CALL(ceedb200_restriction_apply(f.rstr, B200_TRANSPOSE, plan->e_out[i], vec));
+  }
+  return B200_SUCCESS;
+}
+
+static int operator_apply(B200Operator op, B200Vector u, B200Vector v, int add) {
+  B200_CALL(operator_setup(op));
+  if (!b200_compile_only()) B200_CUDA(op->ceed, cudaSetDevice(op->ceed->device_id));
+  if (op->plan->fused) return apply_fused(op, u, v, add);
+  return apply_unfused(op, u, v, add);
+}
+
+extern "C" int ceedb200_operator_apply(B200Operator op, B200Vector u, B200Vector v) { return operator_apply(op, u, v, 0); }
+extern "C" int ceedb200_operator_apply_add(B200Operator op, B200Vector u, B200Vector v) { return operator_apply(op, u, v, 1); }
+
+extern "C" int ceedb200_operator_is_fused(B200Operator op, int *is_fused) {
+  B200_CALL(operator_setup(op));
+  *is_fused = op->plan->fused ? 1 : 0;
+  return B200_SUCCESS;
+}
+
+extern "C" const char *ceedb200_operator_kernel_source(B200Operator op) {
+  if (operator_setup(op) || !op->plan->fused) return "";
+  if (b200_opgen_build(op, op->plan, 0)) return "";
+  return op->plan->variant[0].source.c_str();
+}
+
+extern "C" int ceedb200_operator_kernel_info(B200Operator op, int *regs, int *smem_bytes, int *threads, int *elems_per_block, int *grid,
+                                             int *local_bytes) {
+  B200_CALL(operator_setup(op));
+  B200_CHECK(op->plan->fused, op->ceed, B200_ERROR_UNSUPPORTED, "operator is not fused: %s", op->plan->why_not_fused.c_str());
+  B200KernelVariant *var = op->plan->variant[0].built ? &op->plan->variant[0] : &op->plan->variant[1];
+  if (!var->built) {
+    B200_CALL(b200_opgen_build(op, op->plan, 0));
+    var = &op->plan->variant[0];
+  }
+  if (regs) *regs = var->regs;
+  if (local_bytes) *local_bytes = var->local_bytes;
+  if (smem_bytes) *smem_bytes = op->plan->smem_bytes;
+  if (threads) *threads = op->plan->threads;
+  if (elems_per_block) *elems_per_block = op->plan->epb;
+  if (grid) *grid = op->plan->grid;
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_operator_set_timing(B200Operator op, int enabled) {
+  op->timing = enabled != 0;
+  return B200_SUCCESS;
+}
+extern "C" int ceedb200_operator_last_kernel_ms(B200Operator op, float *fused_ms, float *aux_ms) {
+  if (fused_ms) *fused_ms = op->last_fused_ms;
+  if (aux_ms) *aux_ms = op->last_aux_ms;
+  return B200_SUCCESS;
+}

@@ -1,0 +1,726 @@
+// b200_opgen.cpp -- generator of the fused CeedOperatorApply kernel for sm_100a (3-D tensor-product H1 operators).
+//
+// What it replaces: the reference's code generator backends/cuda-gen/ceed-cuda-gen-operator-build.cpp:1158-1681 and the
+// device templates it strings together (include/ceed/jit-source/cuda/cuda-gen-templates.h:324-533,
+// cuda-shared-basis-tensor-templates.h:321-654).  Same contract (one kernel per operator, user QFunction inlined through
+// NVRTC with Q = 1 per call), different design:
+//
+//   * LINE-OWNED CONTRACTIONS.  A block processes a batch of E elements.  Every 1-D contraction stage assigns one whole
+//     tensor line (P inputs -> Q outputs) to a thread: inputs are P shared-memory loads at immediate offsets, the P*Q FMAs
+//     take their basis coefficient straight from the constant bank (matrices live in __constant__ memory and every loop
+//     is fully unrolled, so the coefficient is an instruction operand: no register, no load).  That gives P*Q/(P+Q)
+//     FMAs per shared-memory access (3.7 at p=6) where the reference's thread-per-(x,y)-column scheme needs one LDS per
+//     DFMA plus 2 block barriers per z-layer per contraction (~105 barriers/element at p=6);
+//     here a batch of E elements costs 9 barriers in total.
+//   * Stages are fused where a thread already owns the data: x-interp + d/dx, d/dz + QFunction + (d/dz)^T in one
+//     z-line pass, (d/dx)^T + x-interp^T.
+//   * Gathers/scatters read element offsets with consecutive lanes on consecutive entries (coalesced 4-byte index
+//     loads); quadrature data is streamed straight from HBM into registers at the quadrature point that consumes it.
+//   * DETERMINISTIC SCATTER WITHOUT ATOMICS: the first E-entry referencing an L-node owns the store (plain st.global,
+//     which also gives overwrite semantics without a memset + read-modify-write pass); other entries write a compact
+//     halo buffer that a small finalize kernel folds in, in ascending (elem,node) order -- the order of the serial CPU
+//     reference (backends/ref/ceed-ref-restriction.c:220-242).  Atomic and E-vector modes exist for comparison.
+//   * shared-memory planes are padded to odd line strides (conflict-free line-strided access), sized so that several
+//     blocks are resident per SM; grid = resident blocks x 148 SMs, grid-stride over element batches.
+#include "b200_opgen.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+
+using std::string;
+typedef std::ostringstream oss;
+
+namespace {
+
+int odd_pad(int n) { return (n % 2) ? n : n + 1; }
+
+string hexd(double v) {
+  char buf[64];
+  snprintf(buf, sizeof(buf), "%a", v);
+  return buf;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ planning
+int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
+  B200Ceed      ceed = op->ceed;
+  B200QFunction qf   = op->qf;
+  plan->fused        = false;
+  plan->scatter_mode = ceed->scatter_mode;
+  auto reject        = [&](const string &why) {
+    plan->why_not_fused = why;
+    return B200_SUCCESS;
+  };
+  int dim = 0, Q = 0, num_elem = -1;
+  // bases
+  auto basis_id = [&](B200Basis b) {
+    for (size_t i = 0; i < plan->bases.size(); i++)
+      if (plan->bases[i].basis == b) return (int)i;
+    plan->bases.push_back({b, b->P, b->Q, b->is_collocated});
+    return (int)plan->bases.size() - 1;
+  };
+  auto find_group = [&](std::vector<B200GenGroup> &groups, bool is_input, const B200OpField &f, int bid, int slot) {
+    for (size_t i = 0; i < groups.size(); i++) {
+      if (groups[i].rstr == f.rstr && groups[i].basis_id == bid && groups[i].is_active == f.is_active && (f.is_active || groups[i].vec == f.vec))
+        return (int)i;
+    }
+    B200GenGroup g;
+    g.is_input  = is_input;
+    g.rstr      = f.rstr;
+    g.vec       = f.vec;
+    g.is_active = f.is_active;
+    g.basis_id  = bid;
+    g.nc        = f.rstr->num_comp;
+    g.slot      = slot;
+    groups.push_back(g);
+    return (int)groups.size() - 1;
+  };
+  for (int io = 0; io < 2; io++) {
+    const auto &qfields  = io == 0 ? qf->inputs : qf->outputs;
+    const auto &opfields = io == 0 ? op->in_fields : op->out_fields;
+    auto       &gfields  = io == 0 ? plan->in_fields : plan->out_fields;
+    auto       &groups   = io == 0 ? plan->in_groups : plan->out_groups;
+    for (size_t i = 0; i < qfields.size(); i++) {
+      const B200OpField &f = opfields[i];
+      B200GenField       g;
+      g.emode     = qfields[i].eval_mode;
+      g.size      = qfields[i].size;
+      g.slot      = (int)i;
+      g.vec       = f.vec;
+      g.is_active = f.is_active;
+      g.rstr      = f.rstr;
+      if (f.basis) {
+        if (dim == 0) {
+          dim = f.basis->dim;
+          Q   = f.basis->Q;
+        }
+        if (f.basis->dim != dim || f.basis->Q != Q) return reject("bases with different dim or Q_1d");
+      }
+      if (f.rstr) {
+        if (num_elem < 0) num_elem = f.rstr->num_elem;
+        if (f.rstr->num_elem != num_elem) return reject("restrictions with different numbers of elements");
+      }
+      switch (g.emode) {
+        case B200_EVAL_NONE:
+          if (!f.rstr) return reject("EVAL_NONE field without restriction");
+          g.nc = f.rstr->num_comp;
+          if (g.nc != g.size) return reject("EVAL_NONE field size != restriction components");
+          break;
+        case B200_EVAL_WEIGHT:
+          if (io == 1 || !f.basis) return reject("EVAL_WEIGHT needs an input basis");
+          g.basis_id = basis_id(f.basis);
+          g.nc       = 1;
+          break;
+        case B200_EVAL_INTERP:
+        case B200_EVAL_GRAD: {
+          if (!f.basis || !f.rstr) return reject("INTERP/GRAD field without basis or restriction");
+          if (g.emode == B200_EVAL_GRAD && !f.basis->has_collo_grad) return reject("GRAD with Q < P (no collocated gradient)");
+          const int bid = basis_id(f.basis);
+          g.group       = find_group(groups, io == 0, f, bid, (int)i);
+          g.nc          = f.rstr->num_comp;
+          if (g.emode == B200_EVAL_INTERP) groups[g.group].use_interp = true;
+          else groups[g.group].use_grad = true;
+          if (g.size != g.nc * (g.emode == B200_EVAL_GRAD ? dim : 1)) return reject("field size does not match components x q_comp");
+          int nn = 1;
+          for (int d = 0; d < dim; d++) nn *= f.basis->P;
+          if (f.rstr->elem_size != nn) return reject("restriction element size != P^dim");
+        } break;
+        default: return reject("unsupported eval mode");
+      }
+      gfields.push_back(g);
+    }
+  }
+  if (dim != 3) return reject("fused kernel is generated for dim == 3 only");
+  if (num_elem < 0) return reject("no restriction");
+  if (plan->out_groups.empty()) {
+    bool any = false;
+    for (auto &f : plan->out_fields) any = any || f.emode == B200_EVAL_NONE;
+    if (!any) return reject("no output");
+  }
+  if (plan->in_groups.empty() && plan->out_groups.empty()) return reject("restriction-only operator (no basis action)");
+  // EVAL_NONE fields must be sized Q^3 per element
+  for (int io = 0; io < 2; io++)
+    for (auto &f : (io ? plan->out_fields : plan->in_fields))
+      if (f.emode == B200_EVAL_NONE && f.rstr->elem_size != Q * Q * Q) return reject("EVAL_NONE restriction element size != Q^dim");
+  for (auto &b : plan->bases)
+    if (b.P > 16 || b.Q > 16) return reject("P or Q > 16");
+
+  plan->dim      = dim;
+  plan->Q        = Q;
+  plan->Qs       = odd_pad(Q);
+  plan->num_elem = num_elem;
+  // shared-memory planes
+  int plane_size = Q * Q * plan->Qs;
+  for (auto &b : plan->bases) {
+    plane_size = std::max(plane_size, Q * b.P * b.P);
+    plane_size = std::max(plane_size, Q * Q * odd_pad(b.P));
+  }
+  plan->plane_size = plane_size;
+  int n_in = 0, n_out = 0;
+  for (auto &g : plan->in_groups) {
+    g.plane0 = n_in;
+    n_in += g.nc * (g.use_grad ? 3 : 2);
+  }
+  for (auto &g : plan->out_groups) {
+    g.plane0 = n_out;
+    n_out += g.nc * (g.use_grad ? 3 : 2);
+  }
+  plan->num_planes = std::max(n_in, n_out);
+  // elements per block / threads: one thread per quadrature line (Q^2 lines per element), ~256 threads per block
+  const int lines    = Q * Q;
+  const int per_elem = plan->num_planes * plane_size * 8;
+  int       target   = getenv("CEED_B200_THREADS") ? atoi(getenv("CEED_B200_THREADS")) : 256;
+  int       epb      = op->tune_epb > 0 ? op->tune_epb : (getenv("CEED_B200_EPB") ? atoi(getenv("CEED_B200_EPB")) : std::max(1, target / lines));
+  while (epb > 1 && (size_t)epb * per_elem > ceed->smem_optin / 2) epb--;
+  if ((size_t)epb * per_elem > ceed->smem_optin) return reject("element working set exceeds shared memory");
+  if (epb > std::max(1, num_elem)) epb = std::max(1, num_elem);
+  plan->epb        = epb;
+  int threads      = ((epb * lines + 31) / 32) * 32;
+  if (threads > 1024) threads = 1024;
+  if (threads < 64) threads = 64;
+  plan->threads    = threads;
+  plan->smem_bytes = std::max(epb * per_elem, 16);
+  {
+    // occupancy target handed to __launch_bounds__: limited by shared memory and by a ~96 register/thread budget
+    int by_smem = (int)(ceed->smem_sm / (size_t)(plan->smem_bytes + 1024));
+    int by_regs = 65536 / (threads * 96);
+    int minb    = std::max(1, std::min(by_smem, by_regs));
+    if (op->tune_bpsm > 0) minb = op->tune_bpsm;
+    if (getenv("CEED_B200_MINB")) minb = atoi(getenv("CEED_B200_MINB"));
+    plan->blocks_per_sm = std::max(1, minb);
+  }
+  plan->fused      = true;
+  return B200_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------ code generation
+namespace {
+
+struct Gen {
+  B200Operator op;
+  B200OpPlan  *plan;
+  int          add;
+  oss          c;
+  int          Q, Qs, E, NT, S;
+
+  const B200GenBasis &basis(int id) const { return plan->bases[id]; }
+  string plane(int pl, const string &le) const {
+    // address (in doubles) of plane `pl` of local element `le`
+    oss s;
+    s << "sm + ((" << pl << ") * " << E << " + " << le << ") * " << S;
+    return s.str();
+  }
+
+  // L-vector index expression for (entry n of element e, component c) of a restriction
+  string lidx(B200Restriction r, const string &tbl, const string &e, const string &n, const string &comp) const {
+    oss s;
+    if (r->is_strided) {
+      s << "((long long)(" << n << ") * " << r->strides[0] << "LL + (long long)(" << comp << ") * " << r->strides[1] << "LL + (" << e << ") * "
+        << r->strides[2] << "LL)";
+    } else {
+      s << "((long long)" << tbl << "[(" << e << ") * " << r->elem_size << "LL + (" << n << ")] + (long long)(" << comp << ") * " << r->comp_stride
+        << "LL)";
+    }
+    return s.str();
+  }
+
+  // Every stage is its own __noinline__ device function: ptxas then allocates registers / uniform registers per stage
+  // instead of hoisting the coefficient loads of ALL stages to the kernel entry (which spills the uniform register file).
+  std::vector<string> calls;  // kernel body: stage calls and barriers, in order
+  int                 n_stage = 0;
+  void task_loop_begin(const string &ntasks) {
+    const string name = "b200_stage_" + std::to_string(n_stage++);
+    c << "static __device__ __noinline__ void " << name << "(const B200OpArgs &a, const long long e0) {\n";
+    c << "    for (int t = threadIdx.x; t < " << ntasks << "; t += " << NT << ") {\n";
+    calls.push_back("    " + name + "(a, e0);\n");
+  }
+  void task_loop_end() { c << "    }\n}\n\n"; }
+  void barrier() { calls.push_back("    __syncthreads();\n"); }
+  void comment(const string &text) { c << "// " << text << "\n"; }
+
+  // out[0..n_out) = M (n_out x n_in, row-major cM[o*n_in+i]) * in   or transposed: out[o] = sum_i cM[i*n_out+o] in[i]
+  void contract(const string &mat, int n_in, int n_out, bool transposed, const string &in, const string &out, const string &indent) {
+    for (int o = 0; o < n_out; o++) {
+      c << indent << "double " << out << o << " = ";
+      for (int i = 0; i < n_in; i++) {
+        const int idx = transposed ? i * n_out + o : o * n_in + i;
+        if (i == 0) c << mat << "[" << idx << "] * " << in << i;
+      }
+      c << ";\n";
+      for (int i = 1; i < n_in; i++) {
+        const int idx = transposed ? i * n_out + o : o * n_in + i;
+        c << indent << out << o << " = fma(" << mat << "[" << idx << "], " << in << i << ", " << out << o << ");\n";
+      }
+    }
+  }
+
+  void emit_header() {
+    B200QFunction qf = op->qf;
+    c << "// Fused operator kernel generated by ceed-b200 for QFunction " << qf->kernel_name << "\n";
+    c << "#include <b200-jit.h>\n";
+    c << "#include \"" << qf->source_path << "\"\n\n";
+    for (size_t b = 0; b < plan->bases.size(); b++) {
+      const B200Basis bs = plan->bases[b].basis;
+      auto emit_mat      = [&](const string &name, const std::vector<double> &m) {
+        c << "__constant__ double " << name << "[" << m.size() << "] = {";
+        for (size_t i = 0; i < m.size(); i++) c << (i ? ", " : "") << hexd(m[i]);
+        c << "};\n";
+      };
+      emit_mat("cB" + std::to_string(b), bs->interp);
+      if (bs->has_collo_grad) emit_mat("cG" + std::to_string(b), bs->collo_grad);
+      emit_mat("cW" + std::to_string(b), bs->q_weight);
+    }
+    c << "\nstruct B200OpArgs {\n  long long num_elem;\n  void *ctx;\n  const double *in_ptr[16];\n  double *out_ptr[16];\n"
+      << "  const int *in_idx[16];\n  const int *out_idx[16];\n  double *out_aux[16];\n};\n\n";
+    c << "extern __shared__ double sm[];\n\n";
+  }
+
+  // ---- input side -------------------------------------------------------------------------------
+  void emit_gather_z(const B200GenGroup &g) {
+    const B200GenBasis &b  = basis(g.basis_id);
+    const int           P  = b.P;
+    const string        sl = std::to_string(g.slot);
+    comment("gather + z-contraction, input group slot " + std::to_string(g.slot));
+    task_loop_begin(std::to_string(E * g.nc * P * P));
+    c << "      const int ij = t % " << P * P << ", cc = (t / " << P * P << ") % " << g.nc << ", le = t / " << P * P * g.nc << ";\n";
+    c << "      const long long e = e0 + le;\n";
+    for (int k = 0; k < P; k++) c << "      double u" << k << " = 0.0;\n";
+    c << "      if (e < a.num_elem) {\n";
+    for (int k = 0; k < P; k++)
+      c << "        u" << k << " = __ldg(a.in_ptr[" << sl << "] + " << lidx(g.rstr, "a.in_idx[" + sl + "]", "e", "ij + " + std::to_string(k * P * P), "cc")
+        << ");\n";
+    c << "      }\n";
+    if (b.collocated) {
+      // nodes are the quadrature points: straight into the Uq plane [qz][qy][Qs]
+      c << "      double *dst = " << plane(g.plane0, "le") << " + cc * " << E * S << " + (ij / " << P << ") * " << Qs << " + (ij % " << P << ");\n";
+      for (int k = 0; k < P; k++) c << "      dst[" << k * Q * Qs << "] = u" << k << ";\n";
+    } else {
+      c << "      double *dst = " << plane(g.plane0, "le") << " + cc * " << E * S << " + ij;\n";  // T1 [qz][j][i] in plane A
+      contract("cB" + std::to_string(g.basis_id), P, Q, false, "u", "r", "      ");
+      for (int q = 0; q < Q; q++) c << "      dst[" << q * P * P << "] = r" << q << ";\n";
+    }
+    task_loop_end();
+  }
+
+  void emit_interp_y(const B200GenGroup &g) {
+    const B200GenBasis &b = basis(g.basis_id);
+    if (b.collocated) return;
+    const int P = b.P, Ps = odd_pad(P);
+    comment("y-contraction, input group slot " + std::to_string(g.slot));
+    task_loop_begin(std::to_string(E * g.nc * Q * P));
+    c << "      const int i = t % " << P << ", qz = (t / " << P << ") % " << Q << ", cc = (t / " << P * Q << ") % " << g.nc << ", le = t / "
+      << P * Q * g.nc << ";\n";
+    c << "      const double *src = " << plane(g.plane0, "le") << " + cc * " << E * S << " + qz * " << P * P << " + i;\n";
+    c << "      double *dst = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + qz * " << Q * Ps << " + i;\n";  // T2 in plane B
+    for (int j = 0; j < P; j++) c << "      const double u" << j << " = src[" << j * P << "];\n";
+    contract("cB" + std::to_string(g.basis_id), P, Q, false, "u", "r", "      ");
+    for (int q = 0; q < Q; q++) c << "      dst[" << q * Ps << "] = r" << q << ";\n";
+    task_loop_end();
+  }
+
+  void emit_interp_x(const B200GenGroup &g) {
+    const B200GenBasis &b = basis(g.basis_id);
+    const int           P = b.P, Ps = odd_pad(P);
+    if (b.collocated && !g.use_grad) return;
+    comment("x-contraction (+ d/dx), input group slot " + std::to_string(g.slot));
+    task_loop_begin(std::to_string(E * g.nc * Q * Q));
+    c << "      const int row = t % " << Q * Q << ", cc = (t / " << Q * Q << ") % " << g.nc << ", le = t / " << Q * Q * g.nc << ";\n";
+    c << "      double *uq = " << plane(g.plane0, "le") << " + cc * " << E * S << " + row * " << Qs << ";\n";
+    if (b.collocated) {
+      for (int q = 0; q < Q; q++) c << "      const double r" << q << " = uq[" << q << "];\n";
+    } else {
+      c << "      const double *src = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + row * " << Ps << ";\n";
+      for (int i = 0; i < P; i++) c << "      const double u" << i << " = src[" << i << "];\n";
+      contract("cB" + std::to_string(g.basis_id), P, Q, false, "u", "r", "      ");
+      for (int q = 0; q < Q; q++) c << "      uq[" << q << "] = r" << q << ";\n";
+    }
+    if (g.use_grad) {
+      c << "      double *gx = " << plane(g.plane0 + 2 * g.nc, "le") << " + cc * " << E * S << " + row * " << Qs << ";\n";
+      contract("cG" + std::to_string(g.basis_id), Q, Q, false, "r", "d", "      ");
+      for (int q = 0; q < Q; q++) c << "      gx[" << q << "] = d" << q << ";\n";
+    }
+    task_loop_end();
+  }
+
+  void emit_grad_y(const B200GenGroup &g) {
+    if (!g.use_grad) return;
+    comment("d/dy, input group slot " + std::to_string(g.slot));
+    task_loop_begin(std::to_string(E * g.nc * Q * Q));
+    c << "      const int qx = t % " << Q << ", qz = (t / " << Q << ") % " << Q << ", cc = (t / " << Q * Q << ") % " << g.nc << ", le = t / "
+      << Q * Q * g.nc << ";\n";
+    c << "      const double *src = " << plane(g.plane0, "le") << " + cc * " << E * S << " + qz * " << Q * Qs << " + qx;\n";
+    c << "      double *dst = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + qz * " << Q * Qs << " + qx;\n";
+    for (int m = 0; m < Q; m++) c << "      const double u" << m << " = src[" << m * Qs << "];\n";
+    contract("cG" + std::to_string(g.basis_id), Q, Q, false, "u", "d", "      ");
+    for (int q = 0; q < Q; q++) c << "      dst[" << q * Qs << "] = d" << q << ";\n";
+    task_loop_end();
+  }
+
+  // ---- quadrature-point stage -------------------------------------------------------------------
+  void emit_qf_stage() {
+    B200QFunction qf = op->qf;
+    comment("quadrature points: one z-line per thread; d/dz, QFunction, (d/dz)^T in registers");
+    task_loop_begin(std::to_string(E * Q * Q));
+    c << "      const int qx = t % " << Q << ", qy = (t / " << Q << ") % " << Q << ", le = t / " << Q * Q << ";\n";
+    c << "      const long long e = e0 + le;\n";
+    c << "      if (e < a.num_elem) {\n";
+    c << "      const int pxy = qy * " << Qs << " + qx;\n";
+    // z-lines of input groups that need gradients (and their d/dz)
+    for (size_t gi = 0; gi < plan->in_groups.size(); gi++) {
+      const B200GenGroup &g = plan->in_groups[gi];
+      if (!g.use_grad) continue;
+      for (int cc = 0; cc < g.nc; cc++) {
+        const string tag = "g" + std::to_string(gi) + "c" + std::to_string(cc) + "_";
+        c << "      const double *uq_" << tag << " = " << plane(g.plane0 + cc, "le") << " + pxy;\n";
+        for (int m = 0; m < Q; m++) c << "      const double uz_" << tag << m << " = uq_" << tag << "[" << m * Q * Qs << "];\n";
+        contract("cG" + std::to_string(g.basis_id), Q, Q, false, "uz_" + tag, "dz_" + tag, "      ");
+      }
+    }
+    // accumulators of (d/dz)^T for output groups
+    for (size_t gi = 0; gi < plan->out_groups.size(); gi++) {
+      const B200GenGroup &g = plan->out_groups[gi];
+      if (!g.use_grad) continue;
+      for (int cc = 0; cc < g.nc; cc++)
+        for (int m = 0; m < Q; m++) c << "      double vz_g" << gi << "c" << cc << "_" << m << " = 0.0;\n";
+    }
+    // weights
+    for (size_t f = 0; f < plan->in_fields.size(); f++)
+      if (plan->in_fields[f].emode == B200_EVAL_WEIGHT) {
+        const string w = "cW" + std::to_string(plan->in_fields[f].basis_id);
+        c << "      const double wxy_" << f << " = " << w << "[qx] * " << w << "[qy];\n";
+      }
+    c << "      const CeedScalar *in[" << std::max<size_t>(1, qf->inputs.size()) << "];\n";
+    c << "      CeedScalar *out[" << std::max<size_t>(1, qf->outputs.size()) << "];\n";
+    for (size_t f = 0; f < plan->in_fields.size(); f++) c << "      CeedScalar in_" << f << "[" << plan->in_fields[f].size << "];\n";
+    for (size_t f = 0; f < plan->out_fields.size(); f++) c << "      CeedScalar out_" << f << "[" << plan->out_fields[f].size << "];\n";
+    for (size_t f = 0; f < plan->in_fields.size(); f++) c << "      in[" << f << "] = in_" << f << ";\n";
+    for (size_t f = 0; f < plan->out_fields.size(); f++) c << "      out[" << f << "] = out_" << f << ";\n";
+    for (int qz = 0; qz < Q; qz++) {
+      c << "      {  // qz = " << qz << "\n";
+      c << "        const int p = pxy + " << qz * Q * Qs << ";\n";
+      c << "        const int pt = (" << qz * Q << " + qy) * " << Q << " + qx;\n";
+      for (size_t f = 0; f < plan->in_fields.size(); f++) {
+        const B200GenField &fd = plan->in_fields[f];
+        const string        sl = std::to_string(fd.slot);
+        switch (fd.emode) {
+          case B200_EVAL_NONE:
+            for (int cc = 0; cc < fd.nc; cc++)
+              c << "        in_" << f << "[" << cc << "] = __ldg(a.in_ptr[" << sl << "] + "
+                << lidx(fd.rstr, "a.in_idx[" + sl + "]", "e", "pt", std::to_string(cc)) << ");\n";
+            break;
+          case B200_EVAL_WEIGHT: c << "        in_" << f << "[0] = wxy_" << f << " * cW" << fd.basis_id << "[" << qz << "];\n"; break;
+          case B200_EVAL_INTERP: {
+            const B200GenGroup &g = plan->in_groups[fd.group];
+            for (int cc = 0; cc < fd.nc; cc++) {
+              if (g.use_grad) c << "        in_" << f << "[" << cc << "] = uz_g" << fd.group << "c" << cc << "_" << qz << ";\n";
+              else c << "        in_" << f << "[" << cc << "] = (" << plane(g.plane0 + cc, "le") << ")[p];\n";
+            }
+          } break;
+          case B200_EVAL_GRAD: {
+            const B200GenGroup &g = plan->in_groups[fd.group];
+            for (int cc = 0; cc < fd.nc; cc++) {
+              c << "        in_" << f << "[" << cc << "] = (" << plane(g.plane0 + 2 * g.nc + cc, "le") << ")[p];\n";
+              c << "        in_" << f << "[" << cc + fd.nc << "] = (" << plane(g.plane0 + g.nc + cc, "le") << ")[p];\n";
+              c << "        in_" << f << "[" << cc + 2 * fd.nc << "] = dz_g" << fd.group << "c" << cc << "_" << qz << ";\n";
+            }
+          } break;
+        }
+      }
+      c << "        " << qf->kernel_name << "(a.ctx, 1, in, out);\n";
+      // outputs: first group contributions (INTERP stores, then GRAD parts), then EVAL_NONE
+      for (size_t gi = 0; gi < plan->out_groups.size(); gi++) {
+        const B200GenGroup &g = plan->out_groups[gi];
+        for (int cc = 0; cc < g.nc; cc++) {
+          // value part
+          string val;
+          for (size_t f = 0; f < plan->out_fields.size(); f++) {
+            const B200GenField &fd = plan->out_fields[f];
+            if (fd.group == (int)gi && fd.emode == B200_EVAL_INTERP) val += (val.empty() ? "" : " + ") + ("out_" + std::to_string(f) + "[" + std::to_string(cc) + "]");
+          }
+          if (!val.empty()) c << "        (" << plane(g.plane0 + cc, "le") << ")[p] = " << val << ";\n";
+          if (g.use_grad) {
+            string vx, vy, vz;
+            for (size_t f = 0; f < plan->out_fields.size(); f++) {
+              const B200GenField &fd = plan->out_fields[f];
+              if (fd.group == (int)gi && fd.emode == B200_EVAL_GRAD) {
+                const string o = "out_" + std::to_string(f);
+                vx += (vx.empty() ? "" : " + ") + o + "[" + std::to_string(cc) + "]";
+                vy += (vy.empty() ? "" : " + ") + o + "[" + std::to_string(cc + fd.nc) + "]";
+                vz += (vz.empty() ? "" : " + ") + o + "[" + std::to_string(cc + 2 * fd.nc) + "]";
+              }
+            }
+            c << "        (" << plane(g.plane0 + 2 * g.nc + cc, "le") << ")[p] = " << vx << ";\n";
+            c << "        (" << plane(g.plane0 + g.nc + cc, "le") << ")[p] = " << vy << ";\n";
+            c << "        { const double vz = " << vz << ";\n";
+            for (int m = 0; m < Q; m++)
+              c << "          vz_g" << gi << "c" << cc << "_" << m << " = fma(cG" << g.basis_id << "[" << qz * Q + m << "], vz, vz_g" << gi << "c" << cc
+                << "_" << m << ");\n";
+            c << "        }\n";
+          }
+        }
+      }
+      for (size_t f = 0; f < plan->out_fields.size(); f++) {
+        const B200GenField &fd = plan->out_fields[f];
+        if (fd.emode != B200_EVAL_NONE) continue;
+        emit_scatter_value(fd.rstr, fd.slot, "e", "pt", fd.nc, [&](int cc) { return "out_" + std::to_string(f) + "[" + std::to_string(cc) + "]"; },
+                           "        ");
+      }
+      c << "      }\n";
+    }
+    // fold the z-part of the transposed gradient into Vq
+    for (size_t gi = 0; gi < plan->out_groups.size(); gi++) {
+      const B200GenGroup &g = plan->out_groups[gi];
+      if (!g.use_grad) continue;
+      for (int cc = 0; cc < g.nc; cc++) {
+        c << "      { double *vq = " << plane(g.plane0 + cc, "le") << " + pxy;\n";
+        for (int m = 0; m < Q; m++)
+          c << "        vq[" << m * Q * Qs << "] " << (g.use_interp ? "+=" : "=") << " vz_g" << gi << "c" << cc << "_" << m << ";\n";
+        c << "      }\n";
+      }
+    }
+    c << "      }\n";
+    task_loop_end();
+  }
+
+  // ---- output side ------------------------------------------------------------------------------
+  // Add `value(cc)` for E-entry n of element e into the L-vector of restriction r (output slot `slot`).
+  template <typename F>
+  void emit_scatter_value(B200Restriction r, int slot, const string &e, const string &n, int nc, F value, const string &ind) {
+    const string sl = std::to_string(slot);
+    if (r->is_strided) {
+      for (int cc = 0; cc < nc; cc++)
+        c << ind << "a.out_ptr[" << sl << "][" << lidx(r, "", e, n, std::to_string(cc)) << "] " << (add ? "+=" : "=") << " " << value(cc) << ";\n";
+      return;
+    }
+    const long long e_entries = (long long)r->num_elem * r->elem_size;
+    switch (plan->scatter_mode) {
+      case B200_SCATTER_ATOMIC:
+        for (int cc = 0; cc < nc; cc++)
+          c << ind << "atomicAdd(a.out_ptr[" << sl << "] + " << lidx(r, "a.out_idx[" + sl + "]", e, n, std::to_string(cc)) << ", " << value(cc) << ");\n";
+        break;
+      case B200_SCATTER_EVECTOR:
+        for (int cc = 0; cc < nc; cc++)
+          c << ind << "a.out_aux[" << sl << "][(" << e << ") * " << r->elem_size << "LL + (" << n << ") + " << cc * e_entries << "LL] = " << value(cc)
+            << ";\n";
+        break;
+      default:
+        c << ind << "{ const int tg = a.out_idx[" << sl << "][(" << e << ") * " << r->elem_size << "LL + (" << n << ")];\n";
+        c << ind << "  if (tg >= 0) {\n";
+        for (int cc = 0; cc < nc; cc++)
+          c << ind << "    a.out_ptr[" << sl << "][tg + " << (long long)cc * r->comp_stride << "LL] " << (add ? "+=" : "=") << " " << value(cc) << ";\n";
+        c << ind << "  } else {\n";
+        for (int cc = 0; cc < nc; cc++)
+          c << ind << "    a.out_aux[" << sl << "][(long long)(~tg) + " << (long long)cc * r->num_halo << "LL] = " << value(cc) << ";\n";
+        c << ind << "  } }\n";
+    }
+  }
+
+  void emit_gradT_y(const B200GenGroup &g) {
+    if (!g.use_grad) return;
+    comment("(d/dy)^T, output group slot " + std::to_string(g.slot));
+    task_loop_begin(std::to_string(E * g.nc * Q * Q));
+    c << "      const int qx = t % " << Q << ", qz = (t / " << Q << ") % " << Q << ", cc = (t / " << Q * Q << ") % " << g.nc << ", le = t / "
+      << Q * Q * g.nc << ";\n";
+    c << "      const double *src = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + qz * " << Q * Qs << " + qx;\n";
+    c << "      double *vq = " << plane(g.plane0, "le") << " + cc * " << E * S << " + qz * " << Q * Qs << " + qx;\n";
+    for (int m = 0; m < Q; m++) c << "      const double u" << m << " = src[" << m * Qs << "];\n";
+    contract("cG" + std::to_string(g.basis_id), Q, Q, true, "u", "d", "      ");
+    for (int q = 0; q < Q; q++) c << "      vq[" << q * Qs << "] += d" << q << ";\n";
+    task_loop_end();
+  }
+
+  void emit_interpT_x(const B200GenGroup &g) {
+    const B200GenBasis &b = basis(g.basis_id);
+    const int           P = b.P, Ps = odd_pad(P);
+    if (b.collocated && !g.use_grad) return;
+    comment("(d/dx)^T + x-contraction^T, output group slot " + std::to_string(g.slot));
+    task_loop_begin(std::to_string(E * g.nc * Q * Q));
+    c << "      const int row = t % " << Q * Q << ", cc = (t / " << Q * Q << ") % " << g.nc << ", le = t / " << Q * Q * g.nc << ";\n";
+    c << "      double *vq = " << plane(g.plane0, "le") << " + cc * " << E * S << " + row * " << Qs << ";\n";
+    if (g.use_grad) {
+      c << "      const double *vx = " << plane(g.plane0 + 2 * g.nc, "le") << " + cc * " << E * S << " + row * " << Qs << ";\n";
+      for (int m = 0; m < Q; m++) c << "      const double u" << m << " = vx[" << m << "];\n";
+      contract("cG" + std::to_string(g.basis_id), Q, Q, true, "u", "d", "      ");
+      for (int q = 0; q < Q; q++) c << "      const double v" << q << " = vq[" << q << "] + d" << q << ";\n";
+    } else {
+      for (int q = 0; q < Q; q++) c << "      const double v" << q << " = vq[" << q << "];\n";
+    }
+    if (b.collocated) {
+      for (int q = 0; q < Q; q++) c << "      vq[" << q << "] = v" << q << ";\n";
+    } else {
+      c << "      double *dst = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + row * " << Ps << ";\n";
+      contract("cB" + std::to_string(g.basis_id), Q, P, true, "v", "r", "      ");
+      for (int i = 0; i < P; i++) c << "      dst[" << i << "] = r" << i << ";\n";
+    }
+    task_loop_end();
+  }
+
+  void emit_interpT_y(const B200GenGroup &g) {
+    const B200GenBasis &b = basis(g.basis_id);
+    if (b.collocated) return;
+    const int P = b.P, Ps = odd_pad(P);
+    // T1' goes to plane C when the group has a gradient (plane A still holds nothing live, but keep A/B/C rotation simple)
+    const int t1_plane = g.plane0;  // Vq is dead after the x-stage
+    comment("y-contraction^T, output group slot " + std::to_string(g.slot));
+    task_loop_begin(std::to_string(E * g.nc * Q * P));
+    c << "      const int i = t % " << P << ", qz = (t / " << P << ") % " << Q << ", cc = (t / " << P * Q << ") % " << g.nc << ", le = t / "
+      << P * Q * g.nc << ";\n";
+    c << "      const double *src = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + qz * " << Q * Ps << " + i;\n";
+    c << "      double *dst = " << plane(t1_plane, "le") << " + cc * " << E * S << " + qz * " << P * P << " + i;\n";
+    for (int q = 0; q < Q; q++) c << "      const double u" << q << " = src[" << q * Ps << "];\n";
+    contract("cB" + std::to_string(g.basis_id), Q, P, true, "u", "r", "      ");
+    for (int j = 0; j < P; j++) c << "      dst[" << j * P << "] = r" << j << ";\n";
+    task_loop_end();
+  }
+
+  void emit_scatter_z(const B200GenGroup &g) {
+    const B200GenBasis &b = basis(g.basis_id);
+    const int           P = b.P;
+    comment("z-contraction^T + scatter, output group slot " + std::to_string(g.slot));
+    task_loop_begin(std::to_string(E * g.nc * P * P));
+    c << "      const int ij = t % " << P * P << ", cc = (t / " << P * P << ") % " << g.nc << ", le = t / " << P * P * g.nc << ";\n";
+    c << "      const long long e = e0 + le;\n";
+    if (b.collocated) {
+      c << "      const double *src = " << plane(g.plane0, "le") << " + cc * " << E * S << " + (ij / " << P << ") * " << Qs << " + (ij % " << P << ");\n";
+      for (int k = 0; k < P; k++) c << "      const double r" << k << " = src[" << k * Q * Qs << "];\n";
+    } else {
+      c << "      const double *src = " << plane(g.plane0, "le") << " + cc * " << E * S << " + ij;\n";
+      for (int q = 0; q < Q; q++) c << "      const double u" << q << " = src[" << q * P * P << "];\n";
+      contract("cB" + std::to_string(g.basis_id), Q, P, true, "u", "r", "      ");
+    }
+    c << "      if (e < a.num_elem) {\n";
+    // component handled through the (runtime) cc: emit with nc == 1 semantics and an explicit component offset
+    for (int k = 0; k < P; k++) emit_scatter_comp(g.rstr, g.slot, "e", "ij + " + std::to_string(k * P * P), "cc", "r" + std::to_string(k), "        ");
+    c << "      }\n";
+    task_loop_end();
+  }
+
+  // scatter of a single value for runtime component index `cc`
+  void emit_scatter_comp(B200Restriction r, int slot, const string &e, const string &n, const string &cc, const string &val, const string &ind) {
+    const string sl = std::to_string(slot);
+    if (r->is_strided) {
+      c << ind << "a.out_ptr[" << sl << "][" << lidx(r, "", e, n, cc) << "] " << (add ? "+=" : "=") << " " << val << ";\n";
+      return;
+    }
+    const long long e_entries = (long long)r->num_elem * r->elem_size;
+    switch (plan->scatter_mode) {
+      case B200_SCATTER_ATOMIC:
+        c << ind << "atomicAdd(a.out_ptr[" << sl << "] + " << lidx(r, "a.out_idx[" + sl + "]", e, n, cc) << ", " << val << ");\n";
+        break;
+      case B200_SCATTER_EVECTOR:
+        c << ind << "a.out_aux[" << sl << "][(" << e << ") * " << r->elem_size << "LL + (" << n << ") + " << cc << " * " << e_entries << "LL] = " << val
+          << ";\n";
+        break;
+      default:
+        c << ind << "{ const int tg = a.out_idx[" << sl << "][(" << e << ") * " << r->elem_size << "LL + (" << n << ")];\n";
+        c << ind << "  if (tg >= 0) a.out_ptr[" << sl << "][tg + " << cc << " * " << (long long)r->comp_stride << "LL] " << (add ? "+=" : "=") << " " << val
+          << ";\n";
+        c << ind << "  else a.out_aux[" << sl << "][(long long)(~tg) + " << cc << " * " << (long long)r->num_halo << "LL] = " << val << "; }\n";
+    }
+  }
+
+  string generate() {
+    Q  = plan->Q;
+    Qs = plan->Qs;
+    E  = plan->epb;
+    NT = plan->threads;
+    S  = plan->plane_size;
+    emit_header();
+    bool any;
+    // input side
+    for (auto &g : plan->in_groups) emit_gather_z(g);
+    if (!plan->in_groups.empty()) barrier();
+    any = false;
+    for (auto &g : plan->in_groups) any = any || !basis(g.basis_id).collocated;
+    if (any) {
+      for (auto &g : plan->in_groups) emit_interp_y(g);
+      barrier();
+    }
+    any = false;
+    for (auto &g : plan->in_groups) any = any || !(basis(g.basis_id).collocated && !g.use_grad);
+    if (any) {
+      for (auto &g : plan->in_groups) emit_interp_x(g);
+      barrier();
+    }
+    any = false;
+    for (auto &g : plan->in_groups) any = any || g.use_grad;
+    if (any) {
+      for (auto &g : plan->in_groups) emit_grad_y(g);
+      barrier();
+    }
+    emit_qf_stage();
+    if (!plan->out_groups.empty()) {
+      barrier();
+      any = false;
+      for (auto &g : plan->out_groups) any = any || g.use_grad;
+      if (any) {
+        for (auto &g : plan->out_groups) emit_gradT_y(g);
+        barrier();
+      }
+      any = false;
+      for (auto &g : plan->out_groups) any = any || !(basis(g.basis_id).collocated && !g.use_grad);
+      if (any) {
+        for (auto &g : plan->out_groups) emit_interpT_x(g);
+        barrier();
+      }
+      any = false;
+      for (auto &g : plan->out_groups) any = any || !basis(g.basis_id).collocated;
+      if (any) {
+        for (auto &g : plan->out_groups) emit_interpT_y(g);
+        barrier();
+      }
+      for (auto &g : plan->out_groups) emit_scatter_z(g);
+    }
+    barrier();
+    const int minb = std::max(1, plan->blocks_per_sm);
+    c << "extern \"C\" __global__ void __launch_bounds__(" << NT << ", " << minb << ") b200_operator(const __grid_constant__ B200OpArgs a) {\n";
+    c << "  const long long num_batches = (a.num_elem + " << E - 1 << ") / " << E << ";\n";
+    c << "  for (long long batch = blockIdx.x; batch < num_batches; batch += gridDim.x) {\n";
+    c << "    const long long e0 = batch * " << E << ";\n";
+    for (auto &call : calls) c << call;
+    c << "  }\n}\n";
+    return c.str();
+  }
+};
+
+}  // namespace
+
+std::string b200_opgen_source(B200Operator op, B200OpPlan *plan, int add) {
+  Gen g;
+  g.op   = op;
+  g.plan = plan;
+  g.add  = add;
+  return g.generate();
+}
+
+int b200_opgen_build(B200Operator op, B200OpPlan *plan, int add) {
+  B200Ceed           ceed = op->ceed;
+  B200KernelVariant &v    = plan->variant[add ? 1 : 0];
+  if (v.built) return B200_SUCCESS;
+  v.source = b200_opgen_source(op, plan, add);
+  B200_CALL(b200_jit_compile(ceed, v.source, {}, &v.module));
+  B200_CALL(b200_jit_get_kernel(ceed, v.module, "b200_operator", &v.kernel));
+  if (!b200_compile_only()) {
+    B200_CU(ceed, cuFuncSetAttribute(v.kernel, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, plan->smem_bytes));
+    int val = 0;
+    cuFuncGetAttribute(&val, CU_FUNC_ATTRIBUTE_NUM_REGS, v.kernel);
+    v.regs = val;
+    cuFuncGetAttribute(&val, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, v.kernel);
+    v.local_bytes = val;
+    cuFuncGetAttribute(&val, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, v.kernel);
+    v.static_smem = val;
+    int nb = 0;
+    B200_CU(ceed, cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.kernel, plan->threads, plan->smem_bytes));
+    if (nb < 1) return b200_error(ceed, B200_ERROR_BACKEND, "fused kernel cannot be resident (regs %d, smem %d)", v.regs, plan->smem_bytes);
+    plan->blocks_per_sm = op->tune_bpsm > 0 ? std::min(nb, op->tune_bpsm) : nb;
+    const long long num_batches = ((long long)plan->num_elem + plan->epb - 1) / plan->epb;
+    long long       grid        = (long long)plan->blocks_per_sm * ceed->num_sms;
+    if (grid > num_batches) grid = num_batches;
+    if (grid < 1) grid = 1;
+    plan->grid = (int)grid;
+  }
+  v.built = true;
+  return B200_SUCCESS;
+}

@@ -1,0 +1,76 @@
+// b200_opgen.h -- plan of one fused operator kernel (see b200_opgen.cpp)
+#pragma once
+#include <string>
+#include <vector>
+
+#include "b200_internal.h"
+
+struct B200GenBasis {
+  B200Basis basis;
+  int       P, Q;
+  bool      collocated;
+};
+
+// A group = all QFunction fields that share (restriction, vector, basis): gathered / scattered once.
+struct B200GenGroup {
+  bool            is_input   = true;
+  B200Restriction rstr       = nullptr;
+  B200Vector      vec        = nullptr;
+  bool            is_active  = false;
+  int             basis_id   = -1;
+  int             nc         = 1;
+  bool            use_interp = false, use_grad = false;
+  int             plane0     = 0;  // first shared-memory plane
+  int             slot       = 0;  // index into the kernel argument pointer tables
+};
+
+struct B200GenField {
+  int             emode = 0, size = 0, nc = 0;
+  int             group = -1;     // INTERP/GRAD fields
+  int             basis_id = -1;  // WEIGHT fields
+  B200Restriction rstr = nullptr; // NONE fields
+  B200Vector      vec = nullptr;
+  bool            is_active = false;
+  int             slot = 0;
+};
+
+struct B200OpArgs {
+  long long     num_elem;
+  void         *ctx;
+  const double *in_ptr[16];
+  double       *out_ptr[16];
+  const int    *in_idx[16];
+  const int    *out_idx[16];
+  double       *out_aux[16];  // halo buffer (deterministic) or E-vector (evector mode)
+};
+
+struct B200KernelVariant {
+  B200Module *module = nullptr;
+  CUfunction  kernel = nullptr;
+  std::string source;
+  int         regs = 0, local_bytes = 0, static_smem = 0;
+  bool        built = false;
+};
+
+struct B200OpPlan {
+  bool                      fused = false;
+  std::string               why_not_fused;
+  int                       dim = 0, Q = 0, Qs = 0;
+  int                       num_elem = 0;
+  int                       epb = 1, threads = 256, blocks_per_sm = 1, grid = 1;
+  int                       plane_size = 0, num_planes = 0, smem_bytes = 0;
+  int                       scatter_mode = 0;
+  std::vector<B200GenBasis> bases;
+  std::vector<B200GenGroup> in_groups, out_groups;
+  std::vector<B200GenField> in_fields, out_fields;
+  B200KernelVariant         variant[2];  // [0] overwrite (Apply), [1] add (ApplyAdd)
+  // per output slot: auxiliary device buffer (halo or E-vector)
+  double *aux[16]       = {nullptr};
+  size_t  aux_bytes[16] = {0};
+  // unfused fallback scratch
+  std::vector<B200Vector> e_in, q_in, e_out, q_out;
+};
+
+int b200_opgen_plan(B200Operator op, B200OpPlan *plan);
+int b200_opgen_build(B200Operator op, B200OpPlan *plan, int add);
+std::string b200_opgen_source(B200Operator op, B200OpPlan *plan, int add);

@@ -1,0 +1,358 @@
+// b200_restriction.cu -- CeedElemRestriction for the b200 backend (standard offsets + strided).
+//
+// Behaviour follows backends/cuda-ref/ceed-cuda-ref-restriction.c:
+//   * E-vector layout {1, num_elem*elem_size, elem_size} = [comp][elem][node]           (:530-541)
+//   * NoTranspose:  v[n + e*S + c*S*Ne] = u[offsets[n + e*S] + c*comp_stride]            (cuda-ref-restriction-offset.h:15-26)
+//   * Transpose is DETERMINISTIC: per referenced L-node, E-entries are summed in ascending (elem,node) order -- the
+//     order of the serial CPU loop in backends/ref/ceed-ref-restriction.c:220-242 -- through a transpose CSR built
+//     at setup (cuda-ref-restriction.c:416-493), so results are bit-identical to /cpu/self/ref/serial.
+//   * strided: L-index = n*strides[0] + c*strides[1] + e*strides[2]                      (cuda-ref-restriction-strided.h:15-39)
+// In addition, an "owner/halo" decomposition of the transpose is built for the fused operator kernel (see
+// b200_restriction_build_owner): the first E-entry of every L-node owns the store, the remaining entries go through
+// a compact halo buffer that a finalize kernel folds in, again in ascending E-order.
+// All index arithmetic on E-/Q-sized ranges is 64-bit (CeedInt overflows at 100M DoFs).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "b200_internal.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline unsigned grid_for(B200Ceed ceed, int64_t n) {
+  int64_t blocks = (n + kThreads - 1) / kThreads;
+  int64_t cap    = (int64_t)ceed->num_sms * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+__global__ void k_offset_notranspose(const int32_t *__restrict__ offsets, const double *__restrict__ u, double *__restrict__ v, int64_t e_entries,
+                                     int num_comp, int64_t comp_stride) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e_entries; i += stride) {
+    const int64_t l = offsets[i];
+    for (int c = 0; c < num_comp; c++) v[i + c * e_entries] = u[l + c * comp_stride];
+  }
+}
+
+// One thread per referenced L-node; fixed summation order => deterministic and equal to the serial reference.
+__global__ void k_offset_transpose(const int32_t *__restrict__ lvec_indices, const int32_t *__restrict__ t_offsets,
+                                   const int32_t *__restrict__ t_indices, const double *__restrict__ u, double *__restrict__ v, int64_t num_nodes,
+                                   int64_t e_entries, int num_comp, int64_t comp_stride) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_nodes; i += stride) {
+    const int64_t l     = lvec_indices[i];
+    const int32_t begin = t_offsets[i], end = t_offsets[i + 1];
+    for (int c = 0; c < num_comp; c++) {
+      double acc = v[l + c * comp_stride];
+      for (int32_t j = begin; j < end; j++) acc += u[(int64_t)t_indices[j] + c * e_entries];
+      v[l + c * comp_stride] = acc;
+    }
+  }
+}
+
+__global__ void k_strided_notranspose(const double *__restrict__ u, double *__restrict__ v, int64_t num_elem, int elem_size, int num_comp, int64_t s0,
+                                      int64_t s1, int64_t s2) {
+  int64_t e_entries = num_elem * elem_size;
+  int64_t stride    = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e_entries; i += stride) {
+    const int64_t e = i / elem_size, n = i - e * elem_size;
+    for (int c = 0; c < num_comp; c++) v[i + c * e_entries] = u[n * s0 + c * s1 + e * s2];
+  }
+}
+__global__ void k_strided_transpose(const double *__restrict__ u, double *__restrict__ v, int64_t num_elem, int elem_size, int num_comp, int64_t s0,
+                                    int64_t s1, int64_t s2) {
+  int64_t e_entries = num_elem * elem_size;
+  int64_t stride    = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e_entries; i += stride) {
+    const int64_t e = i / elem_size, n = i - e * elem_size;
+    for (int c = 0; c < num_comp; c++) v[n * s0 + c * s1 + e * s2] += u[i + c * e_entries];
+  }
+}
+
+// Fold the halo buffer of the fused operator kernel into v: v[node] += sum of the node's non-owner contributions
+// (ascending E-order).  halo is [comp][num_halo].
+__global__ void k_halo_finalize(const int32_t *__restrict__ halo_node, const int32_t *__restrict__ halo_ptr, const double *__restrict__ halo,
+                                double *__restrict__ v, int64_t num_shared, int64_t num_halo, int num_comp, int64_t comp_stride) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_shared; i += stride) {
+    const int64_t l     = halo_node[i];
+    const int32_t begin = halo_ptr[i], end = halo_ptr[i + 1];
+    for (int c = 0; c < num_comp; c++) {
+      double acc = v[l + c * comp_stride];
+      for (int32_t j = begin; j < end; j++) acc += halo[(int64_t)j + c * num_halo];
+      v[l + c * comp_stride] = acc;
+    }
+  }
+}
+
+}  // namespace
+
+#define LAUNCH(ceed, kernel, n, ...)                                                                                  \
+  do {                                                                                                                \
+    B200_CHECK(!b200_compile_only(), ceed, B200_ERROR_BACKEND, "CEED_B200_COMPILE_ONLY is set; kernels cannot run");   \
+    kernel<<<grid_for(ceed, n), kThreads, 0, (ceed)->stream>>>(__VA_ARGS__);                                          \
+    (ceed)->launch_count++;                                                                                           \
+    B200_CUDA(ceed, cudaGetLastError());                                                                              \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ setup
+extern "C" int ceedb200_restriction_create(B200Ceed ceed, b200_int num_elem, b200_int elem_size, b200_int num_comp, b200_int comp_stride,
+                                           b200_size l_size, int mem_type, int copy_mode, const b200_int *offsets, B200Restriction *rstr_out) {
+  B200_CHECK(num_elem >= 0 && elem_size > 0 && num_comp > 0, ceed, B200_ERROR_DIMENSION, "invalid restriction dimensions");
+  B200Restriction r = new B200Restriction_();
+  r->ceed           = ceed;
+  r->num_elem       = num_elem;
+  r->elem_size      = elem_size;
+  r->num_comp       = num_comp;
+  r->comp_stride    = comp_stride;
+  r->l_size         = l_size;
+  const int64_t n   = (int64_t)num_elem * elem_size;
+  const size_t  bytes = n * sizeof(int32_t);
+  if (mem_type == B200_MEM_HOST) {
+    switch (copy_mode) {
+      case B200_COPY_VALUES:
+        r->h_offsets_owned = (int32_t *)malloc(bytes ? bytes : 4);
+        memcpy(r->h_offsets_owned, offsets, bytes);
+        r->h_offsets = r->h_offsets_owned;
+        break;
+      case B200_OWN_POINTER:
+        r->h_offsets_owned = (int32_t *)offsets;
+        r->h_offsets       = offsets;
+        break;
+      default:
+        r->h_offsets_borrowed = offsets;
+        r->h_offsets          = offsets;
+    }
+    B200_CALL(b200_dmalloc(ceed, (void **)&r->d_offsets, bytes));
+    r->d_offsets_owned = true;
+    B200_CALL(b200_h2d(ceed, r->d_offsets, r->h_offsets, bytes));
+  } else {
+    // device offsets: keep (copy or adopt) the device array and mirror it on the host for the setup analysis
+    if (copy_mode == B200_COPY_VALUES) {
+      B200_CALL(b200_dmalloc(ceed, (void **)&r->d_offsets, bytes));
+      r->d_offsets_owned = true;
+      B200_CALL(b200_d2d(ceed, r->d_offsets, offsets, bytes));
+    } else {
+      r->d_offsets       = (int32_t *)offsets;
+      r->d_offsets_owned = copy_mode == B200_OWN_POINTER;
+    }
+    r->h_offsets_owned = (int32_t *)malloc(bytes ? bytes : 4);
+    B200_CALL(b200_d2h(ceed, r->h_offsets_owned, r->d_offsets, bytes));
+    r->h_offsets = r->h_offsets_owned;
+  }
+  for (int64_t i = 0; i < n; i++) {
+    const int64_t l = r->h_offsets[i];
+    if (l < 0 || l + (int64_t)(num_comp - 1) * comp_stride >= l_size) {
+      int code = b200_error(ceed, B200_ERROR_DIMENSION, "Restriction offset %lld (%lld) out of range [0, %lld)", (long long)i, (long long)l,
+                            (long long)l_size);
+      ceedb200_restriction_destroy(r);
+      return code;
+    }
+  }
+  *rstr_out = r;
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_restriction_create_strided(B200Ceed ceed, b200_int num_elem, b200_int elem_size, b200_int num_comp, b200_size l_size,
+                                                   const b200_int strides[3], B200Restriction *rstr_out) {
+  B200_CHECK(num_elem >= 0 && elem_size > 0 && num_comp > 0, ceed, B200_ERROR_DIMENSION, "invalid restriction dimensions");
+  B200Restriction r = new B200Restriction_();
+  r->ceed           = ceed;
+  r->num_elem       = num_elem;
+  r->elem_size      = elem_size;
+  r->num_comp       = num_comp;
+  r->l_size         = l_size;
+  r->is_strided     = true;
+  if (!strides || (strides[0] == 0 && strides[1] == 0 && strides[2] == 0)) {
+    // CEED_STRIDES_BACKEND: same choice as the reference CUDA backends (cuda-gen-operator-build.cpp:466)
+    r->backend_strides = true;
+    r->strides[0]      = 1;
+    r->strides[1]      = (int64_t)elem_size * num_elem;
+    r->strides[2]      = elem_size;
+  } else {
+    for (int i = 0; i < 3; i++) r->strides[i] = strides[i];
+  }
+  *rstr_out = r;
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_restriction_destroy(B200Restriction r) {
+  if (!r) return B200_SUCCESS;
+  B200Ceed ceed = r->ceed;
+  free(r->h_offsets_owned);
+  if (r->d_offsets_owned) b200_dfree(ceed, r->d_offsets);
+  b200_dfree(ceed, r->d_lvec_indices);
+  b200_dfree(ceed, r->d_t_offsets);
+  b200_dfree(ceed, r->d_t_indices);
+  b200_dfree(ceed, r->d_tgt);
+  b200_dfree(ceed, r->d_halo_node);
+  b200_dfree(ceed, r->d_halo_ptr);
+  delete r;
+  return B200_SUCCESS;
+}
+
+// Host-side transpose CSR (counting sort by L-index; stable => ascending E-order inside each row).
+struct HostTranspose {
+  std::vector<int32_t> lvec_indices, t_offsets, t_indices;
+};
+static void build_host_transpose(B200Restriction r, HostTranspose &t) {
+  const int64_t        n = (int64_t)r->num_elem * r->elem_size;
+  std::vector<int32_t> count(r->l_size + 1, 0);
+  for (int64_t i = 0; i < n; i++) count[r->h_offsets[i] + 1]++;
+  int64_t num_nodes = 0;
+  for (int64_t l = 0; l < r->l_size; l++) num_nodes += count[l + 1] > 0;
+  t.lvec_indices.resize(num_nodes);
+  t.t_offsets.resize(num_nodes + 1);
+  t.t_indices.resize(n);
+  // compact row id per L-index + row starts
+  std::vector<int32_t> row_of(r->l_size, -1);
+  int64_t              row = 0, pos = 0;
+  for (int64_t l = 0; l < r->l_size; l++) {
+    if (count[l + 1] > 0) {
+      row_of[l]            = (int32_t)row;
+      t.lvec_indices[row]  = (int32_t)l;
+      t.t_offsets[row]     = (int32_t)pos;
+      pos += count[l + 1];
+      row++;
+    }
+  }
+  t.t_offsets[num_nodes] = (int32_t)pos;
+  std::vector<int32_t> fill(t.t_offsets.begin(), t.t_offsets.end() - 1);
+  for (int64_t i = 0; i < n; i++) t.t_indices[fill[row_of[r->h_offsets[i]]]++] = (int32_t)i;
+}
+
+int b200_restriction_build_transpose(B200Restriction r) {
+  if (r->transpose_built || r->is_strided) return B200_SUCCESS;
+  B200Ceed      ceed = r->ceed;
+  HostTranspose t;
+  build_host_transpose(r, t);
+  r->num_nodes = (int64_t)t.lvec_indices.size();
+  B200_CALL(b200_dmalloc(ceed, (void **)&r->d_lvec_indices, t.lvec_indices.size() * sizeof(int32_t)));
+  B200_CALL(b200_dmalloc(ceed, (void **)&r->d_t_offsets, t.t_offsets.size() * sizeof(int32_t)));
+  B200_CALL(b200_dmalloc(ceed, (void **)&r->d_t_indices, t.t_indices.size() * sizeof(int32_t)));
+  B200_CALL(b200_h2d(ceed, r->d_lvec_indices, t.lvec_indices.data(), t.lvec_indices.size() * sizeof(int32_t)));
+  B200_CALL(b200_h2d(ceed, r->d_t_offsets, t.t_offsets.data(), t.t_offsets.size() * sizeof(int32_t)));
+  B200_CALL(b200_h2d(ceed, r->d_t_indices, t.t_indices.data(), t.t_indices.size() * sizeof(int32_t)));
+  r->transpose_built = true;
+  return B200_SUCCESS;
+}
+
+// Owner/halo decomposition used by the fused operator kernel's deterministic scatter:
+//   tgt[E-entry] >= 0 : this entry is the FIRST (lowest E-index) reference to its L-node; the kernel stores/accumulates
+//                       its value straight into v[tgt] -- exactly one such entry per node, so no race and no atomics.
+//   tgt[E-entry] <  0 : ~tgt is a slot of the halo buffer.  Slots are grouped by node (halo_ptr CSR over the compact list
+//                       of shared nodes halo_node) and ordered by ascending E-index inside a node, so the finalize kernel
+//                       reads them contiguously and adds them in the same order as the serial reference scatter.
+int b200_restriction_build_owner(B200Restriction r) {
+  if (r->owner_built || r->is_strided) return B200_SUCCESS;
+  B200Ceed      ceed = r->ceed;
+  HostTranspose t;
+  build_host_transpose(r, t);
+  const int64_t        n         = (int64_t)r->num_elem * r->elem_size;
+  const int64_t        num_nodes = (int64_t)t.lvec_indices.size();
+  std::vector<int32_t> tgt(n), halo_node, halo_ptr;
+  int64_t              slot = 0;
+  for (int64_t row = 0; row < num_nodes; row++) {
+    const int32_t begin = t.t_offsets[row], end = t.t_offsets[row + 1];
+    tgt[t.t_indices[begin]] = t.lvec_indices[row];
+    if (end - begin > 1) {
+      halo_node.push_back(t.lvec_indices[row]);
+      halo_ptr.push_back((int32_t)slot);
+      for (int32_t j = begin + 1; j < end; j++) tgt[t.t_indices[j]] = ~(int32_t)(slot++);
+    }
+  }
+  halo_ptr.push_back((int32_t)slot);
+  r->num_shared = (int64_t)halo_node.size();
+  r->num_halo   = slot;
+  r->num_nodes  = num_nodes;
+  B200_CALL(b200_dmalloc(ceed, (void **)&r->d_tgt, n * sizeof(int32_t)));
+  B200_CALL(b200_dmalloc(ceed, (void **)&r->d_halo_node, halo_node.size() * sizeof(int32_t)));
+  B200_CALL(b200_dmalloc(ceed, (void **)&r->d_halo_ptr, halo_ptr.size() * sizeof(int32_t)));
+  B200_CALL(b200_h2d(ceed, r->d_tgt, tgt.data(), n * sizeof(int32_t)));
+  if (!halo_node.empty()) B200_CALL(b200_h2d(ceed, r->d_halo_node, halo_node.data(), halo_node.size() * sizeof(int32_t)));
+  B200_CALL(b200_h2d(ceed, r->d_halo_ptr, halo_ptr.data(), halo_ptr.size() * sizeof(int32_t)));
+  r->owner_built = true;
+  return B200_SUCCESS;
+}
+
+int b200_restriction_e_size(B200Restriction r, int64_t *e_size) {
+  *e_size = (int64_t)r->num_elem * r->elem_size * r->num_comp;
+  return B200_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------ apply
+int b200_restriction_apply_raw(B200Restriction r, int t_mode, const double *d_u, double *d_v) {
+  B200Ceed      ceed      = r->ceed;
+  const int64_t e_entries = (int64_t)r->num_elem * r->elem_size;
+  if (e_entries == 0) return B200_SUCCESS;
+  if (r->is_strided) {
+    if (t_mode == B200_NOTRANSPOSE)
+      LAUNCH(ceed, k_strided_notranspose, e_entries, d_u, d_v, (int64_t)r->num_elem, r->elem_size, r->num_comp, r->strides[0], r->strides[1],
+             r->strides[2]);
+    else
+      LAUNCH(ceed, k_strided_transpose, e_entries, d_u, d_v, (int64_t)r->num_elem, r->elem_size, r->num_comp, r->strides[0], r->strides[1],
+             r->strides[2]);
+  } else if (t_mode == B200_NOTRANSPOSE) {
+    LAUNCH(ceed, k_offset_notranspose, e_entries, r->d_offsets, d_u, d_v, e_entries, r->num_comp, r->comp_stride);
+  } else {
+    B200_CALL(b200_restriction_build_transpose(r));
+    LAUNCH(ceed, k_offset_transpose, r->num_nodes, r->d_lvec_indices, r->d_t_offsets, r->d_t_indices, d_u, d_v, r->num_nodes, e_entries, r->num_comp,
+           r->comp_stride);
+  }
+  return B200_SUCCESS;
+}
+
+int b200_halo_finalize(B200Restriction r, const double *d_halo, double *d_v) {
+  B200Ceed ceed = r->ceed;
+  if (r->num_shared == 0) return B200_SUCCESS;
+  LAUNCH(ceed, k_halo_finalize, r->num_shared, r->d_halo_node, r->d_halo_ptr, d_halo, d_v, r->num_shared, r->num_halo, r->num_comp, r->comp_stride);
+  return B200_SUCCESS;
+}
+
+// CeedElemRestrictionApply: NoTranspose overwrites the E-vector, Transpose ADDS into the L-vector
+// (interface/ceed-elemrestriction.c CeedElemRestrictionApply doc; backends/ref/ceed-ref-restriction.c:220-242).
+extern "C" int ceedb200_restriction_apply(B200Restriction r, int t_mode, B200Vector u, B200Vector v) {
+  B200Ceed ceed = r->ceed;
+  int64_t  e_size;
+  B200_CALL(b200_restriction_e_size(r, &e_size));
+  if (t_mode == B200_NOTRANSPOSE) {
+    B200_CHECK(u->length >= r->l_size && v->length >= e_size, ceed, B200_ERROR_DIMENSION,
+               "Input/output vectors too small for restriction: need L %lld, E %lld", (long long)r->l_size, (long long)e_size);
+  } else {
+    B200_CHECK(v->length >= r->l_size && u->length >= e_size, ceed, B200_ERROR_DIMENSION,
+               "Input/output vectors too small for transpose restriction: need L %lld, E %lld", (long long)r->l_size, (long long)e_size);
+  }
+  const double *d_u;
+  double       *d_v;
+  B200_CALL(b200_vector_device_read(u, &d_u));
+  // NoTranspose writes every E-entry; a longer destination keeps its remaining data
+  B200_CALL(b200_vector_device_write(v, &d_v, t_mode == B200_NOTRANSPOSE && v->length == e_size));
+  return b200_restriction_apply_raw(r, t_mode, d_u, d_v);
+}
+
+extern "C" int ceedb200_restriction_get_offsets(B200Restriction r, int mem_type, const b200_int **offsets) {
+  B200_CHECK(!r->is_strided, r->ceed, B200_ERROR_UNSUPPORTED, "strided restriction has no offsets");
+  *offsets = mem_type == B200_MEM_HOST ? r->h_offsets : r->d_offsets;
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_restriction_get_e_layout(B200Restriction r, b200_int layout[3]) {
+  layout[0] = 1;
+  layout[1] = r->elem_size * r->num_elem;
+  layout[2] = r->elem_size;
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_restriction_get_info(B200Restriction r, b200_int *num_elem, b200_int *elem_size, b200_int *num_comp, b200_size *l_size,
+                                             b200_size *e_size) {
+  if (num_elem) *num_elem = r->num_elem;
+  if (elem_size) *elem_size = r->elem_size;
+  if (num_comp) *num_comp = r->num_comp;
+  if (l_size) *l_size = r->l_size;
+  if (e_size) *e_size = (int64_t)r->num_elem * r->elem_size * r->num_comp;
+  return B200_SUCCESS;
+}

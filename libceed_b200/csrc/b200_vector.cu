@@ -1,0 +1,423 @@
+// b200_vector.cu -- CeedVector for the b200 backend: host/device mirrors with lazy synchronisation and BLAS-1 kernels.
+//
+// Semantics follow the reference CUDA vector (backends/cuda-ref/ceed-cuda-ref-vector.c): a vector has up to two
+// storage sides (host, device), each either owned or borrowed; `h_array`/`d_array` are non-NULL only while that
+// side holds valid data (:116-130); read access syncs lazily (:96-114), write access invalidates the other side.
+// Kernels are grid-stride and vectorised (double2) -- HBM-bound streaming ops sized in multiples of the SM count.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "b200_internal.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline unsigned grid_for(B200Ceed ceed, int64_t n, int per_thread = 2) {
+  int64_t blocks = (n + (int64_t)kThreads * per_thread - 1) / ((int64_t)kThreads * per_thread);
+  int64_t cap    = (int64_t)ceed->num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+__global__ void k_set_value(double *__restrict__ v, int64_t n, double val) {
+  int64_t i      = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // vectorised body when aligned
+  if ((reinterpret_cast<uintptr_t>(v) & 15) == 0) {
+    double2 *v2 = reinterpret_cast<double2 *>(v);
+    int64_t  n2 = n >> 1;
+    for (int64_t j = i; j < n2; j += stride) v2[j] = make_double2(val, val);
+    if (i == 0 && (n & 1)) v[n - 1] = val;
+  } else {
+    for (int64_t j = i; j < n; j += stride) v[j] = val;
+  }
+}
+__global__ void k_set_value_strided(double *__restrict__ v, int64_t start, int64_t stop, int64_t step, double val) {
+  int64_t i      = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t count  = (stop - start + step - 1) / step;
+  for (int64_t j = i; j < count; j += stride) v[start + j * step] = val;
+}
+__global__ void k_copy_strided(const double *__restrict__ src, double *__restrict__ dst, int64_t start, int64_t stop, int64_t step) {
+  int64_t i      = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t count  = (stop - start + step - 1) / step;
+  for (int64_t j = i; j < count; j += stride) dst[start + j * step] = src[start + j * step];
+}
+__global__ void k_scale(double *__restrict__ x, int64_t n, double alpha) {
+  int64_t i      = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = i; j < n; j += stride) x[j] *= alpha;
+}
+__global__ void k_reciprocal(double *__restrict__ x, int64_t n) {
+  int64_t i      = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = i; j < n; j += stride) {
+    double v = x[j];
+    if (fabs(v) > 1e-16) x[j] = 1.0 / v;  // CEED_EPSILON guard as cuda-ref-vector.cu:84-100
+  }
+}
+__global__ void k_filter(double *__restrict__ x, int64_t n, double eps) {
+  int64_t i      = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = i; j < n; j += stride) {
+    if (fabs(x[j]) < eps) x[j] = 0.0;
+  }
+}
+__global__ void k_axpy(double *__restrict__ y, double alpha, const double *__restrict__ x, int64_t n) {
+  int64_t i      = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = i; j < n; j += stride) y[j] += alpha * x[j];
+}
+__global__ void k_axpby(double *__restrict__ y, double alpha, double beta, const double *__restrict__ x, int64_t n) {
+  int64_t i      = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = i; j < n; j += stride) y[j] = alpha * x[j] + beta * y[j];
+}
+__global__ void k_pointwise_mult(double *w, const double *x, const double *y, int64_t n) {
+  int64_t i      = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = i; j < n; j += stride) w[j] = x[j] * y[j];
+}
+
+// norm reduction: mode 0 = sum|x|, 1 = sum x^2, 2 = max|x|.  Deterministic: fixed grid, fixed tree order.
+__global__ void k_norm_partial(const double *__restrict__ x, int64_t n, int mode, double *__restrict__ partial) {
+  __shared__ double s[kThreads];
+  int64_t           i      = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t           stride = (int64_t)gridDim.x * blockDim.x;
+  double            acc    = 0.0;
+  for (int64_t j = i; j < n; j += stride) {
+    double v = fabs(x[j]);
+    if (mode == 0) acc += v;
+    else if (mode == 1) acc += v * v;
+    else acc = fmax(acc, v);
+  }
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = kThreads / 2; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) s[threadIdx.x] = (mode == 2) ? fmax(s[threadIdx.x], s[threadIdx.x + w]) : s[threadIdx.x] + s[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = s[0];
+}
+
+int host_alloc(B200Vector vec) {
+  if (!vec->h_owned && !vec->h_borrowed) {
+    vec->h_owned = (double *)calloc(vec->length > 0 ? vec->length : 1, sizeof(double));
+    B200_CHECK(vec->h_owned, vec->ceed, B200_ERROR_MAJOR, "host allocation of %lld doubles failed", (long long)vec->length);
+  }
+  return B200_SUCCESS;
+}
+int device_alloc(B200Vector vec) {
+  if (!vec->d_owned && !vec->d_borrowed) B200_CALL(b200_dmalloc(vec->ceed, (void **)&vec->d_owned, vec->length * sizeof(double)));
+  return B200_SUCCESS;
+}
+inline double *host_ptr(B200Vector vec) { return vec->h_borrowed ? vec->h_borrowed : vec->h_owned; }
+inline double *device_ptr(B200Vector vec) { return vec->d_borrowed ? vec->d_borrowed : vec->d_owned; }
+
+int sync_to(B200Vector vec, int mem_type) {
+  B200Ceed ceed = vec->ceed;
+  B200_CHECK(vec->h_array || vec->d_array, ceed, B200_ERROR_BACKEND, "Invalid data access: CeedVector has no valid data to sync");
+  size_t bytes = vec->length * sizeof(double);
+  if (mem_type == B200_MEM_HOST && !vec->h_array) {
+    B200_CALL(host_alloc(vec));
+    B200_CALL(b200_d2h(ceed, host_ptr(vec), vec->d_array, bytes));
+    vec->h_array = host_ptr(vec);
+  } else if (mem_type == B200_MEM_DEVICE && !vec->d_array) {
+    B200_CALL(device_alloc(vec));
+    B200_CALL(b200_h2d(ceed, device_ptr(vec), vec->h_array, bytes));
+    vec->d_array = device_ptr(vec);
+  }
+  return B200_SUCCESS;
+}
+
+}  // namespace
+
+#define LAUNCH(ceed, kernel, n, ...)                                                            \
+  do {                                                                                          \
+    B200_CHECK(!b200_compile_only(), ceed, B200_ERROR_BACKEND, "CEED_B200_COMPILE_ONLY is set; kernels cannot run"); \
+    kernel<<<grid_for(ceed, n), kThreads, 0, (ceed)->stream>>>(__VA_ARGS__);                    \
+    (ceed)->launch_count++;                                                                     \
+    B200_CUDA(ceed, cudaGetLastError());                                                        \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ internal access
+int b200_vector_device_read(B200Vector vec, const double **d) {
+  B200_CALL(sync_to(vec, B200_MEM_DEVICE));
+  *d = vec->d_array;
+  return B200_SUCCESS;
+}
+int b200_vector_device_write(B200Vector vec, double **d, bool discard) {
+  if (discard) {
+    B200_CALL(device_alloc(vec));
+    vec->d_array = device_ptr(vec);
+  } else {
+    B200_CALL(sync_to(vec, B200_MEM_DEVICE));
+  }
+  vec->h_array = nullptr;
+  *d           = vec->d_array;
+  return B200_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" int ceedb200_vector_create(B200Ceed ceed, b200_size length, B200Vector *vec) {
+  B200_CHECK(length >= 0, ceed, B200_ERROR_DIMENSION, "negative vector length");
+  B200Vector v = new B200Vector_();
+  v->ceed      = ceed;
+  v->length    = length;
+  *vec         = v;
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_vector_destroy(B200Vector vec) {
+  if (!vec) return B200_SUCCESS;
+  free(vec->h_owned);
+  b200_dfree(vec->ceed, vec->d_owned);
+  delete vec;
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_vector_length(B200Vector vec, b200_size *length) {
+  *length = vec->length;
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_vector_has_valid_array(B200Vector vec, int *has_valid) {
+  *has_valid = (vec->h_array || vec->d_array) ? 1 : 0;
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_vector_has_borrowed_array_of_type(B200Vector vec, int mem_type, int *has_borrowed) {
+  *has_borrowed = mem_type == B200_MEM_HOST ? (vec->h_borrowed != nullptr) : (vec->d_borrowed != nullptr);
+  return B200_SUCCESS;
+}
+
+// CeedVectorSetArray_Cuda (ceed-cuda-ref-vector.c:177-228): the given side becomes the only valid one.
+extern "C" int ceedb200_vector_set_array(B200Vector vec, int mem_type, int copy_mode, b200_scalar *array) {
+  B200Ceed ceed  = vec->ceed;
+  size_t   bytes = vec->length * sizeof(double);
+  if (mem_type == B200_MEM_HOST) {
+    switch (copy_mode) {
+      case B200_COPY_VALUES:
+        B200_CALL(host_alloc(vec));
+        if (array) memcpy(host_ptr(vec), array, bytes);
+        break;
+      case B200_OWN_POINTER:
+        free(vec->h_owned);
+        vec->h_owned    = array;
+        vec->h_borrowed = nullptr;
+        break;
+      case B200_USE_POINTER:
+        free(vec->h_owned);
+        vec->h_owned    = nullptr;
+        vec->h_borrowed = array;
+        break;
+      default:
+        return b200_error(ceed, B200_ERROR_UNSUPPORTED, "unknown copy mode");
+    }
+    vec->h_array = host_ptr(vec);
+    vec->d_array = nullptr;
+  } else {
+    switch (copy_mode) {
+      case B200_COPY_VALUES:
+        B200_CALL(device_alloc(vec));
+        if (array) B200_CALL(b200_d2d(ceed, device_ptr(vec), array, bytes));
+        break;
+      case B200_OWN_POINTER:
+        B200_CALL(b200_dfree(ceed, vec->d_owned));
+        vec->d_owned    = array;
+        vec->d_borrowed = nullptr;
+        break;
+      case B200_USE_POINTER:
+        B200_CALL(b200_dfree(ceed, vec->d_owned));
+        vec->d_owned    = nullptr;
+        vec->d_borrowed = array;
+        break;
+      default:
+        return b200_error(ceed, B200_ERROR_UNSUPPORTED, "unknown copy mode");
+    }
+    vec->d_array = device_ptr(vec);
+    vec->h_array = nullptr;
+  }
+  return B200_SUCCESS;
+}
+
+// CeedVectorTakeArray_Cuda (ceed-cuda-ref-vector.c:307-342): hand back the borrowed pointer of that side, synced.
+extern "C" int ceedb200_vector_take_array(B200Vector vec, int mem_type, b200_scalar **array) {
+  B200_CALL(sync_to(vec, mem_type));
+  if (mem_type == B200_MEM_HOST) {
+    if (array) *array = vec->h_borrowed;
+    vec->h_borrowed = nullptr;
+    vec->h_array    = nullptr;
+  } else {
+    if (array) *array = vec->d_borrowed;
+    vec->d_borrowed = nullptr;
+    vec->d_array    = nullptr;
+  }
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_vector_set_value(B200Vector vec, b200_scalar value) {
+  B200Ceed ceed = vec->ceed;
+  // Same side-selection rule as ceed-cuda-ref-vector.c:307-339: write into the currently valid side (device first);
+  // with nothing valid prefer borrowed-device, borrowed-host, owned-device, owned-host, else allocate on the device.
+  if (!vec->d_array && !vec->h_array) {
+    if (vec->d_borrowed) vec->d_array = vec->d_borrowed;
+    else if (vec->h_borrowed) vec->h_array = vec->h_borrowed;
+    else if (vec->d_owned) vec->d_array = vec->d_owned;
+    else if (vec->h_owned) vec->h_array = vec->h_owned;
+    else {
+      B200_CALL(device_alloc(vec));
+      vec->d_array = device_ptr(vec);
+    }
+  }
+  if (vec->d_array) {
+    if (vec->length > 0) {
+      if (value == 0.0) B200_CALL(b200_memset_async(ceed, vec->d_array, vec->length * sizeof(double)));
+      else LAUNCH(ceed, k_set_value, vec->length, vec->d_array, vec->length, value);
+    }
+    vec->h_array = nullptr;
+  } else {
+    for (int64_t i = 0; i < vec->length; i++) vec->h_array[i] = value;
+    vec->d_array = nullptr;
+  }
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_vector_set_value_strided(B200Vector vec, b200_size start, b200_size stop, b200_size step, b200_scalar value) {
+  B200Ceed ceed = vec->ceed;
+  if (stop < 0) stop = vec->length;
+  B200_CHECK(step > 0 && start >= 0 && stop <= vec->length, ceed, B200_ERROR_DIMENSION, "invalid strided range");
+  if (vec->d_array) {
+    vec->h_array = nullptr;
+    if (stop > start) LAUNCH(ceed, k_set_value_strided, (stop - start) / step + 1, vec->d_array, start, stop, step, value);
+  } else if (vec->h_array) {
+    for (int64_t i = start; i < stop; i += step) vec->h_array[i] = value;
+  } else {
+    return b200_error(ceed, B200_ERROR_BACKEND, "CeedVector must have valid data set");
+  }
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_vector_sync_array(B200Vector vec, int mem_type) { return sync_to(vec, mem_type); }
+
+extern "C" int ceedb200_vector_get_array(B200Vector vec, int mem_type, b200_scalar **array) {
+  B200_CALL(sync_to(vec, mem_type));
+  if (mem_type == B200_MEM_HOST) {
+    *array       = vec->h_array;
+    vec->d_array = nullptr;
+  } else {
+    *array       = vec->d_array;
+    vec->h_array = nullptr;
+  }
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_vector_get_array_read(B200Vector vec, int mem_type, const b200_scalar **array) {
+  B200_CALL(sync_to(vec, mem_type));
+  *array = mem_type == B200_MEM_HOST ? vec->h_array : vec->d_array;
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_vector_get_array_write(B200Vector vec, int mem_type, b200_scalar **array) {
+  if (mem_type == B200_MEM_HOST) {
+    B200_CALL(host_alloc(vec));
+    vec->h_array = host_ptr(vec);
+    vec->d_array = nullptr;
+    *array       = vec->h_array;
+  } else {
+    B200_CALL(device_alloc(vec));
+    vec->d_array = device_ptr(vec);
+    vec->h_array = nullptr;
+    *array       = vec->d_array;
+  }
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_vector_copy_strided(B200Vector src, b200_size start, b200_size stop, b200_size step, B200Vector dst) {
+  B200Ceed ceed = src->ceed;
+  if (stop < 0) stop = src->length < dst->length ? src->length : dst->length;
+  B200_CHECK(step > 0 && start >= 0, ceed, B200_ERROR_DIMENSION, "invalid strided range");
+  const double *d_src;
+  double       *d_dst;
+  B200_CALL(b200_vector_device_read(src, &d_src));
+  B200_CALL(b200_vector_device_write(dst, &d_dst, false));
+  if (stop > start) LAUNCH(ceed, k_copy_strided, (stop - start) / step + 1, d_src, d_dst, start, stop, step);
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_vector_norm(B200Vector vec, int norm_type, b200_scalar *norm) {
+  B200Ceed      ceed = vec->ceed;
+  const double *d;
+  B200_CALL(b200_vector_device_read(vec, &d));
+  *norm = 0.0;
+  if (vec->length == 0) return B200_SUCCESS;
+  B200_CHECK(!b200_compile_only(), ceed, B200_ERROR_BACKEND, "CEED_B200_COMPILE_ONLY is set; kernels cannot run");
+  unsigned grid = grid_for(ceed, vec->length, 8);
+  if (ceed->scratch_len < grid) {
+    B200_CALL(b200_dfree(ceed, ceed->d_scratch));
+    B200_CALL(b200_dmalloc(ceed, (void **)&ceed->d_scratch, (size_t)ceed->num_sms * 16 * sizeof(double)));
+    ceed->scratch_len = (size_t)ceed->num_sms * 16;
+  }
+  int mode = norm_type == B200_NORM_1 ? 0 : (norm_type == B200_NORM_2 ? 1 : 2);
+  k_norm_partial<<<grid, kThreads, 0, ceed->stream>>>(d, vec->length, mode, ceed->d_scratch);
+  ceed->launch_count++;
+  B200_CUDA(ceed, cudaGetLastError());
+  std::vector<double> partial(grid);
+  B200_CALL(b200_d2h(ceed, partial.data(), ceed->d_scratch, grid * sizeof(double)));
+  double acc = 0.0;
+  for (unsigned i = 0; i < grid; i++) acc = (mode == 2) ? fmax(acc, partial[i]) : acc + partial[i];
+  *norm = (mode == 1) ? sqrt(acc) : acc;
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_vector_scale(B200Vector x, b200_scalar alpha) {
+  double *d;
+  B200_CALL(b200_vector_device_write(x, &d, false));
+  if (x->length > 0) LAUNCH(x->ceed, k_scale, x->length, d, x->length, alpha);
+  return B200_SUCCESS;
+}
+extern "C" int ceedb200_vector_reciprocal(B200Vector x) {
+  double *d;
+  B200_CALL(b200_vector_device_write(x, &d, false));
+  if (x->length > 0) LAUNCH(x->ceed, k_reciprocal, x->length, d, x->length);
+  return B200_SUCCESS;
+}
+extern "C" int ceedb200_vector_filter(B200Vector x, b200_scalar epsilon) {
+  double *d;
+  B200_CALL(b200_vector_device_write(x, &d, false));
+  if (x->length > 0) LAUNCH(x->ceed, k_filter, x->length, d, x->length, epsilon);
+  return B200_SUCCESS;
+}
+extern "C" int ceedb200_vector_axpy(B200Vector y, b200_scalar alpha, B200Vector x) {
+  B200_CHECK(x->length == y->length, y->ceed, B200_ERROR_DIMENSION, "AXPY length mismatch");
+  const double *dx;
+  double       *dy;
+  B200_CALL(b200_vector_device_read(x, &dx));
+  B200_CALL(b200_vector_device_write(y, &dy, false));
+  if (y->length > 0) LAUNCH(y->ceed, k_axpy, y->length, dy, alpha, dx, y->length);
+  return B200_SUCCESS;
+}
+extern "C" int ceedb200_vector_axpby(B200Vector y, b200_scalar alpha, b200_scalar beta, B200Vector x) {
+  B200_CHECK(x->length == y->length, y->ceed, B200_ERROR_DIMENSION, "AXPBY length mismatch");
+  const double *dx;
+  double       *dy;
+  B200_CALL(b200_vector_device_read(x, &dx));
+  B200_CALL(b200_vector_device_write(y, &dy, false));
+  if (y->length > 0) LAUNCH(y->ceed, k_axpby, y->length, dy, alpha, beta, dx, y->length);
+  return B200_SUCCESS;
+}
+extern "C" int ceedb200_vector_pointwise_mult(B200Vector w, B200Vector x, B200Vector y) {
+  B200_CHECK(x->length == w->length && y->length == w->length, w->ceed, B200_ERROR_DIMENSION, "PointwiseMult length mismatch");
+  const double *dx, *dy;
+  double       *dw;
+  B200_CALL(b200_vector_device_read(x, &dx));
+  B200_CALL(b200_vector_device_read(y, &dy));
+  // w may alias x and/or y: keep its data if so
+  B200_CALL(b200_vector_device_write(w, &dw, !(w == x || w == y)));
+  if (w->length > 0) LAUNCH(w->ceed, k_pointwise_mult, w->length, dw, dx, dy, w->length);
+  return B200_SUCCESS;
+}
