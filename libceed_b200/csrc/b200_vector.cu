@@ -151,7 +151,7 @@ int b200_vector_device_read(B200Vector vec, const double **d) {
   return B200_SUCCESS;
 }
 int b200_vector_device_write(B200Vector vec, double **d, bool discard) {
-  if (discard) {
+  if (discard || (!vec->h_array && !vec->d_array)) {  // nothing valid to preserve: (allocate and) hand out the device side
     B200_CALL(device_alloc(vec));
     vec->d_array = device_ptr(vec);
   } else {
