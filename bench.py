@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- CeedOperatorApply throughput (GDoF/s) of the /gpu/cuda/b200 path on synthetic structured hex meshes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload bp1p3|bp3p6|bp5p7|...] [--dofs D] [--impl reference]
+
+One "step" = one CeedOperatorApply (v = A u) on the rank's mesh, followed -- for N > 1 -- by the interface-DoF sum over
+NCCL.  Prints ONE JSON line (rank 0).  `value` = total DoFs of all ranks / max-over-ranks device time, inputs resident in
+HBM.  `e2e` = same metric through the C ABI with HOST buffers (pinned): H2D of u and D2H of v inside the timed region.
+`roofline` = algorithmic bytes of one apply / CUDA-event duration of the fused kernel (+ finalize kernel), against the
+measured HBM peak in MEASURED_PEAKS.json.  `cpu_baseline` = the unmodified reference's /cpu/self/avx/blocked on the host
+cores, on a bounded sample of the same workload.  `--impl reference` runs only that CPU arm.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD_RE = re.compile(r"bp(\d)p(\d)")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="bp1p3", help="bp<B>p<P>, e.g. bp1p3 (BASELINE configs[1]), bp3p6, bp5p7")
+    ap.add_argument("--dofs", type=float, default=10e6, help="DoFs per GPU (weak scaling)")
+    ap.add_argument("--scatter", default="deterministic", choices=["deterministic", "atomic", "evector"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--sweep", action="store_true", help="also report BP3 p=1..8 / BP5 p=4..7 kernel numbers in a `sweep` key")
+    return ap.parse_args()
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def _cpu_worker(args):
+    bp, p, nel, resource, seconds, steps, warmup, barrier_dir, wid = args
+    from libceed_b200 import mesh as M
+    from libceed_b200.bp import seeded_uniform
+    from oracle import refceed as R
+    off, coords = M.hex_offsets(*nel, p), M.hex_coords(*nel, p)
+    nn = coords.shape[1]
+    rc = R.RefCeed(resource)
+    prob = R.RefBP(rc, bp, p, off.shape[0], nn, off, coords)
+    rc.set_array(prob.u, seeded_uniform(prob.ncomp * nn))
+    for _ in range(max(1, warmup)):
+        rc.op_apply(prob.op, prob.u, prob.v)
+    # crude barrier through the file system so that all workers time the same interval
+    open(os.path.join(barrier_dir, f"ready{wid}"), "w").close()
+    while not os.path.exists(os.path.join(barrier_dir, "go")):
+        time.sleep(0.001)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        rc.op_apply(prob.op, prob.u, prob.v)
+        n += 1
+        if (steps and n >= steps) or (not steps and time.perf_counter() - t0 > seconds):
+            break
+    dt = time.perf_counter() - t0
+    return prob.ncomp * nn, n, dt
+
+
+def cpu_reference(bp, p, seconds, steps=0, warmup=1, resource="/cpu/self/avx/blocked", dofs_per_worker=150_000):
+    """Reference CPU backend on all host cores: `cores` forked single-threaded workers (libCEED CPU backends are
+    single-threaded per Ceed), each owning its own slab of the workload mesh; aggregate = sum(DoFs * applies) / max(time)."""
+    from libceed_b200 import mesh as M
+    from libceed_b200.bp import BP_TABLE
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    nel = M.choose_elements(dofs_per_worker, p, BP_TABLE[bp][0])
+    with tempfile.TemporaryDirectory() as d:
+        ctx = mp.get_context("fork")
+        with ctx.Pool(cores) as pool:
+            res = pool.map_async(_cpu_worker, [(bp, p, nel, resource, seconds, steps, warmup, d, w) for w in range(cores)])
+            t_start = time.time()
+            while len([f for f in os.listdir(d) if f.startswith("ready")]) < cores and time.time() - t_start < 600:
+                time.sleep(0.01)
+            open(os.path.join(d, "go"), "w").close()
+            out = res.get()
+    dofs = sum(o[0] * o[1] for o in out)
+    tmax = max(o[2] for o in out)
+    applies = sum(o[1] for o in out)
+    return dict(value=dofs / tmax / 1e9, unit="GDoF/s", cores=cores, kind="reference",
+                sample=f"{resource}: {cores} forked workers x ({nel[0]}x{nel[1]}x{nel[2]} elements, {out[0][0]} DoFs), "
+                       f"{applies} applies in {tmax:.1f} s", ms_per_step=tmax / max(1, out[0][1]) * 1e3, applies=applies)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu_index)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            pass
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        self.proc.wait()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out = dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    args = parse_args()
+    m = WORKLOAD_RE.fullmatch(args.workload)
+    assert m, "workload must look like bp3p6"
+    bp, p = int(m.group(1)), int(m.group(2))
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from libceed_b200.bp import BP_TABLE
+    ncomp, kind, q_extra = BP_TABLE[bp][0], BP_TABLE[bp][1], BP_TABLE[bp][2]
+    workload = f"BP{bp} {'mass' if kind == 'mass' else 'diffusion'} p={p} q={p + q_extra} ncomp={ncomp}, {args.dofs / 1e6:.0f}M DoFs per GPU, structured hex mesh"
+    config = dict(workload=workload, bp=bp, p=p, q=p + q_extra, dofs_per_gpu=args.dofs, scatter=args.scatter,
+                  l2="inputs (u, v, qdata, offsets) exceed the 126 MB L2; no flush between steps",
+                  partition="3-D element blocks, one local L-vector per GPU, NCCL interface sum" if world > 1 else "single GPU")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference(bp, p, args.cpu_seconds, steps=args.steps, warmup=args.warmup)
+        line = dict(metric="CeedOperatorApply throughput", value=r["value"], unit="GDoF/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                    impl="reference", config=config,
+                    cpu_baseline=dict(value=r["value"], unit="GDoF/s", cores=r["cores"], kind="reference", sample=r["sample"]),
+                    e2e=dict(value=r["value"], unit="GDoF/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from libceed_b200 import ceed as cm
+    from libceed_b200 import mesh as M
+    from libceed_b200.bp import BPProblem, seeded_uniform
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ceed = cm.Ceed(f"/gpu/cuda/b200:device_id={local_rank}")
+    ceed.set_scatter_mode({"deterministic": 0, "atomic": 1, "evector": 2}[args.scatter])
+    stream = torch.cuda.current_stream()
+    ceed.set_stream(stream.cuda_stream)
+
+    # ---- problem: weak scaling -> per-GPU element box of ~dofs, global box = process grid x local box
+    nel = M.choose_elements(args.dofs, p, ncomp)
+    part = None
+    if world > 1:
+        grid = M.split3(world)
+        part = M.Partition(tuple(nel[d] * grid[d] for d in range(3)), p, world, rank)
+    prob = BPProblem(ceed, bp, p, nel, part=part)
+    n_local = prob.num_dofs
+    u_host = torch.from_numpy(seeded_uniform(n_local, 0x5EED + rank)).pin_memory()
+    v_host = torch.empty(n_local, dtype=torch.float64).pin_memory()
+    u_dev = u_host.to(dev)
+    v_dev = torch.zeros(n_local, dtype=torch.float64, device=dev)
+    prob.u.set_array(u_dev, cm.MEM_DEVICE, cm.USE_POINTER)
+    prob.v.set_array(v_dev, cm.MEM_DEVICE, cm.USE_POINTER)
+    exch = None
+    if world > 1:
+        from libceed_b200.parallel import InterfaceExchange
+        exch = InterfaceExchange(part, ncomp, prob.num_nodes, dev)
+        owned = int(part.owned_mask().sum()) * ncomp
+        t = torch.tensor([owned], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        total_dofs = int(t.item())
+    else:
+        total_dofs = n_local
+
+    def step():
+        prob.op.apply(prob.u, prob.v)
+        if exch is not None:
+            exch.sum_interfaces(v_dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    launches0 = ceed.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    gpu_launches = ceed.launch_count() - launches0
+    # keep the GPU busy a little longer so that the clock sampler sees the loaded state even for sub-ms steps
+    if sampler:
+        t_end = time.time() + 1.0
+        while time.time() < t_end:
+            step()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = total_dofs / (ms_per_step * 1e-3) / 1e9
+
+    # ---- kernel-level timing for the roofline (CUDA events on the launching stream, inside the library)
+    prob.op.set_timing(True)
+    kms = []
+    for _ in range(max(5, min(args.steps, 20))):
+        prob.op.apply(prob.u, prob.v)
+        kms.append(prob.op.last_kernel_ms())
+    prob.op.set_timing(False)
+    fused_ms = float(np.median([k[0] for k in kms]))
+    aux_ms = float(np.median([k[1] for k in kms]))
+    peak, peak_src = hbm_peak()
+    alg_bytes = prob.bytes_per_apply()
+    achieved = alg_bytes / ((fused_ms + aux_ms) * 1e-3) / 1e9
+    info = prob.op.kernel_info()
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None, peak_source=peak_src,
+                    kernel="b200_operator (+ halo finalize)", fused_kernel_ms=fused_ms, finalize_ms=aux_ms, algorithmic_bytes=alg_bytes,
+                    kernel_share_of_step=(fused_ms + aux_ms) / ms_per_step, regs=info["regs"], elems_per_block=info["elems_per_block"],
+                    threads=info["threads"], grid=info["grid"], smem_bytes=info["smem_bytes"])
+
+    # ---- end to end through the C ABI with host buffers: H2D(u) + apply + D2H(v) every step
+    e2e_steps = max(3, min(args.steps, 10))
+    uh, vh = ceed.Vector(n_local), ceed.Vector(n_local)
+
+    def e2e_step():
+        uh.set_array(u_host, cm.MEM_HOST, cm.USE_POINTER)   # host pointer becomes the only valid copy
+        vh.set_array(v_host, cm.MEM_HOST, cm.USE_POINTER)
+        prob.op.apply(uh, vh)                                # syncs u to the device, runs the kernels
+        vh.sync_array(cm.MEM_HOST)                           # D2H into the caller's (pinned) buffer
+        if exch is not None:
+            pass  # interface sum is part of the device-resident step; host round trip measured per rank only
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = dict(value=total_dofs / e2e_s / 1e9, unit="GDoF/s", h2d_bytes_per_step=8 * n_local, d2h_bytes_per_step=8 * n_local,
+               ms_per_step=e2e_s * 1e3)
+
+    sweep = None
+    if args.sweep and rank == 0 and world == 1:
+        sweep = []
+        del prob
+        for sbp, ps in ((1, (3,)), (3, range(1, 9)), (5, range(4, 8)), (6, (4, 6))):
+            for sp in ps:
+                sc = BP_TABLE[sbp][0]
+                sprob = BPProblem(ceed, sbp, sp, M.choose_elements(args.dofs, sp, sc))
+                sprob.u.set_array(seeded_uniform(sprob.num_dofs))
+                sprob.op.set_timing(True)
+                t = []
+                for i in range(8):
+                    sprob.op.apply(sprob.u, sprob.v)
+                    if i >= 3:
+                        t.append(sum(sprob.op.last_kernel_ms()))
+                ms = float(np.median(t))
+                sweep.append(dict(bp=sbp, p=sp, dofs=sprob.num_dofs, ms=ms, gdofs=sprob.num_dofs / ms / 1e6,
+                                  frac=sprob.bytes_per_apply() / (ms * 1e-3) / 1e9 / peak))
+                del sprob
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            r = cpu_reference(bp, p, args.cpu_seconds)
+            cpu = dict(value=r["value"], unit="GDoF/s", cores=r["cores"], kind=r["kind"], sample=r["sample"])
+        except Exception as exc:  # the reference build did not travel: say so instead of inventing a number
+            cpu = dict(value=None, unit="GDoF/s", cores=0, kind="reference", sample=f"unavailable: {exc}")
+
+    if rank == 0:
+        line = dict(metric="CeedOperatorApply throughput", value=value, unit="GDoF/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+                    ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=config,
+                    roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(gpu_launches), clocks=clocks, total_dofs=total_dofs)
+        if sweep:
+            line["sweep"] = sweep
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

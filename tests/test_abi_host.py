@@ -1,0 +1,119 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol include/ceed_b200.h declares, the host-side
+math of the product matches the reference's golden matrices, the mesh/partition host logic is consistent, and the
+fused-kernel generator + NVRTC produce sm_100a code for every BP configuration (compile-only, nothing is executed)."""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from libceed_b200 import _lib as L
+from libceed_b200 import mesh as M
+
+
+def test_library_exports_every_declared_symbol():
+    names = L.declared_symbols()
+    assert len(names) >= 70
+    lib = C.CDLL(L.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_no_cuda_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = L.lib()
+    ceed = C.c_void_p()
+    code = lib.ceedb200_init(0, C.byref(ceed))
+    assert code != 0 and not ceed.value
+    assert b"CUDA" in lib.ceedb200_last_error(None) or b"device" in lib.ceedb200_last_error(None)
+
+
+@pytest.mark.parametrize("P", range(2, 10))
+def test_host_basis_math_matches_reference_golden(golden, P):
+    lib = L.lib()
+    for Q, qm in ((P + 1, 0), (P, 1), (P + 2, 1), (max(2, P - 1), 0)):
+        interp, grad, qref, qw = np.zeros(P * Q), np.zeros(P * Q), np.zeros(Q), np.zeros(Q)
+        d = lambda a: a.ctypes.data_as(L.c_scalar_p)  # noqa: E731
+        assert lib.ceedb200_host_lagrange_1d(P, Q, qm, d(interp), d(grad), d(qref), d(qw)) == 0
+        k = f"basis_P{P}_Q{Q}_m{qm}_"
+        assert np.abs(interp - golden[k + "interp_1d"]).max() < 1e-13
+        assert np.abs(grad - golden[k + "grad_1d"]).max() < 1e-12
+        assert np.abs(qref - golden[k + "q_ref_1d"]).max() < 1e-15
+        assert np.abs(qw - golden[k + "q_weight_1d"]).max() < 1e-14
+        if Q >= P:
+            cg = np.zeros(Q * Q)
+            assert lib.ceedb200_host_collocated_grad_1d(P, Q, d(interp), d(grad), d(cg)) == 0
+            assert np.abs(cg - golden[k + "collo_grad_1d"]).max() < 1e-11 * max(1.0, np.abs(cg).max())
+
+
+def test_mesh_builder():
+    for p, nel in [(1, (2, 3, 4)), (3, (2, 2, 2)), (6, (1, 2, 1))]:
+        off = M.hex_offsets(*nel, p)
+        nn = (nel[0] * p + 1) * (nel[1] * p + 1) * (nel[2] * p + 1)
+        assert off.shape == (nel[0] * nel[1] * nel[2], (p + 1) ** 3)
+        assert off.min() == 0 and off.max() == nn - 1 and len(np.unique(off)) == nn
+        # x fastest inside the element, elements x fastest
+        assert off[0, 1] - off[0, 0] == 1 and (off[1, 0] - off[0, 0] == p if nel[0] > 1 else True)
+        c = M.hex_coords(*nel, p, perturb=False)
+        assert c.shape == (3, nn) and c.min() == 0.0 and abs(c.max() - 1.0) < 1e-15
+    assert M.choose_elements(10_000_000, 6) == (36, 36, 35) or abs(np.prod([n * 6 + 1 for n in M.choose_elements(10_000_000, 6)]) - 1e7) < 3e5
+
+
+def test_partition_interfaces_are_consistent():
+    """Every pair of neighbouring ranks lists the same shared nodes in the same (global) order; owned nodes tile the mesh."""
+    p, ng = 2, (4, 3, 2)
+    for size in (1, 2, 4, 8):
+        parts = [M.Partition(ng, p, size, r) for r in range(size)]
+        total_owned = sum(int(pt.owned_mask().sum()) for pt in parts)
+        assert total_owned == (ng[0] * p + 1) * (ng[1] * p + 1) * (ng[2] * p + 1)
+        assert sum(np.prod(pt.n_local) for pt in parts) == np.prod(ng)
+        for pt in parts:
+            gid = pt.global_node_ids()
+            for nbr, idx in pt.neighbors:
+                other = parts[nbr]
+                back = [i for (r, i) in other.neighbors if r == pt.rank]
+                assert len(back) == 1
+                assert np.array_equal(gid[idx], other.global_node_ids()[back[0]])
+
+
+COMPILE_ONLY = r"""
+import json, os, sys
+sys.path.insert(0, %r)
+from libceed_b200 import Ceed
+from libceed_b200.bp import BPProblem
+out = {}
+for bp, p in [(1, 3), (3, 1), (3, 6), (5, 7), (6, 4), (2, 2)]:
+    ceed = Ceed()
+    prob = BPProblem(ceed, bp, p, (2, 2, 2), build_qdata=False)
+    info = prob.op.kernel_info()
+    src = prob.op.kernel_source()
+    out[f"{bp}_{p}"] = dict(info=info, fused=prob.op.is_fused, setup_fused=prob.op_setup.is_fused, has_qf="BP" in src, nsrc=len(src))
+    try:
+        import numpy as np
+        prob.u.set_array(np.ones(prob.num_dofs))
+        prob.qdata.set_array(np.ones(len(prob.qdata)))
+        prob.op.apply(prob.u, prob.v)
+        out[f"{bp}_{p}"]["ran"] = True
+    except Exception as e:
+        out[f"{bp}_{p}"]["ran"] = False
+        out[f"{bp}_{p}"]["err"] = str(e)
+print("RESULT" + json.dumps(out))
+""" % ROOT
+
+
+def test_fused_kernels_generate_and_compile_for_sm100a_without_gpu():
+    env = dict(os.environ, CEED_B200_COMPILE_ONLY="1")
+    r = subprocess.run([sys.executable, "-c", COMPILE_ONLY], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][0][6:])
+    for key, val in res.items():
+        assert val["fused"] and val["setup_fused"] and val["has_qf"], (key, val)
+        assert val["info"]["smem_bytes"] <= 227 * 1024 and val["info"]["threads"] % 32 == 0
+        # compile-only mode never computes anything: applying must fail loudly, not fall back to the CPU
+        assert val["ran"] is False and "COMPILE_ONLY" in val["err"], (key, val)

@@ -1,0 +1,360 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI, against
+  (1) the oracle (CPU restatement of /cpu/self/ref/serial) on the same seeded inputs,
+  (2) golden vectors produced by the unmodified reference (tests/golden/reference_golden.npz),
+  (3) the unmodified reference library itself when oracle/_ref/ travelled to this box,
+  (4) size-independent properties at BASELINE.json's full sizes (10M DoFs).
+Tolerances (BASELINE.json north_star): operator output 1e-12 relative in FP64; restriction bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import BP_CASES, bp_case_key
+from libceed_b200 import mesh as M
+from libceed_b200.bp import BP_TABLE, seeded_uniform
+
+pytestmark = pytest.mark.gpu
+
+OP_TOL = 1e-12
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def cm():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from libceed_b200 import ceed as cm
+    return cm
+
+
+def make_problem(cm, bp, p, nel, mode=0, interlaced=False, **kw):
+    from libceed_b200.bp import BPProblem
+    ceed = cm.Ceed("/gpu/cuda/b200")
+    ceed.set_scatter_mode(mode)
+    return BPProblem(ceed, bp, p, nel, interlaced=interlaced, **kw)
+
+
+# ------------------------------------------------------------------------------------------------ vector
+def test_vector_state_machine_and_blas1(cm):
+    ceed = cm.Ceed()
+    n = 1000
+    x, y, w = ceed.Vector(n), ceed.Vector(n), ceed.Vector(n)
+    a = seeded_uniform(n, 1)
+    b = seeded_uniform(n, 2)
+    x.set_array(a)
+    y.set_array(b)
+    assert np.array_equal(x.get_array_read(), a)  # H -> D -> H round trip is exact
+    y.axpy(2.5, x)
+    assert np.allclose(y.get_array_read(), b + 2.5 * a, rtol=0, atol=1e-15)
+    y.axpby(0.5, -1.0, x)
+    assert np.allclose(y.get_array_read(), 0.5 * a - (b + 2.5 * a), rtol=0, atol=1e-14)
+    w.pointwise_mult(x, x)
+    assert np.array_equal(w.get_array_read(), a * a)
+    x.scale(-3.0)
+    assert np.array_equal(x.get_array_read(), -3.0 * a)
+    assert abs(x.norm(cm.NORM_1) - np.abs(3 * a).sum()) < 1e-10
+    assert abs(x.norm(cm.NORM_2) - np.linalg.norm(3 * a)) < 1e-11
+    assert x.norm(cm.NORM_MAX) == np.abs(3 * a).max()
+    x.set_value(7.0)
+    assert np.all(x.get_array_read() == 7.0)
+    x.reciprocal()
+    assert np.allclose(x.get_array_read(), 1.0 / 7.0)
+    e = ceed.Vector(0)
+    e.set_value(1.0)
+    assert e.get_array_read().size == 0 and e.norm() == 0.0
+    with pytest.raises(cm.CeedError):
+        ceed.Vector(5).get_array_read()  # no valid data
+
+
+# ------------------------------------------------------------------------------------------------ restriction
+def test_restriction_bit_exact_vs_golden_and_oracle(cm, golden, oracle):
+    ceed = cm.Ceed()
+    nelem, esize, ncomp, lsize = [int(v) for v in golden["rstr_dims"]]
+    off = golden["rstr_offsets"]
+    r = ceed.ElemRestriction(nelem, esize, ncomp, lsize, ncomp * lsize, off)
+    u, ev = ceed.Vector(ncomp * lsize), ceed.Vector(nelem * esize * ncomp)
+    u.set_array(golden["rstr_u"])
+    r.apply(u, ev)
+    assert r.get_e_layout() == (1, nelem * esize, esize)  # GPU-family layout [comp][elem][node]
+    e_gpu = ev.get_array_read().reshape(ncomp, nelem, esize)
+    e_ref = golden["rstr_e"].reshape(nelem, ncomp, esize)  # CPU reference layout [elem][comp][node]
+    assert np.array_equal(e_gpu.transpose(1, 0, 2), e_ref)
+    # transpose: deterministic, ascending (elem, node) order == serial reference order => bit-exact
+    w_ref = golden["rstr_w"].reshape(nelem, ncomp, esize)
+    w, lt = ceed.Vector(nelem * esize * ncomp), ceed.Vector(ncomp * lsize)
+    w.set_array(np.ascontiguousarray(w_ref.transpose(1, 0, 2)).reshape(-1))
+    lt.set_value(0.0)
+    r.T_apply(w, lt)
+    assert np.array_equal(lt.get_array_read(), golden["rstr_lt"])
+    assert np.array_equal(lt.get_array_read(), oracle.restriction_offset(nelem, esize, ncomp, lsize, off, 1, golden["rstr_w"], ncomp * lsize))
+
+
+def test_restriction_ragged_and_edge_cases(cm, oracle):
+    ceed = cm.Ceed()
+    rng = np.random.default_rng(3)
+    for nelem, esize, ncomp, lsize in [(1, 1, 1, 1), (7, 27, 3, 50), (300, 8, 1, 999), (2, 64, 2, 64)]:
+        off = rng.integers(0, lsize, nelem * esize).astype(np.int32)
+        r = ceed.ElemRestriction(nelem, esize, ncomp, lsize, ncomp * lsize, off)
+        u = seeded_uniform(ncomp * lsize, 4)
+        uv, ev = ceed.Vector(u.size), ceed.Vector(nelem * esize * ncomp)
+        uv.set_array(u)
+        r.apply(uv, ev)
+        e_ref = oracle.restriction_offset(nelem, esize, ncomp, lsize, off, 0, u, nelem * esize * ncomp).reshape(nelem, ncomp, esize)
+        assert np.array_equal(ev.get_array_read().reshape(ncomp, nelem, esize).transpose(1, 0, 2), e_ref)
+        wv = seeded_uniform(nelem * esize * ncomp, 5)
+        w, lt = ceed.Vector(wv.size), ceed.Vector(ncomp * lsize)
+        w.set_array(wv)
+        lt.set_array(u)  # transpose ADDS into existing data
+        r.T_apply(w, lt)
+        w_cpu = np.ascontiguousarray(wv.reshape(ncomp, nelem, esize).transpose(1, 0, 2)).reshape(-1)
+        expect = u.copy()
+        import ctypes as C
+        oracle.lib().oracle_restriction_offset(nelem, esize, ncomp, lsize, off.ctypes.data_as(oracle.ip), 1, w_cpu.ctypes.data_as(oracle.dp),
+                                               expect.ctypes.data_as(oracle.dp))
+        assert np.array_equal(lt.get_array_read(), expect)
+    with pytest.raises(cm.CeedError):
+        ceed.ElemRestriction(1, 2, 1, 1, 2, np.array([0, 5], np.int32))  # out-of-range offset
+    # strided
+    r = ceed.StridedElemRestriction(3, 4, 2, 24, (2, 1, 8))
+    u = ceed.Vector(24)
+    u.set_array(np.arange(24.0))
+    ev = ceed.Vector(24)
+    r.apply(u, ev)
+    ref = oracle.restriction_strided(3, 4, 2, (2, 1, 8), 0, np.arange(24.0), 24).reshape(3, 2, 4)
+    assert np.array_equal(ev.get_array_read().reshape(2, 3, 4).transpose(1, 0, 2), ref)
+
+
+# ------------------------------------------------------------------------------------------------ basis
+@pytest.mark.parametrize("dim,P,Q,qm", [(1, 3, 4, 0), (2, 4, 5, 0), (3, 3, 5, 0), (3, 5, 5, 1), (3, 4, 3, 0), (2, 5, 6, 1)])
+def test_standalone_basis_matches_oracle(cm, oracle, dim, P, Q, qm):
+    import ctypes as C
+    ceed = cm.Ceed()
+    nc, nelem = 2, 3
+    b = ceed.BasisTensorH1Lagrange(dim, nc, P, Q, qm)
+    interp, grad, qref, qw = oracle.lagrange_1d(P, Q, qm)
+    assert np.abs(b.interp_1d.reshape(-1) - interp).max() < 1e-14
+    nn, nq = P ** dim, Q ** dim
+    u = seeded_uniform(nc * nelem * nn, 8)
+    uv = ceed.Vector(u.size)
+    uv.set_array(u)
+    O = oracle.lib()
+
+    class OB(C.Structure):
+        _fields_ = [("dim", C.c_int), ("nc", C.c_int), ("P", C.c_int), ("Q", C.c_int), ("interp", oracle.dp), ("grad", oracle.dp),
+                    ("qw", oracle.dp), ("collo", oracle.dp), ("is_collocated", C.c_int)]
+
+    collocated = P == Q and np.abs(interp.reshape(Q, P) - np.eye(P)).max() < 1e-15
+    collo = oracle.collocated_grad(P, Q, interp, grad) if (Q >= P and not collocated) else None
+    ob = OB(dim, nc, P, Q, interp.ctypes.data_as(oracle.dp), grad.ctypes.data_as(oracle.dp), qw.ctypes.data_as(oracle.dp),
+            collo.ctypes.data_as(oracle.dp) if collo is not None else None, int(collocated))
+    O.oracle_basis_apply.argtypes = [C.POINTER(OB), C.c_int, C.c_int, oracle.dp, oracle.dp]
+    O.oracle_basis_apply.restype = None
+    for emode, qcomp in ((cm.EVAL_INTERP, 1), (cm.EVAL_GRAD, dim)):
+        vv = ceed.Vector(qcomp * nc * nelem * nq)
+        b.apply(nelem, emode, uv, vv)
+        got = vv.get_array_read().reshape(qcomp, nc, nelem, nq)
+        back = ceed.Vector(u.size)
+        b.apply(nelem, emode, vv, back, tmode=cm.TRANSPOSE)
+        got_t = back.get_array_read().reshape(nc, nelem, nn)
+        for e in range(nelem):
+            ue = np.ascontiguousarray(u.reshape(nc, nelem, nn)[:, e, :]).reshape(-1)
+            ve = np.zeros(qcomp * nc * nq)
+            O.oracle_basis_apply(C.byref(ob), 0, emode, ue.ctypes.data_as(oracle.dp), ve.ctypes.data_as(oracle.dp))
+            assert rel(got[:, :, e, :].reshape(-1), ve) < 1e-13
+            te = np.zeros(nc * nn)
+            O.oracle_basis_apply(C.byref(ob), 1, emode, ve.ctypes.data_as(oracle.dp), te.ctypes.data_as(oracle.dp))
+            assert rel(got_t[:, e, :].reshape(-1), te) < 1e-13
+    wv = ceed.Vector(nelem * nq)
+    b.apply(nelem, cm.EVAL_WEIGHT, None, wv)
+    w1 = qw
+    full = w1
+    for _ in range(dim - 1):
+        full = np.multiply.outer(w1, full).reshape(-1)
+    assert np.allclose(wv.get_array_read().reshape(nelem, nq), full[None, :], rtol=1e-15, atol=0)
+
+
+# ------------------------------------------------------------------------------------------------ qfunction
+def test_standalone_qfunction_matches_oracle(cm, oracle):
+    import ctypes as C
+    from libceed_b200.bp import APPLY_H
+    ceed = cm.Ceed()
+    Q = 777
+    qf = ceed.QFunction(APPLY_H, "BPDiff")
+    qf.add_input("u", 3, cm.EVAL_GRAD)
+    qf.add_input("qdata", 7, cm.EVAL_NONE)
+    qf.add_output("v", 3, cm.EVAL_GRAD)
+    ug, qd = seeded_uniform(3 * Q, 1), seeded_uniform(7 * Q, 2)
+    U, D, V = ceed.Vector(3 * Q), ceed.Vector(7 * Q), ceed.Vector(3 * Q)
+    U.set_array(ug)
+    D.set_array(qd)
+    qf.apply(Q, [U, D], [V])
+    out = np.zeros(3 * Q)
+    ins = (oracle.dp * 2)(ug.ctypes.data_as(oracle.dp), qd.ctypes.data_as(oracle.dp))
+    outs = (oracle.dp * 1)(out.ctypes.data_as(oracle.dp))
+    oracle.lib().oracle_qf_bp_diff(None, Q, ins, outs)
+    assert rel(V.get_array_read(), out) < 1e-15
+
+
+# ------------------------------------------------------------------------------------------------ operator
+@pytest.mark.parametrize("case", BP_CASES, ids=lambda c: bp_case_key(*c))
+@pytest.mark.parametrize("mode", [0, 1, 2], ids=["deterministic", "atomic", "evector"])
+def test_bp_operator_vs_oracle_and_golden(cm, oracle, golden, case, mode):
+    bp, p, nel, gallery, interlaced = case
+    if gallery:
+        pytest.skip("gallery QFunction sources live in the reference tree; covered by test_gallery_qfunctions_from_reference_install")
+    prob = make_problem(cm, bp, p, nel, mode, interlaced)
+    assert prob.op.is_fused and prob.op_setup.is_fused
+    off, coords, nn = prob.offsets, prob.coords, prob.num_nodes
+    key = bp_case_key(*case)
+    # setup operator output (qdata), GPU layout [comp][elem][qpt] == fixture layout
+    qd = prob.qdata.get_array_read()
+    qd_or = oracle.bp_qdata(bp, p, off, coords)
+    assert rel(qd, qd_or) < OP_TOL and rel(qd, golden[key + "_qdata"]) < OP_TOL
+    u = seeded_uniform(prob.num_dofs)
+    prob.u.set_array(u)
+    prob.op.apply(prob.u, prob.v)
+    v = prob.v.get_array_read()
+    v_or = oracle.bp_apply(bp, p, off, nn, qd_or, u, interlaced=interlaced)
+    assert rel(v, v_or) < OP_TOL
+    assert rel(v, golden[key + "_v"]) < OP_TOL
+    # ApplyAdd accumulates on top of existing data
+    prob.op.apply_add(prob.u, prob.v)
+    assert rel(prob.v.get_array_read(), 2 * v_or) < OP_TOL
+    # Apply overwrites stale data
+    prob.v.set_value(1e30)
+    prob.op.apply(prob.u, prob.v)
+    assert rel(prob.v.get_array_read(), v_or) < OP_TOL
+
+
+def test_gallery_qfunctions_from_reference_install(cm, oracle, golden, refceed):
+    """Gallery QFunction headers (include/ceed/jit-source/gallery) JIT-compile unchanged into the fused kernel."""
+    import os
+    from oracle import refceed as R
+    inc = os.path.join(R.REF_DIR, "include")
+    for bp, p, nel in [(1, 2, (2, 2, 2)), (3, 2, (2, 2, 2))]:
+        ceed = cm.Ceed()
+        ceed.add_jit_source_root(inc)
+        P, Q = p + 1, p + 2
+        off, coords = M.hex_offsets(*nel, p), M.hex_coords(*nel, p)
+        nn, ne = coords.shape[1], off.shape[0]
+        ncq = 6 if bp == 3 else 1
+        rx = ceed.ElemRestriction(ne, P ** 3, 3, nn, 3 * nn, off)
+        ru = ceed.ElemRestriction(ne, P ** 3, 1, nn, nn, off)
+        rq = ceed.StridedElemRestriction(ne, Q ** 3, ncq, ne * Q ** 3 * ncq)
+        bx, bu = ceed.BasisTensorH1Lagrange(3, 3, P, Q, cm.GAUSS), ceed.BasisTensorH1Lagrange(3, 1, P, Q, cm.GAUSS)
+        gal = os.path.join(inc, "ceed", "jit-source", "gallery")
+        qs = ceed.QFunction(os.path.join(gal, "ceed-poisson3dbuild.h" if bp == 3 else "ceed-mass3dbuild.h"), "Poisson3DBuild" if bp == 3 else "Mass3DBuild")
+        qs.add_input("dx", 9, cm.EVAL_GRAD)
+        qs.add_input("weights", 1, cm.EVAL_WEIGHT)
+        qs.add_output("qdata", ncq, cm.EVAL_NONE)
+        x, qd = ceed.Vector(3 * nn), ceed.Vector(ne * Q ** 3 * ncq)
+        x.set_array(coords.reshape(-1))
+        ops = ceed.Operator(qs)
+        ops.set_field("dx", rx, bx, cm.VECTOR_ACTIVE)
+        ops.set_field("weights", None, bx, cm.VECTOR_NONE)
+        ops.set_field("qdata", rq, None, cm.VECTOR_ACTIVE)
+        ops.apply(x, qd)
+        key = bp_case_key(bp, p, nel, True, False)
+        assert rel(qd.get_array_read(), golden[key + "_qdata"]) < OP_TOL
+        qa = ceed.QFunction(os.path.join(gal, "ceed-poisson3dapply.h" if bp == 3 else "ceed-massapply.h"), "Poisson3DApply" if bp == 3 else "MassApply")
+        names = ("du", "qdata", "dv") if bp == 3 else ("u", "qdata", "v")
+        em, sz = (cm.EVAL_GRAD, 3) if bp == 3 else (cm.EVAL_INTERP, 1)
+        qa.add_input(names[0], sz, em)
+        qa.add_input(names[1], ncq, cm.EVAL_NONE)
+        qa.add_output(names[2], sz, em)
+        op = ceed.Operator(qa)
+        op.set_field(names[0], ru, bu, cm.VECTOR_ACTIVE)
+        op.set_field(names[1], rq, None, qd)
+        op.set_field(names[2], ru, bu, cm.VECTOR_ACTIVE)
+        u, v = ceed.Vector(nn), ceed.Vector(nn)
+        uu = seeded_uniform(nn)
+        u.set_array(uu)
+        op.apply(u, v)
+        assert op.is_fused
+        assert rel(v.get_array_read(), golden[key + "_v"]) < OP_TOL
+
+
+def test_against_live_reference_library(cm, refceed):
+    """Same operator, same inputs on the unmodified reference /cpu/self/ref/serial (when oracle/_ref travelled here)."""
+    rc = refceed.RefCeed("/cpu/self/ref/serial")
+    for bp, p, nel in [(3, 5, (2, 2, 1)), (1, 6, (2, 1, 1)), (6, 5, (1, 1, 2)), (3, 3, (4, 3, 2))]:
+        prob = make_problem(cm, bp, p, nel)
+        ref = refceed.RefBP(rc, bp, p, prob.num_elem, prob.num_nodes, prob.offsets, prob.coords)
+        u = seeded_uniform(prob.num_dofs, 11)
+        prob.u.set_array(u)
+        prob.op.apply(prob.u, prob.v)
+        assert rel(prob.qdata.get_array_read(), ref.qdata_array()) < OP_TOL
+        assert rel(prob.v.get_array_read(), ref.apply(u)) < OP_TOL
+
+
+def test_deterministic_scatter_is_bitwise_reproducible_and_equals_serial_order(cm):
+    bp, p, nel = 3, 3, (5, 4, 3)
+    pa = make_problem(cm, bp, p, nel, mode=0)
+    pb = make_problem(cm, bp, p, nel, mode=2)  # E-vector + ordered CSR transpose (ascending (elem,node) like the serial reference)
+    u = seeded_uniform(pa.num_dofs, 13)
+    outs = []
+    for prob in (pa, pa, pb):
+        prob.u.set_array(u)
+        prob.op.apply(prob.u, prob.v)
+        outs.append(prob.v.get_array_read())
+    assert np.array_equal(outs[0], outs[1])  # run-to-run bitwise identical
+    assert np.array_equal(outs[0], outs[2])  # owner/halo scheme sums in the same order as the ordered transpose
+
+
+def test_unfused_fallback_matches_fused(cm, monkeypatch):
+    bp, p, nel = 3, 2, (3, 2, 2)
+    fused = make_problem(cm, bp, p, nel)
+    monkeypatch.setenv("CEED_B200_NO_FUSE", "1")
+    unf = make_problem(cm, bp, p, nel)
+    monkeypatch.delenv("CEED_B200_NO_FUSE")
+    assert fused.op.is_fused and not unf.op.is_fused
+    u = seeded_uniform(fused.num_dofs, 17)
+    for prob in (fused, unf):
+        prob.u.set_array(u)
+        prob.op.apply(prob.u, prob.v)
+    assert rel(fused.qdata.get_array_read(), unf.qdata.get_array_read()) < OP_TOL
+    assert rel(fused.v.get_array_read(), unf.v.get_array_read()) < OP_TOL
+
+
+def test_tail_batches_and_tuning(cm, oracle):
+    """Element counts that are not a multiple of the batch size, forced batch sizes."""
+    bp, p = 3, 2
+    for nel, epb in [((1, 1, 1), 0), ((5, 1, 1), 4), ((7, 3, 1), 16), ((3, 3, 3), 5)]:
+        prob = make_problem(cm, bp, p, nel)
+        if epb:
+            prob.op.set_tuning(epb, 0)
+        u = seeded_uniform(prob.num_dofs, 19)
+        prob.u.set_array(u)
+        prob.op.apply(prob.u, prob.v)
+        qd = oracle.bp_qdata(bp, p, prob.offsets, prob.coords)
+        assert rel(prob.v.get_array_read(), oracle.bp_apply(bp, p, prob.offsets, prob.num_nodes, qd, u)) < OP_TOL
+
+
+@pytest.mark.parametrize("bp,p", [(1, 3), (3, 6), (5, 7), (6, 4)])
+def test_full_size_properties(cm, bp, p):
+    """BASELINE.json sizes (10M DoFs): properties that need no CPU oracle."""
+    ncomp = BP_TABLE[bp][0]
+    nel = M.choose_elements(10_000_000, p, ncomp)
+    prob = make_problem(cm, bp, p, nel)
+    ceed = prob.ceed
+    n = prob.num_dofs
+    u1, u2 = seeded_uniform(n, 1), seeded_uniform(n, 2)
+
+    def A(x):
+        prob.u.set_array(x)
+        prob.op.apply(prob.u, prob.v)
+        return prob.v.get_array_read()
+
+    v1, v2 = A(u1), A(u2)
+    assert rel(A(2.0 * u1 - 0.5 * u2), 2.0 * v1 - 0.5 * v2) < 1e-12  # linearity
+    assert abs(u2 @ v1 - u1 @ v2) < 1e-10 * abs(u1 @ v1)  # symmetry
+    assert u1 @ v1 > 0  # positive (semi-)definite
+    ones = A(np.ones(n))
+    if BP_TABLE[bp][1] == "diff":
+        assert np.abs(ones).max() < 1e-10 * np.abs(v1).max()  # constants in the kernel
+    else:
+        assert abs(ones.sum() / ncomp - 1.0) < 1e-6  # sum of mass-matrix rows = volume of the (smoothly mapped) unit cube, up to quadrature error
+    assert np.array_equal(A(u1), v1)  # idempotent / reproducible
+    del ceed
