@@ -110,6 +110,8 @@ CEEDB200_EXPORT int ceedb200_restriction_create_strided(B200Ceed ceed, b200_int 
                                                         const b200_int strides[3], B200Restriction *rstr);
 CEEDB200_EXPORT int ceedb200_restriction_destroy(B200Restriction rstr);
 CEEDB200_EXPORT int ceedb200_restriction_apply(B200Restriction rstr, int t_mode, B200Vector u, B200Vector v);
+/* same, on raw device pointers (the libCEED plugin passes arrays obtained from CeedVectorGetArray*(CEED_MEM_DEVICE)) */
+CEEDB200_EXPORT int ceedb200_restriction_apply_ptr(B200Restriction rstr, int t_mode, const b200_scalar *d_u, b200_scalar *d_v);
 CEEDB200_EXPORT int ceedb200_restriction_get_offsets(B200Restriction rstr, int mem_type, const b200_int **offsets);
 CEEDB200_EXPORT int ceedb200_restriction_get_e_layout(B200Restriction rstr, b200_int layout[3]);
 CEEDB200_EXPORT int ceedb200_restriction_get_info(B200Restriction rstr, b200_int *num_elem, b200_int *elem_size, b200_int *num_comp,
@@ -129,6 +131,8 @@ CEEDB200_EXPORT int ceedb200_basis_create_tensor_h1_lagrange(B200Ceed ceed, b200
 CEEDB200_EXPORT int ceedb200_basis_destroy(B200Basis basis);
 CEEDB200_EXPORT int ceedb200_basis_apply(B200Basis basis, b200_int num_elem, int t_mode, int eval_mode, B200Vector u, B200Vector v);
 CEEDB200_EXPORT int ceedb200_basis_apply_add(B200Basis basis, b200_int num_elem, int t_mode, int eval_mode, B200Vector u, B200Vector v);
+CEEDB200_EXPORT int ceedb200_basis_apply_ptr(B200Basis basis, b200_int num_elem, int t_mode, int eval_mode, int add, const b200_scalar *d_u,
+                                             b200_scalar *d_v);
 /* which = 0 interp_1d [Q*P], 1 grad_1d [Q*P], 2 q_ref_1d [Q], 3 q_weight_1d [Q], 4 collocated grad [Q*Q] (interface/ceed-basis.c:750-773) */
 CEEDB200_EXPORT int ceedb200_basis_get_matrix(B200Basis basis, int which, b200_scalar *out);
 /* host utilities, no GPU needed (used by host-side tests): */
@@ -161,6 +165,8 @@ CEEDB200_EXPORT int ceedb200_qfunction_add_output(B200QFunction qf, const char *
 CEEDB200_EXPORT int ceedb200_qfunction_set_context(B200QFunction qf, B200QFContext ctx);
 /* standalone apply over Q points: U[i]/V[i] hold field i as [size_i][Q] (doc/sphinx/source/libCEEDdev.md:113-118) */
 CEEDB200_EXPORT int ceedb200_qfunction_apply(B200QFunction qf, b200_int Q, const B200Vector *U, const B200Vector *V);
+
+CEEDB200_EXPORT int ceedb200_qfunction_apply_ptr(B200QFunction qf, b200_int Q, const b200_scalar *const *d_in, b200_scalar *const *d_out);
 
 /* ---------------------------------------------------------------- operator (CeedOperator)
  * replaces CeedOperatorCreate_Cuda_gen / ApplyAdd: backends/cuda-gen/ceed-cuda-gen-operator.c:105-300,879-908 and the kernel

@@ -1,0 +1,106 @@
+// ceed-cuda-b200.c -- registration and Ceed-level setup of the "/gpu/cuda/b200" backend.
+//
+// Replaces, for this resource, what backends/cuda-gen/ceed-cuda-gen.c:19-52 + backends/cuda/ceed-cuda-common.c:19-35 do for
+// "/gpu/cuda/gen": validate the resource, pick the device (":device_id=N"), create the backend context and install the
+// object constructors by name.  Nothing is delegated: Vector, ElemRestriction, tensor H1 Basis, QFunction, QFunctionContext
+// and Operator are all implemented by this backend on top of include/ceed_b200.h.  Object types outside the operator-apply
+// path (non-tensor bases, H(div)/H(curl), at-points, composite operators on streams, assembly) report
+// "Backend does not implement ..." exactly like other backends do for their gaps (tests/junit.py:121-145 treats it as skip).
+#include "ceed-cuda-b200.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+int CeedGetCore_B200(Ceed ceed, B200Ceed *core) {
+  Ceed_B200 *data;
+
+  CeedCallBackend(CeedGetData(ceed, &data));
+  *core = data->core;
+  return CEED_ERROR_SUCCESS;
+}
+
+// Forward CeedAddJitSourceRoot / CeedAddJitDefine (interface/ceed.c:1515,1579) to the core before anything is compiled
+int CeedSyncJitOptions_B200(Ceed ceed) {
+  Ceed_B200    *data;
+  CeedInt       num_roots = 0, num_defines = 0;
+  const char  **roots, **defines;
+
+  CeedCallBackend(CeedGetData(ceed, &data));
+  CeedCallBackend(CeedGetJitSourceRoots(ceed, &num_roots, &roots));
+  for (CeedInt i = data->num_roots_seen; i < num_roots; i++) ceedb200_add_jit_source_root(data->core, roots[i]);
+  data->num_roots_seen = num_roots;
+  CeedCallBackend(CeedRestoreJitSourceRoots(ceed, &roots));
+  CeedCallBackend(CeedGetJitDefines(ceed, &num_defines, &defines));
+  for (CeedInt i = data->num_defines_seen; i < num_defines; i++) ceedb200_add_jit_define(data->core, defines[i]);
+  data->num_defines_seen = num_defines;
+  CeedCallBackend(CeedRestoreJitDefines(ceed, &defines));
+  return CEED_ERROR_SUCCESS;
+}
+
+static int CeedDestroy_B200(Ceed ceed) {
+  Ceed_B200 *data;
+
+  CeedCallBackend(CeedGetData(ceed, &data));
+  if (data) {
+    ceedb200_destroy(data->core);
+    free(data);
+  }
+  return CEED_ERROR_SUCCESS;
+}
+
+static int CeedGetPreferredMemType_B200(CeedMemType *mem_type) {
+  *mem_type = CEED_MEM_DEVICE;
+  return CEED_ERROR_SUCCESS;
+}
+
+static int CeedSetStream_B200(Ceed ceed, void *handle) {
+  B200Ceed core;
+
+  CeedCallBackend(CeedGetCore_B200(ceed, &core));
+  ceedb200_set_stream(core, handle);
+  return CEED_ERROR_SUCCESS;
+}
+
+static int CeedInit_B200(const char *resource, Ceed ceed) {
+  Ceed_B200  *data;
+  const char *root = "/gpu/cuda/b200", *colon = strchr(resource, ':');
+  size_t      root_len = colon ? (size_t)(colon - resource) : strlen(resource);
+  int         device_id = -1;
+
+  // "/gpu/cuda/b200", a prefix of it that resolved here ("/gpu/cuda"), optionally followed by ":device_id=N"
+  CeedCheck(root_len <= strlen(root) && !strncmp(resource, root, root_len), ceed, CEED_ERROR_BACKEND, "B200 backend cannot use resource: %s", resource);
+  if (colon) {
+    const char *id = strstr(colon, "device_id=");
+    if (id) device_id = atoi(id + strlen("device_id="));
+  }
+  data = calloc(1, sizeof(*data));
+  CeedCheck(data, ceed, CEED_ERROR_MAJOR, "allocation failed");
+  if (ceedb200_init(device_id, &data->core)) {
+    free(data);
+    return CeedError(ceed, CEED_ERROR_BACKEND, "%s", ceedb200_last_error(NULL));
+  }
+  data->device_id = device_id < 0 ? 0 : device_id;
+  CeedCallBackend(CeedSetData(ceed, data));
+  CeedCallBackend(CeedSetDeterministic(ceed, true));  // ordered scatter, no atomics (README.md:167-169 semantics)
+
+  CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "Destroy", CeedDestroy_B200));
+  CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "GetPreferredMemType", CeedGetPreferredMemType_B200));
+  CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "SetStream", CeedSetStream_B200));
+  CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "VectorCreate", CeedVectorCreate_B200));
+  CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "ElemRestrictionCreate", CeedElemRestrictionCreate_B200));
+  CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "BasisCreateTensorH1", CeedBasisCreateTensorH1_B200));
+  CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "QFunctionCreate", CeedQFunctionCreate_B200));
+  CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "QFunctionContextCreate", CeedQFunctionContextCreate_B200));
+  CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "OperatorCreate", CeedOperatorCreate_B200));
+  return CEED_ERROR_SUCCESS;
+}
+
+// In-tree: listed as CEED_BACKEND(CeedRegister_Cuda_B200, 1, "/gpu/cuda/b200") in backends/ceed-backend-list-cuda.h.
+// Priority 15 < 20 (/gpu/cuda/gen, backends/cuda-gen/ceed-cuda-gen.c:52) so that "/gpu/cuda" resolves to this backend.
+CEED_EXTERN int CeedRegister_Cuda_B200(void);
+int CeedRegister_Cuda_B200(void) { return CeedRegister("/gpu/cuda/b200", CeedInit_B200, 15); }
+
+#ifdef CEED_B200_PLUGIN
+// Out-of-tree plugin: register before main() / at dlopen() time; libCEED's registry is a static table, no init order issue.
+__attribute__((constructor)) static void CeedRegister_Cuda_B200_Plugin(void) { CeedRegister_Cuda_B200(); }
+#endif

@@ -267,20 +267,28 @@ int get_scratch(B200Ceed ceed, double **buf, size_t bytes) {
   return B200_SUCCESS;
 }
 
+int basis_apply_ptr(B200Basis basis, bool apply_add, int num_elem, int t_mode, int eval_mode, const double *d_u, double *d_v);
+
 int basis_apply_core(B200Basis basis, bool apply_add, int num_elem, int t_mode, int eval_mode, B200Vector U, B200Vector V) {
+  B200Ceed      ceed = basis->ceed;
+  const double *d_u  = nullptr;
+  double       *d_v  = nullptr;
+  if (eval_mode != B200_EVAL_WEIGHT) {
+    B200_CHECK(U && U != B200_VECTOR_NONE, ceed, B200_ERROR_BACKEND, "An input vector is required for this CeedEvalMode");
+    B200_CALL(b200_vector_device_read(U, &d_u));
+  }
+  B200_CALL(b200_vector_device_write(V, &d_v, false));
+  return basis_apply_ptr(basis, apply_add, num_elem, t_mode, eval_mode, d_u, d_v);
+}
+
+int basis_apply_ptr(B200Basis basis, bool apply_add, int num_elem, int t_mode, int eval_mode, const double *d_u, double *d_v) {
   B200Ceed      ceed = basis->ceed;
   const int     dim = basis->dim, nc = basis->num_comp, P = basis->P, Q = basis->Q;
   const int64_t nvec   = (int64_t)nc * num_elem;
   const int64_t n_node = ipow(P, dim), n_qpt = ipow(Q, dim);
-  const double *d_u = nullptr;
-  double       *d_v = nullptr;
-  if (eval_mode != B200_EVAL_WEIGHT) {
-    B200_CHECK(U && U != B200_VECTOR_NONE, ceed, B200_ERROR_BACKEND, "An input vector is required for this CeedEvalMode");
-    B200_CALL(b200_vector_device_read(U, &d_u));
-  } else {
+  if (eval_mode == B200_EVAL_WEIGHT)
     B200_CHECK(t_mode == B200_NOTRANSPOSE, ceed, B200_ERROR_BACKEND, "CEED_EVAL_WEIGHT incompatible with CEED_TRANSPOSE");
-  }
-  B200_CALL(b200_vector_device_write(V, &d_v, false));
+  else B200_CHECK(d_u, ceed, B200_ERROR_BACKEND, "An input vector is required for this CeedEvalMode");
   if (num_elem == 0) return B200_SUCCESS;
   const int     big      = P > Q ? P : Q;
   const size_t  tmp_size = (size_t)nvec * ipow(big, dim) * sizeof(double);
@@ -412,6 +420,11 @@ extern "C" int ceedb200_basis_apply(B200Basis basis, b200_int num_elem, int t_mo
 }
 extern "C" int ceedb200_basis_apply_add(B200Basis basis, b200_int num_elem, int t_mode, int eval_mode, B200Vector u, B200Vector v) {
   return basis_apply_core(basis, true, num_elem, t_mode, eval_mode, u, v);
+}
+
+extern "C" int ceedb200_basis_apply_ptr(B200Basis basis, b200_int num_elem, int t_mode, int eval_mode, int add, const b200_scalar *d_u,
+                                        b200_scalar *d_v) {
+  return basis_apply_ptr(basis, add != 0, num_elem, t_mode, eval_mode, d_u, d_v);
 }
 
 extern "C" int ceedb200_basis_get_matrix(B200Basis b, int which, b200_scalar *out) {

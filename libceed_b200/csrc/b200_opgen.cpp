@@ -169,19 +169,51 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
   }
   plan->num_planes = std::max(n_in, n_out);
   // elements per block / threads: one thread per quadrature line (Q^2 lines per element), ~256 threads per block
-  const int lines    = Q * Q;
-  const int per_elem = plan->num_planes * plane_size * 8;
-  int       target   = getenv("CEED_B200_THREADS") ? atoi(getenv("CEED_B200_THREADS")) : 256;
-  int       epb      = op->tune_epb > 0 ? op->tune_epb : (getenv("CEED_B200_EPB") ? atoi(getenv("CEED_B200_EPB")) : std::max(1, target / lines));
-  while (epb > 1 && (size_t)epb * per_elem > ceed->smem_optin / 2) epb--;
-  if ((size_t)epb * per_elem > ceed->smem_optin) return reject("element working set exceeds shared memory");
+  const int lines = Q * Q;
+  // Shared-memory layout for E elements per block: contraction planes, then the staging buffers that cp.async fills one
+  // batch ahead (quadrature data, gathered inputs + their offsets, scatter targets).  Returns the total in bytes.
+  plan->async_copy = !getenv("CEED_B200_NO_ASYNC");
+  auto layout      = [&](int E) {
+    size_t off  = (size_t)plan->num_planes * plane_size * 8 * E;
+    auto   take = [&](size_t bytes) {
+      size_t at = off;
+      off += (bytes + 15) / 16 * 16;
+      return (int)at;
+    };
+    for (auto &f : plan->in_fields) {
+      f.qd_off = -1;
+      // contiguous per component over the elements of a batch: unit node stride, element stride == element size
+      if (plan->async_copy && f.emode == B200_EVAL_NONE && f.rstr->is_strided && f.rstr->strides[0] == 1 && f.rstr->strides[2] == f.rstr->elem_size)
+        f.qd_off = take((size_t)f.nc * E * Q * Q * Q * 8);
+    }
+    for (auto &g : plan->in_groups) {
+      g.uin_off = g.idx_off = -1;
+      if (plan->async_copy && !g.rstr->is_strided) {
+        g.uin_off = take((size_t)g.nc * E * g.rstr->elem_size * 8);
+        g.idx_off = take((size_t)E * g.rstr->elem_size * 4);
+      }
+    }
+    for (auto &g : plan->out_groups) {
+      g.tgt_off = -1;
+      if (plan->async_copy && !g.rstr->is_strided && plan->scatter_mode != B200_SCATTER_EVECTOR) g.tgt_off = take((size_t)E * g.rstr->elem_size * 4);
+    }
+    return off;
+  };
+  int target = getenv("CEED_B200_THREADS") ? atoi(getenv("CEED_B200_THREADS")) : 256;
+  int epb    = op->tune_epb > 0 ? op->tune_epb : (getenv("CEED_B200_EPB") ? atoi(getenv("CEED_B200_EPB")) : std::max(1, target / lines));
+  // aim for two resident blocks per SM so that one block's barrier / copy waits are covered by the other
+  while (epb > 1 && layout(epb) > (ceed->smem_sm - 2048) / 2) epb--;
+  if (layout(epb) > ceed->smem_optin) {
+    plan->async_copy = false;
+    if (layout(epb) > ceed->smem_optin) return reject("element working set exceeds shared memory");
+  }
   if (epb > std::max(1, num_elem)) epb = std::max(1, num_elem);
   plan->epb        = epb;
   int threads      = ((epb * lines + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
   if (threads < 64) threads = 64;
   plan->threads    = threads;
-  plan->smem_bytes = std::max(epb * per_elem, 16);
+  plan->smem_bytes = (int)std::max<size_t>(layout(epb), 16);
   {
     // occupancy target handed to __launch_bounds__: limited by shared memory and by a ~96 register/thread budget
     int by_smem = (int)(ceed->smem_sm / (size_t)(plan->smem_bytes + 1024));
@@ -275,6 +307,104 @@ struct Gen {
     c << "\nstruct B200OpArgs {\n  long long num_elem;\n  void *ctx;\n  const double *in_ptr[16];\n  double *out_ptr[16];\n"
       << "  const int *in_idx[16];\n  const int *out_idx[16];\n  double *out_aux[16];\n};\n\n";
     c << "extern __shared__ double sm[];\n\n";
+    // cp.async (LDGSTS): global -> shared without staging registers; completion tracked per thread with commit/wait groups
+    c << "__device__ __forceinline__ void b200_cp4(void *dst, const void *src) {\n"
+      << "  asm volatile(\"cp.async.ca.shared.global [%0], [%1], 4;\" ::\"r\"((unsigned)__cvta_generic_to_shared(dst)), \"l\"(src) : \"memory\");\n}\n"
+      << "__device__ __forceinline__ void b200_cp8(void *dst, const void *src) {\n"
+      << "  asm volatile(\"cp.async.ca.shared.global [%0], [%1], 8;\" ::\"r\"((unsigned)__cvta_generic_to_shared(dst)), \"l\"(src) : \"memory\");\n}\n"
+      << "__device__ __forceinline__ void b200_cp16(void *dst, const void *src) {\n"
+      << "  asm volatile(\"cp.async.cg.shared.global [%0], [%1], 16;\" ::\"r\"((unsigned)__cvta_generic_to_shared(dst)), \"l\"(src) : \"memory\");\n}\n"
+      << "__device__ __forceinline__ void b200_cp_commit() { asm volatile(\"cp.async.commit_group;\" ::: \"memory\"); }\n"
+      << "__device__ __forceinline__ void b200_cp_wait_all() { asm volatile(\"cp.async.wait_group 0;\" ::: \"memory\"); }\n\n";
+  }
+
+  string smem_at(int byte_off, const string &type) const {
+    oss s;
+    s << "((" << type << " *)((char *)sm + " << byte_off << "))";
+    return s.str();
+  }
+
+  // ---- asynchronous staging (issued one batch ahead) ---------------------------------------------
+  // offsets of the gathers of batch e0 (all staged input groups) -> IDX buffers
+  bool emit_issue_idx() {
+    bool any = false;
+    for (auto &g : plan->in_groups) any = any || g.idx_off >= 0;
+    if (!any) return false;
+    c << "static __device__ __noinline__ void b200_issue_idx(const B200OpArgs &a, const long long e0) {\n";
+    c << "  if (e0 >= a.num_elem) return;\n";
+    c << "  const int ne = (int)((a.num_elem - e0 < " << E << ") ? a.num_elem - e0 : " << E << ");\n";
+    for (auto &g : plan->in_groups) {
+      if (g.idx_off < 0) continue;
+      const int es = g.rstr->elem_size;
+      c << "  { int *dst = " << smem_at(g.idx_off, "int") << "; const int *src = a.in_idx[" << g.slot << "] + e0 * " << es << "LL;\n";
+      c << "    for (int i = threadIdx.x; i < ne * " << es << "; i += " << NT << ") b200_cp4(dst + i, src + i); }\n";
+    }
+    c << "}\n\n";
+    return true;
+  }
+  // scatter targets of batch e0 (all staged output groups) -> TGT buffers
+  bool emit_issue_tgt() {
+    bool any = false;
+    for (auto &g : plan->out_groups) any = any || g.tgt_off >= 0;
+    if (!any) return false;
+    c << "static __device__ __noinline__ void b200_issue_tgt(const B200OpArgs &a, const long long e0) {\n";
+    c << "  if (e0 >= a.num_elem) return;\n";
+    c << "  const int ne = (int)((a.num_elem - e0 < " << E << ") ? a.num_elem - e0 : " << E << ");\n";
+    for (auto &g : plan->out_groups) {
+      if (g.tgt_off < 0) continue;
+      const int es = g.rstr->elem_size;
+      c << "  { int *dst = " << smem_at(g.tgt_off, "int") << "; const int *src = a.out_idx[" << g.slot << "] + e0 * " << es << "LL;\n";
+      c << "    for (int i = threadIdx.x; i < ne * " << es << "; i += " << NT << ") b200_cp4(dst + i, src + i); }\n";
+    }
+    c << "}\n\n";
+    return true;
+  }
+  // gathers of batch e0 through the staged offsets -> UIN buffers
+  bool emit_issue_gather() {
+    bool any = false;
+    for (auto &g : plan->in_groups) any = any || g.uin_off >= 0;
+    if (!any) return false;
+    c << "static __device__ __noinline__ void b200_issue_gather(const B200OpArgs &a, const long long e0) {\n";
+    c << "  if (e0 >= a.num_elem) return;\n";
+    c << "  const int ne = (int)((a.num_elem - e0 < " << E << ") ? a.num_elem - e0 : " << E << ");\n";
+    for (auto &g : plan->in_groups) {
+      if (g.uin_off < 0) continue;
+      const int es = g.rstr->elem_size;
+      c << "  { const int *idx = " << smem_at(g.idx_off, "int") << "; double *dst = " << smem_at(g.uin_off, "double") << ";\n";
+      c << "    const double *src = a.in_ptr[" << g.slot << "];\n";
+      c << "    for (int i = threadIdx.x; i < ne * " << es << "; i += " << NT << ") {\n";
+      c << "      const long long l = idx[i];\n";
+      for (int cc = 0; cc < g.nc; cc++)
+        c << "      b200_cp8(dst + i + " << cc * E * es << ", src + l + " << (long long)cc * g.rstr->comp_stride << "LL);\n";
+      c << "    } }\n";
+    }
+    c << "}\n\n";
+    return true;
+  }
+  // streamed EVAL_NONE inputs (quadrature data) of batch e0 -> QD buffers; 16-byte copies when the source is aligned
+  bool emit_issue_qd() {
+    bool any = false;
+    for (auto &f : plan->in_fields) any = any || f.qd_off >= 0;
+    if (!any) return false;
+    const int Q3 = Q * Q * Q;
+    c << "static __device__ __noinline__ void b200_issue_qd(const B200OpArgs &a, const long long e0) {\n";
+    c << "  if (e0 >= a.num_elem) return;\n";
+    c << "  const int ne = (int)((a.num_elem - e0 < " << E << ") ? a.num_elem - e0 : " << E << ");\n";
+    for (auto &f : plan->in_fields) {
+      if (f.qd_off < 0) continue;
+      for (int cc = 0; cc < f.nc; cc++) {
+        c << "  { double *dst = " << smem_at(f.qd_off, "double") << " + " << cc * E * Q3 << ";\n";
+        c << "    const double *src = a.in_ptr[" << f.slot << "] + " << (long long)cc * f.rstr->strides[1] << "LL + e0 * " << Q3 << "LL;\n";
+        c << "    const int n = ne * " << Q3 << ";\n";
+        c << "    if (((((unsigned long long)src) | ((unsigned long long)dst)) & 15) == 0 && (n & 1) == 0) {\n";
+        c << "      for (int i = threadIdx.x * 2; i < n; i += " << 2 * NT << ") b200_cp16(dst + i, src + i);\n";
+        c << "    } else {\n";
+        c << "      for (int i = threadIdx.x; i < n; i += " << NT << ") b200_cp8(dst + i, src + i);\n";
+        c << "    } }\n";
+      }
+    }
+    c << "}\n\n";
+    return true;
   }
 
   // ---- input side -------------------------------------------------------------------------------
@@ -286,12 +416,18 @@ struct Gen {
     task_loop_begin(std::to_string(E * g.nc * P * P));
     c << "      const int ij = t % " << P * P << ", cc = (t / " << P * P << ") % " << g.nc << ", le = t / " << P * P * g.nc << ";\n";
     c << "      const long long e = e0 + le;\n";
-    for (int k = 0; k < P; k++) c << "      double u" << k << " = 0.0;\n";
-    c << "      if (e < a.num_elem) {\n";
-    for (int k = 0; k < P; k++)
-      c << "        u" << k << " = __ldg(a.in_ptr[" << sl << "] + " << lidx(g.rstr, "a.in_idx[" + sl + "]", "e", "ij + " + std::to_string(k * P * P), "cc")
-        << ");\n";
-    c << "      }\n";
+    if (g.uin_off >= 0) {
+      // values were gathered into shared memory by cp.async while the previous batch was computing
+      c << "      const double *uin = " << smem_at(g.uin_off, "double") << " + (cc * " << E << " + le) * " << P * P * P << " + ij;\n";
+      for (int k = 0; k < P; k++) c << "      const double u" << k << " = uin[" << k * P * P << "];\n";
+    } else {
+      for (int k = 0; k < P; k++) c << "      double u" << k << " = 0.0;\n";
+      c << "      if (e < a.num_elem) {\n";
+      for (int k = 0; k < P; k++)
+        c << "        u" << k << " = __ldg(a.in_ptr[" << sl << "] + " << lidx(g.rstr, "a.in_idx[" + sl + "]", "e", "ij + " + std::to_string(k * P * P), "cc")
+          << ");\n";
+      c << "      }\n";
+    }
     if (b.collocated) {
       // nodes are the quadrature points: straight into the Uq plane [qz][qy][Qs]
       c << "      double *dst = " << plane(g.plane0, "le") << " + cc * " << E * S << " + (ij / " << P << ") * " << Qs << " + (ij % " << P << ");\n";
@@ -406,9 +542,13 @@ struct Gen {
         const string        sl = std::to_string(fd.slot);
         switch (fd.emode) {
           case B200_EVAL_NONE:
-            for (int cc = 0; cc < fd.nc; cc++)
-              c << "        in_" << f << "[" << cc << "] = __ldg(a.in_ptr[" << sl << "] + "
-                << lidx(fd.rstr, "a.in_idx[" + sl + "]", "e", "pt", std::to_string(cc)) << ");\n";
+            for (int cc = 0; cc < fd.nc; cc++) {
+              if (fd.qd_off >= 0)
+                c << "        in_" << f << "[" << cc << "] = " << smem_at(fd.qd_off, "const double") << "[(" << cc * E << " + le) * " << Q * Q * Q << " + pt];\n";
+              else
+                c << "        in_" << f << "[" << cc << "] = __ldg(a.in_ptr[" << sl << "] + "
+                  << lidx(fd.rstr, "a.in_idx[" + sl + "]", "e", "pt", std::to_string(cc)) << ");\n";
+            }
             break;
           case B200_EVAL_WEIGHT: c << "        in_" << f << "[0] = wxy_" << f << " * cW" << fd.basis_id << "[" << qz << "];\n"; break;
           case B200_EVAL_INTERP: {
@@ -592,29 +732,38 @@ struct Gen {
     }
     c << "      if (e < a.num_elem) {\n";
     // component handled through the (runtime) cc: emit with nc == 1 semantics and an explicit component offset
-    for (int k = 0; k < P; k++) emit_scatter_comp(g.rstr, g.slot, "e", "ij + " + std::to_string(k * P * P), "cc", "r" + std::to_string(k), "        ");
+    for (int k = 0; k < P; k++) {
+      const string n = "ij + " + std::to_string(k * P * P);
+      // index of this E-entry: staged in shared memory by cp.async at the top of the batch, else read from global memory
+      string index;
+      if (g.tgt_off >= 0) index = smem_at(g.tgt_off, "const int") + "[le * " + std::to_string(g.rstr->elem_size) + " + " + n + "]";
+      emit_scatter_comp(g.rstr, g.slot, "e", n, "cc", "r" + std::to_string(k), "        ", index);
+    }
     c << "      }\n";
     task_loop_end();
   }
 
-  // scatter of a single value for runtime component index `cc`
-  void emit_scatter_comp(B200Restriction r, int slot, const string &e, const string &n, const string &cc, const string &val, const string &ind) {
+  // scatter of a single value for runtime component index `cc`; `index` (optional) is an expression for offsets/tgt[E-entry]
+  void emit_scatter_comp(B200Restriction r, int slot, const string &e, const string &n, const string &cc, const string &val, const string &ind,
+                         const string &index = "") {
     const string sl = std::to_string(slot);
     if (r->is_strided) {
       c << ind << "a.out_ptr[" << sl << "][" << lidx(r, "", e, n, cc) << "] " << (add ? "+=" : "=") << " " << val << ";\n";
       return;
     }
     const long long e_entries = (long long)r->num_elem * r->elem_size;
+    const string    entry     = index.empty() ? "a.out_idx[" + sl + "][(" + e + ") * " + std::to_string(r->elem_size) + "LL + (" + n + ")]" : index;
     switch (plan->scatter_mode) {
       case B200_SCATTER_ATOMIC:
-        c << ind << "atomicAdd(a.out_ptr[" << sl << "] + " << lidx(r, "a.out_idx[" + sl + "]", e, n, cc) << ", " << val << ");\n";
+        c << ind << "atomicAdd(a.out_ptr[" << sl << "] + ((long long)" << entry << " + (long long)(" << cc << ") * " << r->comp_stride << "LL), " << val
+          << ");\n";
         break;
       case B200_SCATTER_EVECTOR:
         c << ind << "a.out_aux[" << sl << "][(" << e << ") * " << r->elem_size << "LL + (" << n << ") + " << cc << " * " << e_entries << "LL] = " << val
           << ";\n";
         break;
       default:
-        c << ind << "{ const int tg = a.out_idx[" << sl << "][(" << e << ") * " << r->elem_size << "LL + (" << n << ")];\n";
+        c << ind << "{ const int tg = " << entry << ";\n";
         c << ind << "  if (tg >= 0) a.out_ptr[" << sl << "][tg + " << cc << " * " << (long long)r->comp_stride << "LL] " << (add ? "+=" : "=") << " " << val
           << ";\n";
         c << ind << "  else a.out_aux[" << sl << "][(long long)(~tg) + " << cc << " * " << (long long)r->num_halo << "LL] = " << val << "; }\n";
@@ -650,9 +799,23 @@ struct Gen {
       for (auto &g : plan->in_groups) emit_grad_y(g);
       barrier();
     }
+    // asynchronous staging: emit the issue functions (definitions go to the source stream, calls are placed below)
+    const bool has_idx = emit_issue_idx(), has_tgt = emit_issue_tgt(), has_gather = emit_issue_gather(), has_qd = emit_issue_qd();
+    const bool staged  = has_idx || has_tgt || has_gather || has_qd;
+    if (has_gather) {
+      // before the quadrature stage: the offsets of the next batch have landed (issued at the top of this batch) and the
+      // gather buffer is free (the z-stage consumed it) -> start gathering the next batch's inputs
+      if (!calls.empty() && calls.back().find("__syncthreads") != string::npos) calls.pop_back();
+      calls.push_back("    b200_cp_wait_all();\n    __syncthreads();\n    b200_issue_gather(a, e0n);\n    b200_cp_commit();\n");
+    } else if (has_tgt) {
+      if (!calls.empty() && calls.back().find("__syncthreads") != string::npos) calls.pop_back();
+      calls.push_back("    b200_cp_wait_all();\n    __syncthreads();\n");
+    }
     emit_qf_stage();
+    if (!plan->out_groups.empty() || has_qd) barrier();
+    // the quadrature-data buffer is free again: stream in the next batch's data behind the transpose stages
+    if (has_qd) calls.push_back("    b200_issue_qd(a, e0n);\n    b200_cp_commit();\n");
     if (!plan->out_groups.empty()) {
-      barrier();
       any = false;
       for (auto &g : plan->out_groups) any = any || g.use_grad;
       if (any) {
@@ -673,12 +836,59 @@ struct Gen {
       }
       for (auto &g : plan->out_groups) emit_scatter_z(g);
     }
-    barrier();
+    if (!staged) barrier();  // staged kernels synchronise at the top of the batch loop instead
     const int minb = std::max(1, plan->blocks_per_sm);
-    c << "extern \"C\" __global__ void __launch_bounds__(" << NT << ", " << minb << ") b200_operator(const __grid_constant__ B200OpArgs a) {\n";
+    // L2 prefetch of the NEXT batch this block will process (grid-stride): the streamed quadrature data (the bulk of the
+    // HBM traffic) and the element offsets, so that the demand loads a few microseconds later hit in the 126 MB L2.
+    const bool prefetch = getenv("CEED_B200_PREFETCH") != nullptr && !staged;
+    if (prefetch) {
+      c << "static __device__ __noinline__ void b200_prefetch(const B200OpArgs &a, const long long e0) {\n";
+      c << "  if (e0 >= a.num_elem) return;\n";
+      c << "  const long long ne = (a.num_elem - e0 < " << E << ") ? a.num_elem - e0 : " << E << ";\n";
+      auto emit_range = [&](const string &ptr, const string &first_elem_expr, long long bytes_per_elem) {
+        // byte range [p0, p0 + ne * bytes_per_elem), one 128-byte line per thread per round
+        c << "  { const char *p0 = (const char *)(" << ptr << ") + (" << first_elem_expr << ") * " << bytes_per_elem << "LL;\n";
+        c << "    const long long nbytes = ne * " << bytes_per_elem << "LL;\n";
+        c << "    for (long long off = (long long)threadIdx.x * 128; off < nbytes; off += " << NT * 128 << ")\n";
+        c << "      asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(p0 + off));\n  }\n";
+      };
+      for (size_t f = 0; f < plan->in_fields.size(); f++) {
+        const B200GenField &fd = plan->in_fields[f];
+        if (fd.emode != B200_EVAL_NONE || !fd.rstr->is_strided || fd.rstr->strides[0] != 1) continue;
+        // contiguous per (component, element) when the node stride is 1
+        for (int cc = 0; cc < fd.nc; cc++) {
+          if (fd.rstr->strides[2] == fd.rstr->elem_size) {
+            emit_range("a.in_ptr[" + std::to_string(fd.slot) + "] + " + std::to_string((long long)cc * fd.rstr->strides[1]) + "LL", "e0", 8LL * fd.rstr->elem_size);
+          }
+        }
+      }
+      for (auto &g : plan->in_groups)
+        if (!g.rstr->is_strided) emit_range("a.in_idx[" + std::to_string(g.slot) + "]", "e0", 4LL * g.rstr->elem_size);
+      c << "}\n\n";
+    }
+    c << "extern \"C\" __global__ void __launch_bounds__(" << NT << ", " << minb << ") b200_operator_" << op->qf->kernel_name << "(const __grid_constant__ B200OpArgs a) {\n";
     c << "  const long long num_batches = (a.num_elem + " << E - 1 << ") / " << E << ";\n";
+    if (staged) {
+      // prologue: stage the first batch of this block
+      c << "  if ((long long)blockIdx.x < num_batches) {\n";
+      c << "    const long long e0 = (long long)blockIdx.x * " << E << ";\n";
+      if (has_idx) c << "    b200_issue_idx(a, e0);\n    b200_cp_commit();\n    b200_cp_wait_all();\n    __syncthreads();\n";
+      if (has_gather) c << "    b200_issue_gather(a, e0);\n";
+      if (has_qd) c << "    b200_issue_qd(a, e0);\n";
+      c << "    b200_cp_commit();\n  }\n";
+    }
     c << "  for (long long batch = blockIdx.x; batch < num_batches; batch += gridDim.x) {\n";
-    c << "    const long long e0 = batch * " << E << ";\n";
+    c << "    const long long e0 = batch * " << E << ", e0n = (batch + gridDim.x) * " << E << ";\n";
+    if (staged) {
+      // everything staged for this batch is visible after this point; all reads of the previous batch are done
+      c << "    b200_cp_wait_all();\n    __syncthreads();\n";
+      if (has_idx) c << "    b200_issue_idx(a, e0n);\n";
+      if (has_tgt) c << "    b200_issue_tgt(a, e0);\n";
+      c << "    b200_cp_commit();\n";
+    } else {
+      c << "    (void)e0n;\n";
+      if (prefetch) c << "    b200_prefetch(a, e0n);\n";
+    }
     for (auto &call : calls) c << call;
     c << "  }\n}\n";
     return c.str();
@@ -701,7 +911,7 @@ int b200_opgen_build(B200Operator op, B200OpPlan *plan, int add) {
   if (v.built) return B200_SUCCESS;
   v.source = b200_opgen_source(op, plan, add);
   B200_CALL(b200_jit_compile(ceed, v.source, {}, &v.module));
-  B200_CALL(b200_jit_get_kernel(ceed, v.module, "b200_operator", &v.kernel));
+  B200_CALL(b200_jit_get_kernel(ceed, v.module, ("b200_operator_" + op->qf->kernel_name).c_str(), &v.kernel));
   if (!b200_compile_only()) {
     B200_CU(ceed, cuFuncSetAttribute(v.kernel, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, plan->smem_bytes));
     int val = 0;

@@ -22,6 +22,10 @@ struct B200GenGroup {
   bool            use_interp = false, use_grad = false;
   int             plane0     = 0;  // first shared-memory plane
   int             slot       = 0;  // index into the kernel argument pointer tables
+  // asynchronous staging buffers in shared memory (byte offsets from the dynamic smem base, -1 = not staged)
+  int             uin_off = -1;    // inputs: gathered L-vector values of the NEXT batch   [nc][E][P^3] doubles
+  int             idx_off = -1;    // inputs: element offsets of the next batch             [E][P^3] ints
+  int             tgt_off = -1;    // outputs: scatter targets of the current batch         [E][P^3] ints
 };
 
 struct B200GenField {
@@ -32,6 +36,7 @@ struct B200GenField {
   B200Vector      vec = nullptr;
   bool            is_active = false;
   int             slot = 0;
+  int             qd_off = -1;    // EVAL_NONE inputs streamed with cp.async: [nc][E * Q^3] doubles (byte offset), -1 = direct loads
 };
 
 struct B200OpArgs {
@@ -60,6 +65,7 @@ struct B200OpPlan {
   int                       epb = 1, threads = 256, blocks_per_sm = 1, grid = 1;
   int                       plane_size = 0, num_planes = 0, smem_bytes = 0;
   int                       scatter_mode = 0;
+  bool                      async_copy = true;  // stage global reads through cp.async one batch ahead
   std::vector<B200GenBasis> bases;
   std::vector<B200GenGroup> in_groups, out_groups;
   std::vector<B200GenField> in_fields, out_fields;

@@ -190,7 +190,7 @@ static int qfunction_build(B200QFunction qf) {
   return B200_SUCCESS;
 }
 
-extern "C" int ceedb200_qfunction_apply(B200QFunction qf, b200_int Q, const B200Vector *U, const B200Vector *V) {
+extern "C" int ceedb200_qfunction_apply_ptr(B200QFunction qf, b200_int Q, const b200_scalar *const *d_in, b200_scalar *const *d_out) {
   B200Ceed ceed = qf->ceed;
   B200_CALL(qfunction_build(qf));
   struct {
@@ -198,14 +198,8 @@ extern "C" int ceedb200_qfunction_apply(B200QFunction qf, b200_int Q, const B200
     double       *out[16];
   } ptrs;
   memset(&ptrs, 0, sizeof(ptrs));
-  for (size_t i = 0; i < qf->inputs.size(); i++) {
-    B200_CHECK(U[i]->length >= (int64_t)Q * qf->inputs[i].size, ceed, B200_ERROR_DIMENSION, "QFunction input %zu too short", i);
-    B200_CALL(b200_vector_device_read(U[i], &ptrs.in[i]));
-  }
-  for (size_t i = 0; i < qf->outputs.size(); i++) {
-    B200_CHECK(V[i]->length >= (int64_t)Q * qf->outputs[i].size, ceed, B200_ERROR_DIMENSION, "QFunction output %zu too short", i);
-    B200_CALL(b200_vector_device_write(V[i], &ptrs.out[i], V[i]->length == (int64_t)Q * qf->outputs[i].size));
-  }
+  for (size_t i = 0; i < qf->inputs.size(); i++) ptrs.in[i] = d_in[i];
+  for (size_t i = 0; i < qf->outputs.size(); i++) ptrs.out[i] = d_out[i];
   void *d_ctx = nullptr;
   if (qf->ctx) B200_CALL(ceedb200_qfcontext_get_data(qf->ctx, B200_MEM_DEVICE, &d_ctx));
   if (Q == 0) return B200_SUCCESS;
@@ -214,4 +208,19 @@ extern "C" int ceedb200_qfunction_apply(B200QFunction qf, b200_int Q, const B200
   int64_t   blocks = ((int64_t)Q + 255) / 256, cap = (int64_t)ceed->num_sms * 8;
   if (blocks > cap) blocks = cap;
   return b200_launch(ceed, qf->kernel, (unsigned)blocks, 256, 0, args);
+}
+
+extern "C" int ceedb200_qfunction_apply(B200QFunction qf, b200_int Q, const B200Vector *U, const B200Vector *V) {
+  B200Ceed      ceed = qf->ceed;
+  const double *in[16]  = {nullptr};
+  double       *out[16] = {nullptr};
+  for (size_t i = 0; i < qf->inputs.size(); i++) {
+    B200_CHECK(U[i]->length >= (int64_t)Q * qf->inputs[i].size, ceed, B200_ERROR_DIMENSION, "QFunction input %zu too short", i);
+    B200_CALL(b200_vector_device_read(U[i], &in[i]));
+  }
+  for (size_t i = 0; i < qf->outputs.size(); i++) {
+    B200_CHECK(V[i]->length >= (int64_t)Q * qf->outputs[i].size, ceed, B200_ERROR_DIMENSION, "QFunction output %zu too short", i);
+    B200_CALL(b200_vector_device_write(V[i], &out[i], V[i]->length == (int64_t)Q * qf->outputs[i].size));
+  }
+  return ceedb200_qfunction_apply_ptr(qf, Q, in, out);
 }

@@ -334,6 +334,10 @@ extern "C" int ceedb200_restriction_apply(B200Restriction r, int t_mode, B200Vec
   return b200_restriction_apply_raw(r, t_mode, d_u, d_v);
 }
 
+extern "C" int ceedb200_restriction_apply_ptr(B200Restriction r, int t_mode, const b200_scalar *d_u, b200_scalar *d_v) {
+  return b200_restriction_apply_raw(r, t_mode, d_u, d_v);
+}
+
 extern "C" int ceedb200_restriction_get_offsets(B200Restriction r, int mem_type, const b200_int **offsets) {
   B200_CHECK(!r->is_strided, r->ceed, B200_ERROR_UNSUPPORTED, "strided restriction has no offsets");
   *offsets = mem_type == B200_MEM_HOST ? r->h_offsets : r->d_offsets;

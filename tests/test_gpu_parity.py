@@ -172,7 +172,7 @@ def test_standalone_basis_matches_oracle(cm, oracle, dim, P, Q, qm):
     full = w1
     for _ in range(dim - 1):
         full = np.multiply.outer(w1, full).reshape(-1)
-    assert np.allclose(wv.get_array_read().reshape(nelem, nq), full[None, :], rtol=1e-15, atol=0)
+    assert np.allclose(wv.get_array_read().reshape(nelem, nq), full[None, :], rtol=1e-14, atol=0)  # product order differs by an ulp
 
 
 # ------------------------------------------------------------------------------------------------ qfunction
@@ -308,8 +308,9 @@ def test_unfused_fallback_matches_fused(cm, monkeypatch):
     fused = make_problem(cm, bp, p, nel)
     monkeypatch.setenv("CEED_B200_NO_FUSE", "1")
     unf = make_problem(cm, bp, p, nel)
+    assert not unf.op.is_fused  # operator setup (lazy) happens here, while the switch is still set
     monkeypatch.delenv("CEED_B200_NO_FUSE")
-    assert fused.op.is_fused and not unf.op.is_fused
+    assert fused.op.is_fused
     u = seeded_uniform(fused.num_dofs, 17)
     for prob in (fused, unf):
         prob.u.set_array(u)
