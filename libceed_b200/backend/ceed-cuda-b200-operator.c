@@ -1,0 +1,180 @@
+// ceed-cuda-b200-operator.c -- CeedOperator slots -> ceedb200_operator_*
+//
+// Replaces the host side of backends/cuda-gen/ceed-cuda-gen-operator.c:105-300,879-908.  On the first apply the field
+// wiring of the interface object (CeedOperatorGetFields, interface/ceed-operator.c:931-1038) is mirrored into a core
+// operator; every apply then fetches the DEVICE arrays of the active and passive vectors through the interface
+// (CeedVectorGetArray*(CEED_MEM_DEVICE), so lazy host->device synchronisation and access locking stay with libCEED, as in
+// ceed-cuda-gen-operator.c:131-171) and hands them to the core as borrowed device pointers.
+// Both ApplyAdd (mandatory, interface/ceed-operator.c:2335) and Apply (overwrite; lets the fused kernel store instead of
+// memset + read-modify-write, :2280-2282) are registered.
+#include <stdlib.h>
+#include <string.h>
+
+#include "ceed-cuda-b200.h"
+
+static int CeedOperatorSetup_B200(CeedOperator op) {
+  Ceed               ceed = CeedOperatorReturnCeed(op);
+  B200Ceed           core;
+  CeedOperator_B200 *impl;
+  CeedQFunction      qf;
+  B200QFunction      core_qf;
+  CeedInt            num_in, num_out;
+  CeedOperatorField *in, *out;
+
+  CeedCallBackend(CeedOperatorGetData(op, &impl));
+  if (impl->is_setup) return CEED_ERROR_SUCCESS;
+  CeedCallBackend(CeedGetCore_B200(ceed, &core));
+  CeedCallBackend(CeedSyncJitOptions_B200(ceed));
+  CeedCallBackend(CeedOperatorGetQFunction(op, &qf));
+  CeedCallBackend(CeedQFunctionGetCore_B200(qf, &core_qf));
+  CeedCallBackend(CeedQFunctionDestroy(&qf));
+  CeedCallB200(ceed, core, ceedb200_operator_create(core, core_qf, &impl->core));
+  CeedCallB200(ceed, core, ceedb200_vector_create(core, 0, &impl->view_in));
+  CeedCallB200(ceed, core, ceedb200_vector_create(core, 0, &impl->view_out));
+  CeedCallBackend(CeedOperatorGetFields(op, &num_in, &in, &num_out, &out));
+  impl->num_in  = num_in;
+  impl->num_out = num_out;
+  for (CeedInt i = 0; i < num_in + num_out; i++) {
+    const bool          is_in = i < num_in;
+    CeedOperatorField   field = is_in ? in[i] : out[i - num_in];
+    const char         *name;
+    CeedElemRestriction rstr;
+    CeedBasis           basis;
+    CeedVector          vec;
+    B200Restriction     core_rstr  = NULL;
+    B200Basis           core_basis = NULL;
+    B200Vector          core_vec   = B200_VECTOR_NONE;
+
+    CeedCallBackend(CeedOperatorFieldGetData(field, &name, &rstr, &basis, &vec));
+    if (rstr != CEED_ELEMRESTRICTION_NONE) {
+      CeedElemRestriction_B200 *r;
+      CeedCallBackend(CeedElemRestrictionGetData(rstr, &r));
+      core_rstr = r->core;
+    }
+    if (basis != CEED_BASIS_NONE) {
+      CeedBasis_B200 *b;
+      bool            is_tensor;
+      CeedCallBackend(CeedBasisIsTensor(basis, &is_tensor));
+      CeedCheck(is_tensor, ceed, CEED_ERROR_UNSUPPORTED, "Backend does not implement operators with non-tensor bases");
+      CeedCallBackend(CeedBasisGetData(basis, &b));
+      core_basis = b->core;
+    }
+    if (vec == CEED_VECTOR_ACTIVE) {
+      core_vec = B200_VECTOR_ACTIVE;
+    } else if (vec != CEED_VECTOR_NONE) {
+      // passive vector: a zero-length core vector that borrows the device array at every apply
+      B200Vector *slot = is_in ? &impl->passive_in[i] : &impl->passive_out[i - num_in];
+      CeedSize    len;
+      CeedCallBackend(CeedVectorGetLength(vec, &len));
+      CeedCallB200(ceed, core, ceedb200_vector_create(core, len, slot));
+      core_vec = *slot;
+      if (is_in) impl->passive_in_vec[i] = vec;
+      else impl->passive_out_vec[i - num_in] = vec;
+      CeedCallBackend(CeedVectorReference(vec));  // keep alive as long as the operator
+    }
+    CeedCallB200(ceed, core, ceedb200_operator_set_field(impl->core, name, core_rstr, core_basis, core_vec));
+    CeedCallBackend(CeedElemRestrictionDestroy(&rstr));
+    CeedCallBackend(CeedBasisDestroy(&basis));
+    CeedCallBackend(CeedVectorDestroy(&vec));
+  }
+  impl->is_setup = true;
+  CeedCallBackend(CeedOperatorSetSetupDone(op));
+  return CEED_ERROR_SUCCESS;
+}
+
+static int CeedOperatorApplyCore_B200(CeedOperator op, CeedVector in_vec, CeedVector out_vec, bool add) {
+  Ceed               ceed = CeedOperatorReturnCeed(op);
+  B200Ceed           core;
+  CeedOperator_B200 *impl;
+  const CeedScalar  *d_in = NULL, *d_pin[CEED_FIELD_MAX] = {NULL};
+  CeedScalar        *d_out = NULL, *d_pout[CEED_FIELD_MAX] = {NULL};
+  CeedSize           len;
+  int                ierr;
+
+  CeedCallBackend(CeedGetCore_B200(ceed, &core));
+  CeedCallBackend(CeedOperatorSetup_B200(op));
+  CeedCallBackend(CeedOperatorGetData(op, &impl));
+
+  // device arrays of every vector involved, through the interface
+  if (in_vec != CEED_VECTOR_NONE) {
+    CeedCallBackend(CeedVectorGetLength(in_vec, &len));
+    CeedCallBackend(CeedVectorGetArrayRead(in_vec, CEED_MEM_DEVICE, &d_in));
+    ceedb200_vector_destroy(impl->view_in);
+    CeedCallB200(ceed, core, ceedb200_vector_create(core, len, &impl->view_in));
+    CeedCallB200(ceed, core, ceedb200_vector_set_array(impl->view_in, B200_MEM_DEVICE, B200_USE_POINTER, (CeedScalar *)d_in));
+  }
+  if (out_vec != CEED_VECTOR_NONE) {
+    CeedCallBackend(CeedVectorGetLength(out_vec, &len));
+    if (add) CeedCallBackend(CeedVectorGetArray(out_vec, CEED_MEM_DEVICE, &d_out));
+    else CeedCallBackend(CeedVectorGetArrayWrite(out_vec, CEED_MEM_DEVICE, &d_out));
+    ceedb200_vector_destroy(impl->view_out);
+    CeedCallB200(ceed, core, ceedb200_vector_create(core, len, &impl->view_out));
+    CeedCallB200(ceed, core, ceedb200_vector_set_array(impl->view_out, B200_MEM_DEVICE, B200_USE_POINTER, d_out));
+  }
+  for (CeedInt i = 0; i < impl->num_in; i++) {
+    if (!impl->passive_in_vec[i]) continue;
+    CeedCallBackend(CeedVectorGetArrayRead(impl->passive_in_vec[i], CEED_MEM_DEVICE, &d_pin[i]));
+    CeedCallB200(ceed, core, ceedb200_vector_set_array(impl->passive_in[i], B200_MEM_DEVICE, B200_USE_POINTER, (CeedScalar *)d_pin[i]));
+  }
+  for (CeedInt i = 0; i < impl->num_out; i++) {
+    if (!impl->passive_out_vec[i]) continue;
+    // passive outputs accumulate (the interface zeroed them in CeedOperatorApplyAddActive, interface/ceed-operator.c:2357-2405)
+    CeedCallBackend(CeedVectorGetArray(impl->passive_out_vec[i], CEED_MEM_DEVICE, &d_pout[i]));
+    CeedCallB200(ceed, core, ceedb200_vector_set_array(impl->passive_out[i], B200_MEM_DEVICE, B200_USE_POINTER, d_pout[i]));
+  }
+  {
+    bool has_passive_out = false;
+    for (CeedInt i = 0; i < impl->num_out; i++) has_passive_out = has_passive_out || impl->passive_out_vec[i];
+    // overwrite semantics can only be used when every output is the active vector
+    if (!add && !has_passive_out) ierr = ceedb200_operator_apply(impl->core, in_vec != CEED_VECTOR_NONE ? impl->view_in : NULL, impl->view_out);
+    else {
+      if (!add && out_vec != CEED_VECTOR_NONE) ceedb200_vector_set_value(impl->view_out, 0.0);
+      ierr = ceedb200_operator_apply_add(impl->core, in_vec != CEED_VECTOR_NONE ? impl->view_in : NULL, impl->view_out);
+    }
+  }
+  // restore in every case so that libCEED's access locks are released
+  if (in_vec != CEED_VECTOR_NONE) CeedCallBackend(CeedVectorRestoreArrayRead(in_vec, &d_in));
+  if (out_vec != CEED_VECTOR_NONE) CeedCallBackend(CeedVectorRestoreArray(out_vec, &d_out));
+  for (CeedInt i = 0; i < impl->num_in; i++)
+    if (impl->passive_in_vec[i]) CeedCallBackend(CeedVectorRestoreArrayRead(impl->passive_in_vec[i], &d_pin[i]));
+  for (CeedInt i = 0; i < impl->num_out; i++)
+    if (impl->passive_out_vec[i]) CeedCallBackend(CeedVectorRestoreArray(impl->passive_out_vec[i], &d_pout[i]));
+  if (ierr) return CeedError(ceed, CEED_ERROR_BACKEND, "%s", ceedb200_last_error(core));
+  return CEED_ERROR_SUCCESS;
+}
+
+static int CeedOperatorApplyAdd_B200(CeedOperator op, CeedVector in_vec, CeedVector out_vec, CeedRequest *request) {
+  return CeedOperatorApplyCore_B200(op, in_vec, out_vec, true);
+}
+static int CeedOperatorApply_B200(CeedOperator op, CeedVector in_vec, CeedVector out_vec, CeedRequest *request) {
+  return CeedOperatorApplyCore_B200(op, in_vec, out_vec, false);
+}
+
+static int CeedOperatorDestroy_B200(CeedOperator op) {
+  CeedOperator_B200 *impl;
+
+  CeedCallBackend(CeedOperatorGetData(op, &impl));
+  ceedb200_operator_destroy(impl->core);
+  ceedb200_vector_destroy(impl->view_in);
+  ceedb200_vector_destroy(impl->view_out);
+  for (CeedInt i = 0; i < CEED_FIELD_MAX; i++) {
+    ceedb200_vector_destroy(impl->passive_in[i]);
+    ceedb200_vector_destroy(impl->passive_out[i]);
+    if (impl->passive_in_vec[i]) CeedCallBackend(CeedVectorDestroy(&impl->passive_in_vec[i]));
+    if (impl->passive_out_vec[i]) CeedCallBackend(CeedVectorDestroy(&impl->passive_out_vec[i]));
+  }
+  free(impl);
+  return CEED_ERROR_SUCCESS;
+}
+
+int CeedOperatorCreate_B200(CeedOperator op) {
+  Ceed               ceed = CeedOperatorReturnCeed(op);
+  CeedOperator_B200 *impl;
+
+  impl = calloc(1, sizeof(*impl));
+  CeedCallBackend(CeedOperatorSetData(op, impl));
+  CeedCallBackend(CeedSetBackendFunction(ceed, "Operator", op, "ApplyAdd", CeedOperatorApplyAdd_B200));
+  CeedCallBackend(CeedSetBackendFunction(ceed, "Operator", op, "Apply", CeedOperatorApply_B200));
+  CeedCallBackend(CeedSetBackendFunction(ceed, "Operator", op, "Destroy", CeedOperatorDestroy_B200));
+  return CEED_ERROR_SUCCESS;
+}

@@ -161,7 +161,7 @@ struct B200Operator_ {
   int                      tune_epb = 0, tune_bpsm = 0;
   bool                     timing = false;
   float                    last_fused_ms = 0.f, last_aux_ms = 0.f;
-  cudaEvent_t              ev[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t              ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 // internal helpers shared between translation units

@@ -174,7 +174,8 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
   // batch ahead (quadrature data, gathered inputs + their offsets, scatter targets).  Returns the total in bytes.
   plan->async_copy = !getenv("CEED_B200_NO_ASYNC");
   auto layout      = [&](int E) {
-    size_t off  = (size_t)plan->num_planes * plane_size * 8 * E;
+    size_t off  = ((size_t)plan->num_planes * plane_size * 8 * E + 15) / 16 * 16;
+    const int mask = plan->warp_mode ? plan->stage_mask : 7;
     auto   take = [&](size_t bytes) {
       size_t at = off;
       off += (bytes + 15) / 16 * 16;
@@ -183,37 +184,77 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     for (auto &f : plan->in_fields) {
       f.qd_off = -1;
       // contiguous per component over the elements of a batch: unit node stride, element stride == element size
-      if (plan->async_copy && f.emode == B200_EVAL_NONE && f.rstr->is_strided && f.rstr->strides[0] == 1 && f.rstr->strides[2] == f.rstr->elem_size)
+      if (plan->async_copy && (mask & 4) && f.emode == B200_EVAL_NONE && f.rstr->is_strided && f.rstr->strides[0] == 1 && f.rstr->strides[2] == f.rstr->elem_size)
         f.qd_off = take((size_t)f.nc * E * Q * Q * Q * 8);
     }
     for (auto &g : plan->in_groups) {
       g.uin_off = g.idx_off = -1;
-      if (plan->async_copy && !g.rstr->is_strided) {
+      if (plan->async_copy && (mask & 2) && !g.rstr->is_strided) {
         g.uin_off = take((size_t)g.nc * E * g.rstr->elem_size * 8);
         g.idx_off = take((size_t)E * g.rstr->elem_size * 4);
       }
     }
     for (auto &g : plan->out_groups) {
       g.tgt_off = -1;
-      if (plan->async_copy && !g.rstr->is_strided && plan->scatter_mode != B200_SCATTER_EVECTOR) g.tgt_off = take((size_t)E * g.rstr->elem_size * 4);
+      if (plan->async_copy && (mask & 1) && !g.rstr->is_strided && plan->scatter_mode != B200_SCATTER_EVECTOR) g.tgt_off = take((size_t)E * g.rstr->elem_size * 4);
     }
     return off;
   };
-  int target = getenv("CEED_B200_THREADS") ? atoi(getenv("CEED_B200_THREADS")) : 256;
-  int epb    = op->tune_epb > 0 ? op->tune_epb : (getenv("CEED_B200_EPB") ? atoi(getenv("CEED_B200_EPB")) : std::max(1, target / lines));
-  // aim for two resident blocks per SM so that one block's barrier / copy waits are covered by the other
-  while (epb > 1 && layout(epb) > (ceed->smem_sm - 2048) / 2) epb--;
-  if (layout(epb) > ceed->smem_optin) {
-    plan->async_copy = false;
+  plan->warp_mode = !getenv("CEED_B200_BLOCK_MODE");
+  int epb, threads;
+  if (plan->warp_mode) {
+    // staging defaults in warp mode: offsets + scatter targets only (small); CEED_B200_STAGE=<bitmask 1 idx/tgt, 2 gather, 4 qdata>
+    const int stage = getenv("CEED_B200_STAGE") ? atoi(getenv("CEED_B200_STAGE")) : 1;
+    plan->stage_mask = stage;
+    // elements per warp: fill the 32 lanes in the line stages; prefer the best lane utilisation within ~14 KB per warp
+    int    best = 1;
+    double best_util = -1.0;
+    const int Pmax = plan->bases.empty() ? Q : plan->bases[0].P;
+    for (int e = 1; e <= 16; e++) {
+      if (layout(e) > 14336 && e > 1) break;
+      double work = 0, slots = 0;
+      for (int tasks : {Pmax * Pmax, Pmax * Q, lines, lines, lines}) {
+        work += (double)e * tasks;
+        slots += 32.0 * ((e * tasks + 31) / 32);
+      }
+      const double util = work / slots;
+      if (util > best_util + 0.02) {
+        best_util = util;
+        best      = e;
+      }
+    }
+    epb = op->tune_epb > 0 ? op->tune_epb : (getenv("CEED_B200_EPB") ? atoi(getenv("CEED_B200_EPB")) : best);
+    if (epb > std::max(1, num_elem)) epb = std::max(1, num_elem);
     if (layout(epb) > ceed->smem_optin) return reject("element working set exceeds shared memory");
+    const int warps = getenv("CEED_B200_WARPS") ? atoi(getenv("CEED_B200_WARPS")) : 4;
+    int       w     = warps;
+    while (w > 1 && (size_t)w * layout(epb) > ceed->smem_optin) w--;
+    threads                = 32 * w;
+    plan->group_smem_bytes = (int)layout(epb);
+    plan->epb              = epb;
+    plan->threads          = threads;
+    plan->smem_bytes       = (int)std::max<size_t>((size_t)w * layout(epb), 16);
+  } else {
+    plan->stage_mask = 7;
+    int target = getenv("CEED_B200_THREADS") ? atoi(getenv("CEED_B200_THREADS")) : 256;
+    epb        = op->tune_epb > 0 ? op->tune_epb : (getenv("CEED_B200_EPB") ? atoi(getenv("CEED_B200_EPB")) : std::max(1, target / lines));
+    // aim for two resident blocks per SM so that one block's barrier / copy waits are covered by the other
+    const bool   epb_forced = op->tune_epb > 0 || getenv("CEED_B200_EPB");
+    const size_t smem_goal  = epb_forced ? ceed->smem_optin : (ceed->smem_sm - 2048) / 2;
+    while (epb > 1 && layout(epb) > smem_goal) epb--;
+    if (layout(epb) > ceed->smem_optin) {
+      plan->async_copy = false;
+      if (layout(epb) > ceed->smem_optin) return reject("element working set exceeds shared memory");
+    }
+    if (epb > std::max(1, num_elem)) epb = std::max(1, num_elem);
+    plan->epb = epb;
+    threads   = ((epb * lines + 31) / 32) * 32;
+    if (threads > 1024) threads = 1024;
+    if (threads < 64) threads = 64;
+    plan->threads          = threads;
+    plan->group_smem_bytes = (int)layout(epb);
+    plan->smem_bytes       = (int)std::max<size_t>(layout(epb), 16);
   }
-  if (epb > std::max(1, num_elem)) epb = std::max(1, num_elem);
-  plan->epb        = epb;
-  int threads      = ((epb * lines + 31) / 32) * 32;
-  if (threads > 1024) threads = 1024;
-  if (threads < 64) threads = 64;
-  plan->threads    = threads;
-  plan->smem_bytes = (int)std::max<size_t>(layout(epb), 16);
   {
     // occupancy target handed to __launch_bounds__: limited by shared memory and by a ~96 register/thread budget
     int by_smem = (int)(ceed->smem_sm / (size_t)(plan->smem_bytes + 1024));
@@ -236,12 +277,21 @@ struct Gen {
   int          add;
   oss          c;
   int          Q, Qs, E, NT, S;
+  // work distribution: block mode = all NT threads of the CTA share a batch of E elements and meet at __syncthreads();
+  // warp mode = every warp owns its own group of E elements and its own shared-memory slice and only ever executes
+  // __syncwarp(): warps drift apart, so the global-memory phases of some overlap the FP64 phases of others.
+  bool         warp_mode = false;
+  int          TS        = 0;            // task-loop stride (threads that share a group)
+  string       TID, SMBASE, SYNC;        // lane id expression, shared-memory base, barrier statement
+  string       smw_decl() const {
+    return warp_mode ? "  double *const smw = sm + (threadIdx.x >> 5) * " + std::to_string(plan->group_smem_bytes / 8) + ";\n" : "";
+  }
 
   const B200GenBasis &basis(int id) const { return plan->bases[id]; }
   string plane(int pl, const string &le) const {
     // address (in doubles) of plane `pl` of local element `le`
     oss s;
-    s << "sm + ((" << pl << ") * " << E << " + " << le << ") * " << S;
+    s << SMBASE << " + ((" << pl << ") * " << E << " + " << le << ") * " << S;
     return s.str();
   }
 
@@ -265,11 +315,12 @@ struct Gen {
   void task_loop_begin(const string &ntasks) {
     const string name = "b200_stage_" + std::to_string(n_stage++);
     c << "static __device__ __noinline__ void " << name << "(const B200OpArgs &a, const long long e0) {\n";
-    c << "    for (int t = threadIdx.x; t < " << ntasks << "; t += " << NT << ") {\n";
+    c << smw_decl();
+    c << "    for (int t = " << TID << "; t < " << ntasks << "; t += " << TS << ") {\n";
     calls.push_back("    " + name + "(a, e0);\n");
   }
   void task_loop_end() { c << "    }\n}\n\n"; }
-  void barrier() { calls.push_back("    __syncthreads();\n"); }
+  void barrier() { calls.push_back("    " + SYNC + "\n"); }
   void comment(const string &text) { c << "// " << text << "\n"; }
 
   // out[0..n_out) = M (n_out x n_in, row-major cM[o*n_in+i]) * in   or transposed: out[o] = sum_i cM[i*n_out+o] in[i]
@@ -320,7 +371,7 @@ struct Gen {
 
   string smem_at(int byte_off, const string &type) const {
     oss s;
-    s << "((" << type << " *)((char *)sm + " << byte_off << "))";
+    s << "((" << type << " *)((char *)" << SMBASE << " + " << byte_off << "))";
     return s.str();
   }
 
@@ -332,12 +383,13 @@ struct Gen {
     if (!any) return false;
     c << "static __device__ __noinline__ void b200_issue_idx(const B200OpArgs &a, const long long e0) {\n";
     c << "  if (e0 >= a.num_elem) return;\n";
+    c << smw_decl();
     c << "  const int ne = (int)((a.num_elem - e0 < " << E << ") ? a.num_elem - e0 : " << E << ");\n";
     for (auto &g : plan->in_groups) {
       if (g.idx_off < 0) continue;
       const int es = g.rstr->elem_size;
       c << "  { int *dst = " << smem_at(g.idx_off, "int") << "; const int *src = a.in_idx[" << g.slot << "] + e0 * " << es << "LL;\n";
-      c << "    for (int i = threadIdx.x; i < ne * " << es << "; i += " << NT << ") b200_cp4(dst + i, src + i); }\n";
+      c << "    for (int i = " << TID << "; i < ne * " << es << "; i += " << TS << ") b200_cp4(dst + i, src + i); }\n";
     }
     c << "}\n\n";
     return true;
@@ -349,12 +401,13 @@ struct Gen {
     if (!any) return false;
     c << "static __device__ __noinline__ void b200_issue_tgt(const B200OpArgs &a, const long long e0) {\n";
     c << "  if (e0 >= a.num_elem) return;\n";
+    c << smw_decl();
     c << "  const int ne = (int)((a.num_elem - e0 < " << E << ") ? a.num_elem - e0 : " << E << ");\n";
     for (auto &g : plan->out_groups) {
       if (g.tgt_off < 0) continue;
       const int es = g.rstr->elem_size;
       c << "  { int *dst = " << smem_at(g.tgt_off, "int") << "; const int *src = a.out_idx[" << g.slot << "] + e0 * " << es << "LL;\n";
-      c << "    for (int i = threadIdx.x; i < ne * " << es << "; i += " << NT << ") b200_cp4(dst + i, src + i); }\n";
+      c << "    for (int i = " << TID << "; i < ne * " << es << "; i += " << TS << ") b200_cp4(dst + i, src + i); }\n";
     }
     c << "}\n\n";
     return true;
@@ -366,13 +419,14 @@ struct Gen {
     if (!any) return false;
     c << "static __device__ __noinline__ void b200_issue_gather(const B200OpArgs &a, const long long e0) {\n";
     c << "  if (e0 >= a.num_elem) return;\n";
+    c << smw_decl();
     c << "  const int ne = (int)((a.num_elem - e0 < " << E << ") ? a.num_elem - e0 : " << E << ");\n";
     for (auto &g : plan->in_groups) {
       if (g.uin_off < 0) continue;
       const int es = g.rstr->elem_size;
       c << "  { const int *idx = " << smem_at(g.idx_off, "int") << "; double *dst = " << smem_at(g.uin_off, "double") << ";\n";
       c << "    const double *src = a.in_ptr[" << g.slot << "];\n";
-      c << "    for (int i = threadIdx.x; i < ne * " << es << "; i += " << NT << ") {\n";
+      c << "    for (int i = " << TID << "; i < ne * " << es << "; i += " << TS << ") {\n";
       c << "      const long long l = idx[i];\n";
       for (int cc = 0; cc < g.nc; cc++)
         c << "      b200_cp8(dst + i + " << cc * E * es << ", src + l + " << (long long)cc * g.rstr->comp_stride << "LL);\n";
@@ -389,6 +443,7 @@ struct Gen {
     const int Q3 = Q * Q * Q;
     c << "static __device__ __noinline__ void b200_issue_qd(const B200OpArgs &a, const long long e0) {\n";
     c << "  if (e0 >= a.num_elem) return;\n";
+    c << smw_decl();
     c << "  const int ne = (int)((a.num_elem - e0 < " << E << ") ? a.num_elem - e0 : " << E << ");\n";
     for (auto &f : plan->in_fields) {
       if (f.qd_off < 0) continue;
@@ -397,9 +452,9 @@ struct Gen {
         c << "    const double *src = a.in_ptr[" << f.slot << "] + " << (long long)cc * f.rstr->strides[1] << "LL + e0 * " << Q3 << "LL;\n";
         c << "    const int n = ne * " << Q3 << ";\n";
         c << "    if (((((unsigned long long)src) | ((unsigned long long)dst)) & 15) == 0 && (n & 1) == 0) {\n";
-        c << "      for (int i = threadIdx.x * 2; i < n; i += " << 2 * NT << ") b200_cp16(dst + i, src + i);\n";
+        c << "      for (int i = " << TID << " * 2; i < n; i += " << 2 * TS << ") b200_cp16(dst + i, src + i);\n";
         c << "    } else {\n";
-        c << "      for (int i = threadIdx.x; i < n; i += " << NT << ") b200_cp8(dst + i, src + i);\n";
+        c << "      for (int i = " << TID << "; i < n; i += " << TS << ") b200_cp8(dst + i, src + i);\n";
         c << "    } }\n";
       }
     }
@@ -775,6 +830,11 @@ struct Gen {
     Qs = plan->Qs;
     E  = plan->epb;
     NT = plan->threads;
+    warp_mode = plan->warp_mode;
+    TS        = warp_mode ? 32 : NT;
+    TID       = warp_mode ? "(threadIdx.x & 31)" : "threadIdx.x";
+    SMBASE    = warp_mode ? "smw" : "sm";
+    SYNC      = warp_mode ? "__syncwarp();" : "__syncthreads();";
     S  = plan->plane_size;
     emit_header();
     bool any;
@@ -805,11 +865,11 @@ struct Gen {
     if (has_gather) {
       // before the quadrature stage: the offsets of the next batch have landed (issued at the top of this batch) and the
       // gather buffer is free (the z-stage consumed it) -> start gathering the next batch's inputs
-      if (!calls.empty() && calls.back().find("__syncthreads") != string::npos) calls.pop_back();
-      calls.push_back("    b200_cp_wait_all();\n    __syncthreads();\n    b200_issue_gather(a, e0n);\n    b200_cp_commit();\n");
+      if (!calls.empty() && calls.back().find("__sync") != string::npos) calls.pop_back();
+      calls.push_back("    b200_cp_wait_all();\n    " + SYNC + "\n    b200_issue_gather(a, e0n);\n    b200_cp_commit();\n");
     } else if (has_tgt) {
-      if (!calls.empty() && calls.back().find("__syncthreads") != string::npos) calls.pop_back();
-      calls.push_back("    b200_cp_wait_all();\n    __syncthreads();\n");
+      if (!calls.empty() && calls.back().find("__sync") != string::npos) calls.pop_back();
+      calls.push_back("    b200_cp_wait_all();\n    " + SYNC + "\n");
     }
     emit_qf_stage();
     if (!plan->out_groups.empty() || has_qd) barrier();
@@ -845,11 +905,12 @@ struct Gen {
       c << "static __device__ __noinline__ void b200_prefetch(const B200OpArgs &a, const long long e0) {\n";
       c << "  if (e0 >= a.num_elem) return;\n";
       c << "  const long long ne = (a.num_elem - e0 < " << E << ") ? a.num_elem - e0 : " << E << ";\n";
+      c << smw_decl();
       auto emit_range = [&](const string &ptr, const string &first_elem_expr, long long bytes_per_elem) {
         // byte range [p0, p0 + ne * bytes_per_elem), one 128-byte line per thread per round
         c << "  { const char *p0 = (const char *)(" << ptr << ") + (" << first_elem_expr << ") * " << bytes_per_elem << "LL;\n";
         c << "    const long long nbytes = ne * " << bytes_per_elem << "LL;\n";
-        c << "    for (long long off = (long long)threadIdx.x * 128; off < nbytes; off += " << NT * 128 << ")\n";
+        c << "    for (long long off = (long long)" << TID << " * 128; off < nbytes; off += " << TS * 128 << ")\n";
         c << "      asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(p0 + off));\n  }\n";
       };
       for (size_t f = 0; f < plan->in_fields.size(); f++) {
@@ -868,20 +929,23 @@ struct Gen {
     }
     c << "extern \"C\" __global__ void __launch_bounds__(" << NT << ", " << minb << ") b200_operator_" << op->qf->kernel_name << "(const __grid_constant__ B200OpArgs a) {\n";
     c << "  const long long num_batches = (a.num_elem + " << E - 1 << ") / " << E << ";\n";
+    // block mode: one batch per CTA per iteration; warp mode: one group per warp per iteration
+    const string first  = warp_mode ? "((long long)blockIdx.x * " + std::to_string(NT / 32) + " + (threadIdx.x >> 5))" : "(long long)blockIdx.x";
+    const string stride = warp_mode ? "((long long)gridDim.x * " + std::to_string(NT / 32) + ")" : "(long long)gridDim.x";
     if (staged) {
-      // prologue: stage the first batch of this block
-      c << "  if ((long long)blockIdx.x < num_batches) {\n";
-      c << "    const long long e0 = (long long)blockIdx.x * " << E << ";\n";
-      if (has_idx) c << "    b200_issue_idx(a, e0);\n    b200_cp_commit();\n    b200_cp_wait_all();\n    __syncthreads();\n";
+      // prologue: stage the first batch
+      c << "  if (" << first << " < num_batches) {\n";
+      c << "    const long long e0 = " << first << " * " << E << ";\n";
+      if (has_idx) c << "    b200_issue_idx(a, e0);\n    b200_cp_commit();\n    b200_cp_wait_all();\n    " << SYNC << "\n";
       if (has_gather) c << "    b200_issue_gather(a, e0);\n";
       if (has_qd) c << "    b200_issue_qd(a, e0);\n";
       c << "    b200_cp_commit();\n  }\n";
     }
-    c << "  for (long long batch = blockIdx.x; batch < num_batches; batch += gridDim.x) {\n";
-    c << "    const long long e0 = batch * " << E << ", e0n = (batch + gridDim.x) * " << E << ";\n";
+    c << "  for (long long batch = " << first << "; batch < num_batches; batch += " << stride << ") {\n";
+    c << "    const long long e0 = batch * " << E << ", e0n = (batch + " << stride << ") * " << E << ";\n";
     if (staged) {
       // everything staged for this batch is visible after this point; all reads of the previous batch are done
-      c << "    b200_cp_wait_all();\n    __syncthreads();\n";
+      c << "    b200_cp_wait_all();\n    " << SYNC << "\n";
       if (has_idx) c << "    b200_issue_idx(a, e0n);\n";
       if (has_tgt) c << "    b200_issue_tgt(a, e0);\n";
       c << "    b200_cp_commit();\n";
@@ -925,8 +989,9 @@ int b200_opgen_build(B200Operator op, B200OpPlan *plan, int add) {
     B200_CU(ceed, cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.kernel, plan->threads, plan->smem_bytes));
     if (nb < 1) return b200_error(ceed, B200_ERROR_BACKEND, "fused kernel cannot be resident (regs %d, smem %d)", v.regs, plan->smem_bytes);
     plan->blocks_per_sm = op->tune_bpsm > 0 ? std::min(nb, op->tune_bpsm) : nb;
-    const long long num_batches = ((long long)plan->num_elem + plan->epb - 1) / plan->epb;
-    long long       grid        = (long long)plan->blocks_per_sm * ceed->num_sms;
+    long long num_batches = ((long long)plan->num_elem + plan->epb - 1) / plan->epb;
+    if (plan->warp_mode) num_batches = (num_batches + plan->threads / 32 - 1) / (plan->threads / 32);  // CTAs needed
+    long long grid = (long long)plan->blocks_per_sm * ceed->num_sms;
     if (grid > num_batches) grid = num_batches;
     if (grid < 1) grid = 1;
     plan->grid = (int)grid;

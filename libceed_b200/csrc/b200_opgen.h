@@ -65,6 +65,9 @@ struct B200OpPlan {
   int                       epb = 1, threads = 256, blocks_per_sm = 1, grid = 1;
   int                       plane_size = 0, num_planes = 0, smem_bytes = 0;
   int                       scatter_mode = 0;
+  bool                      warp_mode = true;    // one element group per warp, __syncwarp() only (see b200_opgen.cpp)
+  int                       stage_mask = 1;      // which global reads are staged through cp.async (1 idx/tgt, 2 gather, 4 qdata)
+  int                       group_smem_bytes = 0;  // shared memory of one element group (CTA in block mode, warp in warp mode)
   bool                      async_copy = true;  // stage global reads through cp.async one batch ahead
   std::vector<B200GenBasis> bases;
   std::vector<B200GenGroup> in_groups, out_groups;

@@ -56,10 +56,14 @@ def run(tag, env, epb=0, bpsm=0, scatter=0):
 
 
 print(f"{wl}: {base.num_dofs / 1e6:.2f}M DoFs, {base.num_elem} elements, Q={Q}")
-run("default", {})
-run("no prefetch", {"CEED_B200_NO_PREFETCH": "1"})
-run("atomic scatter", {}, scatter=1)
-lines = Q * Q
-for epb, minb in [(max(1, 128 // lines), 4), (max(1, 128 // lines), 3), (max(1, 256 // lines), 3), (max(1, 256 // lines), 1), (max(1, 512 // lines), 1),
-                  (max(1, 384 // lines), 1), (max(1, 64 // lines), 6), (max(1, 192 // lines), 2)]:
-    run(f"epb={epb} minb={minb}", {"CEED_B200_MINB": str(minb)}, epb=epb)
+run("block mode (async staging)", {"CEED_B200_BLOCK_MODE": "1"})
+run("block mode, no async", {"CEED_B200_BLOCK_MODE": "1", "CEED_B200_NO_ASYNC": "1"})
+run("warp default", {})
+run("warp atomic", {}, scatter=1)
+for stage in (0, 1, 3, 5, 7):
+    for minb in (3, 4, 5):
+        run(f"warp stage={stage} minb={minb}", {"CEED_B200_STAGE": str(stage), "CEED_B200_MINB": str(minb)})
+for warps, minb in ((2, 8), (2, 6), (8, 2), (8, 1), (1, 16), (1, 12)):
+    run(f"warp W={warps} minb={minb} stage=0", {"CEED_B200_STAGE": "0", "CEED_B200_WARPS": str(warps), "CEED_B200_MINB": str(minb)})
+for epb in (1, 2, 3, 4):
+    run(f"warp epb={epb} stage=0", {"CEED_B200_STAGE": "0"}, epb=epb)
