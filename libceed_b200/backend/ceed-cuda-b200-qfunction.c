@@ -136,9 +136,8 @@ int CeedQFunctionGetCore_B200(CeedQFunction qf, B200QFunction *core_qf) {
   if (ctx) {
     B200QFContext c;
 
-    CeedCallBackend(CtxCore(ctx, &c));
+    CeedCallBackend(CtxCore(ctx, &c));  // borrowed reference: CeedQFunctionGetInnerContext does not add one (interface/ceed-qfunction.c:422-437)
     ceedb200_qfunction_set_context(impl->core, c);
-    CeedCallBackend(CeedQFunctionContextDestroy(&ctx));
   } else {
     ceedb200_qfunction_set_context(impl->core, NULL);
   }

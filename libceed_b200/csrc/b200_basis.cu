@@ -363,7 +363,8 @@ extern "C" int ceedb200_basis_create_tensor_h1(B200Ceed ceed, b200_int dim, b200
   b->grad.assign(grad, grad + P * Q);
   if (q_ref) b->q_ref.assign(q_ref, q_ref + Q);
   else b->q_ref.assign(Q, 0.0);
-  b->q_weight.assign(q_weight, q_weight + Q);
+  if (q_weight) b->q_weight.assign(q_weight, q_weight + Q);  // projection bases come without quadrature (interface/ceed-basis.c:1905)
+  else b->q_weight.assign(Q, 0.0);
   // collocated: interp_1d is the identity (interface/ceed-basis.c:840-854 uses a 1e-14-ish tolerance on |B - I|)
   b->is_collocated = P == Q;
   for (int i = 0; i < Q && b->is_collocated; i++)

@@ -64,7 +64,7 @@ __global__ void k_filter(double *__restrict__ x, int64_t n, double eps) {
   int64_t i      = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t j = i; j < n; j += stride) {
-    if (fabs(x[j]) < eps) x[j] = 0.0;
+    if (fabs(x[j]) <= eps) x[j] = 0.0;  // inclusive threshold, cuda-ref-vector.cu:130-136
   }
 }
 __global__ void k_axpy(double *__restrict__ y, double alpha, const double *__restrict__ x, int64_t n) {

@@ -1,0 +1,73 @@
+"""GPU tests of the drop-in boundary: the b200 backend registered as resource /gpu/cuda/b200 inside the UNMODIFIED reference
+library (oracle/_ref/lib-cuda/libceed.so + plugin), driven only through libCEED's public C API.
+  * same BP operators on /gpu/cuda/b200 and on /cpu/self/ref/serial: 1e-12 parity
+  * the reference's own test suite t0xx-t5xx + ex1/ex2/ex3 with argv[1] = /gpu/cuda/b200 (no failures; gaps must skip)"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PLUGIN = os.path.join(ROOT, "libceed_b200", "lib", "libceed_b200_backend.so")
+
+
+@pytest.fixture(scope="module")
+def R():
+    import ctypes as C
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import refceed as R
+    if not R.available(cuda=True) or not os.path.exists(PLUGIN):
+        pytest.skip("oracle/_ref/lib-cuda or the backend plugin not built")
+    lib = C.CDLL(os.path.join(R.REF_DIR, "lib-cuda", "libceed.so"), mode=C.RTLD_GLOBAL)
+    R.RefCeed._libs["lib-cuda"] = lib
+    R.RefCeed._libs["lib"] = lib  # one libceed per process
+    C.CDLL(PLUGIN, mode=C.RTLD_GLOBAL)  # constructor registers /gpu/cuda/b200
+    return R
+
+
+@pytest.mark.parametrize("bp,p,nel", [(1, 3, (3, 2, 2)), (3, 2, (3, 3, 2)), (3, 6, (2, 1, 1)), (5, 4, (2, 2, 1)), (4, 2, (2, 2, 2)), (6, 3, (2, 1, 2))])
+def test_operator_through_libceed_matches_cpu_reference(R, bp, p, nel):
+    from libceed_b200 import mesh as M
+    from libceed_b200.bp import seeded_uniform
+    off, coords = M.hex_offsets(*nel, p), M.hex_coords(*nel, p)
+    nn = coords.shape[1]
+    gpu = R.RefBP(R.RefCeed("/gpu/cuda/b200", cuda=True), bp, p, off.shape[0], nn, off, coords)
+    cpu = R.RefBP(R.RefCeed("/cpu/self/ref/serial", cuda=True), bp, p, off.shape[0], nn, off, coords)
+    u = seeded_uniform(gpu.ncomp * nn, 21)
+    vg, vc = gpu.apply(u), cpu.apply(u)
+    assert np.abs(vg - vc).max() / np.abs(vc).max() < 1e-12
+    qg, qc = gpu.qdata_array(), cpu.qdata_array()
+    assert np.abs(qg - qc).max() / np.abs(qc).max() < 1e-12
+    # ApplyAdd through the interface
+    gpu.rc.op_apply_add(gpu.op, gpu.u, gpu.v)
+    assert np.abs(gpu.rc.get_array(gpu.v, gpu.ncomp * nn) - 2 * vc).max() / np.abs(vc).max() < 1e-12
+
+
+def test_resource_prefix_resolves_to_b200(R):
+    rc = R.RefCeed("/gpu/cuda", cuda=True)  # priority 15 beats /gpu/cuda/gen (20)
+    import ctypes as C
+    res = C.c_char_p()
+    rc.lib.CeedGetResource(rc.ceed, C.byref(res))
+    assert res.value.decode().startswith("/gpu/cuda")
+    v = rc.vector(10, np.arange(10.0))
+    assert np.array_equal(rc.get_array(v, 10), np.arange(10.0))
+
+
+def test_reference_suite_on_b200(R):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from run_ref_suite import run_suite
+    if not os.path.isdir(os.path.join(R.REF_DIR, "tests", "bin")):
+        pytest.skip("reference test binaries not built")
+    res = run_suite("/gpu/cuda/b200")
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "ref_suite_b200.txt"), "w") as f:
+        for r in res:
+            f.write(f"{r[1]:5s} {r[0]} {r[2][:300]}\n")
+    counts = {k: sum(1 for r in res if r[1] == k) for k in ("pass", "skip", "fail")}
+    fails = [r for r in res if r[1] == "fail"]
+    assert not fails, f"{counts}; first failures: {fails[:5]}"
+    assert counts["pass"] >= 100, counts
