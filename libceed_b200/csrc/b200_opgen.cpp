@@ -158,14 +158,19 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     plane_size = std::max(plane_size, Q * Q * odd_pad(b.P));
   }
   plan->plane_size = plane_size;
-  int n_in = 0, n_out = 0;
+  // QFunction stage layout: z-line (default) = d/dz, QFunction and (d/dz)^T fused per z-line in registers;
+  // pointwise (CEED_B200_QF_POINTWISE=1) = d/dz and its transpose are separate line stages through shared memory and the
+  // QFunction runs over independent points (short dependency chains on the streamed quadrature data, one more plane).
+  plan->qf_pointwise = getenv("CEED_B200_QF_POINTWISE") != nullptr;
+  auto planes_of = [&](const B200GenGroup &g) { return g.nc * (g.use_grad ? ((plan->qf_pointwise && g.use_interp) ? 4 : 3) : 2); };
+  int  n_in = 0, n_out = 0;
   for (auto &g : plan->in_groups) {
     g.plane0 = n_in;
-    n_in += g.nc * (g.use_grad ? 3 : 2);
+    n_in += planes_of(g);
   }
   for (auto &g : plan->out_groups) {
     g.plane0 = n_out;
-    n_out += g.nc * (g.use_grad ? 3 : 2);
+    n_out += planes_of(g);
   }
   plan->num_planes = std::max(n_in, n_out);
   // elements per block / threads: one thread per quadrature line (Q^2 lines per element), ~256 threads per block
@@ -192,6 +197,8 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
       if (plan->async_copy && (mask & 2) && !g.rstr->is_strided) {
         g.uin_off = take((size_t)g.nc * E * g.rstr->elem_size * 8);
         g.idx_off = take((size_t)E * g.rstr->elem_size * 4);
+      } else if (plan->async_copy && (mask & 8) && !g.rstr->is_strided) {
+        g.idx_off = take((size_t)E * g.rstr->elem_size * 4);  // offsets only: the gather itself stays a direct load
       }
     }
     for (auto &g : plan->out_groups) {
@@ -467,31 +474,90 @@ struct Gen {
     const B200GenBasis &b  = basis(g.basis_id);
     const int           P  = b.P;
     const string        sl = std::to_string(g.slot);
+    const int           ntasks = E * g.nc * P * P;
     comment("gather + z-contraction, input group slot " + std::to_string(g.slot));
-    task_loop_begin(std::to_string(E * g.nc * P * P));
+    auto emit_compute_store = [&](const string &sfx, const string &ind) {
+      // u<k><sfx> -> z-contraction -> T1 plane (or straight into the Uq plane for collocated bases)
+      if (b.collocated) {
+        c << ind << "double *dst = " << plane(g.plane0, "le" + sfx) << " + cc" << sfx << " * " << E * S << " + (ij" << sfx << " / " << P << ") * " << Qs
+          << " + (ij" << sfx << " % " << P << ");\n";
+        for (int k = 0; k < P; k++) c << ind << "dst[" << k * Q * Qs << "] = u" << k << sfx << ";\n";
+      } else {
+        c << ind << "double *dst = " << plane(g.plane0, "le" + sfx) << " + cc" << sfx << " * " << E * S << " + ij" << sfx << ";\n";  // T1 [qz][j][i]
+        for (int o = 0; o < Q; o++) {
+          c << ind << "double r" << o << " = cB" << g.basis_id << "[" << o * P << "] * u0" << sfx << ";\n";
+          for (int i = 1; i < P; i++) c << ind << "r" << o << " = fma(cB" << g.basis_id << "[" << o * P + i << "], u" << i << sfx << ", r" << o << ");\n";
+        }
+        for (int q = 0; q < Q; q++) c << ind << "dst[" << q * P * P << "] = r" << q << ";\n";
+      }
+    };
+    const int rounds = (ntasks + TS - 1) / TS;
+    if (warp_mode && g.uin_off < 0 && rounds * P <= 32 && !getenv("CEED_B200_NO_GATHER_BATCH")) {
+      // Batched gather: every lane first issues the offset loads of ALL its tasks, then all value loads, and only then
+      // computes -- two memory latencies per group instead of two per task round.
+      const string name = "b200_stage_" + std::to_string(n_stage++);
+      c << "static __device__ __noinline__ void " << name << "(const B200OpArgs &a, const long long e0) {\n";
+      c << smw_decl();
+      calls.push_back("    " + name + "(a, e0);\n");
+      c << "    const int lane = " << TID << ";\n";
+      for (int r = 0; r < rounds; r++) {
+        const string x = "_" + std::to_string(r);
+        c << "    const int t" << x << " = lane + " << r * TS << ", tc" << x << " = t" << x << " < " << ntasks << " ? t" << x << " : " << ntasks - 1 << ";\n";
+        c << "    const int ij" << x << " = tc" << x << " % " << P * P << ", cc" << x << " = (tc" << x << " / " << P * P << ") % " << g.nc << ", le" << x
+          << " = tc" << x << " / " << P * P * g.nc << ";\n";
+        c << "    const long long e" << x << " = (e0 + le" << x << " < a.num_elem) ? e0 + le" << x << " : a.num_elem - 1;\n";
+      }
+      if (!g.rstr->is_strided) {
+        for (int r = 0; r < rounds; r++) {
+          const string x = "_" + std::to_string(r);
+          for (int k = 0; k < P; k++) {
+            if (g.idx_off >= 0)
+              c << "    const long long l" << k << x << " = " << smem_at(g.idx_off, "const int") << "[le" << x << " * " << P * P * P << " + ij" << x << " + "
+                << k * P * P << "];\n";
+            else
+              c << "    const long long l" << k << x << " = __ldg(a.in_idx[" << sl << "] + e" << x << " * " << P * P * P << "LL + ij" << x << " + " << k * P * P
+                << ");\n";
+          }
+        }
+      }
+      for (int r = 0; r < rounds; r++) {
+        const string x = "_" + std::to_string(r);
+        for (int k = 0; k < P; k++) {
+          if (g.rstr->is_strided)
+            c << "    const double u" << k << x << " = __ldg(a.in_ptr[" << sl << "] + "
+              << lidx(g.rstr, "", "e" + x, "ij" + x + " + " + std::to_string(k * P * P), "cc" + x) << ");\n";
+          else
+            c << "    const double u" << k << x << " = __ldg(a.in_ptr[" << sl << "] + l" << k << x << " + (long long)cc" << x << " * " << g.rstr->comp_stride
+              << "LL);\n";
+        }
+      }
+      for (int r = 0; r < rounds; r++) {
+        const string x = "_" + std::to_string(r);
+        c << "    if (t" << x << " < " << ntasks << ") {\n";
+        emit_compute_store(x, "      ");
+        c << "    }\n";
+      }
+      c << "}\n\n";
+      return;
+    }
+    task_loop_begin(std::to_string(ntasks));
     c << "      const int ij = t % " << P * P << ", cc = (t / " << P * P << ") % " << g.nc << ", le = t / " << P * P * g.nc << ";\n";
-    c << "      const long long e = e0 + le;\n";
+    c << "      const long long e = (e0 + le < a.num_elem) ? e0 + le : a.num_elem - 1;  // clamped: tail groups gather a valid element\n";
     if (g.uin_off >= 0) {
       // values were gathered into shared memory by cp.async while the previous batch was computing
       c << "      const double *uin = " << smem_at(g.uin_off, "double") << " + (cc * " << E << " + le) * " << P * P * P << " + ij;\n";
       for (int k = 0; k < P; k++) c << "      const double u" << k << " = uin[" << k * P * P << "];\n";
     } else {
-      for (int k = 0; k < P; k++) c << "      double u" << k << " = 0.0;\n";
-      c << "      if (e < a.num_elem) {\n";
-      for (int k = 0; k < P; k++)
-        c << "        u" << k << " = __ldg(a.in_ptr[" << sl << "] + " << lidx(g.rstr, "a.in_idx[" + sl + "]", "e", "ij + " + std::to_string(k * P * P), "cc")
-          << ");\n";
-      c << "      }\n";
+      for (int k = 0; k < P; k++) {
+        if (g.idx_off >= 0)  // offsets of this group were staged into shared memory while the previous group was computing
+          c << "      const double u" << k << " = __ldg(a.in_ptr[" << sl << "] + (long long)" << smem_at(g.idx_off, "const int") << "[le * " << P * P * P
+            << " + ij + " << k * P * P << "] + (long long)cc * " << g.rstr->comp_stride << "LL);\n";
+        else
+          c << "      const double u" << k << " = __ldg(a.in_ptr[" << sl << "] + "
+            << lidx(g.rstr, "a.in_idx[" + sl + "]", "e", "ij + " + std::to_string(k * P * P), "cc") << ");\n";
+      }
     }
-    if (b.collocated) {
-      // nodes are the quadrature points: straight into the Uq plane [qz][qy][Qs]
-      c << "      double *dst = " << plane(g.plane0, "le") << " + cc * " << E * S << " + (ij / " << P << ") * " << Qs << " + (ij % " << P << ");\n";
-      for (int k = 0; k < P; k++) c << "      dst[" << k * Q * Qs << "] = u" << k << ";\n";
-    } else {
-      c << "      double *dst = " << plane(g.plane0, "le") << " + cc * " << E * S << " + ij;\n";  // T1 [qz][j][i] in plane A
-      contract("cB" + std::to_string(g.basis_id), P, Q, false, "u", "r", "      ");
-      for (int q = 0; q < Q; q++) c << "      dst[" << q * P * P << "] = r" << q << ";\n";
-    }
+    emit_compute_store("", "      ");
     task_loop_end();
   }
 
@@ -550,6 +616,128 @@ struct Gen {
   }
 
   // ---- quadrature-point stage -------------------------------------------------------------------
+  // plane holding d/dz (inputs) or the z-component of the output gradient: in place of the values when they are not needed
+  int gz_plane(const B200GenGroup &g, int cc) const { return g.use_interp ? g.plane0 + 3 * g.nc + cc : g.plane0 + cc; }
+
+  void emit_grad_z(const B200GenGroup &g) {
+    if (!g.use_grad) return;
+    comment("d/dz (z-lines), input group slot " + std::to_string(g.slot));
+    task_loop_begin(std::to_string(E * g.nc * Q * Q));
+    c << "      const int pxy = (t % " << Q << ") + ((t / " << Q << ") % " << Q << ") * " << Qs << ", cc = (t / " << Q * Q << ") % " << g.nc << ", le = t / "
+      << Q * Q * g.nc << ";\n";
+    c << "      const double *src = " << plane(g.plane0, "le") << " + cc * " << E * S << " + pxy;\n";
+    c << "      double *dst = " << plane(gz_plane(g, 0), "le") << " + cc * " << E * S << " + pxy;\n";
+    for (int m = 0; m < Q; m++) c << "      const double u" << m << " = src[" << m * Q * Qs << "];\n";
+    contract("cG" + std::to_string(g.basis_id), Q, Q, false, "u", "d", "      ");
+    for (int q = 0; q < Q; q++) c << "      dst[" << q * Q * Qs << "] = d" << q << ";\n";
+    task_loop_end();
+  }
+
+  void emit_gradT_z(const B200GenGroup &g) {
+    if (!g.use_grad) return;
+    comment("(d/dz)^T (z-lines), output group slot " + std::to_string(g.slot));
+    task_loop_begin(std::to_string(E * g.nc * Q * Q));
+    c << "      const int pxy = (t % " << Q << ") + ((t / " << Q << ") % " << Q << ") * " << Qs << ", cc = (t / " << Q * Q << ") % " << g.nc << ", le = t / "
+      << Q * Q * g.nc << ";\n";
+    c << "      const double *src = " << plane(gz_plane(g, 0), "le") << " + cc * " << E * S << " + pxy;\n";
+    c << "      double *vq = " << plane(g.plane0, "le") << " + cc * " << E * S << " + pxy;\n";
+    for (int m = 0; m < Q; m++) c << "      const double u" << m << " = src[" << m * Q * Qs << "];\n";
+    contract("cG" + std::to_string(g.basis_id), Q, Q, true, "u", "d", "      ");
+    for (int q = 0; q < Q; q++) c << "      vq[" << q * Q * Qs << "] " << (g.use_interp ? "+=" : "=") << " d" << q << ";\n";
+    task_loop_end();
+  }
+
+  // QFunction over independent quadrature points (pointwise mode)
+  void emit_qf_points() {
+    B200QFunction qf = op->qf;
+    const int     Q3 = Q * Q * Q;
+    comment("quadrature points: independent points, inputs from the planes / streamed from global memory");
+    const string name = "b200_stage_" + std::to_string(n_stage++);
+    c << "static __device__ __noinline__ void " << name << "(const B200OpArgs &a, const long long e0) {\n";
+    c << smw_decl();
+    c << "    const CeedScalar *in[" << std::max<size_t>(1, qf->inputs.size()) << "];\n";
+    c << "    CeedScalar *out[" << std::max<size_t>(1, qf->outputs.size()) << "];\n";
+    const int unroll = getenv("CEED_B200_QF_UNROLL") ? atoi(getenv("CEED_B200_QF_UNROLL")) : 4;
+    c << "    #pragma unroll " << unroll << "\n";
+    c << "    for (int t = " << TID << "; t < " << E * Q3 << "; t += " << TS << ") {\n";
+    calls.push_back("    " + name + "(a, e0);\n");
+    c << "      const int pt = t % " << Q3 << ", le = t / " << Q3 << ";\n";
+    c << "      const int qx = pt % " << Q << ", qy = (pt / " << Q << ") % " << Q << ", qz = pt / " << Q * Q << ";\n";
+    c << "      const int p = (qz * " << Q << " + qy) * " << Qs << " + qx;\n";
+    // tail groups: loads use a clamped (valid) element so that there is no branch in the loop body and the compiler can overlap
+    // the global loads of several unrolled points; results of non-existent elements are simply never stored to global memory
+    c << "      const long long e_real = e0 + le;\n";
+    c << "      const long long e = e_real < a.num_elem ? e_real : a.num_elem - 1;\n";
+    c << "      {\n";
+    for (size_t f = 0; f < plan->in_fields.size(); f++) c << "      CeedScalar in_" << f << "[" << plan->in_fields[f].size << "];\n";
+    for (size_t f = 0; f < plan->out_fields.size(); f++) c << "      CeedScalar out_" << f << "[" << plan->out_fields[f].size << "];\n";
+    for (size_t f = 0; f < plan->in_fields.size(); f++) c << "      in[" << f << "] = in_" << f << ";\n";
+    for (size_t f = 0; f < plan->out_fields.size(); f++) c << "      out[" << f << "] = out_" << f << ";\n";
+    for (size_t f = 0; f < plan->in_fields.size(); f++) {
+      const B200GenField &fd = plan->in_fields[f];
+      const string        sl = std::to_string(fd.slot);
+      switch (fd.emode) {
+        case B200_EVAL_NONE:
+          for (int cc = 0; cc < fd.nc; cc++) {
+            if (fd.qd_off >= 0)
+              c << "      in_" << f << "[" << cc << "] = " << smem_at(fd.qd_off, "const double") << "[(" << cc * E << " + le) * " << Q3 << " + pt];\n";
+            else
+              c << "      in_" << f << "[" << cc << "] = __ldg(a.in_ptr[" << sl << "] + " << lidx(fd.rstr, "a.in_idx[" + sl + "]", "e", "pt", std::to_string(cc))
+                << ");\n";
+          }
+          break;
+        case B200_EVAL_WEIGHT:
+          c << "      in_" << f << "[0] = cW" << fd.basis_id << "[qx] * cW" << fd.basis_id << "[qy] * cW" << fd.basis_id << "[qz];\n";
+          break;
+        case B200_EVAL_INTERP: {
+          const B200GenGroup &g = plan->in_groups[fd.group];
+          for (int cc = 0; cc < fd.nc; cc++) c << "      in_" << f << "[" << cc << "] = (" << plane(g.plane0 + cc, "le") << ")[p];\n";
+        } break;
+        case B200_EVAL_GRAD: {
+          const B200GenGroup &g = plan->in_groups[fd.group];
+          for (int cc = 0; cc < fd.nc; cc++) {
+            c << "      in_" << f << "[" << cc << "] = (" << plane(g.plane0 + 2 * g.nc + cc, "le") << ")[p];\n";
+            c << "      in_" << f << "[" << cc + fd.nc << "] = (" << plane(g.plane0 + g.nc + cc, "le") << ")[p];\n";
+            c << "      in_" << f << "[" << cc + 2 * fd.nc << "] = (" << plane(gz_plane(g, cc), "le") << ")[p];\n";
+          }
+        } break;
+      }
+    }
+    c << "      " << qf->kernel_name << "(a.ctx, 1, in, out);\n";
+    for (size_t gi = 0; gi < plan->out_groups.size(); gi++) {
+      const B200GenGroup &g = plan->out_groups[gi];
+      for (int cc = 0; cc < g.nc; cc++) {
+        string val, vx, vy, vz;
+        for (size_t f = 0; f < plan->out_fields.size(); f++) {
+          const B200GenField &fd = plan->out_fields[f];
+          if (fd.group != (int)gi) continue;
+          const string o = "out_" + std::to_string(f);
+          if (fd.emode == B200_EVAL_INTERP) val += (val.empty() ? "" : " + ") + o + "[" + std::to_string(cc) + "]";
+          if (fd.emode == B200_EVAL_GRAD) {
+            vx += (vx.empty() ? "" : " + ") + o + "[" + std::to_string(cc) + "]";
+            vy += (vy.empty() ? "" : " + ") + o + "[" + std::to_string(cc + fd.nc) + "]";
+            vz += (vz.empty() ? "" : " + ") + o + "[" + std::to_string(cc + 2 * fd.nc) + "]";
+          }
+        }
+        if (!val.empty()) c << "      (" << plane(g.plane0 + cc, "le") << ")[p] = " << val << ";\n";
+        if (g.use_grad) {
+          c << "      (" << plane(g.plane0 + 2 * g.nc + cc, "le") << ")[p] = " << vx << ";\n";
+          c << "      (" << plane(g.plane0 + g.nc + cc, "le") << ")[p] = " << vy << ";\n";
+          c << "      (" << plane(gz_plane(g, cc), "le") << ")[p] = " << vz << ";\n";
+        }
+      }
+    }
+    for (size_t f = 0; f < plan->out_fields.size(); f++) {
+      const B200GenField &fd = plan->out_fields[f];
+      if (fd.emode != B200_EVAL_NONE) continue;
+      c << "      if (e_real < a.num_elem) {\n";
+      emit_scatter_value(fd.rstr, fd.slot, "e", "pt", fd.nc, [&](int cc) { return "out_" + std::to_string(f) + "[" + std::to_string(cc) + "]"; }, "        ");
+      c << "      }\n";
+    }
+    c << "      }\n";
+    c << "    }\n}\n\n";
+  }
+
   void emit_qf_stage() {
     B200QFunction qf = op->qf;
     comment("quadrature points: one z-line per thread; d/dz, QFunction, (d/dz)^T in registers");
@@ -588,10 +776,24 @@ struct Gen {
     for (size_t f = 0; f < plan->out_fields.size(); f++) c << "      CeedScalar out_" << f << "[" << plan->out_fields[f].size << "];\n";
     for (size_t f = 0; f < plan->in_fields.size(); f++) c << "      in[" << f << "] = in_" << f << ";\n";
     for (size_t f = 0; f < plan->out_fields.size(); f++) c << "      out[" << f << "] = out_" << f << ";\n";
+    // direct-load EVAL_NONE inputs are fetched one z-layer ahead (software pipelining): the loads of layer qz+1 are in
+    // flight while the QFunction and the transposed z-derivative of layer qz execute
+    const bool qf_ahead = !getenv("CEED_B200_NO_QFPF");
+    auto none_load = [&](const B200GenField &fd, int cc, const string &pt_expr) {
+      const string sl = std::to_string(fd.slot);
+      return "__ldg(a.in_ptr[" + sl + "] + " + lidx(fd.rstr, "a.in_idx[" + sl + "]", "e", pt_expr, std::to_string(cc)) + ")";
+    };
+    c << "      const int pt0 = qy * " << Q << " + qx;\n";
+    if (qf_ahead)
+      for (size_t f = 0; f < plan->in_fields.size(); f++) {
+        const B200GenField &fd = plan->in_fields[f];
+        if (fd.emode != B200_EVAL_NONE || fd.qd_off >= 0) continue;
+        for (int cc = 0; cc < fd.nc; cc++) c << "      double nx_" << f << "_" << cc << " = " << none_load(fd, cc, "pt0") << ";\n";
+      }
     for (int qz = 0; qz < Q; qz++) {
       c << "      {  // qz = " << qz << "\n";
       c << "        const int p = pxy + " << qz * Q * Qs << ";\n";
-      c << "        const int pt = (" << qz * Q << " + qy) * " << Q << " + qx;\n";
+      c << "        const int pt = pt0 + " << qz * Q * Q << ";\n";
       for (size_t f = 0; f < plan->in_fields.size(); f++) {
         const B200GenField &fd = plan->in_fields[f];
         const string        sl = std::to_string(fd.slot);
@@ -600,9 +802,11 @@ struct Gen {
             for (int cc = 0; cc < fd.nc; cc++) {
               if (fd.qd_off >= 0)
                 c << "        in_" << f << "[" << cc << "] = " << smem_at(fd.qd_off, "const double") << "[(" << cc * E << " + le) * " << Q * Q * Q << " + pt];\n";
-              else
-                c << "        in_" << f << "[" << cc << "] = __ldg(a.in_ptr[" << sl << "] + "
-                  << lidx(fd.rstr, "a.in_idx[" + sl + "]", "e", "pt", std::to_string(cc)) << ");\n";
+              else if (qf_ahead) {
+                c << "        in_" << f << "[" << cc << "] = nx_" << f << "_" << cc << ";\n";
+                if (qz + 1 < Q) c << "        nx_" << f << "_" << cc << " = " << none_load(fd, cc, "pt + " + std::to_string(Q * Q)) << ";\n";
+              } else
+                c << "        in_" << f << "[" << cc << "] = " << none_load(fd, cc, "pt") << ";\n";
             }
             break;
           case B200_EVAL_WEIGHT: c << "        in_" << f << "[0] = wxy_" << f << " * cW" << fd.basis_id << "[" << qz << "];\n"; break;
@@ -841,6 +1045,12 @@ struct Gen {
     // input side
     for (auto &g : plan->in_groups) emit_gather_z(g);
     if (!plan->in_groups.empty()) barrier();
+    {
+      // the offsets buffer has been consumed by the gather stage: stream in the next group's offsets
+      bool any_idx = false;
+      for (auto &g : plan->in_groups) any_idx = any_idx || g.idx_off >= 0;
+      if (any_idx && !plan->in_groups.empty()) calls.push_back("    b200_issue_idx(a, e0n);\n    b200_cp_commit();\n");
+    }
     any = false;
     for (auto &g : plan->in_groups) any = any || !basis(g.basis_id).collocated;
     if (any) {
@@ -871,13 +1081,27 @@ struct Gen {
       if (!calls.empty() && calls.back().find("__sync") != string::npos) calls.pop_back();
       calls.push_back("    b200_cp_wait_all();\n    " + SYNC + "\n");
     }
-    emit_qf_stage();
+    if (plan->qf_pointwise) {
+      any = false;
+      for (auto &g : plan->in_groups) any = any || g.use_grad;
+      if (any) {
+        for (auto &g : plan->in_groups) emit_grad_z(g);
+        barrier();
+      }
+      emit_qf_points();
+    } else {
+      emit_qf_stage();
+    }
     if (!plan->out_groups.empty() || has_qd) barrier();
     // the quadrature-data buffer is free again: stream in the next batch's data behind the transpose stages
     if (has_qd) calls.push_back("    b200_issue_qd(a, e0n);\n    b200_cp_commit();\n");
     if (!plan->out_groups.empty()) {
       any = false;
       for (auto &g : plan->out_groups) any = any || g.use_grad;
+      if (any && plan->qf_pointwise) {
+        for (auto &g : plan->out_groups) emit_gradT_z(g);
+        barrier();
+      }
       if (any) {
         for (auto &g : plan->out_groups) emit_gradT_y(g);
         barrier();
@@ -900,7 +1124,7 @@ struct Gen {
     const int minb = std::max(1, plan->blocks_per_sm);
     // L2 prefetch of the NEXT batch this block will process (grid-stride): the streamed quadrature data (the bulk of the
     // HBM traffic) and the element offsets, so that the demand loads a few microseconds later hit in the 126 MB L2.
-    const bool prefetch = getenv("CEED_B200_PREFETCH") != nullptr && !staged;
+    const bool prefetch = getenv("CEED_B200_PREFETCH") != nullptr;
     if (prefetch) {
       c << "static __device__ __noinline__ void b200_prefetch(const B200OpArgs &a, const long long e0) {\n";
       c << "  if (e0 >= a.num_elem) return;\n";
@@ -946,13 +1170,12 @@ struct Gen {
     if (staged) {
       // everything staged for this batch is visible after this point; all reads of the previous batch are done
       c << "    b200_cp_wait_all();\n    " << SYNC << "\n";
-      if (has_idx) c << "    b200_issue_idx(a, e0n);\n";
       if (has_tgt) c << "    b200_issue_tgt(a, e0);\n";
       c << "    b200_cp_commit();\n";
     } else {
       c << "    (void)e0n;\n";
-      if (prefetch) c << "    b200_prefetch(a, e0n);\n";
     }
+    if (prefetch) c << "    b200_prefetch(a, e0n);\n";
     for (auto &call : calls) c << call;
     c << "  }\n}\n";
     return c.str();

@@ -68,6 +68,7 @@ struct B200OpPlan {
   bool                      warp_mode = true;    // one element group per warp, __syncwarp() only (see b200_opgen.cpp)
   int                       stage_mask = 1;      // which global reads are staged through cp.async (1 idx/tgt, 2 gather, 4 qdata)
   int                       group_smem_bytes = 0;  // shared memory of one element group (CTA in block mode, warp in warp mode)
+  bool                      qf_pointwise = false; // QFunction over independent points, d/dz as separate line stages
   bool                      async_copy = true;  // stage global reads through cp.async one batch ahead
   std::vector<B200GenBasis> bases;
   std::vector<B200GenGroup> in_groups, out_groups;

@@ -1,0 +1,55 @@
+"""Tuning sweep (warp mode): env-driven generator options and elements-per-warp.  usage: python scripts/gpu_tune2.py bp3p6 [dofs] [mode]"""
+import itertools, os, re, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from libceed_b200 import Ceed, ceed as cm
+from libceed_b200.bp import BP_TABLE, BPProblem, seeded_uniform
+from libceed_b200.mesh import choose_elements
+
+wl = sys.argv[1]; dofs = float(sys.argv[2]) if len(sys.argv) > 2 else 10e6
+mode = sys.argv[3] if len(sys.argv) > 3 else "opts"
+m = re.fullmatch(r"bp(\d)p(\d)", wl); bp, p = int(m.group(1)), int(m.group(2))
+ceed = Ceed()
+base = BPProblem(ceed, bp, p, choose_elements(dofs, p, BP_TABLE[bp][0]))
+base.u.set_array(seeded_uniform(base.num_dofs))
+kind = BP_TABLE[bp][1]
+
+def run(tag, env, epb=0, scatter=0):
+    for k in list(os.environ):
+        if k.startswith("CEED_B200_") and k != "CEED_B200_JIT_DIR": del os.environ[k]
+    os.environ.update(env)
+    ceed.set_scatter_mode(scatter)
+    op = ceed.Operator(base.qf)
+    op.set_field("u", base.rstr_u, base.basis_u, cm.VECTOR_ACTIVE)
+    op.set_field("qdata", base.rstr_qd, cm.BASIS_NONE, base.qdata)
+    op.set_field("v", base.rstr_u, base.basis_u, cm.VECTOR_ACTIVE)
+    op.set_tuning(epb, 0); op.set_timing(True)
+    try:
+        for _ in range(3): op.apply(base.u, base.v)
+        t = []
+        for _ in range(10):
+            op.apply(base.u, base.v); t.append(op.last_kernel_ms())
+    except Exception as e:
+        print(f"{tag:46s} FAILED {str(e)[:120]}", flush=True); return 1e9
+    f, a = np.median([x[0] for x in t]), np.median([x[1] for x in t])
+    i = op.kernel_info()
+    print(f"{tag:46s} {f:.3f}+{a:.3f} ms {base.num_dofs/(f+a)/1e6:6.2f} GDoF/s {base.bytes_per_apply()/(f+a)/1e6/6550.1*100:5.1f}% regs={i['regs']} epw={i['elems_per_block']} "
+          f"thr={i['threads']} grid={i['grid']} smem={i['smem_bytes']} loc={i['local_bytes']}", flush=True)
+    return f + a
+
+print(f"{wl}: {base.num_dofs/1e6:.2f}M DoFs, {base.num_elem} elements")
+if mode == "opts":
+    run("default", {})
+    run("atomic", {}, scatter=1)
+    run("pointwise QF", {"CEED_B200_QF_POINTWISE": "1"})
+    run("no gather batch", {"CEED_B200_NO_GATHER_BATCH": "1"})
+    run("unroll=8", {"CEED_B200_QF_UNROLL": "8"})
+    run("stage=0", {"CEED_B200_STAGE": "0"})
+    for warps in (1, 2, 8):
+        run(f"W={warps}", {"CEED_B200_WARPS": str(warps)})
+    for epb in (1, 2, 3, 4, 5, 6, 8):
+        run(f"epw={epb}", {}, epb=epb)
+else:
+    for epb in range(1, 9):
+        for warps in (2, 4, 8):
+            run(f"epw={epb} W={warps}", {"CEED_B200_WARPS": str(warps)}, epb=epb)
