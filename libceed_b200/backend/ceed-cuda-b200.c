@@ -96,9 +96,10 @@ static int CeedInit_B200(const char *resource, Ceed ceed) {
 }
 
 // In-tree: listed as CEED_BACKEND(CeedRegister_Cuda_B200, 1, "/gpu/cuda/b200") in backends/ceed-backend-list-cuda.h.
-// Priority 15 < 20 (/gpu/cuda/gen, backends/cuda-gen/ceed-cuda-gen.c:52) so that "/gpu/cuda" resolves to this backend.
+// Priority 45 > 40 (/gpu/cuda/ref, backends/cuda-ref/ceed-cuda-ref.c:72; lower wins): prefix matches such as "/gpu/cuda" keep
+// resolving to the existing backends, this one is selected by its full name only.
 CEED_EXTERN int CeedRegister_Cuda_B200(void);
-int CeedRegister_Cuda_B200(void) { return CeedRegister("/gpu/cuda/b200", CeedInit_B200, 15); }
+int CeedRegister_Cuda_B200(void) { return CeedRegister("/gpu/cuda/b200", CeedInit_B200, 45); }
 
 #ifdef CEED_B200_PLUGIN
 // Out-of-tree plugin: register before main() / at dlopen() time; libCEED's registry is a static table, no init order issue.
