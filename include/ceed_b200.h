@@ -194,6 +194,14 @@ CEEDB200_EXPORT int ceedb200_operator_set_timing(B200Operator op, int enabled);
 CEEDB200_EXPORT int ceedb200_operator_last_kernel_ms(B200Operator op, float *fused_ms, float *aux_ms);
 /* tuning override: elems_per_block (0 = heuristic), blocks_per_sm (0 = heuristic) */
 CEEDB200_EXPORT int ceedb200_operator_set_tuning(B200Operator op, int elems_per_block, int blocks_per_sm);
+/* full kernel shape: int[7] = {elems_per_group, group_warps, cta_warps, min_blocks_per_sm, qf_mode (0 z-line, 1 pointwise),
+ * qf_unroll, stage_mask}; 0 (-1 for qf_mode / stage_mask) = heuristic.  The reference tunes the same knobs by hand per backend
+ * (BlockGridCalculate, backends/cuda-gen/ceed-cuda-gen-operator.c:40-100); here they are data. */
+CEEDB200_EXPORT int ceedb200_operator_set_kernel_shape(B200Operator op, const int *shape);
+CEEDB200_EXPORT int ceedb200_operator_get_kernel_shape(B200Operator op, int *shape, char *signature, int signature_len);
+/* autotuner: 0 off (default), 1 time candidate kernel shapes on the first Apply of every fused operator that has no entry
+ * in the tuning table, 2 always.  Same as the environment variable CEED_B200_AUTOTUNE. */
+CEEDB200_EXPORT int ceedb200_set_autotune(B200Ceed ceed, int level);
 
 #ifdef __cplusplus
 }

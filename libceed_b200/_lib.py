@@ -112,6 +112,9 @@ def load(path=LIB_PATH):
         "ceedb200_operator_set_timing": [handle, C.c_int],
         "ceedb200_operator_last_kernel_ms": [handle, P(C.c_float), P(C.c_float)],
         "ceedb200_operator_set_tuning": [handle, C.c_int, C.c_int],
+        "ceedb200_operator_set_kernel_shape": [handle, P(C.c_int)],
+        "ceedb200_operator_get_kernel_shape": [handle, P(C.c_int), C.c_char_p, C.c_int],
+        "ceedb200_set_autotune": [handle, C.c_int],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)

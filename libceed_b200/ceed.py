@@ -90,6 +90,10 @@ class Ceed:
     def set_scatter_mode(self, mode):
         self._chk(self._lib.ceedb200_set_scatter_mode(self._ptr, mode))
 
+    def set_autotune(self, level=1):
+        """0 off, 1 tune fused operators that have no tuning-table entry on their first apply, 2 always."""
+        self._chk(self._lib.ceedb200_set_autotune(self._ptr, level))
+
     def synchronize(self):
         self._chk(self._lib.ceedb200_synchronize(self._ptr))
 
@@ -339,6 +343,17 @@ class Operator(_Object):
 
     def set_tuning(self, elems_per_block=0, blocks_per_sm=0):
         self._chk(self._ceed._lib.ceedb200_operator_set_tuning(self._ptr, elems_per_block, blocks_per_sm))
+
+    SHAPE_KEYS = ("elems_per_group", "group_warps", "cta_warps", "min_blocks_per_sm", "qf_mode", "qf_unroll", "stage_mask")
+
+    def set_kernel_shape(self, **shape):
+        vals = [shape.get(k, -1 if k in ("qf_mode", "stage_mask") else 0) for k in self.SHAPE_KEYS]
+        self._chk(self._ceed._lib.ceedb200_operator_set_kernel_shape(self._ptr, (C.c_int * 7)(*vals)))
+
+    def get_kernel_shape(self):
+        vals, sig = (C.c_int * 7)(), C.create_string_buffer(512)
+        self._chk(self._ceed._lib.ceedb200_operator_get_kernel_shape(self._ptr, vals, sig, 512))
+        return dict(zip(self.SHAPE_KEYS, list(vals)), signature=sig.value.decode())
 
     def set_timing(self, enabled=True):
         self._chk(self._ceed._lib.ceedb200_operator_set_timing(self._ptr, 1 if enabled else 0))

@@ -27,6 +27,7 @@ const B200Driver *b200_driver() {
     drv.ModuleLoadData                            = missing<CUmodule *, const void *>;
     drv.ModuleUnload                              = missing<CUmodule>;
     drv.ModuleGetFunction                         = missing<CUfunction *, CUmodule, const char *>;
+    drv.ModuleGetGlobal                           = missing<CUdeviceptr *, size_t *, CUmodule, const char *>;
     drv.LaunchKernel                              = missing<CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **>;
     drv.FuncSetAttribute                          = missing<CUfunction, CUfunction_attribute, int>;
     drv.FuncGetAttribute                          = missing<int *, CUfunction_attribute, CUfunction>;
@@ -43,6 +44,7 @@ const B200Driver *b200_driver() {
   B200_SYM(ModuleLoadData, "cuModuleLoadData")
   B200_SYM(ModuleUnload, "cuModuleUnload")
   B200_SYM(ModuleGetFunction, "cuModuleGetFunction")
+  B200_SYM(ModuleGetGlobal, "cuModuleGetGlobal_v2")
   B200_SYM(LaunchKernel, "cuLaunchKernel")
   B200_SYM(FuncSetAttribute, "cuFuncSetAttribute")
   B200_SYM(FuncGetAttribute, "cuFuncGetAttribute")

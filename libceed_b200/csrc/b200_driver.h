@@ -9,6 +9,7 @@ struct B200Driver {
   CUresult (*ModuleLoadData)(CUmodule *, const void *);
   CUresult (*ModuleUnload)(CUmodule);
   CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, const char *);
+  CUresult (*ModuleGetGlobal)(CUdeviceptr *, size_t *, CUmodule, const char *);
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **);
   CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
   CUresult (*FuncGetAttribute)(int *, CUfunction_attribute, CUfunction);
@@ -20,6 +21,8 @@ const B200Driver *b200_driver();
 #define cuModuleLoadData b200_driver()->ModuleLoadData
 #define cuModuleUnload b200_driver()->ModuleUnload
 #define cuModuleGetFunction b200_driver()->ModuleGetFunction
+#undef cuModuleGetGlobal
+#define cuModuleGetGlobal b200_driver()->ModuleGetGlobal
 #define cuLaunchKernel b200_driver()->LaunchKernel
 #define cuFuncSetAttribute b200_driver()->FuncSetAttribute
 #define cuFuncGetAttribute b200_driver()->FuncGetAttribute

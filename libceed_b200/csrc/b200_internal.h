@@ -17,6 +17,20 @@ struct B200Module {
   CUmodule    module = nullptr;
   std::string source;
   std::string log;
+  // fused operator kernels: device address of the __constant__ argument block and the bytes last written to it
+  CUdeviceptr       args_dptr = 0;
+  std::vector<char> last_args;
+};
+
+// Shape of the generated operator kernel.  0 / -1 = let the plan heuristics decide.
+struct B200Tuning {
+  int epw = 0;          // elements per group
+  int group_warps = 0;  // warps that share one element group (1, 2, 4)
+  int cta_warps = 0;    // warps per CTA
+  int minb = 0;         // __launch_bounds__ min blocks per SM
+  int qf_mode = -1;     // 0 z-line QFunction stage, 1 pointwise
+  int qf_unroll = 0;    // pointwise stage: points in flight per lane
+  int stage = -1;       // cp.async staging mask
 };
 
 struct B200Ceed_ {
@@ -32,6 +46,8 @@ struct B200Ceed_ {
   std::vector<std::string>           jit_roots;
   std::vector<std::string>           jit_defines;
   std::map<std::string, B200Module *> module_cache;  // keyed on full source + options
+  std::map<std::string, B200Tuning>   tune_table;    // kernel signature -> tuned shape (tuned/sm_100a.tune, autotuner)
+  int                                 autotune = 0;  // 0 off, 1 tune operators missing from the table, 2 always
   // scratch for norms
   double *d_scratch = nullptr;
   size_t  scratch_len = 0;
@@ -158,7 +174,8 @@ struct B200Operator_ {
   std::vector<B200OpField> in_fields, out_fields;
   bool                     is_setup = false;
   B200OpPlan              *plan = nullptr;
-  int                      tune_epb = 0, tune_bpsm = 0;
+  B200Tuning               tune;           // explicit overrides (ceedb200_operator_set_tuning, autotuner)
+  bool                     tuned = false;  // autotuner has run (or was not applicable)
   bool                     timing = false;
   float                    last_fused_ms = 0.f, last_aux_ms = 0.f;
   cudaEvent_t              ev[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -6,6 +6,8 @@
 // scatter mode).  Operators the generator does not cover (1-D/2-D, mixed Q, Q < P gradients) run through an unfused
 // sequence of this backend's own restriction / basis / QFunction kernels, like /gpu/cuda/ref does
 // (backends/cuda-ref/ceed-cuda-ref-operator.c:519-638) -- never through the CPU.
+#include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -70,13 +72,35 @@ extern "C" int ceedb200_operator_set_field(B200Operator op, const char *field_na
   return b200_error(ceed, B200_ERROR_INCOMPLETE, "QFunction has no field named '%s'", field_name);
 }
 
-extern "C" int ceedb200_operator_set_tuning(B200Operator op, int elems_per_block, int blocks_per_sm) {
-  op->tune_epb  = elems_per_block;
-  op->tune_bpsm = blocks_per_sm;
+static void operator_reset(B200Operator op) {
   if (op->is_setup) {
     plan_free(op);
     op->is_setup = false;
   }
+}
+
+extern "C" int ceedb200_operator_set_tuning(B200Operator op, int elems_per_block, int blocks_per_sm) {
+  op->tune.epw  = elems_per_block;
+  op->tune.minb = blocks_per_sm;
+  op->tuned     = elems_per_block > 0 || blocks_per_sm > 0;  // explicit shape: the autotuner keeps its hands off
+  operator_reset(op);
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_operator_set_kernel_shape(B200Operator op, const int *shape) {
+  op->tune.epw = shape[0], op->tune.group_warps = shape[1], op->tune.cta_warps = shape[2], op->tune.minb = shape[3];
+  op->tune.qf_mode = shape[4], op->tune.qf_unroll = shape[5], op->tune.stage = shape[6];
+  op->tuned = true;
+  operator_reset(op);
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_operator_get_kernel_shape(B200Operator op, int *shape, char *signature, int signature_len) {
+  B200_CHECK(op->is_setup && op->plan && op->plan->fused, op->ceed, B200_ERROR_UNSUPPORTED, "operator is not set up as a fused kernel");
+  const B200Tuning &t = op->plan->resolved;
+  const int         v[7] = {t.epw, t.group_warps, t.cta_warps, t.minb, t.qf_mode, t.qf_unroll, t.stage};
+  if (shape) memcpy(shape, v, sizeof(v));
+  if (signature && signature_len > 0) snprintf(signature, signature_len, "%s", op->plan->signature.c_str());
   return B200_SUCCESS;
 }
 
@@ -195,8 +219,13 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add) {
 
   if (op->timing) B200_CUDA(ceed, cudaEventRecord(op->ev[3], ceed->stream));
   if (plan->num_elem > 0) {
-    void *kargs[] = {&args};
-    B200_CALL(b200_launch(ceed, var.kernel, plan->grid, plan->threads, plan->smem_bytes, kargs));
+    // the argument block is a __constant__ object of the module: rewrite it only when a pointer changed (stream-ordered copy)
+    B200Module *mod = var.module;
+    if (!b200_compile_only() && (mod->last_args.size() != sizeof(args) || memcmp(mod->last_args.data(), &args, sizeof(args)) != 0)) {
+      mod->last_args.assign((const char *)&args, (const char *)&args + sizeof(args));
+      B200_CUDA(ceed, cudaMemcpyAsync((void *)mod->args_dptr, mod->last_args.data(), sizeof(args), cudaMemcpyHostToDevice, ceed->stream));
+    }
+    B200_CALL(b200_launch(ceed, var.kernel, plan->grid, plan->threads, plan->smem_bytes, nullptr));
   }
   if (op->timing) B200_CUDA(ceed, cudaEventRecord(op->ev[1], ceed->stream));
   // second phase of the scatter
@@ -304,9 +333,99 @@ static int apply_unfused(B200Operator op, B200Vector u, B200Vector v, int add) {
   return B200_SUCCESS;
 }
 
+// ------------------------------------------------------------------------------------------------ autotuner
+// Opt-in (ceedb200_set_autotune / CEED_B200_AUTOTUNE): on the first overwrite-apply of a fused operator, time a small set
+// of kernel shapes on the caller's own vectors (Apply is idempotent) and keep the fastest.  Coordinate search: group width
+// x QFunction stage layout, then elements per group, then the launch-bounds occupancy target.  The result goes into the
+// context's tuning table (and, with CEED_B200_TUNE_SAVE=<file>, is appended to a table file that ceedb200_init loads).
+static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
+  B200Ceed ceed = op->ceed;
+  op->tuned     = true;
+  if (!op->plan->fused || b200_compile_only()) return B200_SUCCESS;
+  if ((long long)op->plan->num_elem * op->plan->Q * op->plan->Q * op->plan->Q < 200000) return B200_SUCCESS;  // too small to time
+  if (ceed->autotune < 2 && (ceed->tune_table.count(op->plan->signature) || ceed->tune_table.count(op->plan->shape_signature))) return B200_SUCCESS;
+  const bool        debug = getenv("CEED_B200_DEBUG") != nullptr;
+  const bool        timing0 = op->timing;
+  const std::string sig = op->plan->signature, shape_sig = op->plan->shape_signature;
+  const std::string saved_error = ceed->last_error;
+  op->timing = true;
+  B200Tuning best = op->plan->resolved;
+  float      best_ms = 1e30f;
+  auto trial = [&](B200Tuning t) -> float {
+    operator_reset(op);
+    op->tune = t;
+    float ms = 1e30f;
+    if (operator_setup(op) == B200_SUCCESS && op->plan->fused) {
+      bool ok = true;
+      for (int i = 0; i < 4 && ok; i++) {
+        ok = apply_fused(op, u, v, 0) == B200_SUCCESS;
+        if (ok && i > 0) ms = std::min(ms, op->last_fused_ms + op->last_aux_ms);
+      }
+      if (!ok) ms = 1e30f;
+      t = op->plan->resolved;
+    }
+    if (debug)
+      fprintf(stderr, "[ceed-b200] autotune %s: epw %d gw %d warps %d minb %d qf %d unroll %d -> %.4f ms\n", sig.c_str(), t.epw, t.group_warps, t.cta_warps,
+              t.minb, t.qf_mode, t.qf_unroll, ms);
+    if (ms < best_ms) best_ms = ms, best = t;
+    return ms;
+  };
+  B200Tuning base;  // all heuristic
+  // 1. group width / warps per CTA x QFunction layout (elements per group and occupancy target left to the heuristics)
+  const int shapes[][2] = {{1, 4}, {2, 2}, {2, 8}, {4, 4}, {1, 8}};
+  for (auto &sh : shapes)
+    for (int qf = 0; qf < 2; qf++) {
+      B200Tuning t  = base;
+      t.group_warps = sh[0], t.cta_warps = sh[1], t.qf_mode = qf;
+      trial(t);
+    }
+  // 2. elements per group around the winner
+  {
+    const B200Tuning win = best;
+    for (int epw : {1, 2, 3, 4, 6, 8, 12}) {
+      if (epw == win.epw) continue;
+      B200Tuning t = base;
+      t.group_warps = win.group_warps, t.cta_warps = win.cta_warps, t.qf_mode = win.qf_mode, t.epw = epw;
+      trial(t);
+    }
+  }
+  // 3. occupancy target (register cap) and points in flight
+  {
+    const B200Tuning win = best;
+    for (int minb : {win.minb - 1, win.minb + 1, win.minb + 2, win.minb * 2}) {
+      if (minb < 1 || minb == win.minb || minb * win.cta_warps > 64) continue;
+      B200Tuning t = win;
+      t.minb       = minb;
+      trial(t);
+    }
+    if (best.qf_mode == 1) {
+      B200Tuning t = best;
+      t.qf_unroll  = best.qf_unroll == 4 ? 8 : 4;
+      trial(t);
+    }
+  }
+  operator_reset(op);
+  op->tune   = best;
+  op->timing = timing0;
+  ceed->last_error = saved_error;  // failed candidates are not errors of this call
+  B200_CALL(operator_setup(op));
+  ceed->tune_table[sig] = best;
+  if (!ceed->tune_table.count(shape_sig)) ceed->tune_table[shape_sig] = best;
+  if (const char *path = getenv("CEED_B200_TUNE_SAVE")) {
+    if (FILE *f = fopen(path, "a")) {
+      fprintf(f, "%s %d %d %d %d %d %d %d  # %.4f ms, %d elements\n", sig.c_str(), best.epw, best.group_warps, best.cta_warps, best.minb, best.qf_mode,
+              best.qf_unroll, best.stage, best_ms, op->plan->num_elem);
+      fclose(f);
+    }
+  }
+  if (debug) fprintf(stderr, "[ceed-b200] autotune %s: best %.4f ms\n", sig.c_str(), best_ms);
+  return B200_SUCCESS;
+}
+
 static int operator_apply(B200Operator op, B200Vector u, B200Vector v, int add) {
   B200_CALL(operator_setup(op));
   if (!b200_compile_only()) B200_CUDA(op->ceed, cudaSetDevice(op->ceed->device_id));
+  if (op->ceed->autotune && !op->tuned && !add) B200_CALL(operator_autotune(op, u, v));
   if (op->plan->fused) return apply_fused(op, u, v, add);
   return apply_unfused(op, u, v, add);
 }

@@ -158,10 +158,52 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     plane_size = std::max(plane_size, Q * Q * odd_pad(b.P));
   }
   plan->plane_size = plane_size;
+  // Kernel shape: explicit override (set_tuning / autotuner) > environment > tuning table > heuristic.
+  {
+    std::ostringstream sig;
+    sig << "Q" << Q << "|sc" << plan->scatter_mode;
+    auto group_sig = [&](const B200GenGroup &g) {
+      const B200GenBasis &b = plan->bases[g.basis_id];
+      sig << "P" << b.P << (b.collocated ? "c" : "") << "n" << g.nc << (g.use_interp ? "i" : "") << (g.use_grad ? "g" : "") << (g.rstr->is_strided ? "s" : "o")
+          << (g.rstr->comp_stride == 1 && g.nc > 1 ? "l" : "");
+    };
+    sig << "|in:";
+    for (auto &g : plan->in_groups) group_sig(g);
+    for (auto &f : plan->in_fields)
+      if (f.emode == B200_EVAL_NONE) sig << "N" << f.nc;
+      else if (f.emode == B200_EVAL_WEIGHT) sig << "W";
+    sig << "|out:";
+    for (auto &g : plan->out_groups) group_sig(g);
+    for (auto &f : plan->out_fields)
+      if (f.emode == B200_EVAL_NONE) sig << "N" << f.nc;
+    plan->shape_signature = sig.str();
+    plan->signature       = plan->shape_signature + "|" + op->qf->kernel_name;
+  }
+  B200Tuning tn = op->tune;
+  {
+    B200Tuning table;
+    auto       it = ceed->tune_table.find(plan->signature);
+    if (it == ceed->tune_table.end()) it = ceed->tune_table.find(plan->shape_signature);
+    if (it != ceed->tune_table.end()) table = it->second;
+    auto pick = [&](int &field, int unset, const char *env, int table_value) {
+      if (field != unset) return;
+      if (getenv(env)) field = atoi(getenv(env));
+      else field = table_value;
+    };
+    pick(tn.epw, 0, "CEED_B200_EPB", table.epw);
+    pick(tn.group_warps, 0, "CEED_B200_GROUP_WARPS", table.group_warps);
+    pick(tn.cta_warps, 0, "CEED_B200_WARPS", table.cta_warps);
+    pick(tn.minb, 0, "CEED_B200_MINB", table.minb);
+    pick(tn.qf_mode, -1, "CEED_B200_QF_POINTWISE", table.qf_mode);
+    pick(tn.qf_unroll, 0, "CEED_B200_QF_UNROLL", table.qf_unroll);
+    pick(tn.stage, -1, "CEED_B200_STAGE", table.stage);
+  }
   // QFunction stage layout: z-line (default) = d/dz, QFunction and (d/dz)^T fused per z-line in registers;
-  // pointwise (CEED_B200_QF_POINTWISE=1) = d/dz and its transpose are separate line stages through shared memory and the
-  // QFunction runs over independent points (short dependency chains on the streamed quadrature data, one more plane).
-  plan->qf_pointwise = getenv("CEED_B200_QF_POINTWISE") != nullptr;
+  // pointwise = d/dz and its transpose are separate line stages through shared memory and the QFunction runs over
+  // independent points (short dependency chains on the streamed quadrature data, one more plane).
+  plan->qf_pointwise = tn.qf_mode >= 1;
+  plan->qf_pp        = (tn.qf_mode == 2 && Q % 2 == 0) ? 2 : 1;  // point pairs need x-adjacent points in one row
+  plan->qf_unroll    = tn.qf_unroll > 0 ? tn.qf_unroll : 4;
   auto planes_of = [&](const B200GenGroup &g) { return g.nc * (g.use_grad ? ((plan->qf_pointwise && g.use_interp) ? 4 : 3) : 2); };
   int  n_in = 0, n_out = 0;
   for (auto &g : plan->in_groups) {
@@ -205,24 +247,54 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
       g.tgt_off = -1;
       if (plan->async_copy && (mask & 1) && !g.rstr->is_strided && plan->scatter_mode != B200_SCATTER_EVECTOR) g.tgt_off = take((size_t)E * g.rstr->elem_size * 4);
     }
+    plan->ring_off = -1;
+    for (auto &f : plan->in_fields) f.ring_k = -1;
+    if (plan->async_copy && (mask & 16) && plan->warp_mode && !plan->qf_pointwise) {
+      int comps = 0;
+      for (auto &f : plan->in_fields)
+        if (f.emode == B200_EVAL_NONE && f.qd_off < 0 && f.rstr->is_strided) {
+          f.ring_k = comps;
+          comps += f.nc;
+        }
+      const int lanes  = 32 * plan->group_warps;
+      const int rounds = (E * Q * Q + lanes - 1) / lanes, steps = rounds * Q;
+      const int want   = getenv("CEED_B200_RING") ? atoi(getenv("CEED_B200_RING")) : 4;
+      int       ns     = 0;
+      for (int d = 2; d <= 8 && d <= steps; d++)  // slots must divide the steps of a batch so that slot numbers are compile-time constants
+        if (steps % d == 0 && (ns == 0 || abs(d - want) < abs(ns - want))) ns = d;
+      if (comps > 0 && ns >= 2 && steps <= 64) {
+        plan->ring_slots  = ns;
+        plan->ring_comps  = comps;
+        plan->ring_rounds = rounds;
+        plan->ring_off    = take((size_t)ns * lanes * comps * 8);
+      } else {
+        for (auto &f : plan->in_fields) f.ring_k = -1;
+      }
+    }
     return off;
   };
   plan->warp_mode = !getenv("CEED_B200_BLOCK_MODE");
   int epb, threads;
   if (plan->warp_mode) {
     // staging defaults in warp mode: offsets + scatter targets only (small); CEED_B200_STAGE=<bitmask 1 idx/tgt, 2 gather, 4 qdata>
-    const int stage = getenv("CEED_B200_STAGE") ? atoi(getenv("CEED_B200_STAGE")) : 1;
+    const int stage = tn.stage >= 0 ? tn.stage : 1;
     plan->stage_mask = stage;
-    // elements per warp: fill the 32 lanes in the line stages; prefer the best lane utilisation within ~14 KB per warp
+    // warps that share one element group (1, 2 or 4): more resident warps per byte of shared memory for large Q
+    int gw = tn.group_warps;
+    if (gw != 1 && gw != 2 && gw != 4) gw = 1;
+    plan->group_warps = gw;
+    plan->stage_mask  = stage;
+    const int lanes = 32 * gw;
+    // elements per group: fill the lanes in the line stages; prefer the best lane utilisation within ~14 KB per warp
     int    best = 1;
     double best_util = -1.0;
     const int Pmax = plan->bases.empty() ? Q : plan->bases[0].P;
     for (int e = 1; e <= 16; e++) {
-      if (layout(e) > 14336 && e > 1) break;
+      if (layout(e) > (size_t)14336 * gw && e > 1) break;
       double work = 0, slots = 0;
       for (int tasks : {Pmax * Pmax, Pmax * Q, lines, lines, lines}) {
         work += (double)e * tasks;
-        slots += 32.0 * ((e * tasks + 31) / 32);
+        slots += (double)lanes * ((e * tasks + lanes - 1) / lanes);
       }
       const double util = work / slots;
       if (util > best_util + 0.02) {
@@ -230,13 +302,14 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
         best      = e;
       }
     }
-    epb = op->tune_epb > 0 ? op->tune_epb : (getenv("CEED_B200_EPB") ? atoi(getenv("CEED_B200_EPB")) : best);
+    epb = tn.epw > 0 ? tn.epw : best;
     if (epb > std::max(1, num_elem)) epb = std::max(1, num_elem);
     if (layout(epb) > ceed->smem_optin) return reject("element working set exceeds shared memory");
-    const int warps = getenv("CEED_B200_WARPS") ? atoi(getenv("CEED_B200_WARPS")) : 4;
-    int       w     = warps;
+    const int warps = tn.cta_warps > 0 ? tn.cta_warps : 4;
+    int w = std::max(1, warps / gw);  // groups per CTA
     while (w > 1 && (size_t)w * layout(epb) > ceed->smem_optin) w--;
-    threads                = 32 * w;
+    threads                = 32 * gw * w;
+    plan->group_warps      = gw;
     plan->group_smem_bytes = (int)layout(epb);
     plan->epb              = epb;
     plan->threads          = threads;
@@ -244,9 +317,9 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
   } else {
     plan->stage_mask = 7;
     int target = getenv("CEED_B200_THREADS") ? atoi(getenv("CEED_B200_THREADS")) : 256;
-    epb        = op->tune_epb > 0 ? op->tune_epb : (getenv("CEED_B200_EPB") ? atoi(getenv("CEED_B200_EPB")) : std::max(1, target / lines));
+    epb        = tn.epw > 0 ? tn.epw : std::max(1, target / lines);
     // aim for two resident blocks per SM so that one block's barrier / copy waits are covered by the other
-    const bool   epb_forced = op->tune_epb > 0 || getenv("CEED_B200_EPB");
+    const bool   epb_forced = tn.epw > 0;
     const size_t smem_goal  = epb_forced ? ceed->smem_optin : (ceed->smem_sm - 2048) / 2;
     while (epb > 1 && layout(epb) > smem_goal) epb--;
     if (layout(epb) > ceed->smem_optin) {
@@ -267,9 +340,11 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     int by_smem = (int)(ceed->smem_sm / (size_t)(plan->smem_bytes + 1024));
     int by_regs = 65536 / (threads * 96);
     int minb    = std::max(1, std::min(by_smem, by_regs));
-    if (op->tune_bpsm > 0) minb = op->tune_bpsm;
-    if (getenv("CEED_B200_MINB")) minb = atoi(getenv("CEED_B200_MINB"));
+    if (tn.minb > 0) minb = tn.minb;
     plan->blocks_per_sm = std::max(1, minb);
+    tn.epw = plan->epb, tn.group_warps = plan->group_warps, tn.cta_warps = plan->threads / 32, tn.minb = plan->blocks_per_sm;
+    tn.qf_mode = plan->qf_pointwise ? plan->qf_pp : 0, tn.qf_unroll = plan->qf_unroll, tn.stage = plan->stage_mask;
+    plan->resolved = tn;
   }
   plan->fused      = true;
   return B200_SUCCESS;
@@ -291,7 +366,7 @@ struct Gen {
   int          TS        = 0;            // task-loop stride (threads that share a group)
   string       TID, SMBASE, SYNC;        // lane id expression, shared-memory base, barrier statement
   string       smw_decl() const {
-    return warp_mode ? "  double *const smw = sm + (threadIdx.x >> 5) * " + std::to_string(plan->group_smem_bytes / 8) + ";\n" : "";
+    return warp_mode ? "  double *const smw = sm + (threadIdx.x / " + std::to_string(TS) + ") * " + std::to_string(plan->group_smem_bytes / 8) + ";\n" : "";
   }
 
   const B200GenBasis &basis(int id) const { return plan->bases[id]; }
@@ -321,10 +396,10 @@ struct Gen {
   int                 n_stage = 0;
   void task_loop_begin(const string &ntasks) {
     const string name = "b200_stage_" + std::to_string(n_stage++);
-    c << "static __device__ __noinline__ void " << name << "(const B200OpArgs &a, const long long e0) {\n";
+    c << "static __device__ __noinline__ void " << name << "(const long long e0) {\n";
     c << smw_decl();
     c << "    for (int t = " << TID << "; t < " << ntasks << "; t += " << TS << ") {\n";
-    calls.push_back("    " + name + "(a, e0);\n");
+    calls.push_back("    " + name + "(e0);\n");
   }
   void task_loop_end() { c << "    }\n}\n\n"; }
   void barrier() { calls.push_back("    " + SYNC + "\n"); }
@@ -349,6 +424,7 @@ struct Gen {
   void emit_header() {
     B200QFunction qf = op->qf;
     c << "// Fused operator kernel generated by ceed-b200 for QFunction " << qf->kernel_name << "\n";
+    if (plan->qf_pointwise && plan->qf_pp > 1) c << "#define CEED_Q_VLA " << plan->qf_pp << "  // the QFunction is called with Q = " << plan->qf_pp << " points\n";
     c << "#include <b200-jit.h>\n";
     c << "#include \"" << qf->source_path << "\"\n\n";
     for (size_t b = 0; b < plan->bases.size(); b++) {
@@ -363,7 +439,10 @@ struct Gen {
       emit_mat("cW" + std::to_string(b), bs->q_weight);
     }
     c << "\nstruct B200OpArgs {\n  long long num_elem;\n  void *ctx;\n  const double *in_ptr[16];\n  double *out_ptr[16];\n"
-      << "  const int *in_idx[16];\n  const int *out_idx[16];\n  double *out_aux[16];\n};\n\n";
+      << "  const int *in_idx[16];\n  const int *out_idx[16];\n  double *out_aux[16];\n};\n"
+      // the argument block lives in constant memory (written by the host before the launch): every stage function reads its
+      // pointers with uniform constant loads instead of generic loads through a reference to the kernel parameter
+      << "__constant__ B200OpArgs b200a;\n\n";
     c << "extern __shared__ double sm[];\n\n";
     // cp.async (LDGSTS): global -> shared without staging registers; completion tracked per thread with commit/wait groups
     c << "__device__ __forceinline__ void b200_cp4(void *dst, const void *src) {\n"
@@ -388,14 +467,14 @@ struct Gen {
     bool any = false;
     for (auto &g : plan->in_groups) any = any || g.idx_off >= 0;
     if (!any) return false;
-    c << "static __device__ __noinline__ void b200_issue_idx(const B200OpArgs &a, const long long e0) {\n";
-    c << "  if (e0 >= a.num_elem) return;\n";
+    c << "static __device__ __noinline__ void b200_issue_idx(const long long e0) {\n";
+    c << "  if (e0 >= b200a.num_elem) return;\n";
     c << smw_decl();
-    c << "  const int ne = (int)((a.num_elem - e0 < " << E << ") ? a.num_elem - e0 : " << E << ");\n";
+    c << "  const int ne = (int)((b200a.num_elem - e0 < " << E << ") ? b200a.num_elem - e0 : " << E << ");\n";
     for (auto &g : plan->in_groups) {
       if (g.idx_off < 0) continue;
       const int es = g.rstr->elem_size;
-      c << "  { int *dst = " << smem_at(g.idx_off, "int") << "; const int *src = a.in_idx[" << g.slot << "] + e0 * " << es << "LL;\n";
+      c << "  { int *dst = " << smem_at(g.idx_off, "int") << "; const int *src = b200a.in_idx[" << g.slot << "] + e0 * " << es << "LL;\n";
       c << "    for (int i = " << TID << "; i < ne * " << es << "; i += " << TS << ") b200_cp4(dst + i, src + i); }\n";
     }
     c << "}\n\n";
@@ -406,14 +485,14 @@ struct Gen {
     bool any = false;
     for (auto &g : plan->out_groups) any = any || g.tgt_off >= 0;
     if (!any) return false;
-    c << "static __device__ __noinline__ void b200_issue_tgt(const B200OpArgs &a, const long long e0) {\n";
-    c << "  if (e0 >= a.num_elem) return;\n";
+    c << "static __device__ __noinline__ void b200_issue_tgt(const long long e0) {\n";
+    c << "  if (e0 >= b200a.num_elem) return;\n";
     c << smw_decl();
-    c << "  const int ne = (int)((a.num_elem - e0 < " << E << ") ? a.num_elem - e0 : " << E << ");\n";
+    c << "  const int ne = (int)((b200a.num_elem - e0 < " << E << ") ? b200a.num_elem - e0 : " << E << ");\n";
     for (auto &g : plan->out_groups) {
       if (g.tgt_off < 0) continue;
       const int es = g.rstr->elem_size;
-      c << "  { int *dst = " << smem_at(g.tgt_off, "int") << "; const int *src = a.out_idx[" << g.slot << "] + e0 * " << es << "LL;\n";
+      c << "  { int *dst = " << smem_at(g.tgt_off, "int") << "; const int *src = b200a.out_idx[" << g.slot << "] + e0 * " << es << "LL;\n";
       c << "    for (int i = " << TID << "; i < ne * " << es << "; i += " << TS << ") b200_cp4(dst + i, src + i); }\n";
     }
     c << "}\n\n";
@@ -424,15 +503,15 @@ struct Gen {
     bool any = false;
     for (auto &g : plan->in_groups) any = any || g.uin_off >= 0;
     if (!any) return false;
-    c << "static __device__ __noinline__ void b200_issue_gather(const B200OpArgs &a, const long long e0) {\n";
-    c << "  if (e0 >= a.num_elem) return;\n";
+    c << "static __device__ __noinline__ void b200_issue_gather(const long long e0) {\n";
+    c << "  if (e0 >= b200a.num_elem) return;\n";
     c << smw_decl();
-    c << "  const int ne = (int)((a.num_elem - e0 < " << E << ") ? a.num_elem - e0 : " << E << ");\n";
+    c << "  const int ne = (int)((b200a.num_elem - e0 < " << E << ") ? b200a.num_elem - e0 : " << E << ");\n";
     for (auto &g : plan->in_groups) {
       if (g.uin_off < 0) continue;
       const int es = g.rstr->elem_size;
       c << "  { const int *idx = " << smem_at(g.idx_off, "int") << "; double *dst = " << smem_at(g.uin_off, "double") << ";\n";
-      c << "    const double *src = a.in_ptr[" << g.slot << "];\n";
+      c << "    const double *src = b200a.in_ptr[" << g.slot << "];\n";
       c << "    for (int i = " << TID << "; i < ne * " << es << "; i += " << TS << ") {\n";
       c << "      const long long l = idx[i];\n";
       for (int cc = 0; cc < g.nc; cc++)
@@ -448,15 +527,15 @@ struct Gen {
     for (auto &f : plan->in_fields) any = any || f.qd_off >= 0;
     if (!any) return false;
     const int Q3 = Q * Q * Q;
-    c << "static __device__ __noinline__ void b200_issue_qd(const B200OpArgs &a, const long long e0) {\n";
-    c << "  if (e0 >= a.num_elem) return;\n";
+    c << "static __device__ __noinline__ void b200_issue_qd(const long long e0) {\n";
+    c << "  if (e0 >= b200a.num_elem) return;\n";
     c << smw_decl();
-    c << "  const int ne = (int)((a.num_elem - e0 < " << E << ") ? a.num_elem - e0 : " << E << ");\n";
+    c << "  const int ne = (int)((b200a.num_elem - e0 < " << E << ") ? b200a.num_elem - e0 : " << E << ");\n";
     for (auto &f : plan->in_fields) {
       if (f.qd_off < 0) continue;
       for (int cc = 0; cc < f.nc; cc++) {
         c << "  { double *dst = " << smem_at(f.qd_off, "double") << " + " << cc * E * Q3 << ";\n";
-        c << "    const double *src = a.in_ptr[" << f.slot << "] + " << (long long)cc * f.rstr->strides[1] << "LL + e0 * " << Q3 << "LL;\n";
+        c << "    const double *src = b200a.in_ptr[" << f.slot << "] + " << (long long)cc * f.rstr->strides[1] << "LL + e0 * " << Q3 << "LL;\n";
         c << "    const int n = ne * " << Q3 << ";\n";
         c << "    if (((((unsigned long long)src) | ((unsigned long long)dst)) & 15) == 0 && (n & 1) == 0) {\n";
         c << "      for (int i = " << TID << " * 2; i < n; i += " << 2 * TS << ") b200_cp16(dst + i, src + i);\n";
@@ -496,16 +575,16 @@ struct Gen {
       // Batched gather: every lane first issues the offset loads of ALL its tasks, then all value loads, and only then
       // computes -- two memory latencies per group instead of two per task round.
       const string name = "b200_stage_" + std::to_string(n_stage++);
-      c << "static __device__ __noinline__ void " << name << "(const B200OpArgs &a, const long long e0) {\n";
+      c << "static __device__ __noinline__ void " << name << "(const long long e0) {\n";
       c << smw_decl();
-      calls.push_back("    " + name + "(a, e0);\n");
+      calls.push_back("    " + name + "(e0);\n");
       c << "    const int lane = " << TID << ";\n";
       for (int r = 0; r < rounds; r++) {
         const string x = "_" + std::to_string(r);
         c << "    const int t" << x << " = lane + " << r * TS << ", tc" << x << " = t" << x << " < " << ntasks << " ? t" << x << " : " << ntasks - 1 << ";\n";
         c << "    const int ij" << x << " = tc" << x << " % " << P * P << ", cc" << x << " = (tc" << x << " / " << P * P << ") % " << g.nc << ", le" << x
           << " = tc" << x << " / " << P * P * g.nc << ";\n";
-        c << "    const long long e" << x << " = (e0 + le" << x << " < a.num_elem) ? e0 + le" << x << " : a.num_elem - 1;\n";
+        c << "    const long long e" << x << " = (e0 + le" << x << " < b200a.num_elem) ? e0 + le" << x << " : b200a.num_elem - 1;\n";
       }
       if (!g.rstr->is_strided) {
         for (int r = 0; r < rounds; r++) {
@@ -515,7 +594,7 @@ struct Gen {
               c << "    const long long l" << k << x << " = " << smem_at(g.idx_off, "const int") << "[le" << x << " * " << P * P * P << " + ij" << x << " + "
                 << k * P * P << "];\n";
             else
-              c << "    const long long l" << k << x << " = __ldg(a.in_idx[" << sl << "] + e" << x << " * " << P * P * P << "LL + ij" << x << " + " << k * P * P
+              c << "    const long long l" << k << x << " = __ldg(b200a.in_idx[" << sl << "] + e" << x << " * " << P * P * P << "LL + ij" << x << " + " << k * P * P
                 << ");\n";
           }
         }
@@ -524,10 +603,10 @@ struct Gen {
         const string x = "_" + std::to_string(r);
         for (int k = 0; k < P; k++) {
           if (g.rstr->is_strided)
-            c << "    const double u" << k << x << " = __ldg(a.in_ptr[" << sl << "] + "
+            c << "    const double u" << k << x << " = __ldg(b200a.in_ptr[" << sl << "] + "
               << lidx(g.rstr, "", "e" + x, "ij" + x + " + " + std::to_string(k * P * P), "cc" + x) << ");\n";
           else
-            c << "    const double u" << k << x << " = __ldg(a.in_ptr[" << sl << "] + l" << k << x << " + (long long)cc" << x << " * " << g.rstr->comp_stride
+            c << "    const double u" << k << x << " = __ldg(b200a.in_ptr[" << sl << "] + l" << k << x << " + (long long)cc" << x << " * " << g.rstr->comp_stride
               << "LL);\n";
         }
       }
@@ -542,7 +621,7 @@ struct Gen {
     }
     task_loop_begin(std::to_string(ntasks));
     c << "      const int ij = t % " << P * P << ", cc = (t / " << P * P << ") % " << g.nc << ", le = t / " << P * P * g.nc << ";\n";
-    c << "      const long long e = (e0 + le < a.num_elem) ? e0 + le : a.num_elem - 1;  // clamped: tail groups gather a valid element\n";
+    c << "      const long long e = (e0 + le < b200a.num_elem) ? e0 + le : b200a.num_elem - 1;  // clamped: tail groups gather a valid element\n";
     if (g.uin_off >= 0) {
       // values were gathered into shared memory by cp.async while the previous batch was computing
       c << "      const double *uin = " << smem_at(g.uin_off, "double") << " + (cc * " << E << " + le) * " << P * P * P << " + ij;\n";
@@ -550,11 +629,11 @@ struct Gen {
     } else {
       for (int k = 0; k < P; k++) {
         if (g.idx_off >= 0)  // offsets of this group were staged into shared memory while the previous group was computing
-          c << "      const double u" << k << " = __ldg(a.in_ptr[" << sl << "] + (long long)" << smem_at(g.idx_off, "const int") << "[le * " << P * P * P
+          c << "      const double u" << k << " = __ldg(b200a.in_ptr[" << sl << "] + (long long)" << smem_at(g.idx_off, "const int") << "[le * " << P * P * P
             << " + ij + " << k * P * P << "] + (long long)cc * " << g.rstr->comp_stride << "LL);\n";
         else
-          c << "      const double u" << k << " = __ldg(a.in_ptr[" << sl << "] + "
-            << lidx(g.rstr, "a.in_idx[" + sl + "]", "e", "ij + " + std::to_string(k * P * P), "cc") << ");\n";
+          c << "      const double u" << k << " = __ldg(b200a.in_ptr[" << sl << "] + "
+            << lidx(g.rstr, "b200a.in_idx[" + sl + "]", "e", "ij + " + std::to_string(k * P * P), "cc") << ");\n";
       }
     }
     emit_compute_store("", "      ");
@@ -647,91 +726,106 @@ struct Gen {
     task_loop_end();
   }
 
-  // QFunction over independent quadrature points (pointwise mode)
+  // QFunction over independent quadrature points (pointwise mode).  PP = points per lane: with PP == 2 a lane owns two
+  // x-adjacent points, streams the quadrature data with 16-byte loads (the per-warp load-instruction rate, not bytes in
+  // flight, limits HBM throughput at low occupancy -- scripts/ubench/stream_model.cu) and calls the QFunction with Q = 2.
   void emit_qf_points() {
     B200QFunction qf = op->qf;
-    const int     Q3 = Q * Q * Q;
+    const int     Q3 = Q * Q * Q, PP = plan->qf_pp;
     comment("quadrature points: independent points, inputs from the planes / streamed from global memory");
     const string name = "b200_stage_" + std::to_string(n_stage++);
-    c << "static __device__ __noinline__ void " << name << "(const B200OpArgs &a, const long long e0) {\n";
+    c << "static __device__ __noinline__ void " << name << "(const long long e0) {\n";
     c << smw_decl();
     c << "    const CeedScalar *in[" << std::max<size_t>(1, qf->inputs.size()) << "];\n";
     c << "    CeedScalar *out[" << std::max<size_t>(1, qf->outputs.size()) << "];\n";
-    const int unroll = getenv("CEED_B200_QF_UNROLL") ? atoi(getenv("CEED_B200_QF_UNROLL")) : 4;
+    const int unroll = plan->qf_unroll;
     c << "    #pragma unroll " << unroll << "\n";
-    c << "    for (int t = " << TID << "; t < " << E * Q3 << "; t += " << TS << ") {\n";
-    calls.push_back("    " + name + "(a, e0);\n");
-    c << "      const int pt = t % " << Q3 << ", le = t / " << Q3 << ";\n";
+    c << "    for (int t = " << TID << "; t < " << E * Q3 / PP << "; t += " << TS << ") {\n";
+    calls.push_back("    " + name + "(e0);\n");
+    c << "      const int pt = (t * " << PP << ") % " << Q3 << ", le = (t * " << PP << ") / " << Q3 << ";\n";
     c << "      const int qx = pt % " << Q << ", qy = (pt / " << Q << ") % " << Q << ", qz = pt / " << Q * Q << ";\n";
     c << "      const int p = (qz * " << Q << " + qy) * " << Qs << " + qx;\n";
     // tail groups: loads use a clamped (valid) element so that there is no branch in the loop body and the compiler can overlap
     // the global loads of several unrolled points; results of non-existent elements are simply never stored to global memory
     c << "      const long long e_real = e0 + le;\n";
-    c << "      const long long e = e_real < a.num_elem ? e_real : a.num_elem - 1;\n";
+    c << "      const long long e = e_real < b200a.num_elem ? e_real : b200a.num_elem - 1;\n";
     c << "      {\n";
-    for (size_t f = 0; f < plan->in_fields.size(); f++) c << "      CeedScalar in_" << f << "[" << plan->in_fields[f].size << "];\n";
-    for (size_t f = 0; f < plan->out_fields.size(); f++) c << "      CeedScalar out_" << f << "[" << plan->out_fields[f].size << "];\n";
+    for (size_t f = 0; f < plan->in_fields.size(); f++) c << "      CeedScalar in_" << f << "[" << plan->in_fields[f].size * PP << "];\n";
+    for (size_t f = 0; f < plan->out_fields.size(); f++) c << "      CeedScalar out_" << f << "[" << plan->out_fields[f].size * PP << "];\n";
     for (size_t f = 0; f < plan->in_fields.size(); f++) c << "      in[" << f << "] = in_" << f << ";\n";
     for (size_t f = 0; f < plan->out_fields.size(); f++) c << "      out[" << f << "] = out_" << f << ";\n";
+    auto at = [&](int k, int h) { return "[" + std::to_string(k * PP + h) + "]"; };
     for (size_t f = 0; f < plan->in_fields.size(); f++) {
       const B200GenField &fd = plan->in_fields[f];
       const string        sl = std::to_string(fd.slot);
       switch (fd.emode) {
         case B200_EVAL_NONE:
           for (int cc = 0; cc < fd.nc; cc++) {
-            if (fd.qd_off >= 0)
-              c << "      in_" << f << "[" << cc << "] = " << smem_at(fd.qd_off, "const double") << "[(" << cc * E << " + le) * " << Q3 << " + pt];\n";
-            else
-              c << "      in_" << f << "[" << cc << "] = __ldg(a.in_ptr[" << sl << "] + " << lidx(fd.rstr, "a.in_idx[" + sl + "]", "e", "pt", std::to_string(cc))
-                << ");\n";
+            if (fd.qd_off >= 0) {
+              for (int h = 0; h < PP; h++)
+                c << "      in_" << f << at(cc, h) << " = " << smem_at(fd.qd_off, "const double") << "[(" << cc * E << " + le) * " << Q3 << " + pt + " << h << "];\n";
+            } else if (PP == 2 && fd.rstr->is_strided && fd.rstr->strides[0] == 1 && fd.rstr->strides[1] % 2 == 0 && fd.rstr->strides[2] % 2 == 0) {
+              c << "      { const double2 v2 = __ldg((const double2 *)(b200a.in_ptr[" << sl << "] + " << lidx(fd.rstr, "", "e", "pt", std::to_string(cc)) << "));\n";
+              c << "        in_" << f << at(cc, 0) << " = v2.x; in_" << f << at(cc, 1) << " = v2.y; }\n";
+            } else {
+              for (int h = 0; h < PP; h++)
+                c << "      in_" << f << at(cc, h) << " = __ldg(b200a.in_ptr[" << sl << "] + "
+                  << lidx(fd.rstr, "b200a.in_idx[" + sl + "]", "e", "pt + " + std::to_string(h), std::to_string(cc)) << ");\n";
+            }
           }
           break;
         case B200_EVAL_WEIGHT:
-          c << "      in_" << f << "[0] = cW" << fd.basis_id << "[qx] * cW" << fd.basis_id << "[qy] * cW" << fd.basis_id << "[qz];\n";
+          for (int h = 0; h < PP; h++)
+            c << "      in_" << f << at(0, h) << " = cW" << fd.basis_id << "[qx + " << h << "] * cW" << fd.basis_id << "[qy] * cW" << fd.basis_id << "[qz];\n";
           break;
         case B200_EVAL_INTERP: {
           const B200GenGroup &g = plan->in_groups[fd.group];
-          for (int cc = 0; cc < fd.nc; cc++) c << "      in_" << f << "[" << cc << "] = (" << plane(g.plane0 + cc, "le") << ")[p];\n";
+          for (int cc = 0; cc < fd.nc; cc++)
+            for (int h = 0; h < PP; h++) c << "      in_" << f << at(cc, h) << " = (" << plane(g.plane0 + cc, "le") << ")[p + " << h << "];\n";
         } break;
         case B200_EVAL_GRAD: {
           const B200GenGroup &g = plan->in_groups[fd.group];
-          for (int cc = 0; cc < fd.nc; cc++) {
-            c << "      in_" << f << "[" << cc << "] = (" << plane(g.plane0 + 2 * g.nc + cc, "le") << ")[p];\n";
-            c << "      in_" << f << "[" << cc + fd.nc << "] = (" << plane(g.plane0 + g.nc + cc, "le") << ")[p];\n";
-            c << "      in_" << f << "[" << cc + 2 * fd.nc << "] = (" << plane(gz_plane(g, cc), "le") << ")[p];\n";
-          }
+          for (int cc = 0; cc < fd.nc; cc++)
+            for (int h = 0; h < PP; h++) {
+              c << "      in_" << f << at(cc, h) << " = (" << plane(g.plane0 + 2 * g.nc + cc, "le") << ")[p + " << h << "];\n";
+              c << "      in_" << f << at(cc + fd.nc, h) << " = (" << plane(g.plane0 + g.nc + cc, "le") << ")[p + " << h << "];\n";
+              c << "      in_" << f << at(cc + 2 * fd.nc, h) << " = (" << plane(gz_plane(g, cc), "le") << ")[p + " << h << "];\n";
+            }
         } break;
       }
     }
-    c << "      " << qf->kernel_name << "(a.ctx, 1, in, out);\n";
+    c << "      " << qf->kernel_name << "(b200a.ctx, " << PP << ", in, out);\n";
     for (size_t gi = 0; gi < plan->out_groups.size(); gi++) {
       const B200GenGroup &g = plan->out_groups[gi];
-      for (int cc = 0; cc < g.nc; cc++) {
-        string val, vx, vy, vz;
-        for (size_t f = 0; f < plan->out_fields.size(); f++) {
-          const B200GenField &fd = plan->out_fields[f];
-          if (fd.group != (int)gi) continue;
-          const string o = "out_" + std::to_string(f);
-          if (fd.emode == B200_EVAL_INTERP) val += (val.empty() ? "" : " + ") + o + "[" + std::to_string(cc) + "]";
-          if (fd.emode == B200_EVAL_GRAD) {
-            vx += (vx.empty() ? "" : " + ") + o + "[" + std::to_string(cc) + "]";
-            vy += (vy.empty() ? "" : " + ") + o + "[" + std::to_string(cc + fd.nc) + "]";
-            vz += (vz.empty() ? "" : " + ") + o + "[" + std::to_string(cc + 2 * fd.nc) + "]";
+      for (int cc = 0; cc < g.nc; cc++)
+        for (int h = 0; h < PP; h++) {
+          string val, vx, vy, vz;
+          for (size_t f = 0; f < plan->out_fields.size(); f++) {
+            const B200GenField &fd = plan->out_fields[f];
+            if (fd.group != (int)gi) continue;
+            const string o = "out_" + std::to_string(f);
+            if (fd.emode == B200_EVAL_INTERP) val += (val.empty() ? "" : " + ") + o + at(cc, h);
+            if (fd.emode == B200_EVAL_GRAD) {
+              vx += (vx.empty() ? "" : " + ") + o + at(cc, h);
+              vy += (vy.empty() ? "" : " + ") + o + at(cc + fd.nc, h);
+              vz += (vz.empty() ? "" : " + ") + o + at(cc + 2 * fd.nc, h);
+            }
+          }
+          if (!val.empty()) c << "      (" << plane(g.plane0 + cc, "le") << ")[p + " << h << "] = " << val << ";\n";
+          if (g.use_grad) {
+            c << "      (" << plane(g.plane0 + 2 * g.nc + cc, "le") << ")[p + " << h << "] = " << vx << ";\n";
+            c << "      (" << plane(g.plane0 + g.nc + cc, "le") << ")[p + " << h << "] = " << vy << ";\n";
+            c << "      (" << plane(gz_plane(g, cc), "le") << ")[p + " << h << "] = " << vz << ";\n";
           }
         }
-        if (!val.empty()) c << "      (" << plane(g.plane0 + cc, "le") << ")[p] = " << val << ";\n";
-        if (g.use_grad) {
-          c << "      (" << plane(g.plane0 + 2 * g.nc + cc, "le") << ")[p] = " << vx << ";\n";
-          c << "      (" << plane(g.plane0 + g.nc + cc, "le") << ")[p] = " << vy << ";\n";
-          c << "      (" << plane(gz_plane(g, cc), "le") << ")[p] = " << vz << ";\n";
-        }
-      }
     }
     for (size_t f = 0; f < plan->out_fields.size(); f++) {
       const B200GenField &fd = plan->out_fields[f];
       if (fd.emode != B200_EVAL_NONE) continue;
-      c << "      if (e_real < a.num_elem) {\n";
-      emit_scatter_value(fd.rstr, fd.slot, "e", "pt", fd.nc, [&](int cc) { return "out_" + std::to_string(f) + "[" + std::to_string(cc) + "]"; }, "        ");
+      c << "      if (e_real < b200a.num_elem) {\n";
+      for (int h = 0; h < PP; h++)
+        emit_scatter_value(fd.rstr, fd.slot, "e", "pt + " + std::to_string(h), fd.nc,
+                           [&](int cc) { return "out_" + std::to_string(f) + at(cc, h); }, "        ");
       c << "      }\n";
     }
     c << "      }\n";
@@ -744,7 +838,7 @@ struct Gen {
     task_loop_begin(std::to_string(E * Q * Q));
     c << "      const int qx = t % " << Q << ", qy = (t / " << Q << ") % " << Q << ", le = t / " << Q * Q << ";\n";
     c << "      const long long e = e0 + le;\n";
-    c << "      if (e < a.num_elem) {\n";
+    c << "      if (e < b200a.num_elem) {\n";
     c << "      const int pxy = qy * " << Qs << " + qx;\n";
     // z-lines of input groups that need gradients (and their d/dz)
     for (size_t gi = 0; gi < plan->in_groups.size(); gi++) {
@@ -781,7 +875,7 @@ struct Gen {
     const bool qf_ahead = !getenv("CEED_B200_NO_QFPF");
     auto none_load = [&](const B200GenField &fd, int cc, const string &pt_expr) {
       const string sl = std::to_string(fd.slot);
-      return "__ldg(a.in_ptr[" + sl + "] + " + lidx(fd.rstr, "a.in_idx[" + sl + "]", "e", pt_expr, std::to_string(cc)) + ")";
+      return "__ldg(b200a.in_ptr[" + sl + "] + " + lidx(fd.rstr, "b200a.in_idx[" + sl + "]", "e", pt_expr, std::to_string(cc)) + ")";
     };
     c << "      const int pt0 = qy * " << Q << " + qx;\n";
     if (qf_ahead)
@@ -827,7 +921,7 @@ struct Gen {
           } break;
         }
       }
-      c << "        " << qf->kernel_name << "(a.ctx, 1, in, out);\n";
+      c << "        " << qf->kernel_name << "(b200a.ctx, 1, in, out);\n";
       // outputs: first group contributions (INTERP stores, then GRAD parts), then EVAL_NONE
       for (size_t gi = 0; gi < plan->out_groups.size(); gi++) {
         const B200GenGroup &g = plan->out_groups[gi];
@@ -883,6 +977,216 @@ struct Gen {
     task_loop_end();
   }
 
+  // ---- z-line QFunction stage with the per-lane quadrature-data ring ------------------------------
+  // The streamed EVAL_NONE inputs are the bulk of the HBM traffic.  Every lane prefetches exactly the values it will consume
+  // itself with cp.async into a small ring in shared memory: step s = (task round r, z-layer qz); ring_slots - 1 steps are
+  // always in flight, also while the warp runs its contraction stages and across element groups (the last steps of a group
+  // issue the first steps of the NEXT group this warp will process).  No registers are held by loads in flight and no
+  // synchronisation is needed (a lane only reads what it copied itself; cp.async.wait_group orders it).
+  struct RingStep { int round, qz; bool next; };
+  void emit_ring_bases(const string &ind) {
+    // per task round: clamped task decode and base pointers of the current (qc) and the next (qn) element group
+    const int ntasks = E * Q * Q;
+    for (int r = 0; r < plan->ring_rounds; r++) {
+      const string x = "_" + std::to_string(r);
+      c << ind << "const int t" << x << " = lane + " << r * TS << ", tc" << x << " = t" << x << " < " << ntasks << " ? t" << x << " : " << ntasks - 1 << ";\n";
+      c << ind << "const int le" << x << " = tc" << x << " / " << Q * Q << ", pt0" << x << " = tc" << x << " % " << Q * Q << ";\n";
+      c << ind << "const long long ec" << x << " = (e0 + le" << x << " < b200a.num_elem) ? e0 + le" << x << " : b200a.num_elem - 1;\n";
+      c << ind << "const long long en" << x << " = (e0n + le" << x << " < b200a.num_elem) ? e0n + le" << x << " : b200a.num_elem - 1;\n";
+      for (size_t f = 0; f < plan->in_fields.size(); f++) {
+        const B200GenField &fd = plan->in_fields[f];
+        if (fd.ring_k < 0) continue;
+        const string sl = std::to_string(fd.slot);
+        c << ind << "const double *qc" << f << x << " = b200a.in_ptr[" << sl << "] + " << lidx(fd.rstr, "", "ec" + x, "pt0" + x, "0") << ";\n";
+        c << ind << "const double *qn" << f << x << " = b200a.in_ptr[" << sl << "] + " << lidx(fd.rstr, "", "en" + x, "pt0" + x, "0") << ";\n";
+      }
+    }
+  }
+  void emit_ring_issue(const RingStep &st, int slot, const string &ind) {
+    const int    slot_doubles = TS * plan->ring_comps;
+    const string x            = "_" + std::to_string(st.round);
+    for (size_t f = 0; f < plan->in_fields.size(); f++) {
+      const B200GenField &fd = plan->in_fields[f];
+      if (fd.ring_k < 0) continue;
+      for (int cc = 0; cc < fd.nc; cc++) {
+        const long long goff = (long long)cc * fd.rstr->strides[1] + (long long)st.qz * Q * Q * fd.rstr->strides[0];
+        c << ind << "b200_cp8(ring + " << slot * slot_doubles + (fd.ring_k + cc) * TS << " + lane, " << (st.next ? "qn" : "qc") << f << x << " + " << goff << "LL);\n";
+      }
+    }
+    c << ind << "b200_cp_commit();\n";
+  }
+  RingStep ring_step(int s) const {
+    const int S = plan->ring_rounds * Q;
+    RingStep  st;
+    st.next = s >= S;
+    if (st.next) s -= S;
+    st.round = s / Q;
+    st.qz    = s % Q;
+    return st;
+  }
+  // prologue (before the batch loop): the first D steps of the first group of this warp
+  void emit_ring_prologue() {
+    c << "static __device__ __noinline__ void b200_ring_prologue(const long long e0) {\n";
+    c << smw_decl();
+    c << "  const int lane = " << TID << ";\n  const long long e0n = e0;\n";
+    c << "  double *const ring = " << smem_at(plan->ring_off, "double") << ";\n";
+    emit_ring_bases("  ");
+    for (int s = 0; s < plan->ring_slots - 1; s++) emit_ring_issue(ring_step(s), s % plan->ring_slots, "  ");
+    c << "}\n\n";
+  }
+
+  void emit_qf_stage_ring() {
+    B200QFunction qf     = op->qf;
+    const int     D      = plan->ring_slots - 1, NS = plan->ring_slots;
+    const int     ntasks = E * Q * Q, S = plan->ring_rounds * Q;
+    const int     slot_doubles = TS * plan->ring_comps;
+    comment("quadrature points: one z-line per thread; d/dz, QFunction, (d/dz)^T in registers; quadrature data through the cp.async ring");
+    const string name = "b200_stage_" + std::to_string(n_stage++);
+    c << "static __device__ __noinline__ void " << name << "(const long long e0, const long long e0n) {\n";
+    c << smw_decl();
+    calls.push_back("    " + name + "(e0, e0n);\n");
+    c << "    const int lane = " << TID << ";\n";
+    c << "    double *const ring = " << smem_at(plan->ring_off, "double") << ";\n";
+    emit_ring_bases("    ");
+    c << "    const CeedScalar *in[" << std::max<size_t>(1, qf->inputs.size()) << "];\n";
+    c << "    CeedScalar *out[" << std::max<size_t>(1, qf->outputs.size()) << "];\n";
+    for (size_t f = 0; f < plan->in_fields.size(); f++) c << "    CeedScalar in_" << f << "[" << plan->in_fields[f].size << "];\n";
+    for (size_t f = 0; f < plan->out_fields.size(); f++) c << "    CeedScalar out_" << f << "[" << plan->out_fields[f].size << "];\n";
+    for (size_t f = 0; f < plan->in_fields.size(); f++) c << "    in[" << f << "] = in_" << f << ";\n";
+    for (size_t f = 0; f < plan->out_fields.size(); f++) c << "    out[" << f << "] = out_" << f << ";\n";
+    for (int r = 0; r < plan->ring_rounds; r++) {
+      const string x = "_" + std::to_string(r);
+      c << "    {  // task round " << r << "\n";
+      c << "      const int le = le" << x << ", qx = pt0" << x << " % " << Q << ", qy = pt0" << x << " / " << Q << ";\n";
+      c << "      const long long e = ec" << x << ";\n";
+      c << "      const bool act = t" << x << " < " << ntasks << " && e0 + le < b200a.num_elem;\n";
+      c << "      const int pxy = qy * " << Qs << " + qx, pt0 = pt0" << x << ";\n";
+      c << "      (void)e; (void)pt0;\n";
+      for (size_t gi = 0; gi < plan->in_groups.size(); gi++) {
+        const B200GenGroup &g = plan->in_groups[gi];
+        if (!g.use_grad) continue;
+        for (int cc = 0; cc < g.nc; cc++) {
+          const string tag = "g" + std::to_string(gi) + "c" + std::to_string(cc) + "_";
+          c << "      const double *uq_" << tag << " = " << plane(g.plane0 + cc, "le") << " + pxy;\n";
+          for (int m = 0; m < Q; m++) c << "      const double uz_" << tag << m << " = uq_" << tag << "[" << m * Q * Qs << "];\n";
+          contract("cG" + std::to_string(g.basis_id), Q, Q, false, "uz_" + tag, "dz_" + tag, "      ");
+        }
+      }
+      for (size_t gi = 0; gi < plan->out_groups.size(); gi++) {
+        const B200GenGroup &g = plan->out_groups[gi];
+        if (!g.use_grad) continue;
+        for (int cc = 0; cc < g.nc; cc++)
+          for (int m = 0; m < Q; m++) c << "      double vz_g" << gi << "c" << cc << "_" << m << " = 0.0;\n";
+      }
+      for (size_t f = 0; f < plan->in_fields.size(); f++)
+        if (plan->in_fields[f].emode == B200_EVAL_WEIGHT) {
+          const string w = "cW" + std::to_string(plan->in_fields[f].basis_id);
+          c << "      const double wxy_" << f << " = " << w << "[qx] * " << w << "[qy];\n";
+        }
+      for (int qz = 0; qz < Q; qz++) {
+        const int s = r * Q + qz;
+        c << "      {  // step " << s << ": qz = " << qz << "\n";
+        c << "        asm volatile(\"cp.async.wait_group " << D - 1 << ";\" ::: \"memory\");\n";
+        c << "        const int p = pxy + " << qz * Q * Qs << ";\n";
+        c << "        const int pt = pt0 + " << qz * Q * Q << ";\n        (void)pt;\n";
+        // ring values into registers first (the slot is re-used D steps later), then refill the ring, then compute
+        for (size_t f = 0; f < plan->in_fields.size(); f++) {
+          const B200GenField &fd = plan->in_fields[f];
+          if (fd.ring_k < 0) continue;
+          for (int cc = 0; cc < fd.nc; cc++)
+            c << "        in_" << f << "[" << cc << "] = ring[" << (s % NS) * slot_doubles + (fd.ring_k + cc) * TS << " + lane];\n";
+        }
+        emit_ring_issue(ring_step(s + D), (s + D) % NS, "        ");
+        c << "        if (act) {\n";
+        for (size_t f = 0; f < plan->in_fields.size(); f++) {
+          const B200GenField &fd = plan->in_fields[f];
+          const string        sl = std::to_string(fd.slot);
+          switch (fd.emode) {
+            case B200_EVAL_NONE:
+              if (fd.ring_k >= 0) break;
+              for (int cc = 0; cc < fd.nc; cc++) {
+                if (fd.qd_off >= 0)
+                  c << "        in_" << f << "[" << cc << "] = " << smem_at(fd.qd_off, "const double") << "[(" << cc * E << " + le) * " << Q * Q * Q << " + pt];\n";
+                else
+                  c << "        in_" << f << "[" << cc << "] = __ldg(b200a.in_ptr[" << sl << "] + " << lidx(fd.rstr, "b200a.in_idx[" + sl + "]", "e", "pt", std::to_string(cc)) << ");\n";
+              }
+              break;
+            case B200_EVAL_WEIGHT: c << "        in_" << f << "[0] = wxy_" << f << " * cW" << fd.basis_id << "[" << qz << "];\n"; break;
+            case B200_EVAL_INTERP: {
+              const B200GenGroup &g = plan->in_groups[fd.group];
+              for (int cc = 0; cc < fd.nc; cc++) {
+                if (g.use_grad) c << "        in_" << f << "[" << cc << "] = uz_g" << fd.group << "c" << cc << "_" << qz << ";\n";
+                else c << "        in_" << f << "[" << cc << "] = (" << plane(g.plane0 + cc, "le") << ")[p];\n";
+              }
+            } break;
+            case B200_EVAL_GRAD: {
+              const B200GenGroup &g = plan->in_groups[fd.group];
+              for (int cc = 0; cc < fd.nc; cc++) {
+                c << "        in_" << f << "[" << cc << "] = (" << plane(g.plane0 + 2 * g.nc + cc, "le") << ")[p];\n";
+                c << "        in_" << f << "[" << cc + fd.nc << "] = (" << plane(g.plane0 + g.nc + cc, "le") << ")[p];\n";
+                c << "        in_" << f << "[" << cc + 2 * fd.nc << "] = dz_g" << fd.group << "c" << cc << "_" << qz << ";\n";
+              }
+            } break;
+          }
+        }
+        c << "        " << qf->kernel_name << "(b200a.ctx, 1, in, out);\n";
+        for (size_t gi = 0; gi < plan->out_groups.size(); gi++) {
+          const B200GenGroup &g = plan->out_groups[gi];
+          for (int cc = 0; cc < g.nc; cc++) {
+            string val;
+            for (size_t f = 0; f < plan->out_fields.size(); f++) {
+              const B200GenField &fd = plan->out_fields[f];
+              if (fd.group == (int)gi && fd.emode == B200_EVAL_INTERP) val += (val.empty() ? "" : " + ") + ("out_" + std::to_string(f) + "[" + std::to_string(cc) + "]");
+            }
+            if (!val.empty()) c << "        (" << plane(g.plane0 + cc, "le") << ")[p] = " << val << ";\n";
+            if (g.use_grad) {
+              string vx, vy, vz;
+              for (size_t f = 0; f < plan->out_fields.size(); f++) {
+                const B200GenField &fd = plan->out_fields[f];
+                if (fd.group == (int)gi && fd.emode == B200_EVAL_GRAD) {
+                  const string o = "out_" + std::to_string(f);
+                  vx += (vx.empty() ? "" : " + ") + o + "[" + std::to_string(cc) + "]";
+                  vy += (vy.empty() ? "" : " + ") + o + "[" + std::to_string(cc + fd.nc) + "]";
+                  vz += (vz.empty() ? "" : " + ") + o + "[" + std::to_string(cc + 2 * fd.nc) + "]";
+                }
+              }
+              c << "        (" << plane(g.plane0 + 2 * g.nc + cc, "le") << ")[p] = " << vx << ";\n";
+              c << "        (" << plane(g.plane0 + g.nc + cc, "le") << ")[p] = " << vy << ";\n";
+              c << "        { const double vz = " << vz << ";\n";
+              for (int m = 0; m < Q; m++)
+                c << "          vz_g" << gi << "c" << cc << "_" << m << " = fma(cG" << g.basis_id << "[" << qz * Q + m << "], vz, vz_g" << gi << "c" << cc
+                  << "_" << m << ");\n";
+              c << "        }\n";
+            }
+          }
+        }
+        for (size_t f = 0; f < plan->out_fields.size(); f++) {
+          const B200GenField &fd = plan->out_fields[f];
+          if (fd.emode != B200_EVAL_NONE) continue;
+          emit_scatter_value(fd.rstr, fd.slot, "e", "pt", fd.nc, [&](int cc) { return "out_" + std::to_string(f) + "[" + std::to_string(cc) + "]"; },
+                             "        ");
+        }
+        c << "        }\n";  // act
+        c << "      }\n";    // step
+      }
+      c << "      if (act) {\n";
+      for (size_t gi = 0; gi < plan->out_groups.size(); gi++) {
+        const B200GenGroup &g = plan->out_groups[gi];
+        if (!g.use_grad) continue;
+        for (int cc = 0; cc < g.nc; cc++) {
+          c << "      { double *vq = " << plane(g.plane0 + cc, "le") << " + pxy;\n";
+          for (int m = 0; m < Q; m++)
+            c << "        vq[" << m * Q * Qs << "] " << (g.use_interp ? "+=" : "=") << " vz_g" << gi << "c" << cc << "_" << m << ";\n";
+          c << "      }\n";
+        }
+      }
+      c << "      }\n";
+      c << "    }\n";  // round
+    }
+    (void)S;
+    c << "}\n\n";
+  }
+
   // ---- output side ------------------------------------------------------------------------------
   // Add `value(cc)` for E-entry n of element e into the L-vector of restriction r (output slot `slot`).
   template <typename F>
@@ -890,28 +1194,28 @@ struct Gen {
     const string sl = std::to_string(slot);
     if (r->is_strided) {
       for (int cc = 0; cc < nc; cc++)
-        c << ind << "a.out_ptr[" << sl << "][" << lidx(r, "", e, n, std::to_string(cc)) << "] " << (add ? "+=" : "=") << " " << value(cc) << ";\n";
+        c << ind << "b200a.out_ptr[" << sl << "][" << lidx(r, "", e, n, std::to_string(cc)) << "] " << (add ? "+=" : "=") << " " << value(cc) << ";\n";
       return;
     }
     const long long e_entries = (long long)r->num_elem * r->elem_size;
     switch (plan->scatter_mode) {
       case B200_SCATTER_ATOMIC:
         for (int cc = 0; cc < nc; cc++)
-          c << ind << "atomicAdd(a.out_ptr[" << sl << "] + " << lidx(r, "a.out_idx[" + sl + "]", e, n, std::to_string(cc)) << ", " << value(cc) << ");\n";
+          c << ind << "atomicAdd(b200a.out_ptr[" << sl << "] + " << lidx(r, "b200a.out_idx[" + sl + "]", e, n, std::to_string(cc)) << ", " << value(cc) << ");\n";
         break;
       case B200_SCATTER_EVECTOR:
         for (int cc = 0; cc < nc; cc++)
-          c << ind << "a.out_aux[" << sl << "][(" << e << ") * " << r->elem_size << "LL + (" << n << ") + " << cc * e_entries << "LL] = " << value(cc)
+          c << ind << "b200a.out_aux[" << sl << "][(" << e << ") * " << r->elem_size << "LL + (" << n << ") + " << cc * e_entries << "LL] = " << value(cc)
             << ";\n";
         break;
       default:
-        c << ind << "{ const int tg = a.out_idx[" << sl << "][(" << e << ") * " << r->elem_size << "LL + (" << n << ")];\n";
+        c << ind << "{ const int tg = b200a.out_idx[" << sl << "][(" << e << ") * " << r->elem_size << "LL + (" << n << ")];\n";
         c << ind << "  if (tg >= 0) {\n";
         for (int cc = 0; cc < nc; cc++)
-          c << ind << "    a.out_ptr[" << sl << "][tg + " << (long long)cc * r->comp_stride << "LL] " << (add ? "+=" : "=") << " " << value(cc) << ";\n";
+          c << ind << "    b200a.out_ptr[" << sl << "][tg + " << (long long)cc * r->comp_stride << "LL] " << (add ? "+=" : "=") << " " << value(cc) << ";\n";
         c << ind << "  } else {\n";
         for (int cc = 0; cc < nc; cc++)
-          c << ind << "    a.out_aux[" << sl << "][(long long)(~tg) + " << (long long)cc * r->num_halo << "LL] = " << value(cc) << ";\n";
+          c << ind << "    b200a.out_aux[" << sl << "][(long long)(~tg) + " << (long long)cc * r->num_halo << "LL] = " << value(cc) << ";\n";
         c << ind << "  } }\n";
     }
   }
@@ -989,7 +1293,7 @@ struct Gen {
       for (int q = 0; q < Q; q++) c << "      const double u" << q << " = src[" << q * P * P << "];\n";
       contract("cB" + std::to_string(g.basis_id), Q, P, true, "u", "r", "      ");
     }
-    c << "      if (e < a.num_elem) {\n";
+    c << "      if (e < b200a.num_elem) {\n";
     // component handled through the (runtime) cc: emit with nc == 1 semantics and an explicit component offset
     for (int k = 0; k < P; k++) {
       const string n = "ij + " + std::to_string(k * P * P);
@@ -1007,25 +1311,25 @@ struct Gen {
                          const string &index = "") {
     const string sl = std::to_string(slot);
     if (r->is_strided) {
-      c << ind << "a.out_ptr[" << sl << "][" << lidx(r, "", e, n, cc) << "] " << (add ? "+=" : "=") << " " << val << ";\n";
+      c << ind << "b200a.out_ptr[" << sl << "][" << lidx(r, "", e, n, cc) << "] " << (add ? "+=" : "=") << " " << val << ";\n";
       return;
     }
     const long long e_entries = (long long)r->num_elem * r->elem_size;
-    const string    entry     = index.empty() ? "a.out_idx[" + sl + "][(" + e + ") * " + std::to_string(r->elem_size) + "LL + (" + n + ")]" : index;
+    const string    entry     = index.empty() ? "b200a.out_idx[" + sl + "][(" + e + ") * " + std::to_string(r->elem_size) + "LL + (" + n + ")]" : index;
     switch (plan->scatter_mode) {
       case B200_SCATTER_ATOMIC:
-        c << ind << "atomicAdd(a.out_ptr[" << sl << "] + ((long long)" << entry << " + (long long)(" << cc << ") * " << r->comp_stride << "LL), " << val
+        c << ind << "atomicAdd(b200a.out_ptr[" << sl << "] + ((long long)" << entry << " + (long long)(" << cc << ") * " << r->comp_stride << "LL), " << val
           << ");\n";
         break;
       case B200_SCATTER_EVECTOR:
-        c << ind << "a.out_aux[" << sl << "][(" << e << ") * " << r->elem_size << "LL + (" << n << ") + " << cc << " * " << e_entries << "LL] = " << val
+        c << ind << "b200a.out_aux[" << sl << "][(" << e << ") * " << r->elem_size << "LL + (" << n << ") + " << cc << " * " << e_entries << "LL] = " << val
           << ";\n";
         break;
       default:
         c << ind << "{ const int tg = " << entry << ";\n";
-        c << ind << "  if (tg >= 0) a.out_ptr[" << sl << "][tg + " << cc << " * " << (long long)r->comp_stride << "LL] " << (add ? "+=" : "=") << " " << val
+        c << ind << "  if (tg >= 0) b200a.out_ptr[" << sl << "][tg + " << cc << " * " << (long long)r->comp_stride << "LL] " << (add ? "+=" : "=") << " " << val
           << ";\n";
-        c << ind << "  else a.out_aux[" << sl << "][(long long)(~tg) + " << cc << " * " << (long long)r->num_halo << "LL] = " << val << "; }\n";
+        c << ind << "  else b200a.out_aux[" << sl << "][(long long)(~tg) + " << cc << " * " << (long long)r->num_halo << "LL] = " << val << "; }\n";
     }
   }
 
@@ -1035,10 +1339,13 @@ struct Gen {
     E  = plan->epb;
     NT = plan->threads;
     warp_mode = plan->warp_mode;
-    TS        = warp_mode ? 32 : NT;
-    TID       = warp_mode ? "(threadIdx.x & 31)" : "threadIdx.x";
+    TS        = warp_mode ? 32 * plan->group_warps : NT;
+    TID       = warp_mode ? "(threadIdx.x & " + std::to_string(TS - 1) + ")" : "threadIdx.x";
     SMBASE    = warp_mode ? "smw" : "sm";
-    SYNC      = warp_mode ? "__syncwarp();" : "__syncthreads();";
+    // a group of one warp synchronises with __syncwarp(); wider groups meet at their own named barrier (ids 1..15)
+    if (!warp_mode || NT == TS) SYNC = "__syncthreads();";
+    else if (plan->group_warps == 1) SYNC = "__syncwarp();";
+    else SYNC = "asm volatile(\"bar.sync %0, " + std::to_string(TS) + ";\" ::\"r\"((int)(threadIdx.x / " + std::to_string(TS) + ") + 1) : \"memory\");";
     S  = plan->plane_size;
     emit_header();
     bool any;
@@ -1049,7 +1356,7 @@ struct Gen {
       // the offsets buffer has been consumed by the gather stage: stream in the next group's offsets
       bool any_idx = false;
       for (auto &g : plan->in_groups) any_idx = any_idx || g.idx_off >= 0;
-      if (any_idx && !plan->in_groups.empty()) calls.push_back("    b200_issue_idx(a, e0n);\n    b200_cp_commit();\n");
+      if (any_idx && !plan->in_groups.empty()) calls.push_back("    b200_issue_idx(e0n);\n    b200_cp_commit();\n");
     }
     any = false;
     for (auto &g : plan->in_groups) any = any || !basis(g.basis_id).collocated;
@@ -1075,10 +1382,10 @@ struct Gen {
     if (has_gather) {
       // before the quadrature stage: the offsets of the next batch have landed (issued at the top of this batch) and the
       // gather buffer is free (the z-stage consumed it) -> start gathering the next batch's inputs
-      if (!calls.empty() && calls.back().find("__sync") != string::npos) calls.pop_back();
-      calls.push_back("    b200_cp_wait_all();\n    " + SYNC + "\n    b200_issue_gather(a, e0n);\n    b200_cp_commit();\n");
+      if (!calls.empty() && calls.back() == "    " + SYNC + "\n") calls.pop_back();
+      calls.push_back("    b200_cp_wait_all();\n    " + SYNC + "\n    b200_issue_gather(e0n);\n    b200_cp_commit();\n");
     } else if (has_tgt) {
-      if (!calls.empty() && calls.back().find("__sync") != string::npos) calls.pop_back();
+      if (!calls.empty() && calls.back() == "    " + SYNC + "\n") calls.pop_back();
       calls.push_back("    b200_cp_wait_all();\n    " + SYNC + "\n");
     }
     if (plan->qf_pointwise) {
@@ -1089,12 +1396,15 @@ struct Gen {
         barrier();
       }
       emit_qf_points();
+    } else if (plan->ring_off >= 0) {
+      emit_ring_prologue();
+      emit_qf_stage_ring();
     } else {
       emit_qf_stage();
     }
     if (!plan->out_groups.empty() || has_qd) barrier();
     // the quadrature-data buffer is free again: stream in the next batch's data behind the transpose stages
-    if (has_qd) calls.push_back("    b200_issue_qd(a, e0n);\n    b200_cp_commit();\n");
+    if (has_qd) calls.push_back("    b200_issue_qd(e0n);\n    b200_cp_commit();\n");
     if (!plan->out_groups.empty()) {
       any = false;
       for (auto &g : plan->out_groups) any = any || g.use_grad;
@@ -1126,9 +1436,9 @@ struct Gen {
     // HBM traffic) and the element offsets, so that the demand loads a few microseconds later hit in the 126 MB L2.
     const bool prefetch = getenv("CEED_B200_PREFETCH") != nullptr;
     if (prefetch) {
-      c << "static __device__ __noinline__ void b200_prefetch(const B200OpArgs &a, const long long e0) {\n";
-      c << "  if (e0 >= a.num_elem) return;\n";
-      c << "  const long long ne = (a.num_elem - e0 < " << E << ") ? a.num_elem - e0 : " << E << ";\n";
+      c << "static __device__ __noinline__ void b200_prefetch(const long long e0) {\n";
+      c << "  if (e0 >= b200a.num_elem) return;\n";
+      c << "  const long long ne = (b200a.num_elem - e0 < " << E << ") ? b200a.num_elem - e0 : " << E << ";\n";
       c << smw_decl();
       auto emit_range = [&](const string &ptr, const string &first_elem_expr, long long bytes_per_elem) {
         // byte range [p0, p0 + ne * bytes_per_elem), one 128-byte line per thread per round
@@ -1143,39 +1453,40 @@ struct Gen {
         // contiguous per (component, element) when the node stride is 1
         for (int cc = 0; cc < fd.nc; cc++) {
           if (fd.rstr->strides[2] == fd.rstr->elem_size) {
-            emit_range("a.in_ptr[" + std::to_string(fd.slot) + "] + " + std::to_string((long long)cc * fd.rstr->strides[1]) + "LL", "e0", 8LL * fd.rstr->elem_size);
+            emit_range("b200a.in_ptr[" + std::to_string(fd.slot) + "] + " + std::to_string((long long)cc * fd.rstr->strides[1]) + "LL", "e0", 8LL * fd.rstr->elem_size);
           }
         }
       }
       for (auto &g : plan->in_groups)
-        if (!g.rstr->is_strided) emit_range("a.in_idx[" + std::to_string(g.slot) + "]", "e0", 4LL * g.rstr->elem_size);
+        if (!g.rstr->is_strided) emit_range("b200a.in_idx[" + std::to_string(g.slot) + "]", "e0", 4LL * g.rstr->elem_size);
       c << "}\n\n";
     }
-    c << "extern \"C\" __global__ void __launch_bounds__(" << NT << ", " << minb << ") b200_operator_" << op->qf->kernel_name << "(const __grid_constant__ B200OpArgs a) {\n";
-    c << "  const long long num_batches = (a.num_elem + " << E - 1 << ") / " << E << ";\n";
+    c << "extern \"C\" __global__ void __launch_bounds__(" << NT << ", " << minb << ") b200_operator_" << op->qf->kernel_name << "() {\n";
+    c << "  const long long num_batches = (b200a.num_elem + " << E - 1 << ") / " << E << ";\n";
     // block mode: one batch per CTA per iteration; warp mode: one group per warp per iteration
-    const string first  = warp_mode ? "((long long)blockIdx.x * " + std::to_string(NT / 32) + " + (threadIdx.x >> 5))" : "(long long)blockIdx.x";
-    const string stride = warp_mode ? "((long long)gridDim.x * " + std::to_string(NT / 32) + ")" : "(long long)gridDim.x";
+    const string first  = warp_mode ? "((long long)blockIdx.x * " + std::to_string(NT / TS) + " + (threadIdx.x / " + std::to_string(TS) + "))" : "(long long)blockIdx.x";
+    const string stride = warp_mode ? "((long long)gridDim.x * " + std::to_string(NT / TS) + ")" : "(long long)gridDim.x";
     if (staged) {
       // prologue: stage the first batch
       c << "  if (" << first << " < num_batches) {\n";
       c << "    const long long e0 = " << first << " * " << E << ";\n";
-      if (has_idx) c << "    b200_issue_idx(a, e0);\n    b200_cp_commit();\n    b200_cp_wait_all();\n    " << SYNC << "\n";
-      if (has_gather) c << "    b200_issue_gather(a, e0);\n";
-      if (has_qd) c << "    b200_issue_qd(a, e0);\n";
+      if (has_idx) c << "    b200_issue_idx(e0);\n    b200_cp_commit();\n    b200_cp_wait_all();\n    " << SYNC << "\n";
+      if (has_gather) c << "    b200_issue_gather(e0);\n";
+      if (has_qd) c << "    b200_issue_qd(e0);\n";
       c << "    b200_cp_commit();\n  }\n";
     }
+    if (plan->ring_off >= 0 && !plan->qf_pointwise) c << "  if (" << first << " < num_batches) b200_ring_prologue(" << first << " * " << E << ");\n";
     c << "  for (long long batch = " << first << "; batch < num_batches; batch += " << stride << ") {\n";
     c << "    const long long e0 = batch * " << E << ", e0n = (batch + " << stride << ") * " << E << ";\n";
     if (staged) {
       // everything staged for this batch is visible after this point; all reads of the previous batch are done
       c << "    b200_cp_wait_all();\n    " << SYNC << "\n";
-      if (has_tgt) c << "    b200_issue_tgt(a, e0);\n";
+      if (has_tgt) c << "    b200_issue_tgt(e0);\n";
       c << "    b200_cp_commit();\n";
     } else {
       c << "    (void)e0n;\n";
     }
-    if (prefetch) c << "    b200_prefetch(a, e0n);\n";
+    if (prefetch) c << "    b200_prefetch(e0n);\n";
     for (auto &call : calls) c << call;
     c << "  }\n}\n";
     return c.str();
@@ -1200,6 +1511,11 @@ int b200_opgen_build(B200Operator op, B200OpPlan *plan, int add) {
   B200_CALL(b200_jit_compile(ceed, v.source, {}, &v.module));
   B200_CALL(b200_jit_get_kernel(ceed, v.module, ("b200_operator_" + op->qf->kernel_name).c_str(), &v.kernel));
   if (!b200_compile_only()) {
+    if (!v.module->args_dptr) {
+      size_t bytes = 0;
+      B200_CU(ceed, cuModuleGetGlobal(&v.module->args_dptr, &bytes, v.module->module, "b200a"));
+      B200_CHECK(bytes == sizeof(B200OpArgs), ceed, B200_ERROR_BACKEND, "generated argument block has %zu bytes, expected %zu", bytes, sizeof(B200OpArgs));
+    }
     B200_CU(ceed, cuFuncSetAttribute(v.kernel, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, plan->smem_bytes));
     int val = 0;
     cuFuncGetAttribute(&val, CU_FUNC_ATTRIBUTE_NUM_REGS, v.kernel);
@@ -1211,9 +1527,12 @@ int b200_opgen_build(B200Operator op, B200OpPlan *plan, int add) {
     int nb = 0;
     B200_CU(ceed, cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.kernel, plan->threads, plan->smem_bytes));
     if (nb < 1) return b200_error(ceed, B200_ERROR_BACKEND, "fused kernel cannot be resident (regs %d, smem %d)", v.regs, plan->smem_bytes);
-    plan->blocks_per_sm = op->tune_bpsm > 0 ? std::min(nb, op->tune_bpsm) : nb;
+    plan->blocks_per_sm = nb;
     long long num_batches = ((long long)plan->num_elem + plan->epb - 1) / plan->epb;
-    if (plan->warp_mode) num_batches = (num_batches + plan->threads / 32 - 1) / (plan->threads / 32);  // CTAs needed
+    if (plan->warp_mode) {
+      const int groups = plan->threads / (32 * plan->group_warps);
+      num_batches      = (num_batches + groups - 1) / groups;  // CTAs needed
+    }
     long long grid = (long long)plan->blocks_per_sm * ceed->num_sms;
     if (grid > num_batches) grid = num_batches;
     if (grid < 1) grid = 1;

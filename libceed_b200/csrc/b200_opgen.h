@@ -37,6 +37,7 @@ struct B200GenField {
   bool            is_active = false;
   int             slot = 0;
   int             qd_off = -1;    // EVAL_NONE inputs streamed with cp.async: [nc][E * Q^3] doubles (byte offset), -1 = direct loads
+  int             ring_k = -1;    // EVAL_NONE inputs prefetched through the per-lane ring: first component row in a ring slot
 };
 
 struct B200OpArgs {
@@ -68,8 +69,16 @@ struct B200OpPlan {
   bool                      warp_mode = true;    // one element group per warp, __syncwarp() only (see b200_opgen.cpp)
   int                       stage_mask = 1;      // which global reads are staged through cp.async (1 idx/tgt, 2 gather, 4 qdata)
   int                       group_smem_bytes = 0;  // shared memory of one element group (CTA in block mode, warp in warp mode)
+  int                       group_warps = 1;      // warps sharing one element group (warp mode)
   bool                      qf_pointwise = false; // QFunction over independent points, d/dz as separate line stages
   bool                      async_copy = true;  // stage global reads through cp.async one batch ahead
+  // z-line QFunction stage: per-lane cp.async ring for the streamed quadrature data.  A step = one z-layer of one task round;
+  // ring_slots - 1 steps are always in flight, ACROSS the other stages and across element groups.
+  int                       ring_off = -1, ring_slots = 0, ring_comps = 0, ring_rounds = 0;
+  int                       qf_pp = 1;           // pointwise QFunction stage: points per lane (2 = x-adjacent pair, 16-byte loads)
+  int                       qf_unroll = 4;       // pointwise QFunction stage: points in flight per lane
+  std::string               signature, shape_signature;  // tuning-table keys (with / without the QFunction name)
+  B200Tuning                resolved;            // the shape actually used
   std::vector<B200GenBasis> bases;
   std::vector<B200GenGroup> in_groups, out_groups;
   std::vector<B200GenField> in_fields, out_fields;

@@ -44,6 +44,40 @@ std::string b200_jit_dir() {
   return "libceed_b200/csrc/jit";
 }
 
+// Tuning table: one line per kernel signature, "<signature> epw group_warps cta_warps minb qf_mode qf_unroll stage [# comment]".
+// Loaded from <library dir>/../tuned/sm_100a.tune (shipped, produced by scripts/gpu_autotune.py on a B200) and from
+// CEED_B200_TUNE_FILE; later entries win.  CEED_B200_NO_TUNE_TABLE=1 ignores both (pure heuristics).
+static void b200_load_tune_file(B200Ceed ceed, const std::string &path) {
+  FILE *f = fopen(path.c_str(), "r");
+  if (!f) return;
+  char line[1024], sig[512];
+  while (fgets(line, sizeof(line), f)) {
+    if (line[0] == '#' || line[0] == '\n') continue;
+    B200Tuning t;
+    if (sscanf(line, "%511s %d %d %d %d %d %d %d", sig, &t.epw, &t.group_warps, &t.cta_warps, &t.minb, &t.qf_mode, &t.qf_unroll, &t.stage) == 8) {
+      ceed->tune_table[sig] = t;
+      // shape-only key (signature without the trailing |<QFunction name>): first entry of a shape serves unknown QFunctions
+      std::string s(sig);
+      size_t      pos = s.rfind('|');
+      if (pos != std::string::npos && !ceed->tune_table.count(s.substr(0, pos))) ceed->tune_table[s.substr(0, pos)] = t;
+    }
+  }
+  fclose(f);
+}
+
+static void b200_init_tuning(B200Ceed ceed) {
+  if (!getenv("CEED_B200_NO_TUNE_TABLE")) {
+    b200_load_tune_file(ceed, b200_jit_dir() + "/../../tuned/sm_100a.tune");
+    if (const char *path = getenv("CEED_B200_TUNE_FILE")) b200_load_tune_file(ceed, path);
+  }
+  if (const char *a = getenv("CEED_B200_AUTOTUNE")) ceed->autotune = atoi(a);
+}
+
+extern "C" int ceedb200_set_autotune(B200Ceed ceed, int level) {
+  ceed->autotune = level;
+  return B200_SUCCESS;
+}
+
 // Development aid: with CEED_B200_COMPILE_ONLY=1 a context can be created without a GPU so that the host-side
 // setup analysis, the kernel generator and NVRTC can be exercised (register/SASS inspection, CPU-only CI).
 // Device buffers are then host allocations and every kernel launch FAILS loudly -- nothing is ever computed on the CPU.
@@ -108,6 +142,7 @@ extern "C" int ceedb200_init(int device_id, B200Ceed *ceed_out) {
     ceed->smem_sm    = 233472;
     ceed->cc_major   = 10;
     ceed->jit_roots.push_back(b200_jit_dir());
+    b200_init_tuning(ceed);
     const char *mode = getenv("CEED_B200_SCATTER");
     if (mode && !strcmp(mode, "atomic")) ceed->scatter_mode = B200_SCATTER_ATOMIC;
     if (mode && !strcmp(mode, "evector")) ceed->scatter_mode = B200_SCATTER_EVECTOR;
@@ -149,6 +184,7 @@ extern "C" int ceedb200_init(int device_id, B200Ceed *ceed_out) {
     else ceed->scatter_mode = B200_SCATTER_DETERMINISTIC;
   }
   ceed->jit_roots.push_back(b200_jit_dir());
+  b200_init_tuning(ceed);
   *ceed_out = ceed;
   return B200_SUCCESS;
 }

@@ -33,12 +33,42 @@ def run(tag, env, epb=0, scatter=0):
         print(f"{tag:46s} FAILED {str(e)[:120]}", flush=True); return 1e9
     f, a = np.median([x[0] for x in t]), np.median([x[1] for x in t])
     i = op.kernel_info()
+    global vref
+    v = base.v.get_array_read().copy()
+    if vref is None: vref = v
+    err = np.abs(v - vref).max() / np.abs(vref).max()
+    if err > 1e-13: tag = tag + f" ERR={err:.1e}"
     print(f"{tag:46s} {f:.3f}+{a:.3f} ms {base.num_dofs/(f+a)/1e6:6.2f} GDoF/s {base.bytes_per_apply()/(f+a)/1e6/6550.1*100:5.1f}% regs={i['regs']} epw={i['elems_per_block']} "
           f"thr={i['threads']} grid={i['grid']} smem={i['smem_bytes']} loc={i['local_bytes']}", flush=True)
     return f + a
 
+vref = None
 print(f"{wl}: {base.num_dofs/1e6:.2f}M DoFs, {base.num_elem} elements")
-if mode == "opts":
+if mode == "pairs":
+    run("default", {})
+    run("pointwise", {"CEED_B200_QF_POINTWISE": "1"})
+    for gw, warps in ((1, 4), (1, 8), (2, 2), (2, 8), (4, 4)):
+        for unroll in (1, 2):
+            run(f"pairs gw={gw} warps={warps} unroll={unroll}", {"CEED_B200_QF_POINTWISE": "2", "CEED_B200_QF_UNROLL": str(unroll),
+                                                                  "CEED_B200_GROUP_WARPS": str(gw), "CEED_B200_WARPS": str(warps)})
+elif mode == "ring":
+    run("default", {})
+    for stage in (17, 19):
+        for ring in (2, 4, 8):
+            for warps in (2, 4, 5):
+                run(f"stage={stage} ring={ring} warps={warps}", {"CEED_B200_STAGE": str(stage), "CEED_B200_RING": str(ring), "CEED_B200_WARPS": str(warps)})
+    for gw, warps in ((2, 2), (2, 4), (4, 4)):
+        run(f"stage=17 ring=4 gw={gw} warps={warps}", {"CEED_B200_STAGE": "17", "CEED_B200_GROUP_WARPS": str(gw), "CEED_B200_WARPS": str(warps)})
+elif mode == "gw":
+    run("default", {})
+    for gw in (1, 2, 4):
+        for warps in (4, 8):
+            for qf in (0, 1):
+                for minb in (0,):
+                    env = {"CEED_B200_GROUP_WARPS": str(gw), "CEED_B200_WARPS": str(warps)}
+                    if qf: env["CEED_B200_QF_POINTWISE"] = "1"
+                    run(f"gw={gw} warps={warps} {'pointwise' if qf else 'zline'}", env)
+elif mode == "opts":
     run("default", {})
     run("atomic", {}, scatter=1)
     run("pointwise QF", {"CEED_B200_QF_POINTWISE": "1"})
