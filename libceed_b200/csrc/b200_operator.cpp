@@ -374,9 +374,11 @@ static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
   // 1. group width / warps per CTA x QFunction layout (elements per group and occupancy target left to the heuristics)
   const int shapes[][2] = {{1, 4}, {2, 2}, {2, 8}, {4, 4}, {1, 8}};
   for (auto &sh : shapes)
-    for (int qf = 0; qf < 2; qf++) {
+    for (int qf = 0; qf < 3; qf++) {
+      if (qf == 2 && op->plan->Q % 2) continue;  // point pairs need an even number of points per row
       B200Tuning t  = base;
       t.group_warps = sh[0], t.cta_warps = sh[1], t.qf_mode = qf;
+      if (qf == 2) t.qf_unroll = 2;
       trial(t);
     }
   // 2. elements per group around the winner
@@ -398,9 +400,23 @@ static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
       t.minb       = minb;
       trial(t);
     }
-    if (best.qf_mode == 1) {
-      B200Tuning t = best;
-      t.qf_unroll  = best.qf_unroll == 4 ? 8 : 4;
+    if (best.qf_mode >= 1) {
+      const B200Tuning win2 = best;
+      for (int unroll : {1, 2, 4, 8}) {
+        if (unroll == win2.qf_unroll || (win2.qf_mode == 2 && unroll > 4)) continue;
+        B200Tuning t = win2;
+        t.qf_unroll  = unroll;
+        trial(t);
+      }
+    }
+  }
+  // 4. cp.async staging: scatter targets only (1), + gather offsets (9), nothing (0)
+  {
+    const B200Tuning win = best;
+    for (int stage : {9, 0}) {
+      if (stage == win.stage) continue;
+      B200Tuning t = win;
+      t.stage      = stage;
       trial(t);
     }
   }

@@ -44,7 +44,14 @@ def run(tag, env, epb=0, scatter=0):
 
 vref = None
 print(f"{wl}: {base.num_dofs/1e6:.2f}M DoFs, {base.num_elem} elements")
-if mode == "pairs":
+if mode == "misc":
+    run("default (table)", {})
+    run("L2 prefetch", {"CEED_B200_PREFETCH": "1"})
+    run("stage=9", {"CEED_B200_STAGE": "9"})
+    run("stage=9 + L2 prefetch", {"CEED_B200_STAGE": "9", "CEED_B200_PREFETCH": "1"})
+    run("atomic", {}, scatter=1)
+    run("atomic + L2 prefetch", {"CEED_B200_PREFETCH": "1"}, scatter=1)
+elif mode == "pairs":
     run("default", {})
     run("pointwise", {"CEED_B200_QF_POINTWISE": "1"})
     for gw, warps in ((1, 4), (1, 8), (2, 2), (2, 8), (4, 4)):
