@@ -203,6 +203,15 @@ CEEDB200_EXPORT int ceedb200_operator_get_kernel_shape(B200Operator op, int *sha
  * in the tuning table, 2 always.  Same as the environment variable CEED_B200_AUTOTUNE. */
 CEEDB200_EXPORT int ceedb200_set_autotune(B200Ceed ceed, int level);
 
+/* ---- multi-GPU interface exchange (raw device pointers; the transport between the two calls is NCCL send/recv) ----------
+ * The reference has no communication layer: its examples delegate the interface sum to PETSc VecScatter ADD_VALUES
+ * (examples/petsc/bpsraw.c:240-262).  pack: send[i] = v[idx[i]].  unpack_sum: for interface entry i (L-index node[i]) sum the
+ * contributions src[ptr[i]..ptr[i+1]) in the given (ascending rank) order, src < 0 = this rank's own value v[node[i]],
+ * src >= 0 = recv[src]; the result overwrites v[node[i]]. */
+CEEDB200_EXPORT int ceedb200_iface_pack(B200Ceed ceed, const double *d_v, const long long *d_idx, long long n, double *d_send);
+CEEDB200_EXPORT int ceedb200_iface_unpack_sum(B200Ceed ceed, double *d_v, long long n, const long long *d_node, const int *d_ptr, const int *d_src,
+                                              const double *d_recv);
+
 #ifdef __cplusplus
 }
 #endif

@@ -115,6 +115,8 @@ def load(path=LIB_PATH):
         "ceedb200_operator_set_kernel_shape": [handle, P(C.c_int)],
         "ceedb200_operator_get_kernel_shape": [handle, P(C.c_int), C.c_char_p, C.c_int],
         "ceedb200_set_autotune": [handle, C.c_int],
+        "ceedb200_iface_pack": [handle, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p],
+        "ceedb200_iface_unpack_sum": [handle, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)

@@ -474,8 +474,10 @@ struct Gen {
     for (auto &g : plan->in_groups) {
       if (g.idx_off < 0) continue;
       const int es = g.rstr->elem_size;
+      // tail groups: the gather stage runs branch-free on clamped element numbers, so every slot gets valid offsets
       c << "  { int *dst = " << smem_at(g.idx_off, "int") << "; const int *src = b200a.in_idx[" << g.slot << "] + e0 * " << es << "LL;\n";
-      c << "    for (int i = " << TID << "; i < ne * " << es << "; i += " << TS << ") b200_cp4(dst + i, src + i); }\n";
+      c << "    for (int i = " << TID << "; i < " << E * es << "; i += " << TS << ") b200_cp4(dst + i, src + (i < ne * " << es << " ? i : (ne - 1) * " << es
+        << " + i % " << es << ")); }\n";
     }
     c << "}\n\n";
     return true;

@@ -421,3 +421,37 @@ extern "C" int ceedb200_vector_pointwise_mult(B200Vector w, B200Vector x, B200Ve
   if (w->length > 0) LAUNCH(w->ceed, k_pointwise_mult, w->length, dw, dx, dy, w->length);
   return B200_SUCCESS;
 }
+
+// ------------------------------------------------------------------------------------------------ interface exchange
+// Multi-GPU element partition (behaviour reference examples/petsc/bpsraw.c:240-262, the PETSc
+// VecScatter ADD_VALUES the reference examples delegate to): every rank owns a local L-vector with copies of the interface
+// nodes.  After the local operator apply, k_iface_pack gathers this rank's partial sums of all interface entries into one
+// send buffer (one contiguous segment per neighbour), the segments travel with NCCL send/recv, and k_iface_unpack_sum
+// rebuilds every interface entry as the sum of all partial values in ASCENDING RANK ORDER (own value at its place), so all
+// copies of a node carry identical bits on every rank.
+namespace {
+__global__ void k_iface_pack(const double *__restrict__ v, const long long *__restrict__ idx, long long n, double *__restrict__ send) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) send[i] = v[idx[i]];
+}
+__global__ void k_iface_unpack_sum(double *__restrict__ v, long long n, const long long *__restrict__ node, const int *__restrict__ ptr,
+                                   const int *__restrict__ src, const double *__restrict__ recv) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long l = node[i];
+    const int       b = ptr[i], e = ptr[i + 1];
+    double          acc = src[b] < 0 ? v[l] : recv[src[b]];
+    for (int k = b + 1; k < e; k++) acc += src[k] < 0 ? v[l] : recv[src[k]];
+    v[l] = acc;
+  }
+}
+}  // namespace
+
+extern "C" int ceedb200_iface_pack(B200Ceed ceed, const double *d_v, const long long *d_idx, long long n, double *d_send) {
+  if (n > 0) LAUNCH(ceed, k_iface_pack, n, d_v, d_idx, n, d_send);
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_iface_unpack_sum(B200Ceed ceed, double *d_v, long long n, const long long *d_node, const int *d_ptr, const int *d_src,
+                                         const double *d_recv) {
+  if (n > 0) LAUNCH(ceed, k_iface_unpack_sum, n, d_v, n, d_node, d_ptr, d_src, d_recv);
+  return B200_SUCCESS;
+}

@@ -333,6 +333,81 @@ def test_tail_batches_and_tuning(cm, oracle):
         assert rel(prob.v.get_array_read(), oracle.bp_apply(bp, p, prob.offsets, prob.num_nodes, qd, u)) < OP_TOL
 
 
+SHAPES = [dict(group_warps=2, cta_warps=2), dict(group_warps=2, cta_warps=8), dict(group_warps=4, cta_warps=4), dict(qf_mode=1, qf_unroll=2),
+          dict(qf_mode=2, qf_unroll=2), dict(qf_mode=2, group_warps=2, cta_warps=4, elems_per_group=3), dict(stage_mask=17), dict(stage_mask=9),
+          dict(stage_mask=0, cta_warps=1), dict(stage_mask=19, group_warps=2, cta_warps=4)]
+
+
+@pytest.mark.parametrize("bp,p,nel", [(3, 2, (5, 3, 2)), (5, 3, (3, 3, 2)), (1, 3, (4, 3, 3)), (6, 2, (3, 2, 2)), (3, 4, (3, 2, 2))])
+def test_kernel_shapes_give_identical_results(cm, oracle, monkeypatch, bp, p, nel):
+    """Every kernel shape the autotuner may pick (multi-warp groups, pointwise / point-pair QFunction stage, cp.async staging
+    variants incl. the quadrature-data ring) computes the same operator: compared with the oracle and with the default shape."""
+    monkeypatch.setenv("CEED_B200_NO_TUNE_TABLE", "1")  # knobs a shape leaves open come from the heuristics, not the table
+    prob = make_problem(cm, bp, p, nel)
+    u = seeded_uniform(prob.num_dofs, 23)
+    prob.u.set_array(u)
+    qd = oracle.bp_qdata(bp, p, prob.offsets, prob.coords)
+    ref = oracle.bp_apply(bp, p, prob.offsets, prob.num_nodes, qd, u)
+    prob.op.apply(prob.u, prob.v)
+    v0 = prob.v.get_array_read()
+    assert rel(v0, ref) < OP_TOL
+    for shape in SHAPES:
+        prob.op.set_kernel_shape(**shape)
+        prob.v.set_value(-7.0)
+        prob.op.apply(prob.u, prob.v)
+        got = prob.op.get_kernel_shape()
+        for k, val in shape.items():
+            if k == "qf_mode" and val == 2 and (p + BP_TABLE[bp][2]) % 2:
+                continue  # point pairs fall back to single points for odd Q
+            assert got[k] == val, (shape, got)
+        assert rel(prob.v.get_array_read(), ref) < OP_TOL, shape
+        assert rel(prob.v.get_array_read(), v0) < 1e-13, shape
+
+
+def test_autotuner_picks_a_shape_and_keeps_results(cm, oracle, tmp_path, monkeypatch):
+    bp, p, nel = 3, 3, (12, 12, 12)
+    monkeypatch.setenv("CEED_B200_TUNE_SAVE", str(tmp_path / "t.tune"))
+    monkeypatch.setenv("CEED_B200_NO_TUNE_TABLE", "1")
+    prob = make_problem(cm, bp, p, nel)
+    prob.ceed.set_autotune(2)
+    u = seeded_uniform(prob.num_dofs, 29)
+    prob.u.set_array(u)
+    prob.op.apply(prob.u, prob.v)  # tunes on this call
+    qd = oracle.bp_qdata(bp, p, prob.offsets, prob.coords)
+    assert rel(prob.v.get_array_read(), oracle.bp_apply(bp, p, prob.offsets, prob.num_nodes, qd, u)) < OP_TOL
+    line = open(tmp_path / "t.tune").read().split()
+    assert line[0] == prob.op.get_kernel_shape()["signature"] and len(line) >= 8
+
+
+def test_interface_pack_unpack_kernels(cm):
+    """ceedb200_iface_pack / ceedb200_iface_unpack_sum against the host interpretation of the same tables."""
+    import torch
+    from libceed_b200.parallel import CudaInterfaceKernels, build_interface_tables
+    ceed = cm.Ceed("/gpu/cuda/b200")
+    part = M.Partition((4, 4, 2), 2, 4, 1)
+    ncomp, nloc = 2, part.num_local_nodes
+    ranks, seg, send_idx, node, ptr, src = build_interface_tables(part, ncomp, nloc)
+    rng = np.random.default_rng(5)
+    v = rng.uniform(-1, 1, ncomp * nloc)
+    recv = rng.uniform(-1, 1, send_idx.size)
+    expect = v.copy()
+    for i in range(node.size):
+        terms = [v[node[i]] if s < 0 else recv[s] for s in src[ptr[i]:ptr[i + 1]]]
+        acc = terms[0]
+        for x in terms[1:]:
+            acc = acc + x
+        expect[node[i]] = acc
+    dev = torch.device("cuda")
+    k = CudaInterfaceKernels(ceed)
+    v_d, send_d = torch.from_numpy(v).to(dev), torch.empty(send_idx.size, dtype=torch.float64, device=dev)
+    k.pack(v_d, torch.from_numpy(send_idx).to(dev), send_d)
+    ceed.synchronize()
+    assert np.array_equal(send_d.cpu().numpy(), v[send_idx])
+    k.unpack_sum(v_d, torch.from_numpy(node).to(dev), torch.from_numpy(ptr).to(dev), torch.from_numpy(src).to(dev), torch.from_numpy(recv).to(dev))
+    ceed.synchronize()
+    assert np.array_equal(v_d.cpu().numpy(), expect)  # same order of additions -> same bits
+
+
 @pytest.mark.parametrize("bp,p", [(1, 3), (3, 6), (5, 7), (6, 4)])
 def test_full_size_properties(cm, bp, p):
     """BASELINE.json sizes (10M DoFs): properties that need no CPU oracle."""

@@ -33,6 +33,24 @@ def _global_problem(bp, p, n_global):
     return u, v, num_nodes, nc
 
 
+class HostKernels:
+    """Test-side executor of the exchange tables (the product runs ceedb200_iface_pack / ceedb200_iface_unpack_sum on the GPU;
+    tests/test_gpu_parity.py checks those kernels against exactly this interpretation)."""
+
+    def pack(self, v, idx, send):
+        send.copy_(v[idx])
+
+    def unpack_sum(self, v, node, ptr, src, recv):
+        vn, rn = v.numpy(), recv.numpy()
+        node, ptr, src = node.numpy(), ptr.numpy(), src.numpy()
+        for i in range(node.size):
+            terms = [vn[node[i]] if s < 0 else rn[s] for s in src[ptr[i]:ptr[i + 1]]]
+            acc = terms[0]
+            for x in terms[1:]:
+                acc = acc + x
+            vn[node[i]] = acc
+
+
 def _worker(rank, world, port, bp, p, n_global, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -51,7 +69,7 @@ def _worker(rank, world, port, bp, p, n_global, out_dir):
         u_loc = np.concatenate([u_glob[gid + c * n_glob] for c in range(nc)])
         qd = oracle.bp_qdata(bp, p, off, coords)
         v_loc = oracle.bp_apply(bp, p, off, nloc, qd, u_loc)
-        ex = InterfaceExchange(part, nc, nloc, torch.device("cpu"))
+        ex = InterfaceExchange(part, nc, nloc, torch.device("cpu"), kernels=HostKernels())
         v_t = torch.from_numpy(v_loc.copy())
         ex.sum_interfaces(v_t)
         # second exchange on fresh data must give the same bits (deterministic order)
@@ -87,6 +105,14 @@ def test_partitioned_apply_matches_single_rank(tmp_path, oracle, world, bp, p, n
     # copies of a shared node carry identical bits on all ranks (fixed rank-ordered sum)
     for g, vals in shared_vals.items():
         assert all(x == vals[0] for x in vals), g
+
+
+def test_exchange_requires_cuda_library():
+    """No silent host fallback in the product path."""
+    part = mesh.Partition((2, 1, 1), 1, 2, 0)
+    from libceed_b200.parallel import InterfaceExchange
+    with pytest.raises(RuntimeError):
+        InterfaceExchange(part, 1, part.num_local_nodes, torch.device("cpu"))
 
 
 def test_partition_tables_consistent():
