@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--scatter", default="deterministic", choices=["deterministic", "atomic", "evector"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--sweep", action="store_true", help="also report BP3 p=1..8 / BP5 p=4..7 kernel numbers in a `sweep` key")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the `sweep` key (kernel numbers of BP1 p=3, BP3 p=1..8, BP5 p=4..7, BP6 p=4,6)")
     return ap.parse_args()
 
 
@@ -144,6 +144,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------ main
 def main():
     args = parse_args()
+    # the contract is ONE JSON line on stdout: route everything libraries print to fd 1 (e.g. the NCCL version banner) to stderr
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     m = WORKLOAD_RE.fullmatch(args.workload)
     assert m, "workload must look like bp3p6"
     bp, p = int(m.group(1)), int(m.group(2))
@@ -166,7 +169,7 @@ def main():
                     impl="reference", config=config,
                     cpu_baseline=dict(value=r["value"], unit="GDoF/s", cores=r["cores"], kind="reference", sample=r["sample"]),
                     e2e=dict(value=r["value"], unit="GDoF/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
         return
 
     import torch
@@ -260,7 +263,14 @@ def main():
     alg_bytes = prob.bytes_per_apply()
     achieved = alg_bytes / ((fused_ms + aux_ms) * 1e-3) / 1e9
     info = prob.op.kernel_info()
-    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None, peak_source=peak_src,
+    # DRAM bytes of one launch of the fused kernel from the committed ncu capture of this workload (profiles/), when there is one
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tpath) and world == 1 and abs(args.dofs - 10e6) < 1 and args.scatter == "deterministic":
+        t = json.load(open(tpath)).get(args.workload)
+        if t:
+            traffic, traffic_src = t["traffic"], t["source"]
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
                     kernel="b200_operator (+ halo finalize)", fused_kernel_ms=fused_ms, finalize_ms=aux_ms, algorithmic_bytes=alg_bytes,
                     kernel_share_of_step=(fused_ms + aux_ms) / ms_per_step, regs=info["regs"], elems_per_block=info["elems_per_block"],
                     threads=info["threads"], grid=info["grid"], smem_bytes=info["smem_bytes"])
@@ -292,7 +302,7 @@ def main():
                ms_per_step=e2e_s * 1e3)
 
     sweep = None
-    if args.sweep and rank == 0 and world == 1:
+    if not args.no_sweep and rank == 0 and world == 1:
         sweep = []
         del prob
         for sbp, ps in ((1, (3,)), (3, range(1, 9)), (5, range(4, 8)), (6, (4, 6))):
@@ -325,7 +335,7 @@ def main():
                     roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(gpu_launches), clocks=clocks, total_dofs=total_dofs)
         if sweep:
             line["sweep"] = sweep
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
