@@ -99,7 +99,7 @@ def cpu_reference(bp, p, seconds, steps=0, warmup=1, resource="/cpu/self/avx/blo
     applies = sum(o[1] for o in out)
     return dict(value=dofs / tmax / 1e9, unit="GDoF/s", cores=cores, kind="reference",
                 sample=f"{resource}: {cores} forked workers x ({nel[0]}x{nel[1]}x{nel[2]} elements, {out[0][0]} DoFs), "
-                       f"{applies} applies in {tmax:.1f} s", ms_per_step=tmax / max(1, out[0][1]) * 1e3, applies=applies)
+                       f"{applies} applies in {tmax:.3f} s", ms_per_step=tmax / max(1, out[0][1]) * 1e3, applies=applies)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
