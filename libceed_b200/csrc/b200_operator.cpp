@@ -371,11 +371,15 @@ static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
     return ms;
   };
   B200Tuning base;  // all heuristic
+  bool       xline_ok = true;
+  for (auto &g : op->plan->in_groups) xline_ok = xline_ok && !g.use_grad;
+  for (auto &g : op->plan->out_groups) xline_ok = xline_ok && !g.use_grad;
   // 1. group width / warps per CTA x QFunction layout (elements per group and occupancy target left to the heuristics)
   const int shapes[][2] = {{1, 4}, {2, 2}, {2, 8}, {4, 4}, {1, 8}};
   for (auto &sh : shapes)
-    for (int qf = 0; qf < 3; qf++) {
+    for (int qf = 0; qf < 4; qf++) {
       if (qf == 2 && op->plan->Q % 2) continue;  // point pairs need an even number of points per row
+      if (qf == 3 && !xline_ok) continue;        // x-line fusion exists for gradient-free operators only
       B200Tuning t  = base;
       t.group_warps = sh[0], t.cta_warps = sh[1], t.qf_mode = qf;
       if (qf == 2) t.qf_unroll = 2;

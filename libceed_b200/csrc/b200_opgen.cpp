@@ -201,7 +201,19 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
   // QFunction stage layout: z-line (default) = d/dz, QFunction and (d/dz)^T fused per z-line in registers;
   // pointwise = d/dz and its transpose are separate line stages through shared memory and the QFunction runs over
   // independent points (short dependency chains on the streamed quadrature data, one more plane).
-  plan->qf_pointwise = tn.qf_mode >= 1;
+  // x-line = operators without gradients (mass-like: BP1/BP2): the QFunction runs on whole x-lines INSIDE the x-contraction
+  // stage (X, QFunction with Q points, X^T in registers) -- no quadrature-point plane round trip and no separate stage.
+  {
+    bool no_grad = !plan->in_groups.empty() && !plan->out_groups.empty();
+    for (auto &g : plan->in_groups) no_grad = no_grad && !g.use_grad && !plan->bases[g.basis_id].collocated;
+    for (auto &g : plan->out_groups) no_grad = no_grad && !g.use_grad && !plan->bases[g.basis_id].collocated;
+    for (auto &f : plan->in_fields) no_grad = no_grad && !(f.emode == B200_EVAL_NONE && !f.rstr->is_strided);
+    for (auto &f : plan->out_fields) no_grad = no_grad && f.emode != B200_EVAL_NONE;
+    if (tn.qf_mode == 3 && !no_grad) tn.qf_mode = 0;
+    if (tn.qf_mode < 0 && no_grad && !getenv("CEED_B200_NO_XLINE")) tn.qf_mode = 3;
+    plan->qf_xline = tn.qf_mode == 3;
+  }
+  plan->qf_pointwise = tn.qf_mode == 1 || tn.qf_mode == 2;
   plan->qf_pp        = (tn.qf_mode == 2 && Q % 2 == 0) ? 2 : 1;  // point pairs need x-adjacent points in one row
   plan->qf_unroll    = tn.qf_unroll > 0 ? tn.qf_unroll : 4;
   auto planes_of = [&](const B200GenGroup &g) { return g.nc * (g.use_grad ? ((plan->qf_pointwise && g.use_interp) ? 4 : 3) : 2); };
@@ -249,7 +261,7 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     }
     plan->ring_off = -1;
     for (auto &f : plan->in_fields) f.ring_k = -1;
-    if (plan->async_copy && (mask & 16) && plan->warp_mode && !plan->qf_pointwise) {
+    if (plan->async_copy && (mask & 16) && plan->warp_mode && !plan->qf_pointwise && !plan->qf_xline) {
       int comps = 0;
       for (auto &f : plan->in_fields)
         if (f.emode == B200_EVAL_NONE && f.qd_off < 0 && f.rstr->is_strided) {
@@ -343,7 +355,7 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     if (tn.minb > 0) minb = tn.minb;
     plan->blocks_per_sm = std::max(1, minb);
     tn.epw = plan->epb, tn.group_warps = plan->group_warps, tn.cta_warps = plan->threads / 32, tn.minb = plan->blocks_per_sm;
-    tn.qf_mode = plan->qf_pointwise ? plan->qf_pp : 0, tn.qf_unroll = plan->qf_unroll, tn.stage = plan->stage_mask;
+    tn.qf_mode = plan->qf_xline ? 3 : (plan->qf_pointwise ? plan->qf_pp : 0), tn.qf_unroll = plan->qf_unroll, tn.stage = plan->stage_mask;
     plan->resolved = tn;
   }
   plan->fused      = true;
@@ -425,6 +437,7 @@ struct Gen {
     B200QFunction qf = op->qf;
     c << "// Fused operator kernel generated by ceed-b200 for QFunction " << qf->kernel_name << "\n";
     if (plan->qf_pointwise && plan->qf_pp > 1) c << "#define CEED_Q_VLA " << plan->qf_pp << "  // the QFunction is called with Q = " << plan->qf_pp << " points\n";
+    if (plan->qf_xline) c << "#define CEED_Q_VLA " << Q << "  // the QFunction is called on whole x-lines (Q = " << Q << " points)\n";
     c << "#include <b200-jit.h>\n";
     c << "#include \"" << qf->source_path << "\"\n\n";
     for (size_t b = 0; b < plan->bases.size(); b++) {
@@ -979,6 +992,73 @@ struct Gen {
     task_loop_end();
   }
 
+  // ---- x-line stage for operators without gradients: X contraction, QFunction on the line, X^T contraction --------------
+  void emit_xline_qf() {
+    B200QFunction qf = op->qf;
+    comment("x-lines: x-contraction, QFunction on the Q points of the line, x-contraction^T (all components of one line per lane)");
+    task_loop_begin(std::to_string(E * Q * Q));
+    c << "      const int row = t % " << Q * Q << ", le = t / " << Q * Q << ";\n";
+    c << "      const int qy = row % " << Q << ", qz = row / " << Q << ";\n";
+    c << "      const long long e_real = e0 + le;\n";
+    c << "      const long long e = e_real < b200a.num_elem ? e_real : b200a.num_elem - 1;\n      (void)qy; (void)qz; (void)e;\n";
+    c << "      const CeedScalar *in[" << std::max<size_t>(1, qf->inputs.size()) << "];\n";
+    c << "      CeedScalar *out[" << std::max<size_t>(1, qf->outputs.size()) << "];\n";
+    for (size_t f = 0; f < plan->in_fields.size(); f++) c << "      CeedScalar in_" << f << "[" << plan->in_fields[f].size * Q << "];\n";
+    for (size_t f = 0; f < plan->out_fields.size(); f++) c << "      CeedScalar out_" << f << "[" << plan->out_fields[f].size * Q << "];\n";
+    for (size_t f = 0; f < plan->in_fields.size(); f++) c << "      in[" << f << "] = in_" << f << ";\n";
+    for (size_t f = 0; f < plan->out_fields.size(); f++) c << "      out[" << f << "] = out_" << f << ";\n";
+    // streamed inputs first (their latency overlaps the contractions below), then weights, then the interpolated fields
+    for (size_t f = 0; f < plan->in_fields.size(); f++) {
+      const B200GenField &fd = plan->in_fields[f];
+      const string        sl = std::to_string(fd.slot);
+      if (fd.emode == B200_EVAL_NONE) {
+        for (int cc = 0; cc < fd.nc; cc++)
+          for (int q = 0; q < Q; q++)
+            c << "      in_" << f << "[" << cc * Q + q << "] = __ldg(b200a.in_ptr[" << sl << "] + "
+              << lidx(fd.rstr, "", "e", "row * " + std::to_string(Q) + " + " + std::to_string(q), std::to_string(cc)) << ");\n";
+      } else if (fd.emode == B200_EVAL_WEIGHT) {
+        c << "      { const double wyz = cW" << fd.basis_id << "[qy] * cW" << fd.basis_id << "[qz];\n";
+        for (int q = 0; q < Q; q++) c << "        in_" << f << "[" << q << "] = cW" << fd.basis_id << "[" << q << "] * wyz; }\n";
+      }
+    }
+    for (size_t f = 0; f < plan->in_fields.size(); f++) {
+      const B200GenField &fd = plan->in_fields[f];
+      if (fd.emode != B200_EVAL_INTERP) continue;
+      const B200GenGroup &g = plan->in_groups[fd.group];
+      const B200GenBasis &b = basis(g.basis_id);
+      const int           P = b.P, Ps = odd_pad(P);
+      for (int cc = 0; cc < fd.nc; cc++) {
+        c << "      { const double *src = " << plane(g.plane0 + g.nc + cc, "le") << " + row * " << Ps << ";\n";
+        for (int i = 0; i < P; i++) c << "        const double u" << i << " = src[" << i << "];\n";
+        contract("cB" + std::to_string(g.basis_id), P, Q, false, "u", "r", "        ");
+        for (int q = 0; q < Q; q++) c << "        in_" << f << "[" << cc * Q + q << "] = r" << q << ";\n";
+        c << "      }\n";
+      }
+    }
+    c << "      " << qf->kernel_name << "(b200a.ctx, " << Q << ", in, out);\n";
+    for (size_t gi = 0; gi < plan->out_groups.size(); gi++) {
+      const B200GenGroup &g = plan->out_groups[gi];
+      const B200GenBasis &b = basis(g.basis_id);
+      const int           P = b.P, Ps = odd_pad(P);
+      for (int cc = 0; cc < g.nc; cc++) {
+        c << "      {\n";
+        for (int q = 0; q < Q; q++) {
+          string val;
+          for (size_t f = 0; f < plan->out_fields.size(); f++) {
+            const B200GenField &fd = plan->out_fields[f];
+            if (fd.group == (int)gi && fd.emode == B200_EVAL_INTERP) val += (val.empty() ? "" : " + ") + ("out_" + std::to_string(f) + "[" + std::to_string(cc * Q + q) + "]");
+          }
+          c << "        const double v" << q << " = " << val << ";\n";
+        }
+        contract("cB" + std::to_string(g.basis_id), Q, P, true, "v", "r", "        ");
+        c << "        double *dst = " << plane(g.plane0 + g.nc + cc, "le") << " + row * " << Ps << ";\n";
+        for (int i = 0; i < P; i++) c << "        dst[" << i << "] = r" << i << ";\n";
+        c << "      }\n";
+      }
+    }
+    task_loop_end();
+  }
+
   // ---- z-line QFunction stage with the per-lane quadrature-data ring ------------------------------
   // The streamed EVAL_NONE inputs are the bulk of the HBM traffic.  Every lane prefetches exactly the values it will consume
   // itself with cp.async into a small ring in shared memory: step s = (task round r, z-layer qz); ring_slots - 1 steps are
@@ -1368,7 +1448,7 @@ struct Gen {
     }
     any = false;
     for (auto &g : plan->in_groups) any = any || !(basis(g.basis_id).collocated && !g.use_grad);
-    if (any) {
+    if (any && !plan->qf_xline) {
       for (auto &g : plan->in_groups) emit_interp_x(g);
       barrier();
     }
@@ -1390,7 +1470,9 @@ struct Gen {
       if (!calls.empty() && calls.back() == "    " + SYNC + "\n") calls.pop_back();
       calls.push_back("    b200_cp_wait_all();\n    " + SYNC + "\n");
     }
-    if (plan->qf_pointwise) {
+    if (plan->qf_xline) {
+      emit_xline_qf();
+    } else if (plan->qf_pointwise) {
       any = false;
       for (auto &g : plan->in_groups) any = any || g.use_grad;
       if (any) {
@@ -1420,7 +1502,7 @@ struct Gen {
       }
       any = false;
       for (auto &g : plan->out_groups) any = any || !(basis(g.basis_id).collocated && !g.use_grad);
-      if (any) {
+      if (any && !plan->qf_xline) {
         for (auto &g : plan->out_groups) emit_interpT_x(g);
         barrier();
       }

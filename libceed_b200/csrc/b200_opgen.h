@@ -75,6 +75,7 @@ struct B200OpPlan {
   // z-line QFunction stage: per-lane cp.async ring for the streamed quadrature data.  A step = one z-layer of one task round;
   // ring_slots - 1 steps are always in flight, ACROSS the other stages and across element groups.
   int                       ring_off = -1, ring_slots = 0, ring_comps = 0, ring_rounds = 0;
+  bool                      qf_xline = false;    // gradient-free operators: QFunction on x-lines inside the x-contraction stage
   int                       qf_pp = 1;           // pointwise QFunction stage: points per lane (2 = x-adjacent pair, 16-byte loads)
   int                       qf_unroll = 4;       // pointwise QFunction stage: points in flight per lane
   std::string               signature, shape_signature;  // tuning-table keys (with / without the QFunction name)

@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 bp, p, nel = int(sys.argv[1]), int(sys.argv[2]), tuple(int(x) for x in sys.argv[3:6])
 SHAPES = [dict(group_warps=2, cta_warps=2), dict(group_warps=2, cta_warps=8), dict(group_warps=4, cta_warps=4), dict(qf_mode=1, qf_unroll=2),
           dict(qf_mode=2, qf_unroll=2), dict(qf_mode=2, group_warps=2, cta_warps=4, elems_per_group=3), dict(stage_mask=17), dict(stage_mask=9),
-          dict(stage_mask=0, cta_warps=1), dict(stage_mask=19, group_warps=2, cta_warps=4)]
+          dict(stage_mask=0, cta_warps=1), dict(stage_mask=19, group_warps=2, cta_warps=4), dict(qf_mode=3), dict(qf_mode=0)]
 ceed = Ceed(); prob = BPProblem(ceed, bp, p, nel)
 prob.u.set_array(seeded_uniform(prob.num_dofs, 23))
 prob.op.apply(prob.u, prob.v); v0 = prob.v.get_array_read().copy()

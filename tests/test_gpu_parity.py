@@ -335,7 +335,7 @@ def test_tail_batches_and_tuning(cm, oracle):
 
 SHAPES = [dict(group_warps=2, cta_warps=2), dict(group_warps=2, cta_warps=8), dict(group_warps=4, cta_warps=4), dict(qf_mode=1, qf_unroll=2),
           dict(qf_mode=2, qf_unroll=2), dict(qf_mode=2, group_warps=2, cta_warps=4, elems_per_group=3), dict(stage_mask=17), dict(stage_mask=9),
-          dict(stage_mask=0, cta_warps=1), dict(stage_mask=19, group_warps=2, cta_warps=4)]
+          dict(stage_mask=0, cta_warps=1), dict(stage_mask=19, group_warps=2, cta_warps=4), dict(qf_mode=3), dict(qf_mode=0)]
 
 
 @pytest.mark.parametrize("bp,p,nel", [(3, 2, (5, 3, 2)), (5, 3, (3, 3, 2)), (1, 3, (4, 3, 3)), (6, 2, (3, 2, 2)), (3, 4, (3, 2, 2))])
@@ -357,8 +357,8 @@ def test_kernel_shapes_give_identical_results(cm, oracle, monkeypatch, bp, p, ne
         prob.op.apply(prob.u, prob.v)
         got = prob.op.get_kernel_shape()
         for k, val in shape.items():
-            if k == "qf_mode" and val == 2 and (p + BP_TABLE[bp][2]) % 2:
-                continue  # point pairs fall back to single points for odd Q
+            if k == "qf_mode" and val in (2, 3):
+                continue  # point pairs need an even Q, x-line fusion a gradient-free operator: otherwise they fall back
             assert got[k] == val, (shape, got)
         assert rel(prob.v.get_array_read(), ref) < OP_TOL, shape
         assert rel(prob.v.get_array_read(), v0) < 1e-13, shape
