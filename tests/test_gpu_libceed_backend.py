@@ -48,7 +48,7 @@ def test_operator_through_libceed_matches_cpu_reference(R, bp, p, nel):
 
 
 def test_resource_prefix_resolves_to_b200(R):
-    rc = R.RefCeed("/gpu/cuda", cuda=True)  # priority 15 beats /gpu/cuda/gen (20)
+    rc = R.RefCeed("/gpu/cuda", cuda=True)  # prefix resolves to some CUDA backend (b200 registers with priority 45: only by full name)
     import ctypes as C
     res = C.c_char_p()
     rc.lib.CeedGetResource(rc.ceed, C.byref(res))
