@@ -53,7 +53,10 @@ enum {
 enum {
   B200_SCATTER_DETERMINISTIC = 0, /* owner-store + ordered halo sum; bitwise reproducible, no atomics (default) */
   B200_SCATTER_ATOMIC        = 1, /* red.global.add.f64, like /gpu/cuda/gen (cuda-gen-templates.h:385-396)   */
-  B200_SCATTER_EVECTOR       = 2  /* E-vector to HBM + CSR transpose kernel, like /gpu/cuda/ref               */
+  B200_SCATTER_EVECTOR       = 2, /* E-vector to HBM + CSR transpose kernel, like /gpu/cuda/ref               */
+  B200_SCATTER_ORDERED       = 3  /* deterministic, completed INSIDE the operator kernel: the element group holding the last
+                                     E-entry of a shared node waits for the groups of the earlier entries (per-group flags)
+                                     and adds their values in ascending E-order; same bits as DETERMINISTIC, no second pass */
 };
 
 /* ---------------------------------------------------------------- context (Ceed)

@@ -29,6 +29,7 @@ const B200Driver *b200_driver() {
     drv.ModuleGetFunction                         = missing<CUfunction *, CUmodule, const char *>;
     drv.ModuleGetGlobal                           = missing<CUdeviceptr *, size_t *, CUmodule, const char *>;
     drv.LaunchKernel                              = missing<CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **>;
+    drv.LaunchCooperativeKernel                   = missing<CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **>;
     drv.FuncSetAttribute                          = missing<CUfunction, CUfunction_attribute, int>;
     drv.FuncGetAttribute                          = missing<int *, CUfunction_attribute, CUfunction>;
     drv.OccupancyMaxActiveBlocksPerMultiprocessor = missing<int *, CUfunction, int, size_t>;
@@ -46,6 +47,7 @@ const B200Driver *b200_driver() {
   B200_SYM(ModuleGetFunction, "cuModuleGetFunction")
   B200_SYM(ModuleGetGlobal, "cuModuleGetGlobal_v2")
   B200_SYM(LaunchKernel, "cuLaunchKernel")
+  B200_SYM(LaunchCooperativeKernel, "cuLaunchCooperativeKernel")
   B200_SYM(FuncSetAttribute, "cuFuncSetAttribute")
   B200_SYM(FuncGetAttribute, "cuFuncGetAttribute")
   B200_SYM(OccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor")

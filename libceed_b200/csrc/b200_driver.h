@@ -11,6 +11,7 @@ struct B200Driver {
   CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, const char *);
   CUresult (*ModuleGetGlobal)(CUdeviceptr *, size_t *, CUmodule, const char *);
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **);
+  CUresult (*LaunchCooperativeKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **);
   CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
   CUresult (*FuncGetAttribute)(int *, CUfunction_attribute, CUfunction);
   CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int *, CUfunction, int, size_t);
@@ -24,6 +25,7 @@ const B200Driver *b200_driver();
 #undef cuModuleGetGlobal
 #define cuModuleGetGlobal b200_driver()->ModuleGetGlobal
 #define cuLaunchKernel b200_driver()->LaunchKernel
+#define cuLaunchCooperativeKernel b200_driver()->LaunchCooperativeKernel
 #define cuFuncSetAttribute b200_driver()->FuncSetAttribute
 #define cuFuncGetAttribute b200_driver()->FuncGetAttribute
 #define cuOccupancyMaxActiveBlocksPerMultiprocessor b200_driver()->OccupancyMaxActiveBlocksPerMultiprocessor

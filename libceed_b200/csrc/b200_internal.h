@@ -83,7 +83,7 @@ int b200_error(B200Ceed ceed, int code, const char *fmt, ...) __attribute__((for
 // NVRTC compile (cached).  `defines` are extra -D options.
 int b200_jit_compile(B200Ceed ceed, const std::string &source, const std::vector<std::string> &defines, B200Module **module);
 int b200_jit_get_kernel(B200Ceed ceed, B200Module *module, const char *name, CUfunction *kernel);
-int b200_launch(B200Ceed ceed, CUfunction kernel, unsigned grid, unsigned block, unsigned smem_bytes, void **args);
+int b200_launch(B200Ceed ceed, CUfunction kernel, unsigned grid, unsigned block, unsigned smem_bytes, void **args, bool cooperative = false);
 std::string b200_jit_dir();
 bool b200_compile_only();
 int  b200_dmalloc(B200Ceed ceed, void **p, size_t bytes);
@@ -165,6 +165,24 @@ struct B200OpField {
   B200Vector      vec = nullptr;
   bool            is_active = false, is_set = false;
 };
+
+// Tables of the ORDERED scatter mode (in-kernel completion of shared nodes, b200_restriction_build_ordered): like the
+// owner/halo tables, but the LAST E-entry of a shared node is the direct one -- its element group waits for the groups of
+// the earlier entries (flags) and adds their halo values in ascending E-order before storing.
+struct B200OrderedScatter {
+  int32_t *d_tgt = nullptr;       // per E-entry: >=0 plain L-index; <0: ~(slot | last << 27 | (touchers - 2) << 28)
+  int32_t *d_node = nullptr;      // per shared node: L-index      } written once into the halo buffer (id slots),
+  int32_t *d_ptr = nullptr;       // per shared node: its id slot  } see b200_ordered_init_halo
+  bool     supported = true;      // false: too many slots / touchers for the 31-bit encoding -> two-pass scheme
+  int32_t *d_pred_ptr = nullptr;  // per element group: predecessor groups (CSR, num_groups + 1)
+  int32_t *d_pred_idx = nullptr;
+  int32_t *d_flags = nullptr;     // per element group: epoch of the last launch whose halo values are complete
+  int32_t *d_sync = nullptr;      // {epoch of the last finished launch, CTAs finished in the running launch}
+  int64_t  num_shared = 0, num_halo = 0, num_groups = 0, num_pred = 0;
+};
+int  b200_restriction_build_ordered(B200Restriction r, int group_elems, B200OrderedScatter *out);
+int  b200_ordered_init_halo(B200Restriction r, const B200OrderedScatter *t, double *d_halo);
+void b200_ordered_scatter_free(B200Ceed ceed, B200OrderedScatter *t);
 
 struct B200OpPlan;  // generated-kernel plan (b200_opgen.cpp)
 

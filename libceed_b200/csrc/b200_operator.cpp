@@ -28,6 +28,7 @@ static void plan_free(B200Operator op) {
   B200OpPlan *plan = op->plan;
   if (!plan) return;
   for (int i = 0; i < 16; i++) b200_dfree(op->ceed, plan->aux[i]);
+  b200_ordered_scatter_free(op->ceed, &plan->ordered);
   for (auto *vecs : {&plan->e_in, &plan->q_in, &plan->e_out, &plan->q_out})
     for (auto v : *vecs) ceedb200_vector_destroy(v);
   delete plan;
@@ -120,7 +121,16 @@ static int operator_setup(B200Operator op) {
     // auxiliary buffers of offset-restricted outputs
     auto prepare = [&](B200Restriction r, int slot) -> int {
       if (!r || r->is_strided) return B200_SUCCESS;
-      if (plan->scatter_mode == B200_SCATTER_DETERMINISTIC) {
+      if (plan->scatter_mode == B200_SCATTER_ORDERED && slot == plan->ordered_slot) {
+        B200_CALL(b200_restriction_build_ordered(r, plan->epb, &plan->ordered));
+        if (!plan->ordered.supported) {  // encoding limits exceeded: same results through the two-pass scheme
+          plan->scatter_mode = B200_SCATTER_DETERMINISTIC;
+          plan->ordered_slot = -1;
+        }
+      }
+      if (plan->scatter_mode == B200_SCATTER_ORDERED && slot == plan->ordered_slot) {
+        plan->aux_bytes[slot] = (size_t)std::max<int64_t>(plan->ordered.num_halo, 1) * r->num_comp * sizeof(double);
+      } else if (plan->scatter_mode == B200_SCATTER_DETERMINISTIC || plan->scatter_mode == B200_SCATTER_ORDERED) {
         B200_CALL(b200_restriction_build_owner(r));
         plan->aux_bytes[slot] = (size_t)r->num_halo * r->num_comp * sizeof(double);
       } else if (plan->scatter_mode == B200_SCATTER_EVECTOR) {
@@ -128,6 +138,7 @@ static int operator_setup(B200Operator op) {
         plan->aux_bytes[slot] = (size_t)r->num_elem * r->elem_size * r->num_comp * sizeof(double);
       }
       if (plan->aux_bytes[slot]) B200_CALL(b200_dmalloc(ceed, (void **)&plan->aux[slot], plan->aux_bytes[slot]));
+      if (plan->scatter_mode == B200_SCATTER_ORDERED && slot == plan->ordered_slot) B200_CALL(b200_ordered_init_halo(r, &plan->ordered, plan->aux[slot]));
       return B200_SUCCESS;
     };
     for (auto &g : plan->out_groups) B200_CALL(prepare(g.rstr, g.slot));
@@ -200,7 +211,8 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add) {
     for (auto &o : outs) need_zero = need_zero || o.writers > 1 || !o.covers;
     bool offset_non_det = false;
     for (size_t i = 0; i < op->out_fields.size(); i++)
-      if (!op->out_fields[i].rstr->is_strided && plan->scatter_mode != B200_SCATTER_DETERMINISTIC) offset_non_det = true;
+      if (!op->out_fields[i].rstr->is_strided && plan->scatter_mode != B200_SCATTER_DETERMINISTIC && plan->scatter_mode != B200_SCATTER_ORDERED)
+        offset_non_det = true;
     if (need_zero || offset_non_det) {
       for (auto &o : outs) B200_CALL(ceedb200_vector_set_value(o.vec, 0.0));
       kernel_add = 1;
@@ -211,8 +223,17 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add) {
     B200Vector         vec = f.is_active ? v : f.vec;
     // discard previous contents only when the kernel overwrites everything
     B200_CALL(b200_vector_device_write(vec, &args.out_ptr[i], !kernel_add));
-    if (!f.rstr->is_strided) args.out_idx[i] = plan->scatter_mode == B200_SCATTER_DETERMINISTIC ? f.rstr->d_tgt : f.rstr->d_offsets;
+    if (!f.rstr->is_strided) {
+      if (plan->scatter_mode == B200_SCATTER_ORDERED && (int)i == plan->ordered_slot) args.out_idx[i] = plan->ordered.d_tgt;
+      else args.out_idx[i] = plan->scatter_mode == B200_SCATTER_DETERMINISTIC ? f.rstr->d_tgt : f.rstr->d_offsets;
+    }
     args.out_aux[i] = plan->aux[i];
+  }
+  const bool ordered = plan->scatter_mode == B200_SCATTER_ORDERED;
+  if (ordered) {
+    args.ord_pred_ptr = plan->ordered.d_pred_ptr, args.ord_pred_idx = plan->ordered.d_pred_idx;
+    args.ord_flags = plan->ordered.d_flags, args.ord_sync = plan->ordered.d_sync;
+    args.ord_num_halo = plan->ordered.num_halo;
   }
   B200_CALL(b200_opgen_build(op, plan, kernel_add));
   B200KernelVariant &var = plan->variant[kernel_add ? 1 : 0];
@@ -225,7 +246,8 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add) {
       mod->last_args.assign((const char *)&args, (const char *)&args + sizeof(args));
       B200_CUDA(ceed, cudaMemcpyAsync((void *)mod->args_dptr, mod->last_args.data(), sizeof(args), cudaMemcpyHostToDevice, ceed->stream));
     }
-    B200_CALL(b200_launch(ceed, var.kernel, plan->grid, plan->threads, plan->smem_bytes, nullptr));
+    // element groups of the ordered scatter wait for each other: all CTAs must be resident (cooperative launch)
+    B200_CALL(b200_launch(ceed, var.kernel, plan->grid, plan->threads, plan->smem_bytes, nullptr, ordered));
   }
   if (op->timing) B200_CUDA(ceed, cudaEventRecord(op->ev[1], ceed->stream));
   // second phase of the scatter
@@ -234,7 +256,8 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add) {
     if (f.rstr->is_strided || !plan->aux[i]) continue;
     bool is_writer = plan->out_fields[i].emode == B200_EVAL_NONE || plan->out_groups[plan->out_fields[i].group].slot == (int)i;
     if (!is_writer) continue;
-    if (plan->scatter_mode == B200_SCATTER_DETERMINISTIC) B200_CALL(b200_halo_finalize(f.rstr, plan->aux[i], args.out_ptr[i]));
+    if (ordered && (int)i == plan->ordered_slot) continue;  // completed inside the kernel
+    if (plan->scatter_mode == B200_SCATTER_DETERMINISTIC || ordered) B200_CALL(b200_halo_finalize(f.rstr, plan->aux[i], args.out_ptr[i]));
     else if (plan->scatter_mode == B200_SCATTER_EVECTOR) B200_CALL(b200_restriction_apply_raw(f.rstr, B200_TRANSPOSE, plan->aux[i], args.out_ptr[i]));
   }
   if (op->timing) {

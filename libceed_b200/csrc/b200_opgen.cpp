@@ -49,6 +49,7 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
   B200QFunction qf   = op->qf;
   plan->fused        = false;
   plan->scatter_mode = ceed->scatter_mode;
+  plan->ordered_slot = -1;
   auto reject        = [&](const string &why) {
     plan->why_not_fused = why;
     return B200_SUCCESS;
@@ -147,6 +148,18 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
   for (auto &b : plan->bases)
     if (b.P > 16 || b.Q > 16) return reject("P or Q > 16");
 
+  if (plan->scatter_mode == B200_SCATTER_ORDERED) {
+    // in-kernel ordered completion: one offset-restricted output group, no other offset-restricted outputs
+    int n_offset = 0;
+    for (auto &g : plan->out_groups)
+      if (!g.rstr->is_strided) n_offset++, plan->ordered_slot = g.slot;
+    for (auto &f : plan->out_fields)
+      if (f.emode == B200_EVAL_NONE && !f.rstr->is_strided) n_offset += 2;
+    if (n_offset != 1 || getenv("CEED_B200_BLOCK_MODE")) {
+      plan->scatter_mode = B200_SCATTER_DETERMINISTIC;  // same results, two-pass scheme
+      plan->ordered_slot = -1;
+    }
+  }
   plan->dim      = dim;
   plan->Q        = Q;
   plan->Qs       = odd_pad(Q);
@@ -184,6 +197,16 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     B200Tuning table;
     auto       it = ceed->tune_table.find(plan->signature);
     if (it == ceed->tune_table.end()) it = ceed->tune_table.find(plan->shape_signature);
+    if (it == ceed->tune_table.end() && plan->scatter_mode != B200_SCATTER_DETERMINISTIC) {
+      // no entry for this scatter mode: the shape tuned for the default mode is the best guess
+      auto as_default = [&](std::string key) {
+        const size_t pos = key.find("|sc");
+        if (pos != std::string::npos) key[pos + 3] = '0';
+        return key;
+      };
+      it = ceed->tune_table.find(as_default(plan->signature));
+      if (it == ceed->tune_table.end()) it = ceed->tune_table.find(as_default(plan->shape_signature));
+    }
     if (it != ceed->tune_table.end()) table = it->second;
     auto pick = [&](int &field, int unset, const char *env, int table_value) {
       if (field != unset) return;
@@ -452,7 +475,8 @@ struct Gen {
       emit_mat("cW" + std::to_string(b), bs->q_weight);
     }
     c << "\nstruct B200OpArgs {\n  long long num_elem;\n  void *ctx;\n  const double *in_ptr[16];\n  double *out_ptr[16];\n"
-      << "  const int *in_idx[16];\n  const int *out_idx[16];\n  double *out_aux[16];\n};\n"
+      << "  const int *in_idx[16];\n  const int *out_idx[16];\n  double *out_aux[16];\n"
+      << "  const int *ord_pred_ptr, *ord_pred_idx;\n  int *ord_flags, *ord_sync;\n  long long ord_num_halo;\n};\n"
       // the argument block lives in constant memory (written by the host before the launch): every stage function reads its
       // pointers with uniform constant loads instead of generic loads through a reference to the kernel parameter
       << "__constant__ B200OpArgs b200a;\n\n";
@@ -1360,7 +1384,88 @@ struct Gen {
     task_loop_end();
   }
 
+  // Z^T + scatter with in-kernel ordered completion of shared nodes (B200_SCATTER_ORDERED), see B200OrderedScatter.
+  // Phase A (this group): plain nodes are stored, every contribution to a shared node goes to its halo slot; then the group
+  // publishes its flag.  Phase B runs ONE ITERATION LATER (b200_ordered_complete for the group this warp processed before):
+  // by then the predecessor groups have long published, so the flag wait is free; the completing group adds the slots of
+  // each shared node it holds the last E-entry of in ascending E-order and stores the sum.
+  void emit_scatter_z_ordered(const B200GenGroup &g) {
+    const B200GenBasis &b  = basis(g.basis_id);
+    const int           P  = b.P;
+    const string        sl = std::to_string(g.slot);
+    const long long     cs = (long long)g.rstr->comp_stride;
+    const int           ntasks = E * g.nc * P * P, es = g.rstr->elem_size;
+    // ---- completion of a previously scattered group
+    comment("ordered scatter, phase B: complete the shared nodes whose last E-entry lies in the group starting at element ep");
+    c << "static __device__ __noinline__ void b200_ordered_complete(const long long ep, const int epoch) {\n";
+    c << "    const long long grp = ep / " << E << ";\n";
+    c << "    for (int i = b200a.ord_pred_ptr[grp] + " << TID << "; i < b200a.ord_pred_ptr[grp + 1]; i += " << TS << ") {\n";
+    c << "      const int *flag = b200a.ord_flags + b200a.ord_pred_idx[i];\n      int seen;\n";
+    c << "      do { asm volatile(\"ld.acquire.gpu.global.s32 %0, [%1];\" : \"=r\"(seen) : \"l\"(flag) : \"memory\"); } while (seen != epoch);\n";
+    c << "    }\n";
+    c << "    " << SYNC << "\n";
+    c << "    const int nent = (int)((b200a.num_elem - ep < " << E << ") ? b200a.num_elem - ep : " << E << ") * " << es << ";\n";
+    c << "    const int *tgt = b200a.out_idx[" << sl << "] + ep * " << es << "LL;\n";
+    // U entries per lane at a time: all table loads first, then the first two contributions (every shared node has >= 2), ...
+    const int U = 4;
+    c << "    for (int t0 = " << TID << "; t0 < nent; t0 += " << U * TS << ") {\n";
+    for (int u = 0; u < U; u++) c << "      const int x" << u << " = (t0 + " << u * TS << " < nent) ? ~__ldg(tgt + t0 + " << u * TS << ") : 0;\n";
+    for (int u = 0; u < U; u++) {
+      c << "      const bool last" << u << " = x" << u << " > 0 && ((x" << u << " >> 27) & 1);\n";
+      c << "      const int cnt" << u << " = ((x" << u << " >> 28) & 7) + 2, s" << u << " = (x" << u << " & 0x7ffffff) - (cnt" << u << " - 1);  // first contribution\n";
+    }
+    for (int cc = 0; cc < g.nc; cc++) {
+      c << "      { const double *h = b200a.out_aux[" << sl << "] + " << cc << " * b200a.ord_num_halo;\n";
+      for (int u = 0; u < U; u++)
+        c << "        double a" << u << " = 0.0, b" << u << " = 0.0; if (last" << u << ") { a" << u << " = __ldcg(h + s" << u << "); b" << u << " = __ldcg(h + s" << u
+          << " + 1); }\n";
+      for (int u = 0; u < U; u++) {
+        c << "        if (last" << u << ") {\n";
+        c << "          double acc = a" << u << " + b" << u << ";\n";
+        c << "          for (int k = 2; k < cnt" << u << "; k++) acc += __ldcg(h + s" << u << " + k);\n";
+        c << "          const long long node = __ldcg((const long long *)b200a.out_aux[" << sl << "] + s" << u << " - 1);\n";
+        c << "          b200a.out_ptr[" << sl << "][node + " << cc * cs << "LL] " << (add ? "+=" : "=") << " acc;\n        }\n";
+      }
+      c << "      }\n";
+    }
+    c << "    }\n}\n\n";
+    // ---- phase A
+    comment("z-contraction^T + ordered scatter, phase A (plain stores + halo slots + flag), slot " + sl);
+    const string name = "b200_stage_" + std::to_string(n_stage++);
+    c << "static __device__ __noinline__ void " << name << "(const long long e0, const int epoch) {\n";
+    c << smw_decl();
+    calls.push_back("    " + name + "(e0, epoch);\n    if (e0p >= 0) b200_ordered_complete(e0p, epoch);\n    e0p = e0;\n");
+    c << "    for (int t = " << TID << "; t < " << ntasks << "; t += " << TS << ") {\n";
+    c << "      const int ij = t % " << P * P << ", cc = (t / " << P * P << ") % " << g.nc << ", le = t / " << P * P * g.nc << ";\n";
+    c << "      const long long e = e0 + le;\n";
+    if (b.collocated) {
+      c << "      const double *col = " << plane(g.plane0, "le") << " + cc * " << E * S << " + (ij / " << P << ") * " << Qs << " + (ij % " << P << ");\n";
+      for (int k = 0; k < P; k++) c << "      const double r" << k << " = col[" << k * Q * Qs << "];\n";
+    } else {
+      c << "      const double *col = " << plane(g.plane0, "le") << " + cc * " << E * S << " + ij;\n";
+      for (int q = 0; q < Q; q++) c << "      const double u" << q << " = col[" << q * P * P << "];\n";
+      contract("cB" + std::to_string(g.basis_id), Q, P, true, "u", "r", "      ");
+    }
+    c << "      if (e < b200a.num_elem) {\n";
+    for (int k = 0; k < P; k++) {
+      const string n = "ij + " + std::to_string(k * P * P);
+      string       tgt;
+      if (g.tgt_off >= 0) tgt = smem_at(g.tgt_off, "const int") + "[le * " + std::to_string(es) + " + " + n + "]";
+      else tgt = "b200a.out_idx[" + sl + "][e * " + std::to_string(es) + "LL + (" + n + ")]";
+      c << "        { const int tg = " << tgt << ";\n";
+      c << "          if (tg >= 0) b200a.out_ptr[" << sl << "][tg + cc * " << cs << "LL] " << (add ? "+=" : "=") << " r" << k << ";\n";
+      c << "          else b200a.out_aux[" << sl << "][(long long)((~tg) & 0x7ffffff) + cc * b200a.ord_num_halo] = r" << k << "; }\n";
+    }
+    c << "      }\n    }\n";
+    // one fence + release by one lane after the group barrier publishes the stores of the whole group (cumulativity)
+    c << "    " << SYNC << "\n";
+    c << "    if (" << TID << " == 0) {\n      __threadfence();\n      asm volatile(\"st.release.gpu.global.s32 [%0], %1;\" ::\"l\"(b200a.ord_flags + e0 / " << E
+      << "), \"r\"(epoch) : \"memory\");\n    }\n";
+    c << "}\n\n";
+  }
+
   void emit_scatter_z(const B200GenGroup &g) {
+    if (plan->scatter_mode == B200_SCATTER_ORDERED && g.slot == plan->ordered_slot) return emit_scatter_z_ordered(g);
     const B200GenBasis &b = basis(g.basis_id);
     const int           P = b.P;
     comment("z-contraction^T + scatter, output group slot " + std::to_string(g.slot));
@@ -1547,6 +1652,8 @@ struct Gen {
     }
     c << "extern \"C\" __global__ void __launch_bounds__(" << NT << ", " << minb << ") b200_operator_" << op->qf->kernel_name << "() {\n";
     c << "  const long long num_batches = (b200a.num_elem + " << E - 1 << ") / " << E << ";\n";
+    if (plan->scatter_mode == B200_SCATTER_ORDERED)
+      c << "  const int epoch = *(volatile const int *)b200a.ord_sync + 1;  // this launch\n  long long e0p = -1;  // group whose shared nodes are still to be completed\n";
     // block mode: one batch per CTA per iteration; warp mode: one group per warp per iteration
     const string first  = warp_mode ? "((long long)blockIdx.x * " + std::to_string(NT / TS) + " + (threadIdx.x / " + std::to_string(TS) + "))" : "(long long)blockIdx.x";
     const string stride = warp_mode ? "((long long)gridDim.x * " + std::to_string(NT / TS) + ")" : "(long long)gridDim.x";
@@ -1572,7 +1679,15 @@ struct Gen {
     }
     if (prefetch) c << "    b200_prefetch(e0n);\n";
     for (auto &call : calls) c << call;
-    c << "  }\n}\n";
+    c << "  }\n";
+    if (plan->scatter_mode == B200_SCATTER_ORDERED) {
+      c << "  if (e0p >= 0) b200_ordered_complete(e0p, epoch);\n";
+      // the last CTA to finish publishes the epoch of this launch (read by the next one) and resets the counter
+      c << "  __syncthreads();\n  if (threadIdx.x == 0) {\n    __threadfence();\n";
+      c << "    if (atomicAdd(b200a.ord_sync + 1, 1) == (int)gridDim.x - 1) {\n      b200a.ord_sync[1] = 0;\n      __threadfence();\n";
+      c << "      *(volatile int *)b200a.ord_sync = epoch;\n    }\n  }\n";
+    }
+    c << "}\n";
     return c.str();
   }
 };

@@ -48,6 +48,10 @@ struct B200OpArgs {
   const int    *in_idx[16];
   const int    *out_idx[16];
   double       *out_aux[16];  // halo buffer (deterministic) or E-vector (evector mode)
+  // ordered scatter (B200_SCATTER_ORDERED): tables of the one offset-restricted output
+  const int *ord_pred_ptr, *ord_pred_idx;
+  int       *ord_flags, *ord_sync;
+  long long  ord_num_halo;
 };
 
 struct B200KernelVariant {
@@ -87,6 +91,8 @@ struct B200OpPlan {
   // per output slot: auxiliary device buffer (halo or E-vector)
   double *aux[16]       = {nullptr};
   size_t  aux_bytes[16] = {0};
+  B200OrderedScatter ordered;     // ordered scatter tables (scatter_mode == B200_SCATTER_ORDERED)
+  int                ordered_slot = -1;
   // unfused fallback scratch
   std::vector<B200Vector> e_in, q_in, e_out, q_out;
 };

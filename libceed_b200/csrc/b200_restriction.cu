@@ -279,6 +279,93 @@ int b200_restriction_build_owner(B200Restriction r) {
   return B200_SUCCESS;
 }
 
+// Ordered scatter tables for element groups of `group_elems` consecutive elements (see B200OrderedScatter).
+// Halo image of one shared node: [node id (as a 64-bit integer)][contribution of toucher 0]...[contribution of the last toucher].
+// tgt of an E-entry: >= 0 plain L-index; < 0: x = ~tgt, bits 0..26 = slot of this entry's contribution, bit 27 = "last toucher:
+// completes the node", bits 28..30 = number of touchers - 2 (valid on the last toucher).
+namespace {
+__global__ void k_ordered_write_ids(double *__restrict__ halo, const int32_t *__restrict__ id_slot, const int32_t *__restrict__ id_node, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    reinterpret_cast<long long *>(halo)[id_slot[i]] = id_node[i];
+}
+}  // namespace
+
+int b200_restriction_build_ordered(B200Restriction r, int group_elems, B200OrderedScatter *out) {
+  B200Ceed      ceed = r->ceed;
+  HostTranspose t;
+  build_host_transpose(r, t);
+  const int64_t n          = (int64_t)r->num_elem * r->elem_size;
+  const int64_t num_nodes  = (int64_t)t.lvec_indices.size();
+  const int64_t num_groups = ((int64_t)r->num_elem + group_elems - 1) / group_elems;
+  int64_t       num_halo = 0, num_shared = 0;
+  int32_t       max_cnt = 0;
+  for (int64_t row = 0; row < num_nodes; row++) {
+    const int32_t cnt = t.t_offsets[row + 1] - t.t_offsets[row];
+    if (cnt > 1) num_halo += cnt + 1, num_shared++, max_cnt = std::max(max_cnt, cnt);
+  }
+  out->supported = num_halo < (1LL << 27) && max_cnt <= 9;
+  if (!out->supported) return B200_SUCCESS;  // the caller falls back to the two-pass deterministic scheme
+  std::vector<int32_t>              tgt(n), id_slot, id_node;
+  std::vector<std::vector<int32_t>> pred(num_groups);
+  id_slot.reserve(num_shared);
+  id_node.reserve(num_shared);
+  int64_t       slot          = 0;
+  const int64_t group_entries = (int64_t)group_elems * r->elem_size;
+  for (int64_t row = 0; row < num_nodes; row++) {
+    const int32_t begin = t.t_offsets[row], end = t.t_offsets[row + 1], cnt = end - begin;
+    if (cnt == 1) {
+      tgt[t.t_indices[begin]] = t.lvec_indices[row];
+      continue;
+    }
+    id_slot.push_back((int32_t)slot++);
+    id_node.push_back(t.lvec_indices[row]);
+    const int32_t last       = t.t_indices[end - 1];
+    const int32_t last_group = (int32_t)(last / group_entries);
+    for (int32_t k = begin; k < end - 1; k++) {
+      tgt[t.t_indices[k]] = ~(int32_t)(slot++);
+      const int32_t g = (int32_t)(t.t_indices[k] / group_entries);
+      if (g != last_group && (pred[last_group].empty() || pred[last_group].back() != g)) pred[last_group].push_back(g);
+    }
+    tgt[last] = ~(int32_t)((int32_t)(slot++) | (1 << 27) | ((cnt - 2) << 28));
+  }
+  std::vector<int32_t> pred_ptr(num_groups + 1, 0), pred_idx;
+  for (int64_t g = 0; g < num_groups; g++) {
+    std::sort(pred[g].begin(), pred[g].end());
+    pred[g].erase(std::unique(pred[g].begin(), pred[g].end()), pred[g].end());
+    pred_ptr[g + 1] = pred_ptr[g] + (int32_t)pred[g].size();
+    pred_idx.insert(pred_idx.end(), pred[g].begin(), pred[g].end());
+  }
+  out->num_shared = num_shared, out->num_halo = num_halo, out->num_groups = num_groups, out->num_pred = (int64_t)pred_idx.size();
+  auto upload = [&](int32_t **d, const std::vector<int32_t> &h) -> int {
+    B200_CALL(b200_dmalloc(ceed, (void **)d, std::max<size_t>(h.size(), 1) * sizeof(int32_t)));
+    if (!h.empty()) B200_CALL(b200_h2d(ceed, *d, h.data(), h.size() * sizeof(int32_t)));
+    return B200_SUCCESS;
+  };
+  B200_CALL(upload(&out->d_tgt, tgt));
+  B200_CALL(upload(&out->d_node, id_node));
+  B200_CALL(upload(&out->d_ptr, id_slot));
+  B200_CALL(upload(&out->d_pred_ptr, pred_ptr));
+  B200_CALL(upload(&out->d_pred_idx, pred_idx));
+  B200_CALL(upload(&out->d_flags, std::vector<int32_t>(num_groups, 0)));
+  B200_CALL(upload(&out->d_sync, std::vector<int32_t>(2, 0)));
+  r->num_nodes = num_nodes;
+  return B200_SUCCESS;
+}
+
+// write the (static) node ids into a freshly allocated halo buffer
+int b200_ordered_init_halo(B200Restriction r, const B200OrderedScatter *t, double *d_halo) {
+  B200Ceed ceed = r->ceed;
+  if (t->num_shared > 0 && !b200_compile_only()) LAUNCH(ceed, k_ordered_write_ids, t->num_shared, d_halo, t->d_ptr, t->d_node, t->num_shared);
+  return B200_SUCCESS;
+}
+
+void b200_ordered_scatter_free(B200Ceed ceed, B200OrderedScatter *t) {
+  for (int32_t **p : {&t->d_tgt, &t->d_node, &t->d_ptr, &t->d_pred_ptr, &t->d_pred_idx, &t->d_flags, &t->d_sync}) {
+    b200_dfree(ceed, *p);
+    *p = nullptr;
+  }
+}
+
 int b200_restriction_e_size(B200Restriction r, int64_t *e_size) {
   *e_size = (int64_t)r->num_elem * r->elem_size * r->num_comp;
   return B200_SUCCESS;

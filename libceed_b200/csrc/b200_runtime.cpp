@@ -146,6 +146,7 @@ extern "C" int ceedb200_init(int device_id, B200Ceed *ceed_out) {
     const char *mode = getenv("CEED_B200_SCATTER");
     if (mode && !strcmp(mode, "atomic")) ceed->scatter_mode = B200_SCATTER_ATOMIC;
     if (mode && !strcmp(mode, "evector")) ceed->scatter_mode = B200_SCATTER_EVECTOR;
+    if (mode && !strcmp(mode, "ordered")) ceed->scatter_mode = B200_SCATTER_ORDERED;
     *ceed_out = ceed;
     return B200_SUCCESS;
   }
@@ -181,6 +182,7 @@ extern "C" int ceedb200_init(int device_id, B200Ceed *ceed_out) {
   if (mode) {
     if (!strcmp(mode, "atomic")) ceed->scatter_mode = B200_SCATTER_ATOMIC;
     else if (!strcmp(mode, "evector")) ceed->scatter_mode = B200_SCATTER_EVECTOR;
+    else if (!strcmp(mode, "ordered")) ceed->scatter_mode = B200_SCATTER_ORDERED;
     else ceed->scatter_mode = B200_SCATTER_DETERMINISTIC;
   }
   ceed->jit_roots.push_back(b200_jit_dir());
@@ -225,7 +227,7 @@ extern "C" int ceedb200_synchronize(B200Ceed ceed) {
   return B200_SUCCESS;
 }
 extern "C" int ceedb200_set_scatter_mode(B200Ceed ceed, int mode) {
-  B200_CHECK(mode >= 0 && mode <= 2, ceed, B200_ERROR_UNSUPPORTED, "unknown scatter mode %d", mode);
+  B200_CHECK(mode >= 0 && mode <= 3, ceed, B200_ERROR_UNSUPPORTED, "unknown scatter mode %d", mode);
   ceed->scatter_mode = mode;
   return B200_SUCCESS;
 }
@@ -327,9 +329,11 @@ int b200_jit_get_kernel(B200Ceed ceed, B200Module *module, const char *name, CUf
   return B200_SUCCESS;
 }
 
-int b200_launch(B200Ceed ceed, CUfunction kernel, unsigned grid, unsigned block, unsigned smem_bytes, void **args) {
+int b200_launch(B200Ceed ceed, CUfunction kernel, unsigned grid, unsigned block, unsigned smem_bytes, void **args, bool cooperative) {
   B200_CHECK(!b200_compile_only(), ceed, B200_ERROR_BACKEND, "ceed-b200: CEED_B200_COMPILE_ONLY is set; kernels cannot run without a GPU");
-  B200_CU(ceed, cuLaunchKernel(kernel, grid, 1, 1, block, 1, 1, smem_bytes, (CUstream)ceed->stream, args, nullptr));
+  // cooperative = all CTAs guaranteed co-resident (kernels whose element groups wait for each other)
+  if (cooperative) B200_CU(ceed, cuLaunchCooperativeKernel(kernel, grid, 1, 1, block, 1, 1, smem_bytes, (CUstream)ceed->stream, args));
+  else B200_CU(ceed, cuLaunchKernel(kernel, grid, 1, 1, block, 1, 1, smem_bytes, (CUstream)ceed->stream, args, nullptr));
   ceed->launch_count++;
   return B200_SUCCESS;
 }

@@ -38,13 +38,18 @@ def run(tag, env, epb=0, scatter=0):
     if vref is None: vref = v
     err = np.abs(v - vref).max() / np.abs(vref).max()
     if err > 1e-13: tag = tag + f" ERR={err:.1e}"
+    elif scatter == 3: tag = tag + (" bitwise==det" if np.array_equal(v, vref) else f" diff={err:.1e}")
     print(f"{tag:46s} {f:.3f}+{a:.3f} ms {base.num_dofs/(f+a)/1e6:6.2f} GDoF/s {base.bytes_per_apply()/(f+a)/1e6/6550.1*100:5.1f}% regs={i['regs']} epw={i['elems_per_block']} "
           f"thr={i['threads']} grid={i['grid']} smem={i['smem_bytes']} loc={i['local_bytes']}", flush=True)
     return f + a
 
 vref = None
 print(f"{wl}: {base.num_dofs/1e6:.2f}M DoFs, {base.num_elem} elements")
-if mode == "misc":
+if mode == "ordered":
+    run("deterministic (table)", {})
+    run("ordered (in-kernel completion)", {}, scatter=3)
+    run("atomic", {}, scatter=1)
+elif mode == "misc":
     run("default (table)", {})
     run("L2 prefetch", {"CEED_B200_PREFETCH": "1"})
     run("stage=9", {"CEED_B200_STAGE": "9"})

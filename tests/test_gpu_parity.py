@@ -199,7 +199,7 @@ def test_standalone_qfunction_matches_oracle(cm, oracle):
 
 # ------------------------------------------------------------------------------------------------ operator
 @pytest.mark.parametrize("case", BP_CASES, ids=lambda c: bp_case_key(*c))
-@pytest.mark.parametrize("mode", [0, 1, 2], ids=["deterministic", "atomic", "evector"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3], ids=["deterministic", "atomic", "evector", "ordered"])
 def test_bp_operator_vs_oracle_and_golden(cm, oracle, golden, case, mode):
     bp, p, nel, gallery, interlaced = case
     if gallery:
@@ -301,6 +301,21 @@ def test_deterministic_scatter_is_bitwise_reproducible_and_equals_serial_order(c
         outs.append(prob.v.get_array_read())
     assert np.array_equal(outs[0], outs[1])  # run-to-run bitwise identical
     assert np.array_equal(outs[0], outs[2])  # owner/halo scheme sums in the same order as the ordered transpose
+    # in-kernel ordered completion (mode 3, cooperative launch, per-group flags): same bits again, also across element-group
+    # sizes, repeated applies (epoch counter) and ApplyAdd
+    for bp, p, nel, epg in [(3, 3, (5, 4, 3), 0), (3, 2, (7, 5, 3), 4), (1, 3, (6, 5, 4), 3), (6, 2, (4, 3, 3), 2), (5, 4, (4, 4, 3), 1)]:
+        pa, pc = make_problem(cm, bp, p, nel, mode=0), make_problem(cm, bp, p, nel, mode=3)
+        if epg:
+            pc.op.set_tuning(epg, 0)
+        u = seeded_uniform(pa.num_dofs, 17)
+        pa.u.set_array(u), pc.u.set_array(u)
+        pa.op.apply(pa.u, pa.v)
+        for _ in range(3):
+            pc.v.set_value(3.0)
+            pc.op.apply(pc.u, pc.v)
+            assert np.array_equal(pa.v.get_array_read(), pc.v.get_array_read()), (bp, p, nel)
+        pa.op.apply_add(pa.u, pa.v), pc.op.apply_add(pc.u, pc.v)  # v + (c0 + c1 + ..) vs ((v + c0) + c1) + ..: equal up to rounding
+        assert rel(pc.v.get_array_read(), pa.v.get_array_read()) < 1e-14, (bp, p, nel)
 
 
 def test_unfused_fallback_matches_fused(cm, monkeypatch):
