@@ -1037,9 +1037,14 @@ struct Gen {
       const string        sl = std::to_string(fd.slot);
       if (fd.emode == B200_EVAL_NONE) {
         for (int cc = 0; cc < fd.nc; cc++)
-          for (int q = 0; q < Q; q++)
-            c << "      in_" << f << "[" << cc * Q + q << "] = __ldg(b200a.in_ptr[" << sl << "] + "
-              << lidx(fd.rstr, "", "e", "row * " + std::to_string(Q) + " + " + std::to_string(q), std::to_string(cc)) << ");\n";
+          for (int q = 0; q < Q; q++) {
+            if (fd.qd_off >= 0)  // staged one group ahead by cp.async (b200_issue_qd)
+              c << "      in_" << f << "[" << cc * Q + q << "] = " << smem_at(fd.qd_off, "const double") << "[(" << cc * E << " + le) * " << Q * Q * Q << " + row * "
+                << Q << " + " << q << "];\n";
+            else
+              c << "      in_" << f << "[" << cc * Q + q << "] = __ldg(b200a.in_ptr[" << sl << "] + "
+                << lidx(fd.rstr, "", "e", "row * " + std::to_string(Q) + " + " + std::to_string(q), std::to_string(cc)) << ");\n";
+          }
       } else if (fd.emode == B200_EVAL_WEIGHT) {
         c << "      { const double wyz = cW" << fd.basis_id << "[qy] * cW" << fd.basis_id << "[qz];\n";
         for (int q = 0; q < Q; q++) c << "        in_" << f << "[" << q << "] = cW" << fd.basis_id << "[" << q << "] * wyz; }\n";

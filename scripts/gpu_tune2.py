@@ -45,7 +45,10 @@ def run(tag, env, epb=0, scatter=0):
 
 vref = None
 print(f"{wl}: {base.num_dofs/1e6:.2f}M DoFs, {base.num_elem} elements")
-if mode == "ordered":
+if mode == "stage":
+    for st in (1, 5, 3, 7, 9, 13):
+        run(f"stage={st}", {"CEED_B200_STAGE": str(st)})
+elif mode == "ordered":
     run("deterministic (table)", {})
     run("ordered (in-kernel completion)", {}, scatter=3)
     run("atomic", {}, scatter=1)
