@@ -215,6 +215,18 @@ CEEDB200_EXPORT int ceedb200_iface_pack(B200Ceed ceed, const double *d_v, const 
 CEEDB200_EXPORT int ceedb200_iface_unpack_sum(B200Ceed ceed, double *d_v, long long n, const long long *d_node, const int *d_ptr, const int *d_src,
                                               const double *d_recv);
 
+/* ---- device-resident conjugate-gradient pieces (the reference's figure of merit is
+ * "DoFs/sec in CG", examples/petsc/bps.c:218-288, there with PETSc KSPCG).  Raw device pointers; all scalars live on the
+ * device, so one CG iteration = operator apply + these calls needs no host synchronisation.  d_w (nullable) weights the dot
+ * products (1 = entry owned by this rank, 0 = copy of an interface node).
+ *   dot:       *d_out = sum_i w_i x_i y_i                                       (deterministic two-pass reduction)
+ *   update:    alpha = *d_rr / *d_pAp;  x += alpha p;  r -= alpha Ap;  *d_rr_new = sum_i w_i r_i^2
+ *   direction: beta = *d_rr_new / *d_rr;  p = r + beta p */
+CEEDB200_EXPORT int ceedb200_cg_dot(B200Ceed ceed, const double *d_x, const double *d_y, const double *d_w, long long n, double *d_out);
+CEEDB200_EXPORT int ceedb200_cg_update(B200Ceed ceed, double *d_x, double *d_r, const double *d_p, const double *d_Ap, const double *d_w, long long n,
+                                       const double *d_rr, const double *d_pAp, double *d_rr_new);
+CEEDB200_EXPORT int ceedb200_cg_direction(B200Ceed ceed, double *d_p, const double *d_r, long long n, const double *d_rr_new, const double *d_rr);
+
 #ifdef __cplusplus
 }
 #endif

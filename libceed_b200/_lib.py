@@ -115,6 +115,9 @@ def load(path=LIB_PATH):
         "ceedb200_operator_set_kernel_shape": [handle, P(C.c_int)],
         "ceedb200_operator_get_kernel_shape": [handle, P(C.c_int), C.c_char_p, C.c_int],
         "ceedb200_set_autotune": [handle, C.c_int],
+        "ceedb200_cg_dot": [handle, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p],
+        "ceedb200_cg_update": [handle, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p],
+        "ceedb200_cg_direction": [handle, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p],
         "ceedb200_iface_pack": [handle, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p],
         "ceedb200_iface_unpack_sum": [handle, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     }

@@ -455,3 +455,91 @@ extern "C" int ceedb200_iface_unpack_sum(B200Ceed ceed, double *d_v, long long n
   if (n > 0) LAUNCH(ceed, k_iface_unpack_sum, n, d_v, n, d_node, d_ptr, d_src, d_recv);
   return B200_SUCCESS;
 }
+
+// ------------------------------------------------------------------------------------------------ device-resident CG pieces
+// the CG loop around the operator (what the reference's published figure of merit measures,
+// examples/petsc/bps.c:218-288, there with PETSc's KSPCG + VecDot/VecAXPY).  All scalars stay on the device, so an iteration
+// needs no host synchronisation and can be replayed from a CUDA graph; reductions are two-pass with a fixed grid and a fixed
+// tree order (deterministic).  `w` (optional) weights every entry of a dot product: 1 for entries this rank owns, 0 for its
+// copies of interface nodes, so that a multi-GPU dot (local dot + all-reduce) counts every DoF once.
+namespace {
+constexpr int kCgBlocks = 592;  // 4 x 148: fixed, independent of n -> reproducible partial sums
+
+__device__ __forceinline__ void block_sum_to(double acc, double *__restrict__ out) {
+  __shared__ double s[kThreads];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = kThreads / 2; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) s[threadIdx.x] += s[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = s[0];
+}
+__global__ void k_cg_dot_partial(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ w, long long n,
+                                 double *__restrict__ partial) {
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += (w ? w[i] : 1.0) * x[i] * y[i];
+  block_sum_to(acc, partial + blockIdx.x);
+}
+__global__ void k_cg_final(const double *__restrict__ partial, int n, double *__restrict__ out) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+  block_sum_to(acc, out);
+}
+// alpha = rr / pAp;  x += alpha p;  r -= alpha Ap;  partial sums of the new (weighted) r.r
+__global__ void k_cg_update_partial(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p, const double *__restrict__ Ap,
+                                    const double *__restrict__ w, long long n, const double *__restrict__ rr, const double *__restrict__ pAp,
+                                    double *__restrict__ partial) {
+  const double alpha = *rr / *pAp;
+  double       acc   = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double ri = fma(-alpha, Ap[i], r[i]);
+    r[i] = ri;
+    acc += (w ? w[i] : 1.0) * ri * ri;
+  }
+  block_sum_to(acc, partial + blockIdx.x);
+}
+// beta = rr_new / rr;  p = r + beta p
+__global__ void k_cg_direction(double *__restrict__ p, const double *__restrict__ r, long long n, const double *__restrict__ rr_new,
+                               const double *__restrict__ rr) {
+  const double beta = *rr_new / *rr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = fma(beta, p[i], r[i]);
+}
+
+int cg_scratch(B200Ceed ceed) {
+  if (ceed->scratch_len < (size_t)ceed->num_sms * 16) {
+    B200_CALL(b200_dfree(ceed, ceed->d_scratch));
+    B200_CALL(b200_dmalloc(ceed, (void **)&ceed->d_scratch, (size_t)ceed->num_sms * 16 * sizeof(double)));
+    ceed->scratch_len = (size_t)ceed->num_sms * 16;
+  }
+  return B200_SUCCESS;
+}
+}  // namespace
+
+#define CG_LAUNCH(ceed, kernel, grid, ...)                                                                              \
+  do {                                                                                                                  \
+    B200_CHECK(!b200_compile_only(), ceed, B200_ERROR_BACKEND, "CEED_B200_COMPILE_ONLY is set; kernels cannot run");    \
+    kernel<<<grid, kThreads, 0, (ceed)->stream>>>(__VA_ARGS__);                                                         \
+    (ceed)->launch_count++;                                                                                             \
+    B200_CUDA(ceed, cudaGetLastError());                                                                                \
+  } while (0)
+
+extern "C" int ceedb200_cg_dot(B200Ceed ceed, const double *d_x, const double *d_y, const double *d_w, long long n, double *d_out) {
+  B200_CALL(cg_scratch(ceed));
+  CG_LAUNCH(ceed, k_cg_dot_partial, kCgBlocks, d_x, d_y, d_w, n, ceed->d_scratch);
+  CG_LAUNCH(ceed, k_cg_final, 1, ceed->d_scratch, kCgBlocks, d_out);
+  return B200_SUCCESS;
+}
+extern "C" int ceedb200_cg_update(B200Ceed ceed, double *d_x, double *d_r, const double *d_p, const double *d_Ap, const double *d_w, long long n,
+                                  const double *d_rr, const double *d_pAp, double *d_rr_new) {
+  B200_CALL(cg_scratch(ceed));
+  CG_LAUNCH(ceed, k_cg_update_partial, kCgBlocks, d_x, d_r, d_p, d_Ap, d_w, n, d_rr, d_pAp, ceed->d_scratch);
+  CG_LAUNCH(ceed, k_cg_final, 1, ceed->d_scratch, kCgBlocks, d_rr_new);
+  return B200_SUCCESS;
+}
+extern "C" int ceedb200_cg_direction(B200Ceed ceed, double *d_p, const double *d_r, long long n, const double *d_rr_new, const double *d_rr) {
+  CG_LAUNCH(ceed, k_cg_direction, kCgBlocks, d_p, d_r, n, d_rr_new, d_rr);
+  return B200_SUCCESS;
+}

@@ -423,6 +423,32 @@ def test_interface_pack_unpack_kernels(cm):
     assert np.array_equal(v_d.cpu().numpy(), expect)  # same order of additions -> same bits
 
 
+def test_device_resident_cg_converges(cm):
+    """CG around the fused operator with device-resident scalars (cg.DeviceCG): solves M x = b for the BP1 mass operator."""
+    import torch
+    from libceed_b200.cg import DeviceCG
+    prob = make_problem(cm, 1, 3, (4, 4, 3))
+    n, dev = prob.num_dofs, torch.device("cuda")
+    cg = DeviceCG(prob.ceed, prob.op, prob.u, prob.v, n, dev)
+    x_true = torch.from_numpy(seeded_uniform(n, 31)).to(dev)
+    cg.p.copy_(x_true)
+    cg.apply()
+    b = cg.Ap.clone()
+    cg.start(b)
+    r0 = cg.residual_norm2()
+    cg.iterate(40)
+    r40 = cg.residual_norm2()
+    cg.iterate(260)
+    assert r40 < 1e-2 * r0 and cg.residual_norm2() < 1e-9 * r0, (r0, r40, cg.residual_norm2())
+    assert float((cg.x - x_true).abs().max()) < 1e-6 * float(x_true.abs().max())
+    # the dot kernel against numpy, weighted and unweighted
+    a, c, w = (torch.from_numpy(seeded_uniform(n, s)).to(dev) for s in (1, 2, 3))
+    out = torch.zeros(1, dtype=torch.float64, device=dev)
+    lib, C = prob.ceed._lib, __import__("ctypes")
+    prob.ceed._chk(lib.ceedb200_cg_dot(prob.ceed._ptr, C.c_void_p(a.data_ptr()), C.c_void_p(c.data_ptr()), C.c_void_p(w.data_ptr()), n, C.c_void_p(out.data_ptr())))
+    assert abs(float(out.item()) - float((a * c * w).sum().item())) < 1e-12 * n
+
+
 @pytest.mark.parametrize("bp,p", [(1, 3), (3, 6), (5, 7), (6, 4)])
 def test_full_size_properties(cm, bp, p):
     """BASELINE.json sizes (10M DoFs): properties that need no CPU oracle."""
