@@ -53,6 +53,7 @@ struct B200Ceed_ {
   size_t  scratch_len = 0;
 };
 
+std::string b200_reduced_signature(const std::string &shape_signature);
 int b200_error(B200Ceed ceed, int code, const char *fmt, ...) __attribute__((format(printf, 3, 4)));
 
 #define B200_CHECK(cond, ceed, code, ...)                      \

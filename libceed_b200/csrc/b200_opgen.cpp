@@ -197,6 +197,7 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     B200Tuning table;
     auto       it = ceed->tune_table.find(plan->signature);
     if (it == ceed->tune_table.end()) it = ceed->tune_table.find(plan->shape_signature);
+    if (it == ceed->tune_table.end()) it = ceed->tune_table.find(b200_reduced_signature(plan->shape_signature));
     if (it == ceed->tune_table.end() && plan->scatter_mode != B200_SCATTER_DETERMINISTIC) {
       // no entry for this scatter mode: the shape tuned for the default mode is the best guess
       auto as_default = [&](std::string key) {
@@ -206,6 +207,7 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
       };
       it = ceed->tune_table.find(as_default(plan->signature));
       if (it == ceed->tune_table.end()) it = ceed->tune_table.find(as_default(plan->shape_signature));
+      if (it == ceed->tune_table.end()) it = ceed->tune_table.find(b200_reduced_signature(as_default(plan->shape_signature)));
     }
     if (it != ceed->tune_table.end()) table = it->second;
     auto pick = [&](int &field, int unset, const char *env, int table_value) {

@@ -7,6 +7,8 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 
+#include <cctype>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -47,6 +49,21 @@ std::string b200_jit_dir() {
 // Tuning table: one line per kernel signature, "<signature> epw group_warps cta_warps minb qf_mode qf_unroll stage [# comment]".
 // Loaded from <library dir>/../tuned/sm_100a.tune (shipped, produced by scripts/gpu_autotune.py on a B200) and from
 // CEED_B200_TUNE_FILE; later entries win.  CEED_B200_NO_TUNE_TABLE=1 ignores both (pure heuristics).
+// "Q8|sc0|in:P7n1goN7|out:P7n1go" -> "Q8|sc0|in:P7n1go|out:P7n1go~": drops the N<comps> / W tokens of EVAL_NONE / EVAL_WEIGHT fields
+std::string b200_reduced_signature(const std::string &shape_signature) {
+  std::string out;
+  for (size_t i = 0; i < shape_signature.size(); i++) {
+    const char ch = shape_signature[i];
+    if (ch == 'W') continue;
+    if (ch == 'N') {
+      while (i + 1 < shape_signature.size() && isdigit((unsigned char)shape_signature[i + 1])) i++;
+      continue;
+    }
+    out += ch;
+  }
+  return out + "~";
+}
+
 static void b200_load_tune_file(B200Ceed ceed, const std::string &path) {
   FILE *f = fopen(path.c_str(), "r");
   if (!f) return;
@@ -60,6 +77,12 @@ static void b200_load_tune_file(B200Ceed ceed, const std::string &path) {
       std::string s(sig);
       size_t      pos = s.rfind('|');
       if (pos != std::string::npos && !ceed->tune_table.count(s.substr(0, pos))) ceed->tune_table[s.substr(0, pos)] = t;
+      // reduced key (additionally without the streamed-input component counts): e.g. the gallery Poisson operator with 6
+      // quadrature-data components takes the shape tuned for the 7-component BP operator of the same P, Q and eval modes
+      if (pos != std::string::npos) {
+        const std::string red = b200_reduced_signature(s.substr(0, pos));
+        if (!ceed->tune_table.count(red)) ceed->tune_table[red] = t;
+      }
     }
   }
   fclose(f);

@@ -117,3 +117,53 @@ def test_fused_kernels_generate_and_compile_for_sm100a_without_gpu():
         assert val["info"]["smem_bytes"] <= 227 * 1024 and val["info"]["threads"] % 32 == 0
         # compile-only mode never computes anything: applying must fail loudly, not fall back to the CPU
         assert val["ran"] is False and "COMPILE_ONLY" in val["err"], (key, val)
+
+
+TUNE_LOOKUP = r"""
+import json, os, sys
+sys.path.insert(0, %r)
+from libceed_b200 import Ceed
+from libceed_b200.bp import BPProblem
+out = {}
+for key, (bp, p, scatter) in {"exact": (3, 6, 0), "reduced": (4, 2, 0), "other_scatter": (4, 2, 1), "shapes": (3, 4, 0)}.items():
+    c = Ceed(); c.set_scatter_mode(scatter)
+    pr = BPProblem(c, bp, p, (3, 3, 3), build_qdata=False)
+    if key == "shapes":
+        res = {}
+        for name, shape in {"groups": dict(group_warps=2, cta_warps=4), "pairs": dict(qf_mode=2, qf_unroll=2), "ring": dict(stage_mask=17),
+                            "ordered": None}.items():
+            if shape is None:
+                c.set_scatter_mode(3); pr = BPProblem(c, bp, p, (3, 3, 3), build_qdata=False)
+            else:
+                pr.op.set_kernel_shape(**shape)
+            src = pr.op.kernel_source()
+            res[name] = dict(shape=pr.op.get_kernel_shape(), bar="bar.sync" in src, vla2="#define CEED_Q_VLA 2" in src, ring="b200_ring_prologue" in src,
+                             ordered="b200_ordered_complete" in src and "st.release.gpu" in src)
+        out[key] = res
+    else:
+        pr.op.kernel_source()
+        out[key] = pr.op.get_kernel_shape()
+print("RESULT" + json.dumps(out))
+""" % ROOT
+
+
+def test_tuning_table_lookup_and_kernel_shapes_without_gpu(tmp_path):
+    """Kernel shapes are data: exact table hit, reduced-signature hit (other QFunction / other number of quadrature-data
+    components), other scatter mode falling back to the default mode's entry; every shape variant generates and compiles."""
+    tune = tmp_path / "extra.tune"
+    tune.write_text("# test entry: 3-component diffusion, P=3, Q=4, 5 streamed components, QFunction Foo\n"
+                    "Q4|sc0|in:P3n3goN5|out:P3n3go|Foo 2 2 2 3 1 2 0\n")
+    env = dict(os.environ, CEED_B200_COMPILE_ONLY="1", CEED_B200_TUNE_FILE=str(tune))
+    r = subprocess.run([sys.executable, "-c", TUNE_LOOKUP], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][0][6:])
+    shipped = [ln.split() for ln in open(os.path.join(ROOT, "libceed_b200", "tuned", "sm_100a.tune")) if ln.startswith("Q8|sc0|in:P7n1goN7|out:P7n1go|BPDiff")][0]
+    keys = ["elems_per_group", "group_warps", "cta_warps", "min_blocks_per_sm", "qf_mode", "qf_unroll", "stage_mask"]
+    assert [res["exact"][k] for k in keys] == [int(x) for x in shipped[1:8]]
+    for which in ("reduced", "other_scatter"):
+        got = res[which]
+        assert (got["elems_per_group"], got["group_warps"], got["qf_mode"], got["qf_unroll"], got["stage_mask"]) == (2, 2, 1, 2, 0), (which, got)
+    s = res["shapes"]
+    assert s["groups"]["bar"] and s["groups"]["shape"]["group_warps"] == 2
+    assert s["pairs"]["vla2"] and s["pairs"]["shape"]["qf_mode"] == 2
+    assert s["ring"]["ring"] and s["ordered"]["ordered"]
