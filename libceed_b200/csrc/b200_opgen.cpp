@@ -241,6 +241,7 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
   plan->qf_pointwise = tn.qf_mode == 1 || tn.qf_mode == 2;
   plan->qf_pp        = (tn.qf_mode == 2 && Q % 2 == 0) ? 2 : 1;  // point pairs need x-adjacent points in one row
   plan->qf_unroll    = tn.qf_unroll > 0 ? tn.qf_unroll : 4;
+  plan->qf_ahead     = getenv("CEED_B200_QF_AHEAD") ? atoi(getenv("CEED_B200_QF_AHEAD")) : 1;
   auto planes_of = [&](const B200GenGroup &g) { return g.nc * (g.use_grad ? ((plan->qf_pointwise && g.use_interp) ? 4 : 3) : 2); };
   int  n_in = 0, n_out = 0;
   for (auto &g : plan->in_groups) {
@@ -914,17 +915,20 @@ struct Gen {
     // direct-load EVAL_NONE inputs are fetched one z-layer ahead (software pipelining): the loads of layer qz+1 are in
     // flight while the QFunction and the transposed z-derivative of layer qz execute
     const bool qf_ahead = !getenv("CEED_B200_NO_QFPF");
+    const int  depth    = std::max(1, std::min(Q, plan->qf_ahead));  // z-layers of streamed inputs in flight per lane
     auto none_load = [&](const B200GenField &fd, int cc, const string &pt_expr) {
       const string sl = std::to_string(fd.slot);
       return "__ldg(b200a.in_ptr[" + sl + "] + " + lidx(fd.rstr, "b200a.in_idx[" + sl + "]", "e", pt_expr, std::to_string(cc)) + ")";
     };
     c << "      const int pt0 = qy * " << Q << " + qx;\n";
     if (qf_ahead)
-      for (size_t f = 0; f < plan->in_fields.size(); f++) {
-        const B200GenField &fd = plan->in_fields[f];
-        if (fd.emode != B200_EVAL_NONE || fd.qd_off >= 0) continue;
-        for (int cc = 0; cc < fd.nc; cc++) c << "      double nx_" << f << "_" << cc << " = " << none_load(fd, cc, "pt0") << ";\n";
-      }
+      for (int d = 0; d < depth; d++)
+        for (size_t f = 0; f < plan->in_fields.size(); f++) {
+          const B200GenField &fd = plan->in_fields[f];
+          if (fd.emode != B200_EVAL_NONE || fd.qd_off >= 0) continue;
+          for (int cc = 0; cc < fd.nc; cc++)
+            c << "      double nx_" << f << "_" << cc << "_" << d << " = " << none_load(fd, cc, "pt0 + " + std::to_string(d * Q * Q)) << ";\n";
+        }
     for (int qz = 0; qz < Q; qz++) {
       c << "      {  // qz = " << qz << "\n";
       c << "        const int p = pxy + " << qz * Q * Qs << ";\n";
@@ -938,8 +942,9 @@ struct Gen {
               if (fd.qd_off >= 0)
                 c << "        in_" << f << "[" << cc << "] = " << smem_at(fd.qd_off, "const double") << "[(" << cc * E << " + le) * " << Q * Q * Q << " + pt];\n";
               else if (qf_ahead) {
-                c << "        in_" << f << "[" << cc << "] = nx_" << f << "_" << cc << ";\n";
-                if (qz + 1 < Q) c << "        nx_" << f << "_" << cc << " = " << none_load(fd, cc, "pt + " + std::to_string(Q * Q)) << ";\n";
+                const string slot = "nx_" + std::to_string(f) + "_" + std::to_string(cc) + "_" + std::to_string(qz % depth);
+                c << "        in_" << f << "[" << cc << "] = " << slot << ";\n";
+                if (qz + depth < Q) c << "        " << slot << " = " << none_load(fd, cc, "pt + " + std::to_string(depth * Q * Q)) << ";\n";
               } else
                 c << "        in_" << f << "[" << cc << "] = " << none_load(fd, cc, "pt") << ";\n";
             }

@@ -81,6 +81,7 @@ struct B200OpPlan {
   int                       ring_off = -1, ring_slots = 0, ring_comps = 0, ring_rounds = 0;
   bool                      qf_xline = false;    // gradient-free operators: QFunction on x-lines inside the x-contraction stage
   int                       qf_pp = 1;           // pointwise QFunction stage: points per lane (2 = x-adjacent pair, 16-byte loads)
+  int                       qf_ahead = 1;        // z-line QFunction stage: z-layers of streamed inputs in flight per lane
   int                       qf_unroll = 4;       // pointwise QFunction stage: points in flight per lane
   std::string               signature, shape_signature;  // tuning-table keys (with / without the QFunction name)
   B200Tuning                resolved;            // the shape actually used

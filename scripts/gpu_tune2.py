@@ -45,7 +45,14 @@ def run(tag, env, epb=0, scatter=0):
 
 vref = None
 print(f"{wl}: {base.num_dofs/1e6:.2f}M DoFs, {base.num_elem} elements")
-if mode == "stage":
+if mode == "ahead":
+    run("table", {})
+    for d in (2, 3):
+        run(f"ahead={d}", {"CEED_B200_QF_AHEAD": str(d)})
+        for gw, warps, minb in ((1, 4, 3), (1, 4, 2), (2, 2, 8), (2, 2, 6), (2, 8, 1)):
+            run(f"ahead={d} gw={gw} warps={warps} minb={minb}", {"CEED_B200_QF_AHEAD": str(d), "CEED_B200_GROUP_WARPS": str(gw), "CEED_B200_WARPS": str(warps),
+                                                                  "CEED_B200_MINB": str(minb), "CEED_B200_QF_POINTWISE": "0"})
+elif mode == "stage":
     for st in (1, 5, 3, 7, 9, 13):
         run(f"stage={st}", {"CEED_B200_STAGE": str(st)})
 elif mode == "ordered":
