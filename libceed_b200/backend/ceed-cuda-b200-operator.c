@@ -23,6 +23,31 @@ static int CeedOperatorSetup_B200(CeedOperator op) {
 
   CeedCallBackend(CeedOperatorGetData(op, &impl));
   if (impl->is_setup) return CEED_ERROR_SUCCESS;
+  {
+    // objects created by the delegate backend (CEED_B200_FALLBACK): the whole operator goes through its fallback operator
+    Ceed_B200 *data;
+
+    CeedCallBackend(CeedGetData(ceed, &data));
+    if (data->has_fallback) {
+      CeedCallBackend(CeedOperatorGetFields(op, &num_in, &in, &num_out, &out));
+      for (CeedInt i = 0; i < num_in + num_out; i++) {
+        CeedElemRestriction rstr;
+        CeedBasis           basis;
+
+        CeedCallBackend(CeedOperatorFieldGetElemRestriction(i < num_in ? in[i] : out[i - num_in], &rstr));
+        CeedCallBackend(CeedOperatorFieldGetBasis(i < num_in ? in[i] : out[i - num_in], &basis));
+        if (rstr != CEED_ELEMRESTRICTION_NONE && CeedElemRestrictionReturnCeed(rstr) != ceed) impl->use_fallback = true;
+        if (basis != CEED_BASIS_NONE && CeedBasisReturnCeed(basis) != ceed) impl->use_fallback = true;
+        CeedCallBackend(CeedElemRestrictionDestroy(&rstr));
+        CeedCallBackend(CeedBasisDestroy(&basis));
+      }
+      if (impl->use_fallback) {
+        impl->is_setup = true;
+        CeedCallBackend(CeedOperatorSetSetupDone(op));
+        return CEED_ERROR_SUCCESS;
+      }
+    }
+  }
   CeedCallBackend(CeedGetCore_B200(ceed, &core));
   CeedCallBackend(CeedSyncJitOptions_B200(ceed));
   CeedCallBackend(CeedOperatorGetQFunction(op, &qf));
@@ -94,6 +119,26 @@ static int CeedOperatorApplyCore_B200(CeedOperator op, CeedVector in_vec, CeedVe
   CeedCallBackend(CeedGetCore_B200(ceed, &core));
   CeedCallBackend(CeedOperatorSetup_B200(op));
   CeedCallBackend(CeedOperatorGetData(op, &impl));
+  if (impl->use_fallback) {
+    CeedOperator       op_fallback;
+    CeedInt            num_in, num_out;
+    CeedOperatorField *in, *out;
+
+    CeedCallBackend(CeedOperatorGetFallback(op, &op_fallback));
+    CeedCheck(op_fallback, ceed, CEED_ERROR_UNSUPPORTED, "Backend does not implement operators with objects of other backends");
+    if (!add) {  // Apply = zero the outputs, then ApplyAdd (interface/ceed-operator.c:2357-2405)
+      CeedCallBackend(CeedOperatorGetFields(op, &num_in, &in, &num_out, &out));
+      for (CeedInt i = 0; i < num_out; i++) {
+        CeedVector vec;
+
+        CeedCallBackend(CeedOperatorFieldGetVector(out[i], &vec));
+        if (vec != CEED_VECTOR_ACTIVE && vec != CEED_VECTOR_NONE) CeedCallBackend(CeedVectorSetValue(vec, 0.0));
+        CeedCallBackend(CeedVectorDestroy(&vec));
+      }
+      if (out_vec != CEED_VECTOR_NONE) CeedCallBackend(CeedVectorSetValue(out_vec, 0.0));
+    }
+    return CeedOperatorApplyAdd(op_fallback, in_vec, out_vec, CEED_REQUEST_IMMEDIATE);
+  }
 
   // device arrays of every vector involved, through the interface
   if (in_vec != CEED_VECTOR_NONE) {
@@ -156,7 +201,7 @@ static int CeedOperatorDestroy_B200(CeedOperator op) {
   CeedOperator_B200 *impl;
 
   CeedCallBackend(CeedOperatorGetData(op, &impl));
-  ceedb200_operator_destroy(impl->core);
+  if (impl->core) ceedb200_operator_destroy(impl->core);
   ceedb200_vector_destroy(impl->view_in);
   ceedb200_vector_destroy(impl->view_out);
   for (CeedInt i = 0; i < CEED_FIELD_MAX; i++) {
@@ -186,8 +231,15 @@ int CeedOperatorCreate_B200(CeedOperator op) {
   CeedCallBackend(CeedOperatorSetData(op, impl));
   CeedCallBackend(CeedSetBackendFunction(ceed, "Operator", op, "ApplyAdd", CeedOperatorApplyAdd_B200));
   CeedCallBackend(CeedSetBackendFunction(ceed, "Operator", op, "Apply", CeedOperatorApply_B200));
-  CeedCallBackend(CeedSetBackendFunction(ceed, "Operator", op, "LinearAssembleQFunction", CeedOperatorLinearAssembleQFunction_B200));
-  CeedCallBackend(CeedSetBackendFunction(ceed, "Operator", op, "LinearAssembleQFunctionUpdate", CeedOperatorLinearAssembleQFunctionUpdate_B200));
+  {
+    Ceed_B200 *data;
+
+    CeedCallBackend(CeedGetData(ceed, &data));
+    if (!data->has_fallback) {  // with a fallback Ceed the interface routes assembly to the fallback operator by itself
+      CeedCallBackend(CeedSetBackendFunction(ceed, "Operator", op, "LinearAssembleQFunction", CeedOperatorLinearAssembleQFunction_B200));
+      CeedCallBackend(CeedSetBackendFunction(ceed, "Operator", op, "LinearAssembleQFunctionUpdate", CeedOperatorLinearAssembleQFunctionUpdate_B200));
+    }
+  }
   CeedCallBackend(CeedSetBackendFunction(ceed, "Operator", op, "Destroy", CeedOperatorDestroy_B200));
   return CEED_ERROR_SUCCESS;
 }

@@ -8,6 +8,7 @@
 // "Backend does not implement ..." exactly like other backends do for their gaps (tests/junit.py:121-145 treats it as skip).
 #include "ceed-cuda-b200.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -92,6 +93,23 @@ static int CeedInit_B200(const char *resource, Ceed ceed) {
   CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "QFunctionCreate", CeedQFunctionCreate_B200));
   CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "QFunctionContextCreate", CeedQFunctionContextCreate_B200));
   CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "OperatorCreate", CeedOperatorCreate_B200));
+
+  // Opt-in (CEED_B200_FALLBACK=1, needs a libCEED with the CUDA backends): like /gpu/cuda/gen delegates to /gpu/cuda/shared
+  // and falls back to /gpu/cuda/ref (backends/cuda-gen/ceed-cuda-gen.c:33-39), object types this backend does not create
+  // (non-tensor / H(div) / H(curl) bases, at-points restrictions, composite operators) come from /gpu/cuda/ref, operators that
+  // contain such objects are applied through their fallback operator, and the LinearAssemble* family runs on the fallback.
+  // The hot path -- 3-D tensor operators -- is unaffected.
+  if (getenv("CEED_B200_FALLBACK") && atoi(getenv("CEED_B200_FALLBACK"))) {
+    Ceed ceed_ref;
+    char ref_resource[64];
+
+    snprintf(ref_resource, sizeof(ref_resource), "/gpu/cuda/ref:device_id=%d", data->device_id);
+    CeedCallBackend(CeedInit(ref_resource, &ceed_ref));
+    CeedCallBackend(CeedSetDelegate(ceed, ceed_ref));
+    CeedCallBackend(CeedSetOperatorFallbackCeed(ceed, ceed_ref));
+    CeedCallBackend(CeedDestroy(&ceed_ref));
+    data->has_fallback = true;
+  }
   return CEED_ERROR_SUCCESS;
 }
 

@@ -17,6 +17,7 @@
 typedef struct {
   B200Ceed core;
   int      device_id;
+  bool     has_fallback;  // /gpu/cuda/ref is the delegate for object types and the fallback for operators this backend does not cover
   int      num_roots_seen, num_defines_seen;
 } Ceed_B200;
 
@@ -48,6 +49,7 @@ typedef struct {
   CeedVector   passive_in_vec[CEED_FIELD_MAX], passive_out_vec[CEED_FIELD_MAX];
   CeedInt      num_in, num_out;
   bool         is_setup;
+  bool         use_fallback;  // operator with objects of the delegate backend (non-tensor basis, ...): applied through CeedOperatorGetFallback
 } CeedOperator_B200;
 
 // error plumbing: turn a ceedb200_* failure into a CeedError carrying the core's message
