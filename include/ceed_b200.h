@@ -166,6 +166,10 @@ CEEDB200_EXPORT int ceedb200_qfunction_destroy(B200QFunction qf);
 CEEDB200_EXPORT int ceedb200_qfunction_add_input(B200QFunction qf, const char *field_name, b200_int size, int eval_mode);
 CEEDB200_EXPORT int ceedb200_qfunction_add_output(B200QFunction qf, const char *field_name, b200_int size, int eval_mode);
 CEEDB200_EXPORT int ceedb200_qfunction_set_context(B200QFunction qf, B200QFContext ctx);
+/* context owned by another backend (a libCEED operator may carry a CeedQFunctionContext of its fallback backend): raw device
+ * pointer, valid for the applies that follow; obtained through CeedQFunctionGetInnerContextData(qf, CEED_MEM_DEVICE, ...) like
+ * backends/cuda-gen/ceed-cuda-gen-operator.c:207 does */
+CEEDB200_EXPORT int ceedb200_qfunction_set_context_ptr(B200QFunction qf, void *d_ctx);
 /* standalone apply over Q points: U[i]/V[i] hold field i as [size_i][Q] (doc/sphinx/source/libCEEDdev.md:113-118) */
 CEEDB200_EXPORT int ceedb200_qfunction_apply(B200QFunction qf, b200_int Q, const B200Vector *U, const B200Vector *V);
 

@@ -170,7 +170,13 @@ static int CeedOperatorApplyCore_B200(CeedOperator op, CeedVector in_vec, CeedVe
     CeedCallB200(ceed, core, ceedb200_vector_set_array(impl->passive_out[i], B200_MEM_DEVICE, B200_USE_POINTER, d_pout[i]));
   }
   {
-    bool has_passive_out = false;
+    bool          has_passive_out = false;
+    CeedQFunction qf;
+    void         *held_ctx;
+
+    // a QFunction context of another backend is handed over as a raw device pointer for this apply
+    CeedCallBackend(CeedOperatorGetQFunction(op, &qf));
+    CeedCallBackend(CeedQFunctionContextAcquire_B200(qf, &held_ctx));
     for (CeedInt i = 0; i < impl->num_out; i++) has_passive_out = has_passive_out || impl->passive_out_vec[i];
     // overwrite semantics can only be used when every output is the active vector
     if (!add && !has_passive_out) ierr = ceedb200_operator_apply(impl->core, in_vec != CEED_VECTOR_NONE ? impl->view_in : NULL, impl->view_out);
@@ -178,6 +184,8 @@ static int CeedOperatorApplyCore_B200(CeedOperator op, CeedVector in_vec, CeedVe
       if (!add && out_vec != CEED_VECTOR_NONE) ceedb200_vector_set_value(impl->view_out, 0.0);
       ierr = ceedb200_operator_apply_add(impl->core, in_vec != CEED_VECTOR_NONE ? impl->view_in : NULL, impl->view_out);
     }
+    CeedCallBackend(CeedQFunctionContextRelease_B200(qf, &held_ctx));
+    CeedCallBackend(CeedQFunctionDestroy(&qf));
   }
   // restore in every case so that libCEED's access locks are released
   if (in_vec != CEED_VECTOR_NONE) CeedCallBackend(CeedVectorRestoreArrayRead(in_vec, &d_in));

@@ -133,7 +133,13 @@ int CeedQFunctionGetCore_B200(CeedQFunction qf, B200QFunction *core_qf) {
     impl->fields_set = true;
   }
   CeedCallBackend(CeedQFunctionGetInnerContext(qf, &ctx));
-  if (ctx) {
+  impl->foreign_ctx = NULL;
+  if (ctx && CeedQFunctionContextReturnCeed(ctx) != ceed) {
+    // context created on another Ceed (e.g. by the interface on the fallback Ceed, interface/ceed-preconditioning.c:3333): its
+    // backend data is not ours; CeedQFunctionContextAcquire_B200 fetches the device pointer through the interface per apply
+    impl->foreign_ctx = ctx;
+    ceedb200_qfunction_set_context_ptr(impl->core, NULL);
+  } else if (ctx) {
     B200QFContext c;
 
     CeedCallBackend(CtxCore(ctx, &c));  // borrowed reference: CeedQFunctionGetInnerContext does not add one (interface/ceed-qfunction.c:422-437)
@@ -142,6 +148,26 @@ int CeedQFunctionGetCore_B200(CeedQFunction qf, B200QFunction *core_qf) {
     ceedb200_qfunction_set_context(impl->core, NULL);
   }
   *core_qf = impl->core;
+  return CEED_ERROR_SUCCESS;
+}
+
+// Foreign contexts: device pointer through the interface for the duration of one apply
+int CeedQFunctionContextAcquire_B200(CeedQFunction qf, void **held) {
+  CeedQFunction_B200 *impl;
+
+  CeedCallBackend(CeedQFunctionGetData(qf, &impl));
+  *held = NULL;
+  if (impl->foreign_ctx) {
+    CeedCallBackend(CeedQFunctionContextGetDataRead(impl->foreign_ctx, CEED_MEM_DEVICE, held));
+    ceedb200_qfunction_set_context_ptr(impl->core, *held);
+  }
+  return CEED_ERROR_SUCCESS;
+}
+int CeedQFunctionContextRelease_B200(CeedQFunction qf, void **held) {
+  CeedQFunction_B200 *impl;
+
+  CeedCallBackend(CeedQFunctionGetData(qf, &impl));
+  if (impl->foreign_ctx && *held) CeedCallBackend(CeedQFunctionContextRestoreDataRead(impl->foreign_ctx, held));
   return CEED_ERROR_SUCCESS;
 }
 
@@ -158,7 +184,15 @@ static int CeedQFunctionApply_B200(CeedQFunction qf, CeedInt Q, CeedVector *U, C
   CeedCallBackend(CeedQFunctionGetNumArgs(qf, &num_in, &num_out));
   for (CeedInt i = 0; i < num_in; i++) CeedCallBackend(CeedVectorGetArrayRead(U[i], CEED_MEM_DEVICE, &d_in[i]));
   for (CeedInt i = 0; i < num_out; i++) CeedCallBackend(CeedVectorGetArrayWrite(V[i], CEED_MEM_DEVICE, &d_out[i]));
-  CeedCallB200(ceed, core, ceedb200_qfunction_apply_ptr(core_qf, Q, d_in, d_out));
+  {
+    void *held;
+    int   ierr;
+
+    CeedCallBackend(CeedQFunctionContextAcquire_B200(qf, &held));
+    ierr = ceedb200_qfunction_apply_ptr(core_qf, Q, d_in, d_out);
+    CeedCallBackend(CeedQFunctionContextRelease_B200(qf, &held));
+    if (ierr) return CeedError(ceed, CEED_ERROR_BACKEND, "%s", ceedb200_last_error(core));
+  }
   for (CeedInt i = 0; i < num_in; i++) CeedCallBackend(CeedVectorRestoreArrayRead(U[i], &d_in[i]));
   for (CeedInt i = 0; i < num_out; i++) CeedCallBackend(CeedVectorRestoreArray(V[i], &d_out[i]));
   return CEED_ERROR_SUCCESS;

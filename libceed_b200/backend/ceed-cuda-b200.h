@@ -38,8 +38,9 @@ typedef struct {
 } CeedQFunctionContext_B200;
 
 typedef struct {
-  B200QFunction core;
-  bool          fields_set;
+  B200QFunction        core;
+  bool                 fields_set;
+  CeedQFunctionContext foreign_ctx;  // context of another backend (borrowed): accessed through the interface at apply time
 } CeedQFunction_B200;
 
 typedef struct {
@@ -70,6 +71,8 @@ CEED_INTERN int CeedBasisCreateTensorH1_B200(CeedInt dim, CeedInt P_1d, CeedInt 
 CEED_INTERN int CeedQFunctionCreate_B200(CeedQFunction qf);
 CEED_INTERN int CeedQFunctionContextCreate_B200(CeedQFunctionContext ctx);
 CEED_INTERN int CeedOperatorCreate_B200(CeedOperator op);
+CEED_INTERN int CeedQFunctionContextAcquire_B200(CeedQFunction qf, void **held);
+CEED_INTERN int CeedQFunctionContextRelease_B200(CeedQFunction qf, void **held);
 CEED_INTERN int CeedQFunctionGetCore_B200(CeedQFunction qf, B200QFunction *core);
 
 #endif

@@ -156,6 +156,7 @@ struct B200QFunction_ {
   std::string              source_path, kernel_name;
   std::vector<B200QFField> inputs, outputs;
   B200QFContext            ctx = nullptr;
+  void                    *raw_ctx = nullptr;  // device pointer of a context owned by someone else (used when ctx == nullptr)
   B200Module              *module = nullptr;  // standalone apply kernel
   CUfunction               kernel = nullptr;
 };

@@ -159,6 +159,7 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add) {
   memset(&args, 0, sizeof(args));
   args.num_elem = plan->num_elem;
   if (op->qf->ctx) B200_CALL(ceedb200_qfcontext_get_data(op->qf->ctx, B200_MEM_DEVICE, &args.ctx));
+  else args.ctx = op->qf->raw_ctx;
 
   // inputs
   for (size_t i = 0; i < op->in_fields.size(); i++) {

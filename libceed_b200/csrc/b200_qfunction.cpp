@@ -160,7 +160,14 @@ extern "C" int ceedb200_qfunction_add_output(B200QFunction qf, const char *field
   qf->kernel = nullptr;
   return B200_SUCCESS;
 }
+extern "C" int ceedb200_qfunction_set_context_ptr(B200QFunction qf, void *d_ctx) {
+  qf->ctx     = nullptr;
+  qf->raw_ctx = d_ctx;
+  return B200_SUCCESS;
+}
+
 extern "C" int ceedb200_qfunction_set_context(B200QFunction qf, B200QFContext ctx) {
+  qf->raw_ctx = nullptr;
   qf->ctx = ctx;
   return B200_SUCCESS;
 }
@@ -200,7 +207,7 @@ extern "C" int ceedb200_qfunction_apply_ptr(B200QFunction qf, b200_int Q, const 
   memset(&ptrs, 0, sizeof(ptrs));
   for (size_t i = 0; i < qf->inputs.size(); i++) ptrs.in[i] = d_in[i];
   for (size_t i = 0; i < qf->outputs.size(); i++) ptrs.out[i] = d_out[i];
-  void *d_ctx = nullptr;
+  void *d_ctx = qf->raw_ctx;
   if (qf->ctx) B200_CALL(ceedb200_qfcontext_get_data(qf->ctx, B200_MEM_DEVICE, &d_ctx));
   if (Q == 0) return B200_SUCCESS;
   long long q64    = Q;
