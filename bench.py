@@ -79,17 +79,51 @@ def _cpu_worker(args):
     return prob.ncomp * nn, n, dt
 
 
+def _cpu_port_worker(args):
+    bp, p, nel, seconds, steps, warmup, barrier_dir, wid = args
+    from libceed_b200 import mesh as M
+    from libceed_b200.bp import seeded_uniform
+    from oracle import oracle as O
+    off, coords = M.hex_offsets(*nel, p), M.hex_coords(*nel, p)
+    nn = coords.shape[1]
+    _, _, nc, _ = O.bp_sizes(bp, False, p)
+    qd = O.bp_qdata(bp, p, off, coords)
+    u = seeded_uniform(nc * nn)
+    for _ in range(max(1, warmup)):
+        O.bp_apply(bp, p, off, nn, qd, u)
+    open(os.path.join(barrier_dir, f"ready{wid}"), "w").close()
+    while not os.path.exists(os.path.join(barrier_dir, "go")):
+        time.sleep(0.001)
+    t0, n = time.perf_counter(), 0
+    while True:
+        O.bp_apply(bp, p, off, nn, qd, u)
+        n += 1
+        if (steps and n >= steps) or (not steps and time.perf_counter() - t0 > seconds):
+            break
+    return nc * nn, n, time.perf_counter() - t0
+
+
 def cpu_reference(bp, p, seconds, steps=0, warmup=1, resource="/cpu/self/avx/blocked", dofs_per_worker=150_000):
     """Reference CPU backend on all host cores: `cores` forked single-threaded workers (libCEED CPU backends are
     single-threaded per Ceed), each owning its own slab of the workload mesh; aggregate = sum(DoFs * applies) / max(time)."""
     from libceed_b200 import mesh as M
     from libceed_b200.bp import BP_TABLE
+    from oracle import refceed as R
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
     nel = M.choose_elements(dofs_per_worker, p, BP_TABLE[bp][0])
+    # the unmodified reference (oracle/_ref) when it travelled with the repository, else the C restatement of its ref backend
+    have_ref = R.available() and not os.environ.get("CEED_B200_BENCH_FORCE_PORT")
+    kind = "reference" if have_ref else "port"
+    if not have_ref:
+        resource = "oracle/ceed_oracle.c (restatement of /cpu/self/ref/serial)"
     with tempfile.TemporaryDirectory() as d:
         ctx = mp.get_context("fork")
         with ctx.Pool(cores) as pool:
-            res = pool.map_async(_cpu_worker, [(bp, p, nel, resource, seconds, steps, warmup, d, w) for w in range(cores)])
+            if have_ref:
+                jobs = pool.map_async(_cpu_worker, [(bp, p, nel, resource, seconds, steps, warmup, d, w) for w in range(cores)])
+            else:
+                jobs = pool.map_async(_cpu_port_worker, [(bp, p, nel, seconds, steps, warmup, d, w) for w in range(cores)])
+            res = jobs
             t_start = time.time()
             while len([f for f in os.listdir(d) if f.startswith("ready")]) < cores and time.time() - t_start < 600:
                 time.sleep(0.01)
@@ -98,7 +132,7 @@ def cpu_reference(bp, p, seconds, steps=0, warmup=1, resource="/cpu/self/avx/blo
     dofs = sum(o[0] * o[1] for o in out)
     tmax = max(o[2] for o in out)
     applies = sum(o[1] for o in out)
-    return dict(value=dofs / tmax / 1e9, unit="GDoF/s", cores=cores, kind="reference",
+    return dict(value=dofs / tmax / 1e9, unit="GDoF/s", cores=cores, kind=kind,
                 sample=f"{resource}: {cores} forked workers x ({nel[0]}x{nel[1]}x{nel[2]} elements, {out[0][0]} DoFs), "
                        f"{applies} applies in {tmax:.3f} s", ms_per_step=tmax / max(1, out[0][1]) * 1e3, applies=applies)
 
@@ -168,7 +202,7 @@ def main():
         line = dict(metric="CeedOperatorApply throughput", value=r["value"], unit="GDoF/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                     ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                     impl="reference", config=config,
-                    cpu_baseline=dict(value=r["value"], unit="GDoF/s", cores=r["cores"], kind="reference", sample=r["sample"]),
+                    cpu_baseline=dict(value=r["value"], unit="GDoF/s", cores=r["cores"], kind=r["kind"], sample=r["sample"]),
                     e2e=dict(value=r["value"], unit="GDoF/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
         print(json.dumps(line), file=json_out, flush=True)
         return
