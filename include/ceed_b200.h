@@ -119,6 +119,12 @@ CEEDB200_EXPORT int ceedb200_restriction_get_offsets(B200Restriction rstr, int m
 CEEDB200_EXPORT int ceedb200_restriction_get_e_layout(B200Restriction rstr, b200_int layout[3]);
 CEEDB200_EXPORT int ceedb200_restriction_get_info(B200Restriction rstr, b200_int *num_elem, b200_int *elem_size, b200_int *num_comp,
                                                   b200_size *l_size, b200_size *e_size);
+/* diagnostics: host copy of the tables behind the fused kernel's deterministic scatter (no reference counterpart; the
+ * reference scatters with atomics, cuda-gen-templates.h:385-396).  mode B200_SCATTER_DETERMINISTIC: tgt[e-entry] >= 0 L-index of
+ * the owning (first) entry, < 0 ~halo slot.  mode B200_SCATTER_ORDERED (element groups of group_elems): tgt as documented at
+ * B200_SCATTER_ORDERED plus the predecessor-group CSR.  counts = {shared nodes, halo slots, groups, predecessors, supported}. */
+CEEDB200_EXPORT int ceedb200_restriction_debug_scatter_tables(B200Restriction rstr, int mode, int group_elems, int32_t *tgt, int64_t *counts,
+                                                              int32_t *pred_ptr, int32_t *pred_idx, int64_t pred_capacity);
 
 /* ---------------------------------------------------------------- basis (CeedBasis, tensor H1)
  * replaces CeedBasisCreateTensorH1_Cuda_shared / CeedBasisApply: backends/cuda-shared/ceed-cuda-shared-basis.c:24-196,603-666,

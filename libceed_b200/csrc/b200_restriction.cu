@@ -366,6 +366,30 @@ void b200_ordered_scatter_free(B200Ceed ceed, B200OrderedScatter *t) {
   }
 }
 
+// Diagnostics / host-logic tests: host copies of the scatter tables of an offset restriction.
+extern "C" int ceedb200_restriction_debug_scatter_tables(B200Restriction r, int mode, int group_elems, int32_t *tgt, int64_t *counts, int32_t *pred_ptr,
+                                                         int32_t *pred_idx, int64_t pred_capacity) {
+  B200Ceed      ceed = r->ceed;
+  const int64_t n    = (int64_t)r->num_elem * r->elem_size;
+  B200_CHECK(!r->is_strided, ceed, B200_ERROR_UNSUPPORTED, "scatter tables exist for offset restrictions only");
+  if (mode == B200_SCATTER_ORDERED) {
+    B200OrderedScatter t;
+    B200_CALL(b200_restriction_build_ordered(r, group_elems, &t));
+    counts[0] = t.num_shared, counts[1] = t.num_halo, counts[2] = t.num_groups, counts[3] = t.num_pred, counts[4] = t.supported;
+    if (t.supported) {
+      B200_CALL(b200_d2h(ceed, tgt, t.d_tgt, n * sizeof(int32_t)));
+      if (pred_ptr) B200_CALL(b200_d2h(ceed, pred_ptr, t.d_pred_ptr, (t.num_groups + 1) * sizeof(int32_t)));
+      if (pred_idx && t.num_pred <= pred_capacity && t.num_pred > 0) B200_CALL(b200_d2h(ceed, pred_idx, t.d_pred_idx, t.num_pred * sizeof(int32_t)));
+      b200_ordered_scatter_free(ceed, &t);
+    }
+  } else {
+    B200_CALL(b200_restriction_build_owner(r));
+    counts[0] = r->num_shared, counts[1] = r->num_halo, counts[2] = 0, counts[3] = 0, counts[4] = 1;
+    B200_CALL(b200_d2h(ceed, tgt, r->d_tgt, n * sizeof(int32_t)));
+  }
+  return B200_SUCCESS;
+}
+
 int b200_restriction_e_size(B200Restriction r, int64_t *e_size) {
   *e_size = (int64_t)r->num_elem * r->elem_size * r->num_comp;
   return B200_SUCCESS;

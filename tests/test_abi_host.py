@@ -167,3 +167,82 @@ def test_tuning_table_lookup_and_kernel_shapes_without_gpu(tmp_path):
     assert s["groups"]["bar"] and s["groups"]["shape"]["group_warps"] == 2
     assert s["pairs"]["vla2"] and s["pairs"]["shape"]["qf_mode"] == 2
     assert s["ring"]["ring"] and s["ordered"]["ordered"]
+
+
+SCATTER_TABLES = r"""
+import ctypes as C, json, sys
+import numpy as np
+sys.path.insert(0, %r)
+from libceed_b200 import Ceed, mesh as M
+
+def check(nel, p, group_elems, scramble):
+    ceed = Ceed()
+    off = M.hex_offsets(*nel, p).astype(np.int32)
+    if scramble:  # an "unstructured" element order: the tables must not rely on lexicographic numbering
+        off = off[np.random.default_rng(3).permutation(off.shape[0])]
+    num_elem, es = off.shape
+    nnodes = int(off.max()) + 1
+    r = ceed.ElemRestriction(num_elem, es, 1, 1, nnodes, off.reshape(-1))
+    flat = off.reshape(-1).astype(np.int64)
+    lib = ceed._lib
+    # touch lists per L-node in ascending E-order = the order the serial reference adds in
+    order = np.argsort(flat, kind="stable")
+    nodes, starts, counts = np.unique(flat[order], return_index=True, return_counts=True)
+    out = {}
+    # ---- two-pass deterministic tables
+    tgt = np.zeros(flat.size, dtype=np.int32); cnt = np.zeros(5, dtype=np.int64)
+    assert lib.ceedb200_restriction_debug_scatter_tables(r._ptr, 0, 1, tgt.ctypes.data, cnt.ctypes.data, None, None, 0) == 0
+    slot_seen = np.zeros(int(cnt[1]), dtype=bool)
+    next_slot = 0
+    for node, s, c in zip(nodes, starts, counts):
+        entries = order[s:s + c]
+        assert tgt[entries[0]] == node                      # the first E-entry owns the store
+        for e in entries[1:]:                                # the others: consecutive halo slots, ascending E-order
+            slot = ~int(tgt[e]); assert slot == next_slot and not slot_seen[slot]
+            slot_seen[slot] = True; next_slot += 1
+    assert next_slot == cnt[1] == int((counts - 1).sum()) and cnt[0] == int((counts > 1).sum())
+    out["det"] = [int(x) for x in cnt[:2]]
+    # ---- ordered (in-kernel completion) tables
+    ngroups = (num_elem + group_elems - 1) // group_elems
+    pred_ptr = np.zeros(ngroups + 1, dtype=np.int32); pred_idx = np.zeros(64 * ngroups + 64, dtype=np.int32)
+    assert lib.ceedb200_restriction_debug_scatter_tables(r._ptr, 3, group_elems, tgt.ctypes.data, cnt.ctypes.data, pred_ptr.ctypes.data,
+                                                         pred_idx.ctypes.data, pred_idx.size) == 0
+    assert cnt[4] == 1 and cnt[2] == ngroups
+    expect_pred = [set() for _ in range(ngroups)]
+    slot = 0
+    for node, s, c in zip(nodes, starts, counts):
+        entries = order[s:s + c]
+        if c == 1:
+            assert tgt[entries[0]] == node; continue
+        slot += 1                                            # id slot of the node
+        g_last = int(entries[-1]) // (group_elems * es)
+        for k, e in enumerate(entries):
+            x = ~int(tgt[e]); assert x >= 0
+            assert (x & 0x7ffffff) == slot, (node, k); slot += 1
+            is_last = k == c - 1
+            assert ((x >> 27) & 1) == int(is_last)
+            if is_last: assert ((x >> 28) & 7) + 2 == c
+            else:
+                g = int(e) // (group_elems * es)
+                if g != g_last: expect_pred[g_last].add(g)
+    assert slot == cnt[1] == int((counts[counts > 1] + 1).sum())
+    for g in range(ngroups):
+        got = sorted(int(x) for x in pred_idx[pred_ptr[g]:pred_ptr[g + 1]])
+        assert got == sorted(expect_pred[g]) and all(q < g for q in got), g   # waits only ever point to earlier groups
+    out["ordered"] = [int(x) for x in cnt[:4]]
+    return out
+
+res = {"%%dx%%dx%%d p%%d g%%d s%%d" %% (*nel, p, ge, sc): check(nel, p, ge, sc)
+       for nel, p, ge, sc in [((3, 2, 2), 2, 1, 0), ((4, 3, 2), 1, 5, 0), ((2, 2, 3), 3, 2, 1), ((5, 1, 1), 4, 3, 1)]}
+print("RESULT" + json.dumps(res))
+""" % ROOT
+
+
+def test_scatter_tables_match_serial_order_model_without_gpu():
+    """Owner/halo tables (two-pass deterministic scatter) and ordered tables (in-kernel completion): slots, owners, completing
+    entries and predecessor groups against a numpy model of 'add in ascending E-order', structured and scrambled element order."""
+    env = dict(os.environ, CEED_B200_COMPILE_ONLY="1")
+    r = subprocess.run([sys.executable, "-c", SCATTER_TABLES], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][0][6:])
+    assert len(res) == 4 and all(v["det"][1] > 0 and v["ordered"][2] > 0 for v in res.values())
