@@ -103,13 +103,15 @@ def _cpu_port_worker(args):
     return nc * nn, n, time.perf_counter() - t0
 
 
-def cpu_reference(bp, p, seconds, steps=0, warmup=1, resource="/cpu/self/avx/blocked", dofs_per_worker=150_000):
+def cpu_reference(bp, p, seconds, steps=0, warmup=1, resource="/cpu/self/avx/blocked", dofs_per_worker=150_000, max_cores=0):
     """Reference CPU backend on all host cores: `cores` forked single-threaded workers (libCEED CPU backends are
     single-threaded per Ceed), each owning its own slab of the workload mesh; aggregate = sum(DoFs * applies) / max(time)."""
     from libceed_b200 import mesh as M
     from libceed_b200.bp import BP_TABLE
     from oracle import refceed as R
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    if max_cores:
+        cores = min(cores, max_cores)
     nel = M.choose_elements(dofs_per_worker, p, BP_TABLE[bp][0])
     # the unmodified reference (oracle/_ref) when it travelled with the repository, else the C restatement of its ref backend
     have_ref = R.available() and not os.environ.get("CEED_B200_BENCH_FORCE_PORT")
@@ -388,6 +390,15 @@ def main():
         try:
             r = cpu_reference(bp, p, args.cpu_seconds)
             cpu = dict(value=r["value"], unit="GDoF/s", cores=r["cores"], kind=r["kind"], sample=r["sample"])
+            # also the opt/blocked backend on all cores and the one-core figure (short samples)
+            others = []
+            for res_name, mc in (("/cpu/self/opt/blocked", 0), ("/cpu/self/avx/blocked", 1)):
+                try:
+                    o = cpu_reference(bp, p, 4.0, resource=res_name, max_cores=mc)
+                    others.append(dict(value=o["value"], unit="GDoF/s", cores=o["cores"], kind=o["kind"], sample=o["sample"]))
+                except Exception as exc:  # noqa: BLE001
+                    others.append(dict(value=None, sample=f"{res_name}: unavailable: {exc}"))
+            cpu["others"] = others
         except Exception as exc:  # the reference build did not travel: say so instead of inventing a number
             cpu = dict(value=None, unit="GDoF/s", cores=0, kind="reference", sample=f"unavailable: {exc}")
 
