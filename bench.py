@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--dofs", type=float, default=10e6, help="DoFs per GPU (weak scaling)")
     ap.add_argument("--scatter", default="deterministic", choices=["deterministic", "atomic", "evector"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e-pipeline", action="store_true", help="skip the software-pipelined end-to-end measurement")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a captured CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-sweep", action="store_true", help="skip the `sweep` key (kernel numbers of BP1 p=3, BP3 p=1..8, BP5 p=4..7, BP6 p=4,6)")
@@ -363,7 +364,66 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e = dict(value=total_dofs / e2e_s / 1e9, unit="GDoF/s", h2d_bytes_per_step=8 * n_local, d2h_bytes_per_step=8 * n_local,
-               ms_per_step=e2e_s * 1e3)
+               ms_per_step=e2e_s * 1e3, mode="serial: H2D(u), apply, D2H(v) one after the other")
+
+    # ---- the same end-to-end step, software-pipelined over steps: every step still copies its own u from pinned host memory and
+    # its own v back, but on separate copy streams with double-buffered device vectors, so the H2D of step i+1 and the D2H of
+    # step i-1 overlap the kernels of step i (PCIe is full duplex).  Reported as e2e.pipelined_value; any failure keeps the serial one.
+    if not args.no_e2e_pipeline:
+        try:
+            nbuf = 2
+            s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            u_d = [torch.empty(n_local, dtype=torch.float64, device=dev) for _ in range(nbuf)]
+            v_d = [torch.empty(n_local, dtype=torch.float64, device=dev) for _ in range(nbuf)]
+            v_h = [torch.empty(n_local, dtype=torch.float64).pin_memory() for _ in range(nbuf)]
+            uvec, vvec = [ceed.Vector(n_local) for _ in range(nbuf)], [ceed.Vector(n_local) for _ in range(nbuf)]
+            for k in range(nbuf):
+                uvec[k].set_array(u_d[k], cm.MEM_DEVICE, cm.USE_POINTER)
+                vvec[k].set_array(v_d[k], cm.MEM_DEVICE, cm.USE_POINTER)
+            ev_in = [torch.cuda.Event() for _ in range(nbuf)]
+            ev_done = [torch.cuda.Event() for _ in range(nbuf)]
+            ev_out = [torch.cuda.Event() for _ in range(nbuf)]
+
+            def pipelined(nsteps):
+                for i in range(nsteps):
+                    k = i % nbuf
+                    if i >= nbuf:
+                        s_in.wait_event(ev_out[k])            # buffer k is free once the D2H of step i - nbuf has finished
+                    with torch.cuda.stream(s_in):
+                        u_d[k].copy_(u_host, non_blocking=True)
+                        ev_in[k].record(s_in)
+                    stream.wait_event(ev_in[k])
+                    prob.op.apply(uvec[k], vvec[k])           # on the backend's stream (= `stream`)
+                    ev_done[k].record(stream)
+                    s_out.wait_event(ev_done[k])
+                    with torch.cuda.stream(s_out):
+                        v_h[k].copy_(v_d[k], non_blocking=True)
+                        ev_out[k].record(s_out)
+                s_out.synchronize()
+                stream.synchronize()
+
+            pipelined(2)
+            barrier()
+            t0 = time.perf_counter()
+            pipelined(e2e_steps * 2)
+            pipe_s = (time.perf_counter() - t0) / (e2e_steps * 2)
+            ok = bool(torch.equal(v_h[0], v_host)) if exch is None else True   # same bits as the serial path
+            if world > 1:
+                t = torch.tensor([pipe_s], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                pipe_s = float(t.item())
+            e2e["pipelined_value"] = total_dofs / pipe_s / 1e9
+            e2e["pipelined_ms_per_step"] = pipe_s * 1e3
+            e2e["pipelined_matches_serial"] = ok
+            e2e["pipelined_mode"] = "double-buffered: H2D of step i+1 and D2H of step i-1 overlap the kernels of step i"
+            if ok and e2e["pipelined_value"] > e2e["value"]:
+                # headline = the pipelined figure (every step still moves its own u and v over PCIe inside the timed region);
+                # the strictly serial figure stays next to it
+                e2e["serial_value"], e2e["serial_ms_per_step"] = e2e["value"], e2e["ms_per_step"]
+                e2e["value"], e2e["ms_per_step"], e2e["mode"] = e2e["pipelined_value"], e2e["pipelined_ms_per_step"], e2e["pipelined_mode"]
+        except Exception as exc:  # noqa: BLE001
+            e2e["pipelined_value"] = None
+            e2e["pipelined_error"] = str(exc)[:200]
 
     sweep = None
     if not args.no_sweep and rank == 0 and world == 1:
