@@ -246,3 +246,59 @@ def test_scatter_tables_match_serial_order_model_without_gpu():
     assert r.returncode == 0, r.stderr[-3000:]
     res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][0][6:])
     assert len(res) == 4 and all(v["det"][1] > 0 and v["ordered"][2] > 0 for v in res.values())
+
+
+VECTOR_STATE = r"""
+import ctypes as C, json, sys
+import numpy as np
+sys.path.insert(0, %r)
+from libceed_b200 import Ceed, ceed as cm
+ceed = Ceed(); lib = ceed._lib
+out = {}
+def flags(v):
+    a, bh, bd = C.c_int(), C.c_int(), C.c_int()
+    lib.ceedb200_vector_has_valid_array(v._ptr, C.byref(a))
+    lib.ceedb200_vector_has_borrowed_array_of_type(v._ptr, cm.MEM_HOST, C.byref(bh))
+    lib.ceedb200_vector_has_borrowed_array_of_type(v._ptr, cm.MEM_DEVICE, C.byref(bd))
+    return [a.value, bh.value, bd.value]
+def dev_as_numpy(v, n):   # compile-only mode: "device" allocations are host memory, so the mirror can be inspected
+    return np.ctypeslib.as_array(C.cast(v.get_array_read(cm.MEM_DEVICE), C.POINTER(C.c_double)), shape=(n,)).copy()
+n = 11
+v = ceed.Vector(n)
+out["fresh"] = flags(v)                                   # no valid data yet
+a = np.arange(n, dtype=np.float64)
+v.set_array(a, cm.MEM_HOST, cm.COPY_VALUES)
+out["after_copy"] = flags(v)
+out["mirror"] = dev_as_numpy(v, n).tolist()               # lazy host -> device sync on first device access
+b = np.linspace(-1, 1, n)
+v.set_array(b, cm.MEM_HOST, cm.USE_POINTER)
+out["after_borrow"] = flags(v)
+out["borrowed_read"] = v.get_array_read().tolist()
+out["borrowed_mirror"] = dev_as_numpy(v, n).tolist()
+v.take_array(cm.MEM_HOST)
+out["after_take"] = flags(v)                              # the device mirror is still valid after the host array was taken
+out["after_take_read"] = v.get_array_read().tolist()
+w = ceed.Vector(n)
+code = lib.ceedb200_vector_sync_array(w._ptr, cm.MEM_HOST)  # nothing valid to sync: an error, not silence
+out["sync_empty_code"] = code
+code = lib.ceedb200_vector_set_value(v._ptr, C.c_double(1.0))  # a kernel: must fail loudly in compile-only mode
+out["kernel_code"] = code; out["kernel_msg"] = lib.ceedb200_last_error(ceed._ptr).decode()
+print("RESULT" + json.dumps(out))
+""" % ROOT
+
+
+def test_vector_mirrors_and_state_flags_without_gpu():
+    """CeedVector semantics of the core (owned / borrowed host and device mirrors, lazy sync, take) exercised in compile-only mode,
+    where device allocations are host memory and any kernel launch fails loudly (backends/cuda-ref/ceed-cuda-ref-vector.c:21-228)."""
+    env = dict(os.environ, CEED_B200_COMPILE_ONLY="1")
+    r = subprocess.run([sys.executable, "-c", VECTOR_STATE], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][0][6:])
+    n = 11
+    assert res["fresh"] == [0, 0, 0]
+    assert res["after_copy"] == [1, 0, 0] and res["mirror"] == list(map(float, range(n)))
+    assert res["after_borrow"] == [1, 1, 0]
+    assert np.allclose(res["borrowed_read"], np.linspace(-1, 1, n)) and res["borrowed_mirror"] == res["borrowed_read"]
+    assert res["after_take"][0] == 1 and res["after_take"][1] == 0 and res["after_take_read"] == res["borrowed_read"]
+    assert res["sync_empty_code"] != 0
+    assert res["kernel_code"] != 0 and "COMPILE_ONLY" in res["kernel_msg"]
