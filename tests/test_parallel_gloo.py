@@ -129,3 +129,48 @@ def test_partition_tables_consistent():
                 assert np.array_equal(ga[idx_a], b.global_node_ids()[idx_b])
         gx, gy, gz = (n * p + 1 for n in n_global)
         assert total_owned == gx * gy * gz
+
+
+def test_partition_and_exchange_tables_random_grids():
+    """Property test over random process counts / mesh sizes / degrees: ownership is a partition of the global nodes, both sides
+    of every interface agree, and the exchange tables of all ranks reproduce the global sum when executed on the host."""
+    from hypothesis import given, settings, strategies as st
+    from libceed_b200.parallel import build_interface_tables
+
+    @settings(max_examples=25, deadline=None)
+    @given(world=st.sampled_from([1, 2, 3, 4, 6, 8, 12]), p=st.integers(1, 3), ex=st.integers(0, 2), ey=st.integers(0, 2), ez=st.integers(0, 1),
+           ncomp=st.integers(1, 2), seed=st.integers(0, 1000))
+    def run(world, p, ex, ey, ez, ncomp, seed):
+        grid = mesh.split3(world)
+        n_global = (grid[0] + ex, grid[1] + ey, grid[2] + ez)   # at least one element per rank in every direction
+        parts = [mesh.Partition(n_global, p, world, r) for r in range(world)]
+        n_glob = int(np.prod([n * p + 1 for n in n_global]))
+        owners = np.zeros(n_glob, dtype=int)
+        rng = np.random.default_rng(seed)
+        # every rank holds a random partial value for each of its local (node, comp) entries
+        partial = [rng.uniform(-1, 1, ncomp * pt.num_local_nodes) for pt in parts]
+        expect = np.zeros(ncomp * n_glob)
+        for pt, val in zip(parts, partial):
+            gid, nloc = pt.global_node_ids(), pt.num_local_nodes
+            owners[gid[pt.owned_mask()]] += 1
+            for c in range(ncomp):
+                np.add.at(expect, gid + c * n_glob, val[c * nloc:(c + 1) * nloc])
+        assert (owners == 1).all()
+        tables = [build_interface_tables(pt, ncomp, pt.num_local_nodes) for pt in parts]
+        send = [val[t[2]] if t[2].size else np.zeros(0) for val, t in zip(partial, tables)]
+        for r, (pt, t) in enumerate(zip(parts, tables)):
+            ranks, seg, send_idx, node, ptr, src = t
+            recv = np.zeros(send_idx.size)
+            for k, nb in enumerate(ranks):           # what neighbour nb sends to r: its segment addressed to r
+                tn = tables[nb]
+                kk = tn[0].index(r)
+                recv[seg[k]:seg[k + 1]] = send[nb][tn[1][kk]:tn[1][kk + 1]]
+            v = partial[r].copy()
+            for i in range(node.size):
+                terms = [partial[r][node[i]] if s < 0 else recv[s] for s in src[ptr[i]:ptr[i + 1]]]
+                v[node[i]] = sum(terms[1:], terms[0])
+            gid, nloc = pt.global_node_ids(), pt.num_local_nodes
+            for c in range(ncomp):
+                np.testing.assert_allclose(v[c * nloc:(c + 1) * nloc], expect[gid + c * n_glob], rtol=0, atol=1e-13)
+
+    run()
