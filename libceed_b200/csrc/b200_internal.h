@@ -196,6 +196,7 @@ struct B200Operator_ {
   B200OpPlan              *plan = nullptr;
   B200Tuning               tune;           // explicit overrides (ceedb200_operator_set_tuning, autotuner)
   bool                     tuned = false;  // autotuner has run (or was not applicable)
+  bool                     no_tma = false; // an input of a bulk-copied field was not 16-byte aligned: generate without cp.async.bulk
   bool                     timing = false;
   float                    last_fused_ms = 0.f, last_aux_ms = 0.f;
   cudaEvent_t              ev[4] = {nullptr, nullptr, nullptr, nullptr};

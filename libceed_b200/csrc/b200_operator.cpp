@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstdint>
 #include <cstring>
 
 #include "b200_opgen.h"
@@ -170,6 +171,21 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add) {
     B200_CHECK(vec->length >= f.rstr->l_size, ceed, B200_ERROR_DIMENSION, "input vector of field %zu shorter than restriction L-size", i);
     B200_CALL(b200_vector_device_read(vec, &args.in_ptr[i]));
     args.in_idx[i] = f.rstr->is_strided ? nullptr : f.rstr->d_offsets;
+  }
+  // bulk copies (cp.async.bulk) need 16-byte aligned sources: a caller-owned array that is only 8-byte aligned gets the
+  // kernel generated without them (same results)
+  if (plan->qd_tma) {
+    bool misaligned = false;
+    for (size_t i = 0; i < plan->in_fields.size(); i++)
+      if (plan->in_fields[i].qd_tma && ((uintptr_t)args.in_ptr[i] & 15)) misaligned = true;
+    if (misaligned) {
+      op->no_tma = true;
+      plan_free(op);
+      op->is_setup = false;
+      B200_CALL(operator_setup(op));
+      B200_CHECK(op->plan->fused && !op->plan->qd_tma, ceed, B200_ERROR_BACKEND, "could not regenerate the operator kernel without bulk copies");
+      return apply_fused(op, u, v, add);
+    }
   }
   // outputs.  Decide per distinct output vector whether the kernel can store (overwrite) or must accumulate.
   struct OutVec {

@@ -48,6 +48,7 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
   B200Ceed      ceed = op->ceed;
   B200QFunction qf   = op->qf;
   plan->fused        = false;
+  plan->no_tma       = op->no_tma || getenv("CEED_B200_NO_TMA") != nullptr;
   plan->scatter_mode = ceed->scatter_mode;
   plan->ordered_slot = -1;
   auto reject        = [&](const string &why) {
@@ -266,12 +267,25 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
       off += (bytes + 15) / 16 * 16;
       return (int)at;
     };
+    plan->qd_tma   = false;
+    plan->mbar_off = -1;
     for (auto &f : plan->in_fields) {
       f.qd_off = -1;
+      f.qd_tma = false;
+      f.qd_cs  = E * Q * Q * Q;
       // contiguous per component over the elements of a batch: unit node stride, element stride == element size
-      if (plan->async_copy && (mask & 4) && f.emode == B200_EVAL_NONE && f.rstr->is_strided && f.rstr->strides[0] == 1 && f.rstr->strides[2] == f.rstr->elem_size)
+      const bool contiguous = f.emode == B200_EVAL_NONE && f.rstr->is_strided && f.rstr->strides[0] == 1 && f.rstr->strides[2] == f.rstr->elem_size;
+      if (plan->async_copy && (mask & 32) && contiguous && !plan->no_tma) {
+        // bulk copies need 16-byte aligned sources: an odd Q^3 makes every other (component, batch) start 8 bytes off, so the
+        // copy starts one double early and the buffer of a component holds one double more (readers add the same shift)
+        f.qd_tma = plan->qd_tma = true;
+        f.qd_cs  = (E * Q * Q * Q + 1 + 1) / 2 * 2;
+        f.qd_off = take((size_t)f.nc * f.qd_cs * 8);
+      } else if (plan->async_copy && (mask & 4) && contiguous) {
         f.qd_off = take((size_t)f.nc * E * Q * Q * Q * 8);
+      }
     }
+    if (plan->qd_tma) plan->mbar_off = take(16);
     for (auto &g : plan->in_groups) {
       g.uin_off = g.idx_off = -1;
       if (plan->async_copy && (mask & 2) && !g.rstr->is_strided) {
@@ -379,6 +393,9 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     int by_regs = 65536 / (threads * 96);
     int minb    = std::max(1, std::min(by_smem, by_regs));
     if (tn.minb > 0) minb = tn.minb;
+    // never ask ptxas for more resident blocks than shared memory / the thread limit allow: it would only cap registers
+    minb = std::min(minb, std::max(1, by_smem));
+    minb = std::min(minb, std::max(1, 2048 / threads));
     plan->blocks_per_sm = std::max(1, minb);
     tn.epw = plan->epb, tn.group_warps = plan->group_warps, tn.cta_warps = plan->threads / 32, tn.minb = plan->blocks_per_sm;
     tn.qf_mode = plan->qf_xline ? 3 : (plan->qf_pointwise ? plan->qf_pp : 0), tn.qf_unroll = plan->qf_unroll, tn.stage = plan->stage_mask;
@@ -403,6 +420,9 @@ struct Gen {
   bool         warp_mode = false;
   int          TS        = 0;            // task-loop stride (threads that share a group)
   string       TID, SMBASE, SYNC;        // lane id expression, shared-memory base, barrier statement
+  string       smw_expr() const {
+    return warp_mode ? "sm + (threadIdx.x / " + std::to_string(TS) + ") * " + std::to_string(plan->group_smem_bytes / 8) : "sm";
+  }
   string       smw_decl() const {
     return warp_mode ? "  double *const smw = sm + (threadIdx.x / " + std::to_string(TS) + ") * " + std::to_string(plan->group_smem_bytes / 8) + ";\n" : "";
   }
@@ -465,6 +485,7 @@ struct Gen {
     if (plan->qf_pointwise && plan->qf_pp > 1) c << "#define CEED_Q_VLA " << plan->qf_pp << "  // the QFunction is called with Q = " << plan->qf_pp << " points\n";
     if (plan->qf_xline) c << "#define CEED_Q_VLA " << Q << "  // the QFunction is called on whole x-lines (Q = " << Q << " points)\n";
     c << "#include <b200-jit.h>\n";
+    if (plan->qd_tma || (plan->stage_mask & 64)) c << "#include <b200-tma.h>\n";
     c << "#include \"" << qf->source_path << "\"\n\n";
     for (size_t b = 0; b < plan->bases.size(); b++) {
       const B200Basis bs = plan->bases[b].basis;
@@ -498,6 +519,21 @@ struct Gen {
   string smem_at(int byte_off, const string &type) const {
     oss s;
     s << "((" << type << " *)((char *)" << SMBASE << " + " << byte_off << "))";
+    return s.str();
+  }
+
+  // value of component cc of a staged EVAL_NONE input at point `pt` of local element `le` (group starting at element e0)
+  string qd_ref(const B200GenField &fd, int cc, const string &le, const string &pt) const {
+    const int Q3 = Q * Q * Q;
+    oss       s;
+    if (!fd.qd_tma) {
+      s << smem_at(fd.qd_off, "const double") << "[(" << cc * E << " + " << le << ") * " << Q3 << " + " << pt << "]";
+    } else {
+      // bulk copies start at a 16-byte boundary: with an odd Q^3 the component block of this group may begin one double later
+      s << smem_at(fd.qd_off, "const double") << "[" << cc * fd.qd_cs << " + (" << le << ") * " << Q3 << " + " << pt;
+      if (Q3 % 2) s << " + (int)((" << (long long)cc * fd.rstr->strides[1] << "LL + e0 * " << Q3 << "LL) & 1)";
+      s << "]";
+    }
     return s.str();
   }
 
@@ -573,8 +609,38 @@ struct Gen {
     c << "  if (e0 >= b200a.num_elem) return;\n";
     c << smw_decl();
     c << "  const int ne = (int)((b200a.num_elem - e0 < " << E << ") ? b200a.num_elem - e0 : " << E << ");\n";
+    if (plan->qd_tma) {
+      // one elected lane: a bulk copy per (field, component) = the contiguous block of the group's elements, completion on the group's mbarrier
+      c << "  if (" << TID << " == 0) {\n";
+      c << "    const unsigned bar = b200_smem_u32((char *)" << SMBASE << " + " << plan->mbar_off << ");\n";
+      c << "    b200_fence_proxy_async();\n";
+      int k = 0;
+      for (auto &f : plan->in_fields) {
+        if (!f.qd_tma) continue;
+        for (int cc = 0; cc < f.nc; cc++, k++) {
+          c << "    const double *src" << k << " = b200a.in_ptr[" << f.slot << "] + " << (long long)cc * f.rstr->strides[1] << "LL + e0 * " << Q3 << "LL;\n";
+          if (Q3 % 2) {
+            c << "    const unsigned sh" << k << " = (unsigned)((" << (long long)cc * f.rstr->strides[1] << "LL + e0 * " << Q3 << "LL) & 1);\n";
+            c << "    const unsigned nb" << k << " = ((ne * " << Q3 << " + sh" << k << ") * 8 + 15) & ~15u;\n";
+          } else {
+            c << "    const unsigned sh" << k << " = 0, nb" << k << " = ne * " << Q3 * 8 << ";\n";
+          }
+        }
+      }
+      c << "    b200_mbar_expect_tx(bar, 0";
+      for (int i = 0; i < k; i++) c << " + nb" << i;
+      c << ");\n";
+      k = 0;
+      for (auto &f : plan->in_fields) {
+        if (!f.qd_tma) continue;
+        for (int cc = 0; cc < f.nc; cc++, k++)
+          c << "    b200_bulk_g2s(b200_smem_u32((char *)" << SMBASE << " + " << f.qd_off + cc * f.qd_cs * 8 << "), src" << k << " - sh" << k << ", nb" << k
+            << ", bar);\n";
+      }
+      c << "  }\n";
+    }
     for (auto &f : plan->in_fields) {
-      if (f.qd_off < 0) continue;
+      if (f.qd_off < 0 || f.qd_tma) continue;
       for (int cc = 0; cc < f.nc; cc++) {
         c << "  { double *dst = " << smem_at(f.qd_off, "double") << " + " << cc * E * Q3 << ";\n";
         c << "    const double *src = b200a.in_ptr[" << f.slot << "] + " << (long long)cc * f.rstr->strides[1] << "LL + e0 * " << Q3 << "LL;\n";
@@ -584,6 +650,30 @@ struct Gen {
         c << "    } else {\n";
         c << "      for (int i = " << TID << "; i < n; i += " << TS << ") b200_cp8(dst + i, src + i);\n";
         c << "    } }\n";
+      }
+    }
+    c << "}\n\n";
+    return true;
+  }
+
+  // stage bit 64: bulk L2 prefetch (cp.async.bulk.prefetch.L2) of the directly loaded quadrature data of the group's NEXT batch;
+  // one lane, one instruction per (field, component) block -- costs no shared memory, so the occupancy of the kernel is unchanged
+  bool emit_prefetch_qd() {
+    if (!(plan->stage_mask & 64) || !plan->warp_mode) return false;
+    const int Q3 = Q * Q * Q;
+    bool      any = false;
+    for (auto &f : plan->in_fields)
+      any = any || (f.emode == B200_EVAL_NONE && f.qd_off < 0 && f.rstr->is_strided && f.rstr->strides[0] == 1 && f.rstr->strides[2] == f.rstr->elem_size);
+    if (!any) return false;
+    c << "static __device__ __noinline__ void b200_prefetch_qd(const long long e0) {\n";
+    c << "  if (e0 >= b200a.num_elem || " << TID << " != 0) return;\n";
+    c << "  const int ne = (int)((b200a.num_elem - e0 < " << E << ") ? b200a.num_elem - e0 : " << E << ");\n";
+    for (auto &f : plan->in_fields) {
+      if (!(f.emode == B200_EVAL_NONE && f.qd_off < 0 && f.rstr->is_strided && f.rstr->strides[0] == 1 && f.rstr->strides[2] == f.rstr->elem_size)) continue;
+      for (int cc = 0; cc < f.nc; cc++) {
+        c << "  { const unsigned long long a = (unsigned long long)(b200a.in_ptr[" << f.slot << "] + " << (long long)cc * f.rstr->strides[1] << "LL + e0 * " << Q3
+          << "LL);\n";
+        c << "    b200_bulk_prefetch_l2((const void *)(a & ~15ULL), (unsigned)(((a & 15ULL) + (unsigned long long)ne * " << Q3 * 8 << " + 15) & ~15ULL)); }\n";
       }
     }
     c << "}\n\n";
@@ -804,8 +894,7 @@ struct Gen {
         case B200_EVAL_NONE:
           for (int cc = 0; cc < fd.nc; cc++) {
             if (fd.qd_off >= 0) {
-              for (int h = 0; h < PP; h++)
-                c << "      in_" << f << at(cc, h) << " = " << smem_at(fd.qd_off, "const double") << "[(" << cc * E << " + le) * " << Q3 << " + pt + " << h << "];\n";
+              for (int h = 0; h < PP; h++) c << "      in_" << f << at(cc, h) << " = " << qd_ref(fd, cc, "le", "pt + " + std::to_string(h)) << ";\n";
             } else if (PP == 2 && fd.rstr->is_strided && fd.rstr->strides[0] == 1 && fd.rstr->strides[1] % 2 == 0 && fd.rstr->strides[2] % 2 == 0) {
               c << "      { const double2 v2 = __ldg((const double2 *)(b200a.in_ptr[" << sl << "] + " << lidx(fd.rstr, "", "e", "pt", std::to_string(cc)) << "));\n";
               c << "        in_" << f << at(cc, 0) << " = v2.x; in_" << f << at(cc, 1) << " = v2.y; }\n";
@@ -940,7 +1029,7 @@ struct Gen {
           case B200_EVAL_NONE:
             for (int cc = 0; cc < fd.nc; cc++) {
               if (fd.qd_off >= 0)
-                c << "        in_" << f << "[" << cc << "] = " << smem_at(fd.qd_off, "const double") << "[(" << cc * E << " + le) * " << Q * Q * Q << " + pt];\n";
+                c << "        in_" << f << "[" << cc << "] = " << qd_ref(fd, cc, "le", "pt") << ";\n";
               else if (qf_ahead) {
                 const string slot = "nx_" + std::to_string(f) + "_" + std::to_string(cc) + "_" + std::to_string(qz % depth);
                 c << "        in_" << f << "[" << cc << "] = " << slot << ";\n";
@@ -1046,8 +1135,7 @@ struct Gen {
         for (int cc = 0; cc < fd.nc; cc++)
           for (int q = 0; q < Q; q++) {
             if (fd.qd_off >= 0)  // staged one group ahead by cp.async (b200_issue_qd)
-              c << "      in_" << f << "[" << cc * Q + q << "] = " << smem_at(fd.qd_off, "const double") << "[(" << cc * E << " + le) * " << Q * Q * Q << " + row * "
-                << Q << " + " << q << "];\n";
+              c << "      in_" << f << "[" << cc * Q + q << "] = " << qd_ref(fd, cc, "le", "row * " + std::to_string(Q) + " + " + std::to_string(q)) << ";\n";
             else
               c << "      in_" << f << "[" << cc * Q + q << "] = __ldg(b200a.in_ptr[" << sl << "] + "
                 << lidx(fd.rstr, "", "e", "row * " + std::to_string(Q) + " + " + std::to_string(q), std::to_string(cc)) << ");\n";
@@ -1224,7 +1312,7 @@ struct Gen {
               if (fd.ring_k >= 0) break;
               for (int cc = 0; cc < fd.nc; cc++) {
                 if (fd.qd_off >= 0)
-                  c << "        in_" << f << "[" << cc << "] = " << smem_at(fd.qd_off, "const double") << "[(" << cc * E << " + le) * " << Q * Q * Q << " + pt];\n";
+                  c << "        in_" << f << "[" << cc << "] = " << qd_ref(fd, cc, "le", "pt") << ";\n";
                 else
                   c << "        in_" << f << "[" << cc << "] = __ldg(b200a.in_ptr[" << sl << "] + " << lidx(fd.rstr, "b200a.in_idx[" + sl + "]", "e", "pt", std::to_string(cc)) << ");\n";
               }
@@ -1587,6 +1675,8 @@ struct Gen {
       if (!calls.empty() && calls.back() == "    " + SYNC + "\n") calls.pop_back();
       calls.push_back("    b200_cp_wait_all();\n    " + SYNC + "\n");
     }
+    // bulk-copied quadrature data of this batch: all lanes of the group wait on the mbarrier phase of this iteration
+    if (plan->qd_tma) calls.push_back("    b200_mbar_wait(b200_smem_u32((char *)(" + smw_expr() + ") + " + std::to_string(plan->mbar_off) + "), it & 1);\n");
     if (plan->qf_xline) {
       emit_xline_qf();
     } else if (plan->qf_pointwise) {
@@ -1606,6 +1696,7 @@ struct Gen {
     if (!plan->out_groups.empty() || has_qd) barrier();
     // the quadrature-data buffer is free again: stream in the next batch's data behind the transpose stages
     if (has_qd) calls.push_back("    b200_issue_qd(e0n);\n    b200_cp_commit();\n");
+    if (emit_prefetch_qd()) calls.push_back("    b200_prefetch_qd(e0n);\n");
     if (!plan->out_groups.empty()) {
       any = false;
       for (auto &g : plan->out_groups) any = any || g.use_grad;
@@ -1669,6 +1760,10 @@ struct Gen {
     // block mode: one batch per CTA per iteration; warp mode: one group per warp per iteration
     const string first  = warp_mode ? "((long long)blockIdx.x * " + std::to_string(NT / TS) + " + (threadIdx.x / " + std::to_string(TS) + "))" : "(long long)blockIdx.x";
     const string stride = warp_mode ? "((long long)gridDim.x * " + std::to_string(NT / TS) + ")" : "(long long)gridDim.x";
+    if (plan->qd_tma) {
+      c << "  int it = 0;  // iteration of this group: parity of the mbarrier phase its bulk copies complete\n";
+      c << "  if (" << TID << " == 0) b200_mbar_init(b200_smem_u32((char *)(" << smw_expr() << ") + " << plan->mbar_off << "), 1);\n  " << SYNC << "\n";
+    }
     if (staged) {
       // prologue: stage the first batch
       c << "  if (" << first << " < num_batches) {\n";
@@ -1691,6 +1786,7 @@ struct Gen {
     }
     if (prefetch) c << "    b200_prefetch(e0n);\n";
     for (auto &call : calls) c << call;
+    if (plan->qd_tma) c << "    it++;\n";
     c << "  }\n";
     if (plan->scatter_mode == B200_SCATTER_ORDERED) {
       c << "  if (e0p >= 0) b200_ordered_complete(e0p, epoch);\n";

@@ -38,6 +38,8 @@ struct B200GenField {
   int             slot = 0;
   int             qd_off = -1;    // EVAL_NONE inputs streamed with cp.async: [nc][E * Q^3] doubles (byte offset), -1 = direct loads
   int             ring_k = -1;    // EVAL_NONE inputs prefetched through the per-lane ring: first component row in a ring slot
+  bool            qd_tma = false; // qd_off buffer is filled by cp.async.bulk (1-D TMA) + mbarrier instead of per-lane cp.async
+  int             qd_cs  = 0;     // doubles between the components of the qd_off buffer (E * Q^3, padded for the 16-byte source alignment)
 };
 
 struct B200OpArgs {
@@ -71,7 +73,11 @@ struct B200OpPlan {
   int                       plane_size = 0, num_planes = 0, smem_bytes = 0;
   int                       scatter_mode = 0;
   bool                      warp_mode = true;    // one element group per warp, __syncwarp() only (see b200_opgen.cpp)
-  int                       stage_mask = 1;      // which global reads are staged through cp.async (1 idx/tgt, 2 gather, 4 qdata)
+  int                       stage_mask = 1;      // which global reads are staged one batch ahead: cp.async 1 idx/tgt, 2 gather, 4 qdata, 8 idx only,
+                                                 // 16 per-lane qdata ring; 32 qdata through cp.async.bulk (TMA) + mbarrier
+  bool                      qd_tma = false;      // some EVAL_NONE input is staged by bulk copies
+  int                       mbar_off = -1;       // byte offset of the group's mbarrier (bulk-copy completion)
+  bool                      no_tma = false;      // set by the host when an input pointer is not 16-byte aligned
   int                       group_smem_bytes = 0;  // shared memory of one element group (CTA in block mode, warp in warp mode)
   int                       group_warps = 1;      // warps sharing one element group (warp mode)
   bool                      qf_pointwise = false; // QFunction over independent points, d/dz as separate line stages

@@ -81,6 +81,29 @@ elif mode == "ring":
                 run(f"stage={stage} ring={ring} warps={warps}", {"CEED_B200_STAGE": str(stage), "CEED_B200_RING": str(ring), "CEED_B200_WARPS": str(warps)})
     for gw, warps in ((2, 2), (2, 4), (4, 4)):
         run(f"stage=17 ring=4 gw={gw} warps={warps}", {"CEED_B200_STAGE": "17", "CEED_B200_GROUP_WARPS": str(gw), "CEED_B200_WARPS": str(warps)})
+elif mode == "tma":
+    # quadrature data through cp.async.bulk + mbarrier (stage bit 32) vs the table shape; group width x groups per CTA x elements per group
+    run("table", {})
+    Q = base.Q
+    for gw in (1, 2, 4):
+        lanes = 32 * gw
+        for epw in (1, 2, 3, 4, 6):
+            tasks = epw * Q * Q
+            util = tasks / (lanes * ((tasks + lanes - 1) // lanes))
+            if util < 0.7 or tasks > 2 * lanes:
+                continue
+            for groups in (1, 2, 4):
+                for stage in (33,):
+                    env = {"CEED_B200_STAGE": str(stage), "CEED_B200_GROUP_WARPS": str(gw), "CEED_B200_WARPS": str(gw * groups), "CEED_B200_QF_POINTWISE": "0"}
+                    run(f"tma stage={stage} gw={gw} groups={groups} epw={epw}", env, epb=epw)
+elif mode == "pf":
+    # bulk L2 prefetch of the next batch's quadrature data (stage bit 64) on top of the table shape
+    run("table", {})
+    for st in (65, 73):
+        run(f"stage={st}", {"CEED_B200_STAGE": str(st)})
+        run(f"stage={st} ahead=2", {"CEED_B200_STAGE": str(st), "CEED_B200_QF_AHEAD": "2"})
+    run("stage=65 pointwise unroll 2", {"CEED_B200_STAGE": "65", "CEED_B200_QF_POINTWISE": "1", "CEED_B200_QF_UNROLL": "2"})
+    run("stage=65 pointwise unroll 4", {"CEED_B200_STAGE": "65", "CEED_B200_QF_POINTWISE": "1", "CEED_B200_QF_UNROLL": "4"})
 elif mode == "gw":
     run("default", {})
     for gw in (1, 2, 4):

@@ -46,5 +46,6 @@ BP_CASES = [
     (3, 3, (2, 2, 1), False, False), (3, 4, (2, 1, 1), False, False), (3, 6, (1, 1, 2), False, False), (3, 8, (1, 1, 1), False, False),
     (5, 4, (2, 1, 1), False, False), (5, 7, (1, 1, 1), False, False), (2, 2, (2, 2, 1), False, False), (4, 1, (2, 2, 2), False, False),
     (4, 2, (2, 1, 2), False, True), (6, 2, (2, 2, 1), False, False), (6, 3, (1, 2, 1), False, True), (1, 2, (2, 2, 2), True, False),
-    (3, 2, (2, 2, 2), True, False),
+    (3, 2, (2, 2, 2), True, False), (3, 5, (2, 1, 1), False, False), (3, 7, (1, 1, 1), False, False), (5, 5, (1, 2, 1), False, False),
+    (5, 6, (1, 1, 2), False, False), (6, 4, (2, 1, 1), False, False), (6, 6, (1, 1, 1), False, False), (4, 3, (2, 1, 1), False, False),
 ]

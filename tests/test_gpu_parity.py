@@ -350,7 +350,10 @@ def test_tail_batches_and_tuning(cm, oracle):
 
 SHAPES = [dict(group_warps=2, cta_warps=2), dict(group_warps=2, cta_warps=8), dict(group_warps=4, cta_warps=4), dict(qf_mode=1, qf_unroll=2),
           dict(qf_mode=2, qf_unroll=2), dict(qf_mode=2, group_warps=2, cta_warps=4, elems_per_group=3), dict(stage_mask=17), dict(stage_mask=9),
-          dict(stage_mask=0, cta_warps=1), dict(stage_mask=19, group_warps=2, cta_warps=4), dict(qf_mode=3), dict(qf_mode=0)]
+          dict(stage_mask=0, cta_warps=1), dict(stage_mask=19, group_warps=2, cta_warps=4), dict(qf_mode=3), dict(qf_mode=0),
+          # quadrature data through cp.async.bulk (TMA) + mbarrier (stage bit 32), also with odd Q^3 (8-byte source misalignment)
+          dict(stage_mask=33), dict(stage_mask=33, group_warps=2, cta_warps=4, elems_per_group=3), dict(stage_mask=41, qf_mode=1, qf_unroll=2),
+          dict(stage_mask=32, group_warps=4, cta_warps=4, elems_per_group=2)]
 
 
 @pytest.mark.parametrize("bp,p,nel", [(3, 2, (5, 3, 2)), (5, 3, (3, 3, 2)), (1, 3, (4, 3, 3)), (6, 2, (3, 2, 2)), (3, 4, (3, 2, 2))])
