@@ -117,6 +117,8 @@ CEEDB200_EXPORT int ceedb200_restriction_apply(B200Restriction rstr, int t_mode,
 CEEDB200_EXPORT int ceedb200_restriction_apply_ptr(B200Restriction rstr, int t_mode, const b200_scalar *d_u, b200_scalar *d_v);
 CEEDB200_EXPORT int ceedb200_restriction_get_offsets(B200Restriction rstr, int mem_type, const b200_int **offsets);
 CEEDB200_EXPORT int ceedb200_restriction_get_e_layout(B200Restriction rstr, b200_int layout[3]);
+/* elements [0, split_elem) touch the rank interface of a partitioned mesh and are applied first (ceedb200_operator_apply_part) */
+CEEDB200_EXPORT int ceedb200_restriction_set_split(B200Restriction rstr, b200_int split_elem);
 CEEDB200_EXPORT int ceedb200_restriction_get_info(B200Restriction rstr, b200_int *num_elem, b200_int *elem_size, b200_int *num_comp,
                                                   b200_size *l_size, b200_size *e_size);
 /* diagnostics: host copy of the tables behind the fused kernel's deterministic scatter (no reference counterpart; the
@@ -203,6 +205,11 @@ CEEDB200_EXPORT const char *ceedb200_operator_kernel_source(B200Operator op);
 CEEDB200_EXPORT int         ceedb200_operator_kernel_info(B200Operator op, int *regs, int *smem_bytes, int *threads, int *elems_per_block,
                                                           int *grid, int *local_bytes);
 /* device time (ms) of the most recent apply's kernels, measured with CUDA events on the context stream when enabled */
+/* One half of an apply on a partitioned mesh (multi-GPU overlap; the reference pattern is VecScatterBegin / local work /
+ * VecScatterEnd, examples/petsc/bpsraw.c:240-262): part 1 = elements [0, split) -- the ones touching the rank interface, see
+ * ceedb200_restriction_set_split -- plus the finalize pass of the nodes only they touch; part 2 = the interior elements.
+ * part 1 followed by part 2 produces exactly the bits of ceedb200_operator_apply. */
+CEEDB200_EXPORT int ceedb200_operator_apply_part(B200Operator op, B200Vector u, B200Vector v, int part);
 CEEDB200_EXPORT int ceedb200_operator_set_timing(B200Operator op, int enabled);
 CEEDB200_EXPORT int ceedb200_operator_last_kernel_ms(B200Operator op, float *fused_ms, float *aux_ms);
 /* tuning override: elems_per_block (0 = heuristic), blocks_per_sm (0 = heuristic) */
@@ -224,6 +231,23 @@ CEEDB200_EXPORT int ceedb200_set_autotune(B200Ceed ceed, int level);
 CEEDB200_EXPORT int ceedb200_iface_pack(B200Ceed ceed, const double *d_v, const long long *d_idx, long long n, double *d_send);
 CEEDB200_EXPORT int ceedb200_iface_unpack_sum(B200Ceed ceed, double *d_v, long long n, const long long *d_node, const int *d_ptr, const int *d_src,
                                               const double *d_recv);
+
+/* The same exchange over NVLink peer memory (no NCCL on the data path): `put` gathers the interface values and stores them
+ * directly into the neighbours' receive areas (peer-mapped device pointers obtained through ceedb200_ipc_*), then raises one
+ * flag per neighbour; `wait_unpack_sum` on the receiver waits for its flags and forms the rank-ordered sums.  Layout of a
+ * rank's exposed allocation: double recv[2][half] (halves alternate with the parity of the device-side step counter), then
+ * long long flags[num_nb].  d_ctr = {last completed step, CTAs done} (zero-initialised, private to the rank).  `stream` (nullable:
+ * the context stream) lets the put run on a high-priority stream concurrently with the interior elements. */
+CEEDB200_EXPORT int ceedb200_iface_put(B200Ceed ceed, void *stream, const double *d_v, const long long *d_idx, const int *d_nb_of, const long long *d_seg,
+                                       long long n, int num_nb, double *const *d_peer_recv, const long long *d_peer_half, long long *const *d_peer_flag,
+                                       long long *d_ctr);
+CEEDB200_EXPORT int ceedb200_iface_wait_unpack_sum(B200Ceed ceed, double *d_v, long long n, const long long *d_node, const int *d_ptr, const int *d_src,
+                                                   const double *d_recv, long long half, const long long *d_flags, int num_nb, const long long *d_ctr);
+/* CUDA IPC plumbing (one process per GPU): allocate a zeroed device buffer and export its 64-byte handle / map a peer's buffer */
+CEEDB200_EXPORT int ceedb200_ipc_alloc(B200Ceed ceed, size_t bytes, void **d_ptr, unsigned char *handle64);
+CEEDB200_EXPORT int ceedb200_ipc_open(B200Ceed ceed, const unsigned char *handle64, void **d_ptr);
+CEEDB200_EXPORT int ceedb200_ipc_close(B200Ceed ceed, void *d_ptr);
+CEEDB200_EXPORT int ceedb200_ipc_free(B200Ceed ceed, void *d_ptr);
 
 /* ---- device-resident conjugate-gradient pieces (the reference's figure of merit is
  * "DoFs/sec in CG", examples/petsc/bps.c:218-288, there with PETSc KSPCG).  Raw device pointers; all scalars live on the

@@ -121,6 +121,16 @@ def load(path=LIB_PATH):
         "ceedb200_restriction_debug_scatter_tables": [handle, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64],
         "ceedb200_iface_pack": [handle, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p],
         "ceedb200_iface_unpack_sum": [handle, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+        "ceedb200_iface_put": [handle, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p],
+        "ceedb200_iface_wait_unpack_sum": [handle, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
+                                           C.c_int, C.c_void_p],
+        "ceedb200_ipc_alloc": [handle, C.c_size_t, P(C.c_void_p), C.c_char_p],
+        "ceedb200_ipc_open": [handle, C.c_char_p, P(C.c_void_p)],
+        "ceedb200_ipc_close": [handle, C.c_void_p],
+        "ceedb200_ipc_free": [handle, C.c_void_p],
+        "ceedb200_operator_apply_part": [handle, handle, handle, C.c_int],
+        "ceedb200_restriction_set_split": [handle, C.c_int32],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)

@@ -47,7 +47,9 @@ def seeded_uniform(n, seed=0x5EED):
 class BPProblem:
     """One BP operator on one structured hex (sub-)mesh, built on a `Ceed` context of the b200 backend."""
 
-    def __init__(self, ceed, bp, p, nelem_xyz, part=None, interlaced=False, build_qdata=True):
+    def __init__(self, ceed, bp, p, nelem_xyz, part=None, interlaced=False, build_qdata=True, elem_perm=None, split=None):
+        """elem_perm / split: element order of a partitioned mesh with the `split` interface-touching elements first
+        (mesh.Partition.boundary_first_permutation) -- enables Operator.apply_part."""
         ncomp, kind, q_extra, qmode, setup_name, apply_name, ncq = BP_TABLE[bp]
         self.ceed, self.bp, self.p, self.ncomp, self.kind, self.ncq = ceed, bp, p, ncomp, kind, ncq
         P, Q = p + 1, p + q_extra
@@ -63,6 +65,8 @@ class BPProblem:
         self.num_nodes = (nx * p + 1) * (ny * p + 1) * (nz * p + 1)
         self.num_dofs = self.num_nodes * ncomp
         offsets = M.hex_offsets(nx, ny, nz, p)
+        if elem_perm is not None:
+            offsets = np.ascontiguousarray(offsets[elem_perm])
         self.offsets = offsets
         nn = self.num_nodes
         # restrictions
@@ -72,6 +76,8 @@ class BPProblem:
             self.rstr_u = ceed.ElemRestriction(self.num_elem, P ** 3, ncomp, 1, ncomp * nn, offsets * ncomp)
         else:
             self.rstr_u = ceed.ElemRestriction(self.num_elem, P ** 3, ncomp, nn, ncomp * nn, offsets)
+        if split is not None:
+            self.rstr_u.set_split(split)
         self.rstr_qd = ceed.StridedElemRestriction(self.num_elem, Q ** 3, ncq, self.num_elem * Q ** 3 * ncq, None)
         # bases
         self.basis_x = ceed.BasisTensorH1Lagrange(3, 3, P, Q, qmode)

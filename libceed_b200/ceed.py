@@ -228,6 +228,9 @@ class ElemRestriction(_Object):
     def apply(self, u, v, tmode=NOTRANSPOSE):
         self._chk(self._ceed._lib.ceedb200_restriction_apply(self._ptr, tmode, u._ptr, v._ptr))
 
+    def set_split(self, split_elem):
+        self._chk(self._ceed._lib.ceedb200_restriction_set_split(self._ptr, int(split_elem)))
+
     def T_apply(self, u, v):
         self.apply(u, v, TRANSPOSE)
 
@@ -340,6 +343,11 @@ class Operator(_Object):
 
     def apply_add(self, u, v):
         self._chk(self._ceed._lib.ceedb200_operator_apply_add(self._ptr, u._ptr if u is not None else None, v._ptr))
+
+    def apply_part(self, u, v, part):
+        """part 1: the interface-touching elements [0, split) of a partitioned mesh, part 2: the interior elements
+        (ElemRestriction.set_split); 1 followed by 2 equals apply()."""
+        self._chk(self._ceed._lib.ceedb200_operator_apply_part(self._ptr, u._ptr, v._ptr, part))
 
     def set_tuning(self, elems_per_block=0, blocks_per_sm=0):
         self._chk(self._ceed._lib.ceedb200_operator_set_tuning(self._ptr, elems_per_block, blocks_per_sm))

@@ -20,10 +20,14 @@ import torch.distributed as dist
 
 
 class DeviceCG:
-    def __init__(self, ceed, op, u_vec, v_vec, n, device, exchange=None, owned_mask=None, group=None):
+    def __init__(self, ceed, op, u_vec, v_vec, n, device, exchange=None, owned_mask=None, group=None, dist_op=None):
         """op: libceed_b200 Operator; u_vec / v_vec: its active input / output Vectors (length n) that wrap the torch tensors
-        created here (USE_POINTER), so the operator reads p and writes Ap in place."""
+        created here (USE_POINTER), so the operator reads p and writes Ap in place.
+        dist_op: a parallel.DistributedOperator instead of (op, u_vec, v_vec, exchange): A p is then its (overlapped) multi-GPU step."""
         from . import ceed as cm
+        self.dist_op = dist_op
+        if dist_op is not None:
+            op, u_vec, v_vec, exchange = dist_op.prob.op, dist_op.prob.u, dist_op.prob.v, dist_op.exchange
         self.ceed, self.op, self.n, self.exchange, self.group = ceed, op, n, exchange, group
         f64 = dict(dtype=torch.float64, device=device)
         self.x, self.r, self.p, self.Ap = (torch.zeros(n, **f64) for _ in range(4))
@@ -43,6 +47,9 @@ class DeviceCG:
 
     def apply(self):
         """Ap = A p (including the interface sum)."""
+        if self.dist_op is not None:
+            self.dist_op.apply(self.u_vec, self.v_vec, v_t=self.Ap)
+            return
         self.op.apply(self.u_vec, self.v_vec)
         if self.exchange is not None:
             self.exchange.sum_interfaces(self.Ap)

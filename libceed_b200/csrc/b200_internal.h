@@ -126,6 +126,11 @@ struct B200Restriction_ {
   int32_t *d_halo_node = nullptr;   // per shared node: L-index
   int32_t *d_halo_ptr = nullptr;    // per shared node: start slot (CSR), size num_shared+1
   int64_t  num_shared = 0, num_halo = 0;
+  // element split of a partitioned mesh (multi-GPU overlap): elements [0, split_elem) touch the rank interface and are applied first.
+  // Shared nodes all of whose touchers lie in that range come first in halo_node / halo_ptr (num_shared_first of them), so that
+  // the boundary part of the scatter can be finalized -- and sent -- while the interior elements are still being applied.
+  int      split_elem = -1;
+  int64_t  num_shared_first = 0;
   bool     transpose_built = false, owner_built = false;
 };
 
@@ -210,5 +215,5 @@ int b200_restriction_build_owner(B200Restriction rstr);
 int b200_restriction_e_size(B200Restriction rstr, int64_t *e_size);
 // raw device-pointer restriction kernels (used by the unfused operator path and EVECTOR scatter mode)
 int b200_restriction_apply_raw(B200Restriction rstr, int t_mode, const double *d_u, double *d_v);
-int b200_halo_finalize(B200Restriction rstr, const double *d_halo, double *d_v);
+int b200_halo_finalize(B200Restriction rstr, const double *d_halo, double *d_v, int part = 0);  // part 0 all, 1 boundary-only nodes, 2 the rest
 int b200_memset_async(B200Ceed ceed, void *d, size_t bytes);

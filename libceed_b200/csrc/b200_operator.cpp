@@ -153,7 +153,9 @@ static int operator_setup(B200Operator op) {
 }
 
 // ------------------------------------------------------------------------------------------------ fused apply
-static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add) {
+// part: 0 = the whole operator; 1 / 2 = boundary / interior elements of a partitioned mesh (ceedb200_operator_apply_part):
+// part 1 applies elements [0, split) and finalizes the shared nodes touched by those elements only, part 2 the rest.
+static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int part = 0) {
   B200Ceed    ceed = op->ceed;
   B200OpPlan *plan = op->plan;
   B200OpArgs  args;
@@ -184,7 +186,7 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add) {
       op->is_setup = false;
       B200_CALL(operator_setup(op));
       B200_CHECK(op->plan->fused && !op->plan->qd_tma, ceed, B200_ERROR_BACKEND, "could not regenerate the operator kernel without bulk copies");
-      return apply_fused(op, u, v, add);
+      return apply_fused(op, u, v, add, part);
     }
   }
   // outputs.  Decide per distinct output vector whether the kernel can store (overwrite) or must accumulate.
@@ -222,6 +224,23 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add) {
   if (op->timing && !op->ev[0])
     for (int i = 0; i < 4; i++) B200_CUDA(ceed, cudaEventCreate(&op->ev[i]));
   if (op->timing) B200_CUDA(ceed, cudaEventRecord(op->ev[0], ceed->stream));  // aux time includes the memset of non-overwriting modes
+  // element range of this launch
+  long long e_begin = 0, e_end = plan->num_elem;
+  if (part) {
+    int split = -1;
+    for (size_t i = 0; i < op->out_fields.size(); i++) {
+      const B200Restriction r = op->out_fields[i].rstr;
+      B200_CHECK(r->is_strided || r->split_elem >= 0, ceed, B200_ERROR_INCOMPLETE, "apply_part needs ceedb200_restriction_set_split on the output restriction");
+      if (!r->is_strided) {
+        B200_CHECK(split < 0 || split == r->split_elem, ceed, B200_ERROR_INCOMPATIBLE, "output restrictions with different element splits");
+        split = r->split_elem;
+      }
+    }
+    B200_CHECK(split >= 0, ceed, B200_ERROR_INCOMPLETE, "apply_part needs an offset-restricted output");
+    B200_CHECK(plan->scatter_mode == B200_SCATTER_DETERMINISTIC, ceed, B200_ERROR_UNSUPPORTED, "apply_part needs the deterministic scatter mode");
+    if (part == 1) e_end = split;
+    else e_begin = split;
+  }
   int kernel_add = add;
   if (!add) {
     bool need_zero = false;
@@ -231,7 +250,8 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add) {
       if (!op->out_fields[i].rstr->is_strided && plan->scatter_mode != B200_SCATTER_DETERMINISTIC && plan->scatter_mode != B200_SCATTER_ORDERED)
         offset_non_det = true;
     if (need_zero || offset_non_det) {
-      for (auto &o : outs) B200_CALL(ceedb200_vector_set_value(o.vec, 0.0));
+      if (part != 2)  // the interior part continues what the boundary part started
+        for (auto &o : outs) B200_CALL(ceedb200_vector_set_value(o.vec, 0.0));
       kernel_add = 1;
     }
   }
@@ -239,7 +259,7 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add) {
     const B200OpField &f   = op->out_fields[i];
     B200Vector         vec = f.is_active ? v : f.vec;
     // discard previous contents only when the kernel overwrites everything
-    B200_CALL(b200_vector_device_write(vec, &args.out_ptr[i], !kernel_add));
+    B200_CALL(b200_vector_device_write(vec, &args.out_ptr[i], !kernel_add && part != 2));
     if (!f.rstr->is_strided) {
       if (plan->scatter_mode == B200_SCATTER_ORDERED && (int)i == plan->ordered_slot) args.out_idx[i] = plan->ordered.d_tgt;
       else args.out_idx[i] = plan->scatter_mode == B200_SCATTER_DETERMINISTIC ? f.rstr->d_tgt : f.rstr->d_offsets;
@@ -256,7 +276,8 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add) {
   B200KernelVariant &var = plan->variant[kernel_add ? 1 : 0];
 
   if (op->timing) B200_CUDA(ceed, cudaEventRecord(op->ev[3], ceed->stream));
-  if (plan->num_elem > 0) {
+  B200_CHECK(!(ordered && part), ceed, B200_ERROR_UNSUPPORTED, "apply_part is not available with the in-kernel ordered scatter");
+  if (e_end > e_begin) {
     // the argument block is a __constant__ object of the module: rewrite it only when a pointer changed (stream-ordered copy)
     B200Module *mod = var.module;
     if (!b200_compile_only() && (mod->last_args.size() != sizeof(args) || memcmp(mod->last_args.data(), &args, sizeof(args)) != 0)) {
@@ -264,7 +285,8 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add) {
       B200_CUDA(ceed, cudaMemcpyAsync((void *)mod->args_dptr, mod->last_args.data(), sizeof(args), cudaMemcpyHostToDevice, ceed->stream));
     }
     // element groups of the ordered scatter wait for each other: all CTAs must be resident (cooperative launch)
-    B200_CALL(b200_launch(ceed, var.kernel, plan->grid, plan->threads, plan->smem_bytes, nullptr, ordered));
+    void *params[2] = {&e_begin, &e_end};
+    B200_CALL(b200_launch(ceed, var.kernel, b200_opgen_grid(ceed, plan, var, e_end - e_begin), plan->threads, plan->smem_bytes, params, ordered));
   }
   if (op->timing) B200_CUDA(ceed, cudaEventRecord(op->ev[1], ceed->stream));
   // second phase of the scatter
@@ -274,7 +296,7 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add) {
     bool is_writer = plan->out_fields[i].emode == B200_EVAL_NONE || plan->out_groups[plan->out_fields[i].group].slot == (int)i;
     if (!is_writer) continue;
     if (ordered && (int)i == plan->ordered_slot) continue;  // completed inside the kernel
-    if (plan->scatter_mode == B200_SCATTER_DETERMINISTIC || ordered) B200_CALL(b200_halo_finalize(f.rstr, plan->aux[i], args.out_ptr[i]));
+    if (plan->scatter_mode == B200_SCATTER_DETERMINISTIC || ordered) B200_CALL(b200_halo_finalize(f.rstr, plan->aux[i], args.out_ptr[i], part));
     else if (plan->scatter_mode == B200_SCATTER_EVECTOR) B200_CALL(b200_restriction_apply_raw(f.rstr, B200_TRANSPOSE, plan->aux[i], args.out_ptr[i]));
   }
   if (op->timing) {
@@ -491,6 +513,18 @@ static int operator_apply(B200Operator op, B200Vector u, B200Vector v, int add) 
 }
 
 extern "C" int ceedb200_operator_apply(B200Operator op, B200Vector u, B200Vector v) { return operator_apply(op, u, v, 0); }
+
+// One half of an apply on a partitioned mesh (multi-GPU overlap): part 1 = the boundary elements
+// [0, split) (+ the finalize pass of the nodes only they touch), part 2 = the interior elements.  After part 1 every interface
+// DoF holds this rank's complete partial sum, so the exchange can run while part 2 executes.  part 1 followed by part 2 gives
+// exactly the bits of ceedb200_operator_apply.
+extern "C" int ceedb200_operator_apply_part(B200Operator op, B200Vector u, B200Vector v, int part) {
+  B200_CHECK(part == 1 || part == 2, op->ceed, B200_ERROR_DIMENSION, "part must be 1 (boundary elements) or 2 (interior elements)");
+  B200_CALL(operator_setup(op));
+  if (!b200_compile_only()) B200_CUDA(op->ceed, cudaSetDevice(op->ceed->device_id));
+  B200_CHECK(op->plan->fused, op->ceed, B200_ERROR_UNSUPPORTED, "apply_part needs a fused operator: %s", op->plan->why_not_fused.c_str());
+  return apply_fused(op, u, v, 0, part);
+}
 extern "C" int ceedb200_operator_apply_add(B200Operator op, B200Vector u, B200Vector v) { return operator_apply(op, u, v, 1); }
 
 extern "C" int ceedb200_operator_is_fused(B200Operator op, int *is_fused) {

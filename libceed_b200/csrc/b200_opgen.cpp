@@ -420,6 +420,7 @@ struct Gen {
   bool         warp_mode = false;
   int          TS        = 0;            // task-loop stride (threads that share a group)
   string       TID, SMBASE, SYNC;        // lane id expression, shared-memory base, barrier statement
+  string       QLD = "__ldg";            // load intrinsic of streamed EVAL_NONE inputs (stage bit 128: __ldcs = evict-first in L2)
   string       smw_expr() const {
     return warp_mode ? "sm + (threadIdx.x / " + std::to_string(TS) + ") * " + std::to_string(plan->group_smem_bytes / 8) : "sm";
   }
@@ -504,7 +505,9 @@ struct Gen {
       // the argument block lives in constant memory (written by the host before the launch): every stage function reads its
       // pointers with uniform constant loads instead of generic loads through a reference to the kernel parameter
       << "__constant__ B200OpArgs b200a;\n\n";
-    c << "extern __shared__ double sm[];\n\n";
+    c << "extern __shared__ double sm[];\n";
+    // end of the element range of this launch (kernel parameter e_end, published by thread 0): stage functions clamp tail groups with it
+    c << "__shared__ long long b200_ne;\n\n";
     // cp.async (LDGSTS): global -> shared without staging registers; completion tracked per thread with commit/wait groups
     c << "__device__ __forceinline__ void b200_cp4(void *dst, const void *src) {\n"
       << "  asm volatile(\"cp.async.ca.shared.global [%0], [%1], 4;\" ::\"r\"((unsigned)__cvta_generic_to_shared(dst)), \"l\"(src) : \"memory\");\n}\n"
@@ -544,9 +547,9 @@ struct Gen {
     for (auto &g : plan->in_groups) any = any || g.idx_off >= 0;
     if (!any) return false;
     c << "static __device__ __noinline__ void b200_issue_idx(const long long e0) {\n";
-    c << "  if (e0 >= b200a.num_elem) return;\n";
+    c << "  if (e0 >= b200_ne) return;\n";
     c << smw_decl();
-    c << "  const int ne = (int)((b200a.num_elem - e0 < " << E << ") ? b200a.num_elem - e0 : " << E << ");\n";
+    c << "  const int ne = (int)((b200_ne - e0 < " << E << ") ? b200_ne - e0 : " << E << ");\n";
     for (auto &g : plan->in_groups) {
       if (g.idx_off < 0) continue;
       const int es = g.rstr->elem_size;
@@ -564,9 +567,9 @@ struct Gen {
     for (auto &g : plan->out_groups) any = any || g.tgt_off >= 0;
     if (!any) return false;
     c << "static __device__ __noinline__ void b200_issue_tgt(const long long e0) {\n";
-    c << "  if (e0 >= b200a.num_elem) return;\n";
+    c << "  if (e0 >= b200_ne) return;\n";
     c << smw_decl();
-    c << "  const int ne = (int)((b200a.num_elem - e0 < " << E << ") ? b200a.num_elem - e0 : " << E << ");\n";
+    c << "  const int ne = (int)((b200_ne - e0 < " << E << ") ? b200_ne - e0 : " << E << ");\n";
     for (auto &g : plan->out_groups) {
       if (g.tgt_off < 0) continue;
       const int es = g.rstr->elem_size;
@@ -582,9 +585,9 @@ struct Gen {
     for (auto &g : plan->in_groups) any = any || g.uin_off >= 0;
     if (!any) return false;
     c << "static __device__ __noinline__ void b200_issue_gather(const long long e0) {\n";
-    c << "  if (e0 >= b200a.num_elem) return;\n";
+    c << "  if (e0 >= b200_ne) return;\n";
     c << smw_decl();
-    c << "  const int ne = (int)((b200a.num_elem - e0 < " << E << ") ? b200a.num_elem - e0 : " << E << ");\n";
+    c << "  const int ne = (int)((b200_ne - e0 < " << E << ") ? b200_ne - e0 : " << E << ");\n";
     for (auto &g : plan->in_groups) {
       if (g.uin_off < 0) continue;
       const int es = g.rstr->elem_size;
@@ -606,9 +609,9 @@ struct Gen {
     if (!any) return false;
     const int Q3 = Q * Q * Q;
     c << "static __device__ __noinline__ void b200_issue_qd(const long long e0) {\n";
-    c << "  if (e0 >= b200a.num_elem) return;\n";
+    c << "  if (e0 >= b200_ne) return;\n";
     c << smw_decl();
-    c << "  const int ne = (int)((b200a.num_elem - e0 < " << E << ") ? b200a.num_elem - e0 : " << E << ");\n";
+    c << "  const int ne = (int)((b200_ne - e0 < " << E << ") ? b200_ne - e0 : " << E << ");\n";
     if (plan->qd_tma) {
       // one elected lane: a bulk copy per (field, component) = the contiguous block of the group's elements, completion on the group's mbarrier
       c << "  if (" << TID << " == 0) {\n";
@@ -666,8 +669,8 @@ struct Gen {
       any = any || (f.emode == B200_EVAL_NONE && f.qd_off < 0 && f.rstr->is_strided && f.rstr->strides[0] == 1 && f.rstr->strides[2] == f.rstr->elem_size);
     if (!any) return false;
     c << "static __device__ __noinline__ void b200_prefetch_qd(const long long e0) {\n";
-    c << "  if (e0 >= b200a.num_elem || " << TID << " != 0) return;\n";
-    c << "  const int ne = (int)((b200a.num_elem - e0 < " << E << ") ? b200a.num_elem - e0 : " << E << ");\n";
+    c << "  if (e0 >= b200_ne || " << TID << " != 0) return;\n";
+    c << "  const int ne = (int)((b200_ne - e0 < " << E << ") ? b200_ne - e0 : " << E << ");\n";
     for (auto &f : plan->in_fields) {
       if (!(f.emode == B200_EVAL_NONE && f.qd_off < 0 && f.rstr->is_strided && f.rstr->strides[0] == 1 && f.rstr->strides[2] == f.rstr->elem_size)) continue;
       for (int cc = 0; cc < f.nc; cc++) {
@@ -716,7 +719,7 @@ struct Gen {
         c << "    const int t" << x << " = lane + " << r * TS << ", tc" << x << " = t" << x << " < " << ntasks << " ? t" << x << " : " << ntasks - 1 << ";\n";
         c << "    const int ij" << x << " = tc" << x << " % " << P * P << ", cc" << x << " = (tc" << x << " / " << P * P << ") % " << g.nc << ", le" << x
           << " = tc" << x << " / " << P * P * g.nc << ";\n";
-        c << "    const long long e" << x << " = (e0 + le" << x << " < b200a.num_elem) ? e0 + le" << x << " : b200a.num_elem - 1;\n";
+        c << "    const long long e" << x << " = (e0 + le" << x << " < b200_ne) ? e0 + le" << x << " : b200_ne - 1;\n";
       }
       if (!g.rstr->is_strided) {
         for (int r = 0; r < rounds; r++) {
@@ -753,7 +756,7 @@ struct Gen {
     }
     task_loop_begin(std::to_string(ntasks));
     c << "      const int ij = t % " << P * P << ", cc = (t / " << P * P << ") % " << g.nc << ", le = t / " << P * P * g.nc << ";\n";
-    c << "      const long long e = (e0 + le < b200a.num_elem) ? e0 + le : b200a.num_elem - 1;  // clamped: tail groups gather a valid element\n";
+    c << "      const long long e = (e0 + le < b200_ne) ? e0 + le : b200_ne - 1;  // clamped: tail groups gather a valid element\n";
     if (g.uin_off >= 0) {
       // values were gathered into shared memory by cp.async while the previous batch was computing
       c << "      const double *uin = " << smem_at(g.uin_off, "double") << " + (cc * " << E << " + le) * " << P * P * P << " + ij;\n";
@@ -880,7 +883,7 @@ struct Gen {
     // tail groups: loads use a clamped (valid) element so that there is no branch in the loop body and the compiler can overlap
     // the global loads of several unrolled points; results of non-existent elements are simply never stored to global memory
     c << "      const long long e_real = e0 + le;\n";
-    c << "      const long long e = e_real < b200a.num_elem ? e_real : b200a.num_elem - 1;\n";
+    c << "      const long long e = e_real < b200_ne ? e_real : b200_ne - 1;\n";
     c << "      {\n";
     for (size_t f = 0; f < plan->in_fields.size(); f++) c << "      CeedScalar in_" << f << "[" << plan->in_fields[f].size * PP << "];\n";
     for (size_t f = 0; f < plan->out_fields.size(); f++) c << "      CeedScalar out_" << f << "[" << plan->out_fields[f].size * PP << "];\n";
@@ -896,11 +899,11 @@ struct Gen {
             if (fd.qd_off >= 0) {
               for (int h = 0; h < PP; h++) c << "      in_" << f << at(cc, h) << " = " << qd_ref(fd, cc, "le", "pt + " + std::to_string(h)) << ";\n";
             } else if (PP == 2 && fd.rstr->is_strided && fd.rstr->strides[0] == 1 && fd.rstr->strides[1] % 2 == 0 && fd.rstr->strides[2] % 2 == 0) {
-              c << "      { const double2 v2 = __ldg((const double2 *)(b200a.in_ptr[" << sl << "] + " << lidx(fd.rstr, "", "e", "pt", std::to_string(cc)) << "));\n";
+              c << "      { const double2 v2 = " << QLD << "((const double2 *)(b200a.in_ptr[" << sl << "] + " << lidx(fd.rstr, "", "e", "pt", std::to_string(cc)) << "));\n";
               c << "        in_" << f << at(cc, 0) << " = v2.x; in_" << f << at(cc, 1) << " = v2.y; }\n";
             } else {
               for (int h = 0; h < PP; h++)
-                c << "      in_" << f << at(cc, h) << " = __ldg(b200a.in_ptr[" << sl << "] + "
+                c << "      in_" << f << at(cc, h) << " = " + QLD + "(b200a.in_ptr[" << sl << "] + "
                   << lidx(fd.rstr, "b200a.in_idx[" + sl + "]", "e", "pt + " + std::to_string(h), std::to_string(cc)) << ");\n";
             }
           }
@@ -953,7 +956,7 @@ struct Gen {
     for (size_t f = 0; f < plan->out_fields.size(); f++) {
       const B200GenField &fd = plan->out_fields[f];
       if (fd.emode != B200_EVAL_NONE) continue;
-      c << "      if (e_real < b200a.num_elem) {\n";
+      c << "      if (e_real < b200_ne) {\n";
       for (int h = 0; h < PP; h++)
         emit_scatter_value(fd.rstr, fd.slot, "e", "pt + " + std::to_string(h), fd.nc,
                            [&](int cc) { return "out_" + std::to_string(f) + at(cc, h); }, "        ");
@@ -969,7 +972,7 @@ struct Gen {
     task_loop_begin(std::to_string(E * Q * Q));
     c << "      const int qx = t % " << Q << ", qy = (t / " << Q << ") % " << Q << ", le = t / " << Q * Q << ";\n";
     c << "      const long long e = e0 + le;\n";
-    c << "      if (e < b200a.num_elem) {\n";
+    c << "      if (e < b200_ne) {\n";
     c << "      const int pxy = qy * " << Qs << " + qx;\n";
     // z-lines of input groups that need gradients (and their d/dz)
     for (size_t gi = 0; gi < plan->in_groups.size(); gi++) {
@@ -1007,7 +1010,7 @@ struct Gen {
     const int  depth    = std::max(1, std::min(Q, plan->qf_ahead));  // z-layers of streamed inputs in flight per lane
     auto none_load = [&](const B200GenField &fd, int cc, const string &pt_expr) {
       const string sl = std::to_string(fd.slot);
-      return "__ldg(b200a.in_ptr[" + sl + "] + " + lidx(fd.rstr, "b200a.in_idx[" + sl + "]", "e", pt_expr, std::to_string(cc)) + ")";
+      return QLD + "(b200a.in_ptr[" + sl + "] + " + lidx(fd.rstr, "b200a.in_idx[" + sl + "]", "e", pt_expr, std::to_string(cc)) + ")";
     };
     c << "      const int pt0 = qy * " << Q << " + qx;\n";
     if (qf_ahead)
@@ -1120,7 +1123,7 @@ struct Gen {
     c << "      const int row = t % " << Q * Q << ", le = t / " << Q * Q << ";\n";
     c << "      const int qy = row % " << Q << ", qz = row / " << Q << ";\n";
     c << "      const long long e_real = e0 + le;\n";
-    c << "      const long long e = e_real < b200a.num_elem ? e_real : b200a.num_elem - 1;\n      (void)qy; (void)qz; (void)e;\n";
+    c << "      const long long e = e_real < b200_ne ? e_real : b200_ne - 1;\n      (void)qy; (void)qz; (void)e;\n";
     c << "      const CeedScalar *in[" << std::max<size_t>(1, qf->inputs.size()) << "];\n";
     c << "      CeedScalar *out[" << std::max<size_t>(1, qf->outputs.size()) << "];\n";
     for (size_t f = 0; f < plan->in_fields.size(); f++) c << "      CeedScalar in_" << f << "[" << plan->in_fields[f].size * Q << "];\n";
@@ -1137,7 +1140,7 @@ struct Gen {
             if (fd.qd_off >= 0)  // staged one group ahead by cp.async (b200_issue_qd)
               c << "      in_" << f << "[" << cc * Q + q << "] = " << qd_ref(fd, cc, "le", "row * " + std::to_string(Q) + " + " + std::to_string(q)) << ";\n";
             else
-              c << "      in_" << f << "[" << cc * Q + q << "] = __ldg(b200a.in_ptr[" << sl << "] + "
+              c << "      in_" << f << "[" << cc * Q + q << "] = " + QLD + "(b200a.in_ptr[" << sl << "] + "
                 << lidx(fd.rstr, "", "e", "row * " + std::to_string(Q) + " + " + std::to_string(q), std::to_string(cc)) << ");\n";
           }
       } else if (fd.emode == B200_EVAL_WEIGHT) {
@@ -1197,8 +1200,8 @@ struct Gen {
       const string x = "_" + std::to_string(r);
       c << ind << "const int t" << x << " = lane + " << r * TS << ", tc" << x << " = t" << x << " < " << ntasks << " ? t" << x << " : " << ntasks - 1 << ";\n";
       c << ind << "const int le" << x << " = tc" << x << " / " << Q * Q << ", pt0" << x << " = tc" << x << " % " << Q * Q << ";\n";
-      c << ind << "const long long ec" << x << " = (e0 + le" << x << " < b200a.num_elem) ? e0 + le" << x << " : b200a.num_elem - 1;\n";
-      c << ind << "const long long en" << x << " = (e0n + le" << x << " < b200a.num_elem) ? e0n + le" << x << " : b200a.num_elem - 1;\n";
+      c << ind << "const long long ec" << x << " = (e0 + le" << x << " < b200_ne) ? e0 + le" << x << " : b200_ne - 1;\n";
+      c << ind << "const long long en" << x << " = (e0n + le" << x << " < b200_ne) ? e0n + le" << x << " : b200_ne - 1;\n";
       for (size_t f = 0; f < plan->in_fields.size(); f++) {
         const B200GenField &fd = plan->in_fields[f];
         if (fd.ring_k < 0) continue;
@@ -1265,7 +1268,7 @@ struct Gen {
       c << "    {  // task round " << r << "\n";
       c << "      const int le = le" << x << ", qx = pt0" << x << " % " << Q << ", qy = pt0" << x << " / " << Q << ";\n";
       c << "      const long long e = ec" << x << ";\n";
-      c << "      const bool act = t" << x << " < " << ntasks << " && e0 + le < b200a.num_elem;\n";
+      c << "      const bool act = t" << x << " < " << ntasks << " && e0 + le < b200_ne;\n";
       c << "      const int pxy = qy * " << Qs << " + qx, pt0 = pt0" << x << ";\n";
       c << "      (void)e; (void)pt0;\n";
       for (size_t gi = 0; gi < plan->in_groups.size(); gi++) {
@@ -1314,7 +1317,7 @@ struct Gen {
                 if (fd.qd_off >= 0)
                   c << "        in_" << f << "[" << cc << "] = " << qd_ref(fd, cc, "le", "pt") << ";\n";
                 else
-                  c << "        in_" << f << "[" << cc << "] = __ldg(b200a.in_ptr[" << sl << "] + " << lidx(fd.rstr, "b200a.in_idx[" + sl + "]", "e", "pt", std::to_string(cc)) << ");\n";
+                  c << "        in_" << f << "[" << cc << "] = " + QLD + "(b200a.in_ptr[" << sl << "] + " << lidx(fd.rstr, "b200a.in_idx[" + sl + "]", "e", "pt", std::to_string(cc)) << ");\n";
               }
               break;
             case B200_EVAL_WEIGHT: c << "        in_" << f << "[0] = wxy_" << f << " * cW" << fd.basis_id << "[" << qz << "];\n"; break;
@@ -1504,7 +1507,7 @@ struct Gen {
     c << "      do { asm volatile(\"ld.acquire.gpu.global.s32 %0, [%1];\" : \"=r\"(seen) : \"l\"(flag) : \"memory\"); } while (seen != epoch);\n";
     c << "    }\n";
     c << "    " << SYNC << "\n";
-    c << "    const int nent = (int)((b200a.num_elem - ep < " << E << ") ? b200a.num_elem - ep : " << E << ") * " << es << ";\n";
+    c << "    const int nent = (int)((b200_ne - ep < " << E << ") ? b200_ne - ep : " << E << ") * " << es << ";\n";
     c << "    const int *tgt = b200a.out_idx[" << sl << "] + ep * " << es << "LL;\n";
     // U entries per lane at a time: all table loads first, then the first two contributions (every shared node has >= 2), ...
     const int U = 4;
@@ -1546,7 +1549,7 @@ struct Gen {
       for (int q = 0; q < Q; q++) c << "      const double u" << q << " = col[" << q * P * P << "];\n";
       contract("cB" + std::to_string(g.basis_id), Q, P, true, "u", "r", "      ");
     }
-    c << "      if (e < b200a.num_elem) {\n";
+    c << "      if (e < b200_ne) {\n";
     for (int k = 0; k < P; k++) {
       const string n = "ij + " + std::to_string(k * P * P);
       string       tgt;
@@ -1580,7 +1583,7 @@ struct Gen {
       for (int q = 0; q < Q; q++) c << "      const double u" << q << " = src[" << q * P * P << "];\n";
       contract("cB" + std::to_string(g.basis_id), Q, P, true, "u", "r", "      ");
     }
-    c << "      if (e < b200a.num_elem) {\n";
+    c << "      if (e < b200_ne) {\n";
     // component handled through the (runtime) cc: emit with nc == 1 semantics and an explicit component offset
     for (int k = 0; k < P; k++) {
       const string n = "ij + " + std::to_string(k * P * P);
@@ -1634,6 +1637,8 @@ struct Gen {
     else if (plan->group_warps == 1) SYNC = "__syncwarp();";
     else SYNC = "asm volatile(\"bar.sync %0, " + std::to_string(TS) + ";\" ::\"r\"((int)(threadIdx.x / " + std::to_string(TS) + ") + 1) : \"memory\");";
     S  = plan->plane_size;
+    // quadrature data is read exactly once per apply: mark it evict-first so that u, v, the halo buffer and the offsets keep the L2
+    if (plan->stage_mask & 128) QLD = "__ldcs";
     emit_header();
     bool any;
     // input side
@@ -1729,8 +1734,8 @@ struct Gen {
     const bool prefetch = getenv("CEED_B200_PREFETCH") != nullptr;
     if (prefetch) {
       c << "static __device__ __noinline__ void b200_prefetch(const long long e0) {\n";
-      c << "  if (e0 >= b200a.num_elem) return;\n";
-      c << "  const long long ne = (b200a.num_elem - e0 < " << E << ") ? b200a.num_elem - e0 : " << E << ";\n";
+      c << "  if (e0 >= b200_ne) return;\n";
+      c << "  const long long ne = (b200_ne - e0 < " << E << ") ? b200_ne - e0 : " << E << ";\n";
       c << smw_decl();
       auto emit_range = [&](const string &ptr, const string &first_elem_expr, long long bytes_per_elem) {
         // byte range [p0, p0 + ne * bytes_per_elem), one 128-byte line per thread per round
@@ -1753,8 +1758,11 @@ struct Gen {
         if (!g.rstr->is_strided) emit_range("b200a.in_idx[" + std::to_string(g.slot) + "]", "e0", 4LL * g.rstr->elem_size);
       c << "}\n\n";
     }
-    c << "extern \"C\" __global__ void __launch_bounds__(" << NT << ", " << minb << ") b200_operator_" << op->qf->kernel_name << "() {\n";
-    c << "  const long long num_batches = (b200a.num_elem + " << E - 1 << ") / " << E << ";\n";
+    c << "extern \"C\" __global__ void __launch_bounds__(" << NT << ", " << minb << ") b200_operator_" << op->qf->kernel_name
+      << "(const long long e_begin, const long long e_end) {\n";
+    // the launch processes elements [e_begin, e_end): the whole mesh, or the boundary / interior part of a partitioned mesh
+    c << "  if (threadIdx.x == 0) b200_ne = e_end;\n  __syncthreads();\n";
+    c << "  const long long num_batches = (e_end - e_begin + " << E - 1 << ") / " << E << ";\n";
     if (plan->scatter_mode == B200_SCATTER_ORDERED)
       c << "  const int epoch = *(volatile const int *)b200a.ord_sync + 1;  // this launch\n  long long e0p = -1;  // group whose shared nodes are still to be completed\n";
     // block mode: one batch per CTA per iteration; warp mode: one group per warp per iteration
@@ -1767,15 +1775,15 @@ struct Gen {
     if (staged) {
       // prologue: stage the first batch
       c << "  if (" << first << " < num_batches) {\n";
-      c << "    const long long e0 = " << first << " * " << E << ";\n";
+      c << "    const long long e0 = e_begin + " << first << " * " << E << ";\n";
       if (has_idx) c << "    b200_issue_idx(e0);\n    b200_cp_commit();\n    b200_cp_wait_all();\n    " << SYNC << "\n";
       if (has_gather) c << "    b200_issue_gather(e0);\n";
       if (has_qd) c << "    b200_issue_qd(e0);\n";
       c << "    b200_cp_commit();\n  }\n";
     }
-    if (plan->ring_off >= 0 && !plan->qf_pointwise) c << "  if (" << first << " < num_batches) b200_ring_prologue(" << first << " * " << E << ");\n";
+    if (plan->ring_off >= 0 && !plan->qf_pointwise) c << "  if (" << first << " < num_batches) b200_ring_prologue(e_begin + " << first << " * " << E << ");\n";
     c << "  for (long long batch = " << first << "; batch < num_batches; batch += " << stride << ") {\n";
-    c << "    const long long e0 = batch * " << E << ", e0n = (batch + " << stride << ") * " << E << ";\n";
+    c << "    const long long e0 = e_begin + batch * " << E << ", e0n = e_begin + (batch + " << stride << ") * " << E << ";\n";
     if (staged) {
       // everything staged for this batch is visible after this point; all reads of the previous batch are done
       c << "    b200_cp_wait_all();\n    " << SYNC << "\n";
@@ -1834,17 +1842,22 @@ int b200_opgen_build(B200Operator op, B200OpPlan *plan, int add) {
     int nb = 0;
     B200_CU(ceed, cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.kernel, plan->threads, plan->smem_bytes));
     if (nb < 1) return b200_error(ceed, B200_ERROR_BACKEND, "fused kernel cannot be resident (regs %d, smem %d)", v.regs, plan->smem_bytes);
-    plan->blocks_per_sm = nb;
-    long long num_batches = ((long long)plan->num_elem + plan->epb - 1) / plan->epb;
-    if (plan->warp_mode) {
-      const int groups = plan->threads / (32 * plan->group_warps);
-      num_batches      = (num_batches + groups - 1) / groups;  // CTAs needed
-    }
-    long long grid = (long long)plan->blocks_per_sm * ceed->num_sms;
-    if (grid > num_batches) grid = num_batches;
-    if (grid < 1) grid = 1;
-    plan->grid = (int)grid;
+    v.blocks_per_sm = nb;  // per variant: the store and the accumulate kernels may differ in registers
+    plan->grid      = b200_opgen_grid(ceed, plan, v, plan->num_elem);
   }
   v.built = true;
   return B200_SUCCESS;
+}
+
+// persistent grid of a launch over `num_elem` elements: resident CTAs of this variant x SMs, capped by the CTAs the range needs
+int b200_opgen_grid(B200Ceed ceed, const B200OpPlan *plan, const B200KernelVariant &v, long long num_elem) {
+  long long num_batches = (num_elem + plan->epb - 1) / plan->epb;
+  if (plan->warp_mode) {
+    const int groups = plan->threads / (32 * plan->group_warps);
+    num_batches      = (num_batches + groups - 1) / groups;  // CTAs needed
+  }
+  long long grid = (long long)v.blocks_per_sm * ceed->num_sms;
+  if (grid > num_batches) grid = num_batches;
+  if (grid < 1) grid = 1;
+  return (int)grid;
 }

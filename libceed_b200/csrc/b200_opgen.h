@@ -61,6 +61,7 @@ struct B200KernelVariant {
   CUfunction  kernel = nullptr;
   std::string source;
   int         regs = 0, local_bytes = 0, static_smem = 0;
+  int         blocks_per_sm = 1;  // resident CTAs per SM of THIS variant (occupancy query); the persistent grid is sized from it
   bool        built = false;
 };
 
@@ -107,3 +108,4 @@ struct B200OpPlan {
 int b200_opgen_plan(B200Operator op, B200OpPlan *plan);
 int b200_opgen_build(B200Operator op, B200OpPlan *plan, int add);
 std::string b200_opgen_source(B200Operator op, B200OpPlan *plan, int add);
+int b200_opgen_grid(B200Ceed ceed, const B200OpPlan *plan, const B200KernelVariant &v, long long num_elem);

@@ -254,16 +254,23 @@ int b200_restriction_build_owner(B200Restriction r) {
   build_host_transpose(r, t);
   const int64_t        n         = (int64_t)r->num_elem * r->elem_size;
   const int64_t        num_nodes = (int64_t)t.lvec_indices.size();
+  B200_CHECK(n < INT32_MAX, ceed, B200_ERROR_UNSUPPORTED, "Backend does not implement restrictions with more than 2^31 - 1 E-vector entries (%lld)",
+             (long long)n);
   std::vector<int32_t> tgt(n), halo_node, halo_ptr;
   int64_t              slot = 0;
-  for (int64_t row = 0; row < num_nodes; row++) {
-    const int32_t begin = t.t_offsets[row], end = t.t_offsets[row + 1];
-    tgt[t.t_indices[begin]] = t.lvec_indices[row];
-    if (end - begin > 1) {
+  // two passes over the shared nodes: first those touched by boundary elements only (see split_elem), then the rest
+  for (int pass = 0; pass < 2; pass++) {
+    for (int64_t row = 0; row < num_nodes; row++) {
+      const int32_t begin = t.t_offsets[row], end = t.t_offsets[row + 1];
+      if (pass == 0) tgt[t.t_indices[begin]] = t.lvec_indices[row];
+      if (end - begin <= 1) continue;
+      const bool boundary_only = r->split_elem > 0 && t.t_indices[end - 1] / r->elem_size < r->split_elem;  // last toucher = highest element
+      if (boundary_only != (pass == 0)) continue;
       halo_node.push_back(t.lvec_indices[row]);
       halo_ptr.push_back((int32_t)slot);
       for (int32_t j = begin + 1; j < end; j++) tgt[t.t_indices[j]] = ~(int32_t)(slot++);
     }
+    if (pass == 0) r->num_shared_first = (int64_t)halo_node.size();
   }
   halo_ptr.push_back((int32_t)slot);
   r->num_shared = (int64_t)halo_node.size();
@@ -417,10 +424,29 @@ int b200_restriction_apply_raw(B200Restriction r, int t_mode, const double *d_u,
   return B200_SUCCESS;
 }
 
-int b200_halo_finalize(B200Restriction r, const double *d_halo, double *d_v) {
+int b200_halo_finalize(B200Restriction r, const double *d_halo, double *d_v, int part) {
+  B200Ceed      ceed  = r->ceed;
+  const int64_t first = part == 2 ? r->num_shared_first : 0;
+  const int64_t count = part == 1 ? r->num_shared_first : r->num_shared - first;
+  if (count <= 0) return B200_SUCCESS;
+  LAUNCH(ceed, k_halo_finalize, count, r->d_halo_node + first, r->d_halo_ptr + first, d_halo, d_v, count, r->num_halo, r->num_comp, r->comp_stride);
+  return B200_SUCCESS;
+}
+
+// Element split of a partitioned mesh: elements [0, split_elem) are the ones touching the rank interface (mesh.Partition orders
+// them first).  Must be set before the restriction is first used by a fused operator (the owner/halo tables depend on it).
+extern "C" int ceedb200_restriction_set_split(B200Restriction r, b200_int split_elem) {
   B200Ceed ceed = r->ceed;
-  if (r->num_shared == 0) return B200_SUCCESS;
-  LAUNCH(ceed, k_halo_finalize, r->num_shared, r->d_halo_node, r->d_halo_ptr, d_halo, d_v, r->num_shared, r->num_halo, r->num_comp, r->comp_stride);
+  B200_CHECK(!r->is_strided, ceed, B200_ERROR_UNSUPPORTED, "element split applies to offset restrictions");
+  B200_CHECK(split_elem >= 0 && split_elem <= r->num_elem, ceed, B200_ERROR_DIMENSION, "element split %d outside [0, %d]", split_elem, r->num_elem);
+  if (r->owner_built && r->split_elem != split_elem) {
+    b200_dfree(ceed, r->d_tgt);
+    b200_dfree(ceed, r->d_halo_node);
+    b200_dfree(ceed, r->d_halo_ptr);
+    r->d_tgt = r->d_halo_node = r->d_halo_ptr = nullptr;
+    r->owner_built = false;
+  }
+  r->split_elem = split_elem;
   return B200_SUCCESS;
 }
 

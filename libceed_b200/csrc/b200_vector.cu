@@ -456,6 +456,119 @@ extern "C" int ceedb200_iface_unpack_sum(B200Ceed ceed, double *d_v, long long n
   return B200_SUCCESS;
 }
 
+// ---- the same exchange over NVLink peer memory, without NCCL on the data path ---------------------------------------
+// Every rank exposes ONE device allocation to its neighbours (CUDA IPC): a double-buffered receive area [2][total] followed by
+// one arrival flag per neighbour.  k_iface_put gathers the interface values and stores them STRAIGHT INTO THE NEIGHBOURS'
+// receive areas (st.global on peer-mapped addresses travel over NVLink 5 / NVSwitch), then the last CTA to finish publishes the
+// step number in each neighbour's flag (fence + st.release.sys).  k_iface_wait_unpack_sum on the receiving GPU spins on its
+// flags (ld.acquire.sys) and then forms the rank-ordered sums as above.  The step counter lives on the device and the buffer
+// half alternates with its parity, so the pair needs no host-side arguments that change from step to step (CUDA-graph friendly)
+// and a neighbour that is one step ahead writes the other half.  The put needs no SM resources to speak of (a few CTAs, no
+// shared memory): launched at high priority right after the boundary elements it completes while the interior-element kernel runs.
+namespace {
+constexpr int kPutBlocks = 16;
+
+__global__ void k_iface_put(const double *__restrict__ v, const long long *__restrict__ idx, const int *__restrict__ nb_of, const long long *__restrict__ seg,
+                            long long n, int num_nb, double *const *__restrict__ peer_recv, const long long *__restrict__ peer_half,
+                            long long *const *__restrict__ peer_flag, long long *__restrict__ ctr) {
+  const long long step = ctr[0] + 1;  // ctr[0] = last completed put; every CTA reads it before the last one to finish updates it
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int k = nb_of[i];
+    peer_recv[k][(step & 1) * peer_half[k] + (i - seg[k])] = v[idx[i]];
+  }
+  __threadfence_system();  // this thread's peer stores are ordered before what follows
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long done = atomicAdd((unsigned long long *)(ctr + 1), 1ULL);
+    if (done == gridDim.x - 1) {  // all CTAs have stored and fenced
+      __threadfence_system();
+      for (int k = 0; k < num_nb; k++) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(peer_flag[k]), "l"(step) : "memory");
+      ctr[1] = 0;
+      ctr[0] = step;
+    }
+  }
+}
+
+__global__ void k_iface_wait_unpack_sum(double *__restrict__ v, long long n, const long long *__restrict__ node, const int *__restrict__ ptr,
+                                        const int *__restrict__ src, const double *__restrict__ recv, long long half, const long long *__restrict__ flags,
+                                        int num_nb, const long long *__restrict__ ctr) {
+  const long long step = ctr[0];  // the put of this step ran before this kernel (same GPU, stream/event ordered)
+  if (threadIdx.x < num_nb) {
+    long long seen;
+    do {
+      asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(seen) : "l"(flags + threadIdx.x) : "memory");
+    } while (seen < step);
+  }
+  __syncthreads();
+  const double *r = recv + (step & 1) * half;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long l = node[i];
+    const int       b = ptr[i], e = ptr[i + 1];
+    double          acc = src[b] < 0 ? v[l] : __ldcg(r + src[b]);
+    for (int k = b + 1; k < e; k++) acc += src[k] < 0 ? v[l] : __ldcg(r + src[k]);
+    v[l] = acc;
+  }
+}
+}  // namespace
+
+extern "C" int ceedb200_iface_put(B200Ceed ceed, void *stream, const double *d_v, const long long *d_idx, const int *d_nb_of, const long long *d_seg,
+                                  long long n, int num_nb, double *const *d_peer_recv, const long long *d_peer_half, long long *const *d_peer_flag,
+                                  long long *d_ctr) {
+  B200_CHECK(!b200_compile_only(), ceed, B200_ERROR_BACKEND, "CEED_B200_COMPILE_ONLY is set; kernels cannot run");
+  B200_CHECK(num_nb <= kThreads, ceed, B200_ERROR_UNSUPPORTED, "more than %d neighbour ranks", kThreads);
+  if (num_nb == 0) return B200_SUCCESS;
+  int blocks = (int)std::min<long long>(kPutBlocks, (n + kThreads - 1) / kThreads);
+  if (blocks < 1) blocks = 1;
+  k_iface_put<<<blocks, kThreads, 0, stream ? (cudaStream_t)stream : ceed->stream>>>(d_v, d_idx, d_nb_of, d_seg, n, num_nb, d_peer_recv, d_peer_half,
+                                                                                     d_peer_flag, d_ctr);
+  ceed->launch_count++;
+  B200_CUDA(ceed, cudaGetLastError());
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_iface_wait_unpack_sum(B200Ceed ceed, double *d_v, long long n, const long long *d_node, const int *d_ptr, const int *d_src,
+                                              const double *d_recv, long long half, const long long *d_flags, int num_nb, const long long *d_ctr) {
+  B200_CHECK(!b200_compile_only(), ceed, B200_ERROR_BACKEND, "CEED_B200_COMPILE_ONLY is set; kernels cannot run");
+  if (num_nb == 0) return B200_SUCCESS;
+  // few CTAs: every one of them waits for the flags itself (no grid-wide dependency)
+  int blocks = (int)std::min<long long>(4 * ceed->num_sms, (n + kThreads - 1) / kThreads);
+  if (blocks < 1) blocks = 1;
+  k_iface_wait_unpack_sum<<<blocks, kThreads, 0, ceed->stream>>>(d_v, n, d_node, d_ptr, d_src, d_recv, half, d_flags, num_nb, d_ctr);
+  ceed->launch_count++;
+  B200_CUDA(ceed, cudaGetLastError());
+  return B200_SUCCESS;
+}
+
+// CUDA IPC plumbing for the peer-memory exchange: one process per GPU, handles travel through the caller's bootstrap
+// channel (torch.distributed all_gather_object in libceed_b200/parallel.py).
+extern "C" int ceedb200_ipc_alloc(B200Ceed ceed, size_t bytes, void **d_ptr, unsigned char *handle64) {
+  B200_CHECK(!b200_compile_only(), ceed, B200_ERROR_BACKEND, "CEED_B200_COMPILE_ONLY is set; no device");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  B200_CUDA(ceed, cudaSetDevice(ceed->device_id));
+  B200_CUDA(ceed, cudaMalloc(d_ptr, bytes ? bytes : 8));
+  B200_CUDA(ceed, cudaMemset(*d_ptr, 0, bytes ? bytes : 8));
+  cudaIpcMemHandle_t h;
+  B200_CUDA(ceed, cudaIpcGetMemHandle(&h, *d_ptr));
+  memcpy(handle64, &h, 64);
+  return B200_SUCCESS;
+}
+extern "C" int ceedb200_ipc_open(B200Ceed ceed, const unsigned char *handle64, void **d_ptr) {
+  B200_CHECK(!b200_compile_only(), ceed, B200_ERROR_BACKEND, "CEED_B200_COMPILE_ONLY is set; no device");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  B200_CUDA(ceed, cudaSetDevice(ceed->device_id));
+  B200_CUDA(ceed, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return B200_SUCCESS;
+}
+extern "C" int ceedb200_ipc_close(B200Ceed ceed, void *d_ptr) {
+  if (d_ptr) B200_CUDA(ceed, cudaIpcCloseMemHandle(d_ptr));
+  return B200_SUCCESS;
+}
+extern "C" int ceedb200_ipc_free(B200Ceed ceed, void *d_ptr) {
+  if (d_ptr) B200_CUDA(ceed, cudaFree(d_ptr));
+  return B200_SUCCESS;
+}
+
 // ------------------------------------------------------------------------------------------------ device-resident CG pieces
 // the CG loop around the operator (what the reference's published figure of merit measures,
 // examples/petsc/bps.c:218-288, there with PETSc's KSPCG + VecDot/VecAXPY).  All scalars stay on the device, so an iteration

@@ -145,6 +145,23 @@ class Partition:
         out.sort(key=lambda t: t[0])
         return out
 
+    def boundary_first_permutation(self):
+        """(perm, n_boundary): order of the local elements with the ones touching a rank interface first (each class keeps its
+        lexicographic order).  Used for the overlapped multi-GPU step: the boundary elements are applied first, their interface
+        values travel while the interior elements are applied (the reference pattern is
+        VecScatterBegin / local work / VecScatterEnd, examples/petsc/bpsraw.c:240-262)."""
+        nx, ny, nz = self.n_local
+        ez, ey, ex = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+        touch = np.zeros((nz, ny, nx), dtype=bool)
+        for d, e in enumerate((ex, ey, ez)):
+            if self.coord[d] > 0:
+                touch |= e == 0
+            if self.coord[d] < self.grid[d] - 1:
+                touch |= e == self.n_local[d] - 1
+        touch = touch.reshape(-1)
+        perm = np.concatenate([np.nonzero(touch)[0], np.nonzero(~touch)[0]]).astype(np.int64)
+        return perm, int(touch.sum())
+
     @property
     def num_local_nodes(self):
         return int(np.prod(self.node_n))

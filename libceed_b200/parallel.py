@@ -71,9 +71,13 @@ def build_interface_tables(part, ncomp, comp_stride):
 
 
 class InterfaceExchange:
+    """Interface-DoF sum with NCCL send/recv as the transport (pack -> grouped P2P -> rank-ordered unpack)."""
+    transport = "nccl"
+
     def __init__(self, part, ncomp, comp_stride, device, ceed=None, group=None, kernels=None):
         """part: mesh.Partition; the L-vector entry of (node n, component c) is n + c * comp_stride."""
         self.part, self.device, self.group = part, device, group
+        self.ceed = ceed
         self.kernels = kernels if kernels is not None else CudaInterfaceKernels(ceed)
         ranks, seg, send_idx, node, ptr, src = build_interface_tables(part, ncomp, comp_stride)
         self.ranks, self.seg = ranks, [int(x) for x in seg]
@@ -83,17 +87,198 @@ class InterfaceExchange:
         self.recv = torch.empty(send_idx.size, dtype=torch.float64, device=device)
         self.bytes_per_exchange = 2 * 8 * int(send_idx.size)
 
-    def sum_interfaces(self, v):
-        """v: 1-D float64 torch tensor (the local L-vector after the local apply); updated in place."""
+    def begin(self, v, stream=None):
+        """Start the exchange of the interface values of v (complete partial sums).  `stream`: a torch CUDA stream to run the
+        pack kernel and the NCCL operations on (overlap with work on the caller's stream); None = the current stream."""
+        if not self.ranks:
+            return
+        ctx = torch.cuda.stream(stream) if stream is not None else _NullCtx()
+        main_ptr = self._main_stream_ptr()
+        with ctx:
+            if stream is not None and self.ceed is not None:
+                self.ceed.set_stream(stream.cuda_stream)
+            try:
+                self.kernels.pack(v, self.send_idx, self.send)
+            finally:
+                if stream is not None and self.ceed is not None:
+                    self.ceed.set_stream(main_ptr)
+            ops = []
+            for k, rank in enumerate(self.ranks):
+                a, b = self.seg[k], self.seg[k + 1]
+                ops.append(dist.P2POp(dist.isend, self.send[a:b], rank, group=self.group))
+                ops.append(dist.P2POp(dist.irecv, self.recv[a:b], rank, group=self.group))
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def _main_stream_ptr(self):
+        return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
+
+    def end(self, v):
+        """Finish the exchange: every interface entry of v becomes the rank-ordered sum of all partial values."""
         if not self.ranks:
             return v
-        self.kernels.pack(v, self.send_idx, self.send)
-        ops = []
-        for k, rank in enumerate(self.ranks):
-            a, b = self.seg[k], self.seg[k + 1]
-            ops.append(dist.P2POp(dist.isend, self.send[a:b], rank, group=self.group))
-            ops.append(dist.P2POp(dist.irecv, self.recv[a:b], rank, group=self.group))
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
         self.kernels.unpack_sum(v, self.node, self.ptr, self.src, self.recv)
         return v
+
+    def sum_interfaces(self, v):
+        """v: 1-D float64 torch tensor (the local L-vector after the local apply); updated in place."""
+        self.begin(v)
+        return self.end(v)
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+class PeerInterfaceExchange:
+    """The same interface sum over NVLink peer memory, without NCCL on the data path.
+
+    Every rank exposes one device allocation (CUDA IPC): double recv[2][total] + one arrival flag per neighbour.  `begin`
+    launches ONE kernel (ceedb200_iface_put) that gathers the interface values and stores them straight into the neighbours'
+    receive areas, then raises their flags; `end` launches ceedb200_iface_wait_unpack_sum, which waits for this rank's flags and
+    forms the sums in ascending rank order (same bits as the NCCL transport).  The step counter lives on the device and the
+    buffer halves alternate with its parity: nothing changes on the host from step to step, so the pair can be captured in a
+    CUDA graph, and the put -- a few CTAs without shared memory -- runs next to the interior-element kernel.
+    torch.distributed is used once, at construction, to swap the IPC handles and buffer offsets."""
+    transport = "peer"
+
+    def __init__(self, part, ncomp, comp_stride, device, ceed, group=None):
+        if ceed is None:
+            raise RuntimeError("PeerInterfaceExchange needs a libceed_b200 Ceed (CUDA kernels); there is no host fallback")
+        self.part, self.device, self.group, self.ceed = part, device, group, ceed
+        ranks, seg, send_idx, node, ptr, src = build_interface_tables(part, ncomp, comp_stride)
+        self.ranks, self.seg = ranks, [int(x) for x in seg]
+        total = int(send_idx.size)
+        self.total = total
+        lib, cp = ceed._lib, ceed._ptr
+        # this rank's exposed allocation
+        self._local = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        nbytes = 2 * total * 8 + max(1, len(ranks)) * 8
+        ceed._chk(lib.ceedb200_ipc_alloc(cp, nbytes, C.byref(self._local), handle))
+        info = dict(rank=part.rank, handle=handle.raw, total=total, seg={r: self.seg[k] for k, r in enumerate(ranks)},
+                    flag={r: k for k, r in enumerate(ranks)})
+        world = dist.get_world_size(group)
+        infos = [None] * world
+        dist.all_gather_object(infos, info, group=group)
+        self._remote = []
+        peer_recv, peer_half, peer_flag = [], [], []
+        for r in ranks:
+            ri = infos[r]
+            base = C.c_void_p()
+            ceed._chk(lib.ceedb200_ipc_open(cp, ri["handle"], C.byref(base)))
+            self._remote.append(base)
+            peer_recv.append(base.value + 8 * ri["seg"][part.rank])          # my segment inside the neighbour's receive area
+            peer_half.append(ri["total"])
+            peer_flag.append(base.value + 16 * ri["total"] + 8 * ri["flag"][part.rank])
+        dev = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=dt))).to(device)
+        nb_of = np.zeros(total, dtype=np.int32)
+        for k in range(len(ranks)):
+            nb_of[self.seg[k]:self.seg[k + 1]] = k
+        self.send_idx, self.nb_of, self.seg_d = dev(send_idx, np.int64), dev(nb_of, np.int32), dev(seg, np.int64)
+        self.node, self.ptr, self.src = dev(node, np.int64), dev(ptr, np.int32), dev(src, np.int32)
+        self.peer_recv, self.peer_half, self.peer_flag = dev(peer_recv, np.uint64), dev(peer_half, np.int64), dev(peer_flag, np.uint64)
+        self.ctr = torch.zeros(2, dtype=torch.int64, device=device)
+        self.bytes_per_exchange = 2 * 8 * total
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)  # every rank has mapped its neighbours before the first put
+
+    def begin(self, v, stream=None):
+        if not self.ranks:
+            return
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self.ceed._chk(self.ceed._lib.ceedb200_iface_put(self.ceed._ptr, C.c_void_p(stream.cuda_stream if stream is not None else 0), p(v), p(self.send_idx),
+                                                         p(self.nb_of), p(self.seg_d), self.total, len(self.ranks), p(self.peer_recv), p(self.peer_half),
+                                                         p(self.peer_flag), p(self.ctr)))
+
+    def end(self, v):
+        if not self.ranks:
+            return v
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self.ceed._chk(self.ceed._lib.ceedb200_iface_wait_unpack_sum(self.ceed._ptr, p(v), self.node.numel(), p(self.node), p(self.ptr), p(self.src),
+                                                                     C.c_void_p(self._local.value), self.total, C.c_void_p(self._local.value + 16 * self.total),
+                                                                     len(self.ranks), p(self.ctr)))
+        return v
+
+    def sum_interfaces(self, v):
+        self.begin(v)
+        return self.end(v)
+
+    def close(self):
+        lib, cp = self.ceed._lib, self.ceed._ptr
+        for base in self._remote:
+            lib.ceedb200_ipc_close(cp, base)
+        self._remote = []
+        if self._local:
+            lib.ceedb200_ipc_free(cp, self._local)
+            self._local = None
+
+
+class DistributedOperator:
+    """One BP operator on one rank's element box of a partitioned mesh + the interface-DoF sum: `apply()` is the multi-GPU step.
+
+    overlap=True: the elements touching the rank interface are ordered first; the step applies them (operator part 1), starts
+    the exchange of their -- now complete -- interface values on a second, high-priority stream, applies the interior elements
+    (part 2) on the main stream meanwhile, and finishes with the rank-ordered sum.  overlap=False: apply, then exchange, serially.
+    transport: "peer" (NVLink peer-memory stores from our own kernel), "nccl" (grouped send/recv), "auto" (peer, else nccl)."""
+
+    def __init__(self, ceed, bp, p, part, device, overlap=True, transport="auto", group=None):
+        from . import ceed as cm
+        from .bp import BP_TABLE, BPProblem
+        self.ceed, self.part, self.device, self.overlap = ceed, part, device, overlap
+        ncomp = BP_TABLE[bp][0]
+        perm, split = part.boundary_first_permutation() if overlap else (None, None)
+        self.prob = BPProblem(ceed, bp, p, part.n_local, part=part, elem_perm=perm, split=split)
+        self.n_local = self.prob.num_dofs
+        self.u_t = torch.zeros(self.n_local, dtype=torch.float64, device=device)
+        self.v_t = torch.zeros(self.n_local, dtype=torch.float64, device=device)
+        self.prob.u.set_array(self.u_t, cm.MEM_DEVICE, cm.USE_POINTER)
+        self.prob.v.set_array(self.v_t, cm.MEM_DEVICE, cm.USE_POINTER)
+        self.exchange = None
+        if part.size > 1:
+            if transport in ("auto", "peer"):
+                try:
+                    self.exchange = PeerInterfaceExchange(part, ncomp, self.prob.num_nodes, device, ceed, group=group)
+                except Exception as exc:  # noqa: BLE001 -- e.g. CUDA IPC not permitted in this container
+                    if transport == "peer":
+                        raise
+                    print(f"[libceed_b200] peer-memory exchange unavailable ({exc}); using NCCL send/recv", flush=True)
+                ok = torch.tensor([1 if self.exchange is not None else 0], device=device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # all ranks use the same transport
+                if int(ok.item()) == 0:
+                    self.exchange = None
+            if self.exchange is None:
+                self.exchange = InterfaceExchange(part, ncomp, self.prob.num_nodes, device, ceed=ceed, group=group)
+        self.comm_stream = torch.cuda.Stream(device=device, priority=-1) if (overlap and self.exchange is not None) else None
+        self.ev_boundary, self.ev_comm = torch.cuda.Event(), torch.cuda.Event()
+
+    @property
+    def transport(self):
+        return self.exchange.transport if self.exchange is not None else "none"
+
+    def apply(self, u_vec=None, v_vec=None, v_t=None):
+        """v = A u on this rank's box, interface DoFs summed over all ranks (every copy of a shared node ends with the same bits)."""
+        prob = self.prob
+        u_vec, v_vec = u_vec or prob.u, v_vec or prob.v
+        v_t = self.v_t if v_t is None else v_t
+        if self.exchange is None:
+            prob.op.apply(u_vec, v_vec)
+        elif not self.overlap:
+            prob.op.apply(u_vec, v_vec)
+            self.exchange.begin(v_t)
+            self.exchange.end(v_t)
+        else:
+            main = torch.cuda.current_stream(self.device)
+            prob.op.apply_part(u_vec, v_vec, 1)        # boundary elements: interface values are complete after this
+            self.ev_boundary.record(main)
+            self.comm_stream.wait_event(self.ev_boundary)
+            self.exchange.begin(v_t, stream=self.comm_stream)
+            self.ev_comm.record(self.comm_stream)
+            prob.op.apply_part(u_vec, v_vec, 2)        # interior elements, concurrently with the exchange
+            main.wait_event(self.ev_comm)
+            self.exchange.end(v_t)
+        return v_t

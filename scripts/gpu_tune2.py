@@ -99,9 +99,10 @@ elif mode == "tma":
 elif mode == "pf":
     # bulk L2 prefetch of the next batch's quadrature data (stage bit 64) on top of the table shape
     run("table", {})
-    for st in (65, 73):
+    for st in (65, 73, 129, 193, 201):
         run(f"stage={st}", {"CEED_B200_STAGE": str(st)})
-        run(f"stage={st} ahead=2", {"CEED_B200_STAGE": str(st), "CEED_B200_QF_AHEAD": "2"})
+        if st in (65, 193):
+            run(f"stage={st} ahead=2", {"CEED_B200_STAGE": str(st), "CEED_B200_QF_AHEAD": "2"})
     run("stage=65 pointwise unroll 2", {"CEED_B200_STAGE": "65", "CEED_B200_QF_POINTWISE": "1", "CEED_B200_QF_UNROLL": "2"})
     run("stage=65 pointwise unroll 4", {"CEED_B200_STAGE": "65", "CEED_B200_QF_POINTWISE": "1", "CEED_B200_QF_UNROLL": "4"})
 elif mode == "gw":

@@ -51,6 +51,7 @@ def main():
         torch.cuda.synchronize()
         assert np.array_equal(v1, dop.v_t.cpu().numpy()), "multi-rank step is not bitwise reproducible"
         res["v_overlap" if overlap else "v_serial"] = v1
+        res["transport"] = dop.transport
         if overlap and cg_iters:
             # distributed CG (dot products all-reduced over NCCL): solve A x = A x_true for the mass operator
             from libceed_b200.cg import DeviceCG

@@ -453,6 +453,27 @@ def test_device_resident_cg_converges(cm):
 
 
 @pytest.mark.parametrize("bp,p", [(1, 3), (3, 6), (5, 7), (6, 4)])
+def test_full_size_vs_reference_cpu_backend(cm, refceed, bp, p):
+    """BASELINE.json sizes (10M DoFs) against the UNMODIFIED reference's /cpu/self/opt/blocked on the same mesh and input: the
+    persistent grid-stride path with its full grid, tail groups and the tuned kernel shape, checked value by value (<= 1e-12)."""
+    ncomp = BP_TABLE[bp][0]
+    nel = M.choose_elements(10_000_000, p, ncomp)
+    prob = make_problem(cm, bp, p, nel)
+    rc = refceed.RefCeed("/cpu/self/opt/blocked")
+    ref = refceed.RefBP(rc, bp, p, prob.num_elem, prob.num_nodes, prob.offsets, prob.coords)
+    u = seeded_uniform(prob.num_dofs, 41)
+    prob.u.set_array(u)
+    prob.op.apply(prob.u, prob.v)
+    v = prob.v.get_array_read()
+    v_ref = ref.apply(u)
+    assert rel(v, v_ref) < OP_TOL, (bp, p, rel(v, v_ref))
+    # a second apply into a poisoned vector: overwrite semantics and bitwise reproducibility at full size
+    prob.v.set_value(-3.0)
+    prob.op.apply(prob.u, prob.v)
+    assert np.array_equal(prob.v.get_array_read(), v)
+
+
+@pytest.mark.parametrize("bp,p", [(1, 3), (3, 6), (5, 7), (6, 4)])
 def test_full_size_properties(cm, bp, p):
     """BASELINE.json sizes (10M DoFs): properties that need no CPU oracle."""
     ncomp = BP_TABLE[bp][0]

@@ -174,3 +174,21 @@ def test_partition_and_exchange_tables_random_grids():
                 np.testing.assert_allclose(v[c * nloc:(c + 1) * nloc], expect[gid + c * n_glob], rtol=0, atol=1e-13)
 
     run()
+
+
+def test_boundary_first_permutation_splits_interface_elements():
+    """The overlapped multi-GPU step applies the elements that touch a rank interface first: the split must contain exactly
+    the elements holding an interface node, in lexicographic order within both classes."""
+    for world, n_global, p in [(2, (4, 3, 2), 2), (4, (5, 4, 3), 1), (8, (4, 4, 4), 3), (6, (6, 4, 2), 2)]:
+        for r in range(world):
+            part = mesh.Partition(n_global, p, world, r)
+            perm, split = part.boundary_first_permutation()
+            nel = int(np.prod(part.n_local))
+            assert sorted(perm.tolist()) == list(range(nel))
+            assert (np.diff(perm[:split]) > 0).all() and (np.diff(perm[split:]) > 0).all()
+            iface = np.zeros(part.num_local_nodes, dtype=bool)
+            for _, idx in part.neighbors:
+                iface[idx] = True
+            off = mesh.hex_offsets(*part.n_local, p)
+            touches = iface[off].any(axis=1)
+            assert np.array_equal(np.sort(perm[:split]), np.nonzero(touches)[0])
