@@ -137,6 +137,11 @@ CEEDB200_EXPORT int ceedb200_basis_create_tensor_h1(B200Ceed ceed, b200_int dim,
                                                     const b200_scalar *interp_1d, const b200_scalar *grad_1d, const b200_scalar *q_ref_1d,
                                                     const b200_scalar *q_weight_1d, B200Basis *basis);
 /* host construction of Lagrange matrices: restates interface/ceed-basis.c:1617-1680 (Fornberg), :2529 (Gauss), :2581 (Lobatto) */
+/* CeedBasisCreateH1 (interface/ceed-basis.c:1434): non-tensor H1 basis, interp [num_qpts x num_nodes], grad [dim][num_qpts x num_nodes].
+ * Operators using it run on the unfused path (mixed-topology / composite operators). */
+CEEDB200_EXPORT int ceedb200_basis_create_h1(B200Ceed ceed, b200_int dim, b200_int num_comp, b200_int num_nodes, b200_int num_qpts,
+                                             const b200_scalar *interp, const b200_scalar *grad, const b200_scalar *q_ref, const b200_scalar *q_weight,
+                                             B200Basis *basis);
 CEEDB200_EXPORT int ceedb200_basis_create_tensor_h1_lagrange(B200Ceed ceed, b200_int dim, b200_int num_comp, b200_int P, b200_int Q, int quad_mode,
                                                              B200Basis *basis);
 CEEDB200_EXPORT int ceedb200_basis_destroy(B200Basis basis);
@@ -205,6 +210,14 @@ CEEDB200_EXPORT const char *ceedb200_operator_kernel_source(B200Operator op);
 CEEDB200_EXPORT int         ceedb200_operator_kernel_info(B200Operator op, int *regs, int *smem_bytes, int *threads, int *elems_per_block,
                                                           int *grid, int *local_bytes);
 /* device time (ms) of the most recent apply's kernels, measured with CUDA events on the context stream when enabled */
+/* CeedOperatorLinearAssembleQFunction[Update] (interface/ceed-preconditioning.c; the reference's GPU twin is
+ * backends/cuda-ref/ceed-cuda-ref-operator.c:1000-1130): the pointwise linear map of the QFunction at every quadrature point.
+ * assembled (length num_elem * num_qpts * size_in * size_out) is laid out with strides {1, num_elem * num_qpts, num_qpts}:
+ * entry ((a * size_out + b) * num_elem + e) * num_qpts + q = d out_b / d in_a, a / b counting the components of the ACTIVE
+ * QFunction inputs / outputs in field order.  The interface builds LinearAssembleDiagonal, LinearAssemble and multigrid on it. */
+CEEDB200_EXPORT int ceedb200_operator_assemble_qfunction_sizes(B200Operator op, b200_int *num_elem, b200_int *num_qpts, b200_int *size_in,
+                                                               b200_int *size_out);
+CEEDB200_EXPORT int ceedb200_operator_assemble_qfunction(B200Operator op, B200Vector assembled);
 /* One half of an apply on a partitioned mesh (multi-GPU overlap; the reference pattern is VecScatterBegin / local work /
  * VecScatterEnd, examples/petsc/bpsraw.c:240-262): part 1 = elements [0, split) -- the ones touching the rank interface, see
  * ceedb200_restriction_set_split -- plus the finalize pass of the nodes only they touch; part 2 = the interior elements.

@@ -56,6 +56,7 @@ static int CeedOperatorSetup_B200(CeedOperator op) {
   CeedCallB200(ceed, core, ceedb200_operator_create(core, core_qf, &impl->core));
   CeedCallB200(ceed, core, ceedb200_vector_create(core, 0, &impl->view_in));
   CeedCallB200(ceed, core, ceedb200_vector_create(core, 0, &impl->view_out));
+  impl->view_in_len = impl->view_out_len = 0;
   CeedCallBackend(CeedOperatorGetFields(op, &num_in, &in, &num_out, &out));
   impl->num_in  = num_in;
   impl->num_out = num_out;
@@ -78,9 +79,6 @@ static int CeedOperatorSetup_B200(CeedOperator op) {
     }
     if (basis != CEED_BASIS_NONE) {
       CeedBasis_B200 *b;
-      bool            is_tensor;
-      CeedCallBackend(CeedBasisIsTensor(basis, &is_tensor));
-      CeedCheck(is_tensor, ceed, CEED_ERROR_UNSUPPORTED, "Backend does not implement operators with non-tensor bases");
       CeedCallBackend(CeedBasisGetData(basis, &b));
       core_basis = b->core;
     }
@@ -114,7 +112,6 @@ static int CeedOperatorApplyCore_B200(CeedOperator op, CeedVector in_vec, CeedVe
   const CeedScalar  *d_in = NULL, *d_pin[CEED_FIELD_MAX] = {NULL};
   CeedScalar        *d_out = NULL, *d_pout[CEED_FIELD_MAX] = {NULL};
   CeedSize           len;
-  int                ierr;
 
   CeedCallBackend(CeedGetCore_B200(ceed, &core));
   CeedCallBackend(CeedOperatorSetup_B200(op));
@@ -140,62 +137,99 @@ static int CeedOperatorApplyCore_B200(CeedOperator op, CeedVector in_vec, CeedVe
     return CeedOperatorApplyAdd(op_fallback, in_vec, out_vec, CEED_REQUEST_IMMEDIATE);
   }
 
-  // device arrays of every vector involved, through the interface
-  if (in_vec != CEED_VECTOR_NONE) {
-    CeedCallBackend(CeedVectorGetLength(in_vec, &len));
-    CeedCallBackend(CeedVectorGetArrayRead(in_vec, CEED_MEM_DEVICE, &d_in));
-    ceedb200_vector_destroy(impl->view_in);
-    CeedCallB200(ceed, core, ceedb200_vector_create(core, len, &impl->view_in));
-    CeedCallB200(ceed, core, ceedb200_vector_set_array(impl->view_in, B200_MEM_DEVICE, B200_USE_POINTER, (CeedScalar *)d_in));
-  }
-  if (out_vec != CEED_VECTOR_NONE) {
-    CeedCallBackend(CeedVectorGetLength(out_vec, &len));
-    if (add) CeedCallBackend(CeedVectorGetArray(out_vec, CEED_MEM_DEVICE, &d_out));
-    else CeedCallBackend(CeedVectorGetArrayWrite(out_vec, CEED_MEM_DEVICE, &d_out));
-    ceedb200_vector_destroy(impl->view_out);
-    CeedCallB200(ceed, core, ceedb200_vector_create(core, len, &impl->view_out));
-    CeedCallB200(ceed, core, ceedb200_vector_set_array(impl->view_out, B200_MEM_DEVICE, B200_USE_POINTER, d_out));
-  }
-  for (CeedInt i = 0; i < impl->num_in; i++) {
-    if (!impl->passive_in_vec[i]) continue;
-    CeedCallBackend(CeedVectorGetArrayRead(impl->passive_in_vec[i], CEED_MEM_DEVICE, &d_pin[i]));
-    CeedCallB200(ceed, core, ceedb200_vector_set_array(impl->passive_in[i], B200_MEM_DEVICE, B200_USE_POINTER, (CeedScalar *)d_pin[i]));
-  }
-  for (CeedInt i = 0; i < impl->num_out; i++) {
-    if (!impl->passive_out_vec[i]) continue;
-    // passive outputs are overwritten by Apply (zero first, as CeedOperatorApplyAddActive does, interface/ceed-operator.c:2357-2405)
-    // and accumulated into by ApplyAdd
-    if (!add) CeedCallBackend(CeedVectorSetValue(impl->passive_out_vec[i], 0.0));
-    CeedCallBackend(CeedVectorGetArray(impl->passive_out_vec[i], CEED_MEM_DEVICE, &d_pout[i]));
-    CeedCallB200(ceed, core, ceedb200_vector_set_array(impl->passive_out[i], B200_MEM_DEVICE, B200_USE_POINTER, d_pout[i]));
-  }
+  // Device arrays of every vector involved, through the interface.  From here on no early return: the first error is recorded,
+  // every array that was acquired is restored (libCEED's access locks must be released whatever happens) and the error is
+  // reported at the end.
   {
-    bool          has_passive_out = false;
-    CeedQFunction qf;
-    void         *held_ctx;
+    int  status = CEED_ERROR_SUCCESS, core_err = 0;
+    bool got_in = false, got_out = false, got_pin[CEED_FIELD_MAX] = {false}, got_pout[CEED_FIELD_MAX] = {false};
+    bool has_passive_out = false, ctx_held = false;
+    CeedQFunction qf = NULL;
+    void         *held_ctx = NULL;
+#define B200_TRY(call)                \
+  do {                                \
+    if (!status) status = (call);     \
+  } while (0)
+#define B200_TRY_CORE(call)                  \
+  do {                                       \
+    if (!status && !core_err) core_err = (call); \
+  } while (0)
 
-    // a QFunction context of another backend is handed over as a raw device pointer for this apply
-    CeedCallBackend(CeedOperatorGetQFunction(op, &qf));
-    CeedCallBackend(CeedQFunctionContextAcquire_B200(qf, &held_ctx));
-    for (CeedInt i = 0; i < impl->num_out; i++) has_passive_out = has_passive_out || impl->passive_out_vec[i];
-    // overwrite semantics can only be used when every output is the active vector
-    if (!add && !has_passive_out) ierr = ceedb200_operator_apply(impl->core, in_vec != CEED_VECTOR_NONE ? impl->view_in : NULL, impl->view_out);
-    else {
-      if (!add && out_vec != CEED_VECTOR_NONE) ceedb200_vector_set_value(impl->view_out, 0.0);
-      ierr = ceedb200_operator_apply_add(impl->core, in_vec != CEED_VECTOR_NONE ? impl->view_in : NULL, impl->view_out);
+    if (in_vec != CEED_VECTOR_NONE) {
+      B200_TRY(CeedVectorGetLength(in_vec, &len));
+      B200_TRY(CeedVectorGetArrayRead(in_vec, CEED_MEM_DEVICE, &d_in));
+      got_in = !status;
+      if (!status && impl->view_in_len != len) {  // the view vectors are cached: re-created only when the length changes
+        ceedb200_vector_destroy(impl->view_in);
+        impl->view_in = NULL;
+        B200_TRY_CORE(ceedb200_vector_create(core, len, &impl->view_in));
+        impl->view_in_len = len;
+      }
+      B200_TRY_CORE(ceedb200_vector_set_array(impl->view_in, B200_MEM_DEVICE, B200_USE_POINTER, (CeedScalar *)d_in));
     }
-    CeedCallBackend(CeedQFunctionContextRelease_B200(qf, &held_ctx));
-    CeedCallBackend(CeedQFunctionDestroy(&qf));
+    if (out_vec != CEED_VECTOR_NONE) {
+      B200_TRY(CeedVectorGetLength(out_vec, &len));
+      if (add) B200_TRY(CeedVectorGetArray(out_vec, CEED_MEM_DEVICE, &d_out));
+      else B200_TRY(CeedVectorGetArrayWrite(out_vec, CEED_MEM_DEVICE, &d_out));
+      got_out = !status;
+      if (!status && impl->view_out_len != len) {
+        ceedb200_vector_destroy(impl->view_out);
+        impl->view_out = NULL;
+        B200_TRY_CORE(ceedb200_vector_create(core, len, &impl->view_out));
+        impl->view_out_len = len;
+      }
+      B200_TRY_CORE(ceedb200_vector_set_array(impl->view_out, B200_MEM_DEVICE, B200_USE_POINTER, d_out));
+    }
+    for (CeedInt i = 0; i < impl->num_in; i++) {
+      if (!impl->passive_in_vec[i] || status || core_err) continue;
+      B200_TRY(CeedVectorGetArrayRead(impl->passive_in_vec[i], CEED_MEM_DEVICE, &d_pin[i]));
+      got_pin[i] = !status;
+      B200_TRY_CORE(ceedb200_vector_set_array(impl->passive_in[i], B200_MEM_DEVICE, B200_USE_POINTER, (CeedScalar *)d_pin[i]));
+    }
+    for (CeedInt i = 0; i < impl->num_out; i++) {
+      if (!impl->passive_out_vec[i]) continue;
+      has_passive_out = true;
+      if (status || core_err) continue;
+      // passive outputs are overwritten by Apply (zero first, as CeedOperatorApplyAddActive does, interface/ceed-operator.c:2357-2405)
+      // and accumulated into by ApplyAdd
+      if (!add) B200_TRY(CeedVectorSetValue(impl->passive_out_vec[i], 0.0));
+      B200_TRY(CeedVectorGetArray(impl->passive_out_vec[i], CEED_MEM_DEVICE, &d_pout[i]));
+      got_pout[i] = !status;
+      B200_TRY_CORE(ceedb200_vector_set_array(impl->passive_out[i], B200_MEM_DEVICE, B200_USE_POINTER, d_pout[i]));
+    }
+    // a QFunction context of another backend is handed over as a raw device pointer for this apply
+    B200_TRY(CeedOperatorGetQFunction(op, &qf));
+    if (!status && !core_err) {
+      B200_TRY(CeedQFunctionContextAcquire_B200(qf, &held_ctx));
+      ctx_held = !status;
+    }
+    if (!status && !core_err) {
+      // overwrite semantics can only be used when every output is the active vector
+      if (!add && !has_passive_out) core_err = ceedb200_operator_apply(impl->core, in_vec != CEED_VECTOR_NONE ? impl->view_in : NULL, impl->view_out);
+      else {
+        if (!add && out_vec != CEED_VECTOR_NONE) core_err = ceedb200_vector_set_value(impl->view_out, 0.0);
+        if (!core_err) core_err = ceedb200_operator_apply_add(impl->core, in_vec != CEED_VECTOR_NONE ? impl->view_in : NULL, impl->view_out);
+      }
+    }
+    // the core's message has to be fetched before other core calls overwrite it
+    if (core_err && !status) status = CeedError(ceed, CEED_ERROR_BACKEND, "%s", ceedb200_last_error(core));
+    // release / restore everything that was acquired, whatever happened above
+    {
+      int ierr2;
+
+      if (ctx_held && (ierr2 = CeedQFunctionContextRelease_B200(qf, &held_ctx)) && !status) status = ierr2;
+      if (qf && (ierr2 = CeedQFunctionDestroy(&qf)) && !status) status = ierr2;
+      if (got_in && (ierr2 = CeedVectorRestoreArrayRead(in_vec, &d_in)) && !status) status = ierr2;
+      if (got_out && (ierr2 = CeedVectorRestoreArray(out_vec, &d_out)) && !status) status = ierr2;
+      for (CeedInt i = 0; i < impl->num_in; i++)
+        if (got_pin[i] && (ierr2 = CeedVectorRestoreArrayRead(impl->passive_in_vec[i], &d_pin[i])) && !status) status = ierr2;
+      for (CeedInt i = 0; i < impl->num_out; i++)
+        if (got_pout[i] && (ierr2 = CeedVectorRestoreArray(impl->passive_out_vec[i], &d_pout[i])) && !status) status = ierr2;
+    }
+#undef B200_TRY
+#undef B200_TRY_CORE
+    return status;
   }
-  // restore in every case so that libCEED's access locks are released
-  if (in_vec != CEED_VECTOR_NONE) CeedCallBackend(CeedVectorRestoreArrayRead(in_vec, &d_in));
-  if (out_vec != CEED_VECTOR_NONE) CeedCallBackend(CeedVectorRestoreArray(out_vec, &d_out));
-  for (CeedInt i = 0; i < impl->num_in; i++)
-    if (impl->passive_in_vec[i]) CeedCallBackend(CeedVectorRestoreArrayRead(impl->passive_in_vec[i], &d_pin[i]));
-  for (CeedInt i = 0; i < impl->num_out; i++)
-    if (impl->passive_out_vec[i]) CeedCallBackend(CeedVectorRestoreArray(impl->passive_out_vec[i], &d_pout[i]));
-  if (ierr) return CeedError(ceed, CEED_ERROR_BACKEND, "%s", ceedb200_last_error(core));
-  return CEED_ERROR_SUCCESS;
 }
 
 static int CeedOperatorApplyAdd_B200(CeedOperator op, CeedVector in_vec, CeedVector out_vec, CeedRequest *request) {
@@ -222,13 +256,106 @@ static int CeedOperatorDestroy_B200(CeedOperator op) {
   return CEED_ERROR_SUCCESS;
 }
 
-// Assembly is outside the operator-apply path this backend covers; say so in the wording the reference's test runner treats
-// as "not implemented" (tests/junit.py:121-145) instead of the interface's generic "does not support" failure.
+// CeedOperatorLinearAssembleQFunction / ...Update (interface/ceed-preconditioning.c:2234-2330; GPU-side contract of
+// backends/cuda-ref/ceed-cuda-ref-operator.c:1000-1130).  The core evaluates the QFunction's pointwise linear map on the device
+// (ceedb200_operator_assemble_qfunction); this adapter creates the strided restriction + vector that describe its layout and
+// binds the device arrays.  With this slot the interface's own LinearAssembleDiagonal / LinearAssemble / multigrid run on the backend.
+static int CeedOperatorLinearAssembleQFunctionCore_B200(CeedOperator op, bool build_objects, CeedVector *assembled, CeedElemRestriction *rstr) {
+  Ceed               ceed = CeedOperatorReturnCeed(op);
+  B200Ceed           core;
+  CeedOperator_B200 *impl;
+  b200_int           num_elem, num_qpts, size_in, size_out;
+  const CeedScalar  *d_pin[CEED_FIELD_MAX] = {NULL};
+  bool               got_pin[CEED_FIELD_MAX] = {false}, got_asm = false;
+  CeedScalar        *d_asm = NULL;
+  B200Vector         view  = NULL;
+  int                status = CEED_ERROR_SUCCESS, core_err = 0;
+
+  CeedCallBackend(CeedGetCore_B200(ceed, &core));
+  CeedCallBackend(CeedOperatorSetup_B200(op));
+  CeedCallBackend(CeedOperatorGetData(op, &impl));
+  CeedCheck(!impl->use_fallback, ceed, CEED_ERROR_UNSUPPORTED, "Backend does not implement QFunction assembly with objects of other backends");
+  {
+    // The interface's host-side diagonal / full assembly built on top of this slot writes element matrices in the CPU E-vector
+    // layout [elem][comp][node] (interface/ceed-preconditioning.c:361-377); this backend's E-vectors are [comp][elem][node] like
+    // the reference GPU backends, which is only the same thing for single-component fields.
+    CeedInt            num_in, num_out;
+    CeedOperatorField *in, *out;
+
+    CeedCallBackend(CeedOperatorGetFields(op, &num_in, &in, &num_out, &out));
+    for (CeedInt i = 0; i < num_in + num_out; i++) {
+      CeedVector          vec;
+      CeedElemRestriction r;
+      CeedInt             num_comp = 1;
+
+      CeedCallBackend(CeedOperatorFieldGetVector(i < num_in ? in[i] : out[i - num_in], &vec));
+      CeedCallBackend(CeedOperatorFieldGetElemRestriction(i < num_in ? in[i] : out[i - num_in], &r));
+      if (vec == CEED_VECTOR_ACTIVE && r != CEED_ELEMRESTRICTION_NONE) CeedCallBackend(CeedElemRestrictionGetNumComponents(r, &num_comp));
+      CeedCallBackend(CeedVectorDestroy(&vec));
+      CeedCallBackend(CeedElemRestrictionDestroy(&r));
+      CeedCheck(num_comp == 1, ceed, CEED_ERROR_UNSUPPORTED, "Backend does not implement assembly of operators with multi-component active fields");
+    }
+  }
+  CeedCallB200(ceed, core, ceedb200_operator_assemble_qfunction_sizes(impl->core, &num_elem, &num_qpts, &size_in, &size_out));
+  if (build_objects) {
+    Ceed           ceed_parent;
+    const CeedSize l_size     = (CeedSize)num_elem * num_qpts * size_in * size_out;
+    CeedInt        strides[3] = {1, num_elem * num_qpts, num_qpts};
+
+    CeedCallBackend(CeedOperatorGetFallbackParentCeed(op, &ceed_parent));
+    CeedCallBackend(CeedElemRestrictionCreateStrided(ceed_parent, num_elem, num_qpts, size_in * size_out, l_size, strides, rstr));
+    CeedCallBackend(CeedVectorCreate(ceed_parent, l_size, assembled));
+    CeedCallBackend(CeedDestroy(&ceed_parent));
+  }
+  // no early return from here on: whatever was acquired is restored
+  for (CeedInt i = 0; i < impl->num_in && !status && !core_err; i++) {
+    if (!impl->passive_in_vec[i]) continue;
+    status     = CeedVectorGetArrayRead(impl->passive_in_vec[i], CEED_MEM_DEVICE, &d_pin[i]);
+    got_pin[i] = !status;
+    if (!status) core_err = ceedb200_vector_set_array(impl->passive_in[i], B200_MEM_DEVICE, B200_USE_POINTER, (CeedScalar *)d_pin[i]);
+  }
+  if (!status && !core_err) {
+    CeedSize len;
+
+    status = CeedVectorGetLength(*assembled, &len);
+    if (!status) status = CeedVectorGetArrayWrite(*assembled, CEED_MEM_DEVICE, &d_asm);
+    got_asm = !status;
+    if (!status) core_err = ceedb200_vector_create(core, len, &view);
+    if (!status && !core_err) core_err = ceedb200_vector_set_array(view, B200_MEM_DEVICE, B200_USE_POINTER, d_asm);
+  }
+  if (!status && !core_err) {
+    CeedQFunction qf       = NULL;
+    void         *held_ctx = NULL;
+
+    status = CeedOperatorGetQFunction(op, &qf);
+    if (!status) status = CeedQFunctionContextAcquire_B200(qf, &held_ctx);
+    if (!status) {
+      core_err = ceedb200_operator_assemble_qfunction(impl->core, view);
+      if (core_err) status = CeedError(ceed, CEED_ERROR_BACKEND, "%s", ceedb200_last_error(core));
+      int ierr2 = CeedQFunctionContextRelease_B200(qf, &held_ctx);
+      if (ierr2 && !status) status = ierr2;
+    }
+    if (qf) CeedQFunctionDestroy(&qf);
+  }
+  if (core_err && !status) status = CeedError(ceed, CEED_ERROR_BACKEND, "%s", ceedb200_last_error(core));
+  if (view) ceedb200_vector_destroy(view);
+  if (got_asm) {
+    int ierr2 = CeedVectorRestoreArray(*assembled, &d_asm);
+    if (ierr2 && !status) status = ierr2;
+  }
+  for (CeedInt i = 0; i < impl->num_in; i++) {
+    if (!got_pin[i]) continue;
+    int ierr2 = CeedVectorRestoreArrayRead(impl->passive_in_vec[i], &d_pin[i]);
+    if (ierr2 && !status) status = ierr2;
+  }
+  return status;
+}
+
 static int CeedOperatorLinearAssembleQFunction_B200(CeedOperator op, CeedVector *assembled, CeedElemRestriction *rstr, CeedRequest *request) {
-  return CeedError(CeedOperatorReturnCeed(op), CEED_ERROR_UNSUPPORTED, "Backend does not implement CeedOperatorLinearAssembleQFunction");
+  return CeedOperatorLinearAssembleQFunctionCore_B200(op, true, assembled, rstr);
 }
 static int CeedOperatorLinearAssembleQFunctionUpdate_B200(CeedOperator op, CeedVector assembled, CeedElemRestriction rstr, CeedRequest *request) {
-  return CeedError(CeedOperatorReturnCeed(op), CEED_ERROR_UNSUPPORTED, "Backend does not implement CeedOperatorLinearAssembleQFunctionUpdate");
+  return CeedOperatorLinearAssembleQFunctionCore_B200(op, false, &assembled, &rstr);
 }
 
 int CeedOperatorCreate_B200(CeedOperator op) {

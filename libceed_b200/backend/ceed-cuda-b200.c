@@ -82,7 +82,12 @@ static int CeedInit_B200(const char *resource, Ceed ceed) {
   }
   data->device_id = device_id < 0 ? 0 : device_id;
   CeedCallBackend(CeedSetData(ceed, data));
-  CeedCallBackend(CeedSetDeterministic(ceed, true));  // ordered scatter, no atomics (README.md:167-169 semantics)
+  {
+    // deterministic unless the caller opted into the atomic scatter mode (CEED_B200_SCATTER=atomic|1): ordered scatter, no atomics
+    // (README.md:167-169 semantics)
+    const char *mode = getenv("CEED_B200_SCATTER");
+    CeedCallBackend(CeedSetDeterministic(ceed, !(mode && (!strcmp(mode, "atomic") || !strcmp(mode, "1")))));
+  }
 
   CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "Destroy", CeedDestroy_B200));
   CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "GetPreferredMemType", CeedGetPreferredMemType_B200));
@@ -90,6 +95,7 @@ static int CeedInit_B200(const char *resource, Ceed ceed) {
   CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "VectorCreate", CeedVectorCreate_B200));
   CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "ElemRestrictionCreate", CeedElemRestrictionCreate_B200));
   CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "BasisCreateTensorH1", CeedBasisCreateTensorH1_B200));
+  CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "BasisCreateH1", CeedBasisCreateH1_B200));
   CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "QFunctionCreate", CeedQFunctionCreate_B200));
   CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "QFunctionContextCreate", CeedQFunctionContextCreate_B200));
   CeedCallBackend(CeedSetBackendFunction(ceed, "Ceed", ceed, "OperatorCreate", CeedOperatorCreate_B200));

@@ -45,7 +45,8 @@ typedef struct {
 
 typedef struct {
   B200Operator core;
-  B200Vector   view_in, view_out;     // device-pointer views of the active vectors of the current apply
+  B200Vector   view_in, view_out;     // device-pointer views of the active vectors of the current apply (cached per length)
+  CeedSize     view_in_len, view_out_len;
   B200Vector   passive_in[CEED_FIELD_MAX], passive_out[CEED_FIELD_MAX];
   CeedVector   passive_in_vec[CEED_FIELD_MAX], passive_out_vec[CEED_FIELD_MAX];
   CeedInt      num_in, num_out;
@@ -68,6 +69,8 @@ CEED_INTERN int CeedElemRestrictionCreate_B200(CeedMemType mem_type, CeedCopyMod
                                                const CeedInt8 *curl_orients, CeedElemRestriction rstr);
 CEED_INTERN int CeedBasisCreateTensorH1_B200(CeedInt dim, CeedInt P_1d, CeedInt Q_1d, const CeedScalar *interp_1d, const CeedScalar *grad_1d,
                                              const CeedScalar *q_ref_1d, const CeedScalar *q_weight_1d, CeedBasis basis);
+CEED_INTERN int CeedBasisCreateH1_B200(CeedElemTopology topo, CeedInt dim, CeedInt num_nodes, CeedInt num_qpts, const CeedScalar *interp, const CeedScalar *grad,
+                                       const CeedScalar *q_ref, const CeedScalar *q_weight, CeedBasis basis);
 CEED_INTERN int CeedQFunctionCreate_B200(CeedQFunction qf);
 CEED_INTERN int CeedQFunctionContextCreate_B200(CeedQFunctionContext ctx);
 CEED_INTERN int CeedOperatorCreate_B200(CeedOperator op);

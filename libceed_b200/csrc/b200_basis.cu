@@ -262,8 +262,19 @@ int apply_one_dim(B200Ceed ceed, int dim, int64_t nvec, int n, int d, const doub
   return contract(ceed, pre, n, post, n, mat, transpose, add, u, v);
 }
 
-int get_scratch(B200Ceed ceed, double **buf, size_t bytes) {
-  B200_CALL(b200_dmalloc(ceed, (void **)buf, bytes));
+// grow-only work buffers cached on the context: consecutive applies reuse them in stream order (no cudaMalloc / cudaFree /
+// synchronisation per apply, so unfused operators can be captured in CUDA graphs like the fused path)
+int get_scratch(B200Ceed ceed, int which, double **buf, size_t bytes) {
+  if (ceed->basis_tmp_bytes[which] < bytes) {
+    if (ceed->d_basis_tmp[which]) {
+      if (!b200_compile_only()) B200_CUDA(ceed, cudaStreamSynchronize(ceed->stream));  // kernels in flight may still use the old buffer
+      B200_CALL(b200_dfree(ceed, ceed->d_basis_tmp[which]));
+      ceed->d_basis_tmp[which] = nullptr, ceed->basis_tmp_bytes[which] = 0;
+    }
+    B200_CALL(b200_dmalloc(ceed, (void **)&ceed->d_basis_tmp[which], bytes));
+    ceed->basis_tmp_bytes[which] = bytes;
+  }
+  *buf = ceed->d_basis_tmp[which];
   return B200_SUCCESS;
 }
 
@@ -290,13 +301,35 @@ int basis_apply_ptr(B200Basis basis, bool apply_add, int num_elem, int t_mode, i
     B200_CHECK(t_mode == B200_NOTRANSPOSE, ceed, B200_ERROR_BACKEND, "CEED_EVAL_WEIGHT incompatible with CEED_TRANSPOSE");
   else B200_CHECK(d_u, ceed, B200_ERROR_BACKEND, "An input vector is required for this CeedEvalMode");
   if (num_elem == 0) return B200_SUCCESS;
+  if (!basis->is_tensor) {
+    // CeedBasisCreateH1: dense element matrices, one contraction per evaluation (backends/ref/ceed-ref-basis.c:176-230)
+    const int64_t nq = (int64_t)nvec * Q;
+    switch (eval_mode) {
+      case B200_EVAL_INTERP: return contract(ceed, nvec, t_mode == B200_NOTRANSPOSE ? P : Q, 1, t_mode == B200_NOTRANSPOSE ? Q : P, basis->d_interp,
+                                             t_mode == B200_TRANSPOSE, apply_add, d_u, d_v);
+      case B200_EVAL_GRAD:
+        for (int d = 0; d < dim; d++) {
+          const double *g = basis->d_grad + (int64_t)d * P * Q;
+          if (t_mode == B200_NOTRANSPOSE) B200_CALL(contract(ceed, nvec, P, 1, Q, g, false, apply_add, d_u, d_v + d * nq));
+          else B200_CALL(contract(ceed, nvec, Q, 1, P, g, true, apply_add || d > 0, d_u + d * nq, d_v));
+        }
+        return B200_SUCCESS;
+      case B200_EVAL_WEIGHT:
+        B200_CHECK(!b200_compile_only(), ceed, B200_ERROR_BACKEND, "CEED_B200_COMPILE_ONLY is set; kernels cannot run");
+        k_weight<<<grid_for(ceed, (int64_t)Q * num_elem), kThreads, 0, ceed->stream>>>(1, Q, num_elem, basis->d_q_weight, d_v);
+        ceed->launch_count++;
+        B200_CUDA(ceed, cudaGetLastError());
+        return B200_SUCCESS;
+      default: return b200_error(ceed, B200_ERROR_UNSUPPORTED, "Backend does not implement eval mode %d for non-tensor H1 bases", eval_mode);
+    }
+  }
   const int     big      = P > Q ? P : Q;
   const size_t  tmp_size = (size_t)nvec * ipow(big, dim) * sizeof(double);
   double       *tmp0 = nullptr, *tmp1 = nullptr, *tmp2 = nullptr;
   int           ierr = B200_SUCCESS;
-  B200_CALL(get_scratch(ceed, &tmp0, tmp_size));
-  B200_CALL(get_scratch(ceed, &tmp1, tmp_size));
-  B200_CALL(get_scratch(ceed, &tmp2, tmp_size));
+  B200_CALL(get_scratch(ceed, 0, &tmp0, tmp_size));
+  B200_CALL(get_scratch(ceed, 1, &tmp1, tmp_size));
+  B200_CALL(get_scratch(ceed, 2, &tmp2, tmp_size));
   switch (eval_mode) {
     case B200_EVAL_INTERP:
       if (t_mode == B200_NOTRANSPOSE) ierr = apply_all_dims(ceed, dim, nvec, P, Q, basis->d_interp, false, apply_add, d_u, d_v, tmp0, tmp1);
@@ -341,10 +374,6 @@ int basis_apply_ptr(B200Basis basis, bool apply_add, int num_elem, int t_mode, i
       ierr = b200_error(ceed, B200_ERROR_UNSUPPORTED, "Backend does not implement eval mode %d for tensor H1 bases", eval_mode);
   }
   (void)n_node;
-  if (!b200_compile_only()) cudaStreamSynchronize(ceed->stream);
-  b200_dfree(ceed, tmp0);
-  b200_dfree(ceed, tmp1);
-  b200_dfree(ceed, tmp2);
   return ierr;
 }
 }  // namespace
@@ -389,6 +418,35 @@ extern "C" int ceedb200_basis_create_tensor_h1(B200Ceed ceed, b200_int dim, b200
     B200_CALL(b200_dmalloc(ceed, (void **)&b->d_collo_grad, (size_t)Q * Q * sizeof(double)));
     B200_CALL(b200_h2d(ceed, b->d_collo_grad, b->collo_grad.data(), (size_t)Q * Q * sizeof(double)));
   }
+  *basis_out = b;
+  return B200_SUCCESS;
+}
+
+// CeedBasisCreateH1 (interface/ceed-basis.c:1434; backends/cuda-ref/ceed-cuda-ref-basis.c:340-400): non-tensor H1 basis with
+// num_nodes nodes and num_qpts quadrature points per element, interp [num_qpts x num_nodes], grad [dim][num_qpts x num_nodes].
+// Used by mixed-topology / composite operators (triangles, tets, ...) through the unfused operator path.
+extern "C" int ceedb200_basis_create_h1(B200Ceed ceed, b200_int dim, b200_int num_comp, b200_int num_nodes, b200_int num_qpts, const b200_scalar *interp,
+                                        const b200_scalar *grad, const b200_scalar *q_ref, const b200_scalar *q_weight, B200Basis *basis_out) {
+  B200_CHECK(dim >= 1 && dim <= 3 && num_nodes >= 1 && num_qpts >= 1 && num_comp >= 1, ceed, B200_ERROR_DIMENSION, "invalid basis dimensions");
+  B200Basis b  = new B200Basis_();
+  b->ceed      = ceed;
+  b->dim       = dim;
+  b->num_comp  = num_comp;
+  b->P         = num_nodes;
+  b->Q         = num_qpts;
+  b->is_tensor = false;
+  const size_t n = (size_t)num_nodes * num_qpts;
+  b->interp.assign(interp, interp + n);
+  b->grad.assign(grad, grad + n * dim);
+  if (q_ref) b->q_ref.assign(q_ref, q_ref + (size_t)num_qpts * dim);
+  if (q_weight) b->q_weight.assign(q_weight, q_weight + num_qpts);
+  else b->q_weight.assign(num_qpts, 0.0);
+  B200_CALL(b200_dmalloc(ceed, (void **)&b->d_interp, n * sizeof(double)));
+  B200_CALL(b200_dmalloc(ceed, (void **)&b->d_grad, n * dim * sizeof(double)));
+  B200_CALL(b200_dmalloc(ceed, (void **)&b->d_q_weight, num_qpts * sizeof(double)));
+  B200_CALL(b200_h2d(ceed, b->d_interp, b->interp.data(), n * sizeof(double)));
+  B200_CALL(b200_h2d(ceed, b->d_grad, b->grad.data(), n * dim * sizeof(double)));
+  B200_CALL(b200_h2d(ceed, b->d_q_weight, b->q_weight.data(), num_qpts * sizeof(double)));
   *basis_out = b;
   return B200_SUCCESS;
 }

@@ -51,6 +51,9 @@ struct B200Ceed_ {
   // scratch for norms
   double *d_scratch = nullptr;
   size_t  scratch_len = 0;
+  // grow-only work buffers of the standalone basis kernels (stream-ordered reuse: no allocation, no synchronisation per apply)
+  double *d_basis_tmp[3]     = {nullptr, nullptr, nullptr};
+  size_t  basis_tmp_bytes[3] = {0, 0, 0};
 };
 
 std::string b200_reduced_signature(const std::string &shape_signature);
@@ -140,6 +143,7 @@ struct B200Basis_ {
   std::vector<double> interp, grad, q_ref, q_weight, collo_grad;  // host copies (1-D)
   bool     has_collo_grad = false;  // Q >= P
   bool     is_collocated  = false;  // interp_1d == identity
+  bool     is_tensor      = true;   // false: CeedBasisCreateH1 -- P nodes, Q points per element, interp [Q x P], grad [dim][Q x P]
   double  *d_interp = nullptr, *d_grad = nullptr, *d_q_weight = nullptr, *d_collo_grad = nullptr;
 };
 

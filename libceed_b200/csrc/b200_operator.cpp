@@ -325,7 +325,7 @@ static int apply_unfused(B200Operator op, B200Vector u, B200Vector v, int add) {
   for (auto *fields : {&op->in_fields, &op->out_fields})
     for (auto &f : *fields) {
       if (f.rstr && num_elem < 0) num_elem = f.rstr->num_elem;
-      if (f.basis && nqpts < 0) nqpts = ipow(f.basis->Q, f.basis->dim);
+      if (f.basis && nqpts < 0) nqpts = f.basis->is_tensor ? ipow(f.basis->Q, f.basis->dim) : f.basis->Q;
     }
   if (nqpts < 0)
     for (auto *fields : {&op->in_fields, &op->out_fields})
@@ -395,6 +395,138 @@ static int apply_unfused(B200Operator op, B200Vector u, B200Vector v, int add) {
   return B200_SUCCESS;
 }
 
+// ------------------------------------------------------------------------------------------------ QFunction assembly
+// CeedOperatorLinearAssembleQFunction (interface/ceed-preconditioning.c; backends/cuda-ref/ceed-cuda-ref-operator.c:1000-1130 for
+// the GPU-side contract): the pointwise linear map of the QFunction, evaluated at every quadrature point by feeding unit vectors
+// through the active inputs.  Layout of the result (this backend's choice, published through the strided restriction the host
+// layer creates): assembled[((a * size_out + b) * num_elem + e) * Q + q] = d out_b / d in_a at point q of element e, i.e.
+// strides {1, num_elem * Q, Q}.  Passive inputs (quadrature data, weights, coefficient fields) are evaluated once with the
+// unfused restriction / basis kernels; the QFunction runs size_in times over all points.  This is what the interface needs
+// to provide LinearAssembleDiagonal / LinearAssemble / multigrid on top.
+static int assembly_sizes(B200Operator op, int *num_elem, int *nqpts, int *size_in, int *size_out) {
+  B200QFunction qf = op->qf;
+  *num_elem = -1, *nqpts = -1, *size_in = 0, *size_out = 0;
+  for (auto *fields : {&op->in_fields, &op->out_fields})
+    for (auto &f : *fields) {
+      if (f.rstr && *num_elem < 0) *num_elem = f.rstr->num_elem;
+      if (f.basis && *nqpts < 0) {
+        *nqpts = f.basis->is_tensor ? 1 : f.basis->Q;
+        for (int d = 0; d < f.basis->dim && f.basis->is_tensor; d++) *nqpts *= f.basis->Q;
+      }
+    }
+  if (*nqpts < 0)
+    for (auto *fields : {&op->in_fields, &op->out_fields})
+      for (auto &f : *fields)
+        if (f.rstr && *nqpts < 0) *nqpts = f.rstr->elem_size;
+  for (size_t i = 0; i < op->in_fields.size(); i++)
+    if (op->in_fields[i].is_active) *size_in += qf->inputs[i].size;
+  for (size_t i = 0; i < op->out_fields.size(); i++)
+    if (op->out_fields[i].is_active) *size_out += qf->outputs[i].size;
+  B200_CHECK(*num_elem >= 0 && *nqpts > 0, op->ceed, B200_ERROR_INCOMPLETE, "operator has no restriction / quadrature space");
+  B200_CHECK(*size_in > 0 && *size_out > 0, op->ceed, B200_ERROR_BACKEND, "Cannot assemble QFunction without active inputs and outputs");
+  return B200_SUCCESS;
+}
+
+extern "C" int ceedb200_operator_assemble_qfunction_sizes(B200Operator op, b200_int *num_elem, b200_int *num_qpts, b200_int *size_in, b200_int *size_out) {
+  for (auto *fields : {&op->in_fields, &op->out_fields})
+    for (size_t i = 0; i < fields->size(); i++) B200_CHECK((*fields)[i].is_set, op->ceed, B200_ERROR_INCOMPLETE, "Not all operator fields set");
+  return assembly_sizes(op, num_elem, num_qpts, size_in, size_out);
+}
+
+extern "C" int ceedb200_operator_assemble_qfunction(B200Operator op, B200Vector assembled) {
+  B200Ceed      ceed = op->ceed;
+  B200QFunction qf   = op->qf;
+  int           num_elem, nqpts, size_in, size_out;
+  B200_CALL(ceedb200_operator_assemble_qfunction_sizes(op, &num_elem, &nqpts, &size_in, &size_out));
+  if (!b200_compile_only()) B200_CUDA(ceed, cudaSetDevice(ceed->device_id));
+  const int64_t Qtot = (int64_t)num_elem * nqpts;
+  B200_CHECK(Qtot < (1LL << 31), ceed, B200_ERROR_UNSUPPORTED, "Backend does not implement QFunction assembly with more than 2^31 quadrature points");
+  B200_CHECK(assembled->length == Qtot * size_in * size_out, ceed, B200_ERROR_DIMENSION, "assembled vector has length %lld, expected %lld",
+             (long long)assembled->length, (long long)(Qtot * size_in * size_out));
+  double *d_asm;
+  B200_CALL(b200_vector_device_write(assembled, &d_asm, true));
+  if (Qtot == 0) return B200_SUCCESS;
+  // inputs at the quadrature points: passive ones evaluated, active ones zero
+  std::vector<B200Vector> owned;  // work vectors of this call
+  auto cleanup = [&]() {
+    for (auto v : owned) ceedb200_vector_destroy(v);
+  };
+  std::vector<const double *> in_ptr(std::max<size_t>(1, op->in_fields.size()), nullptr);
+  std::vector<double *>       act_ptr(op->in_fields.size(), nullptr), out_ptr(std::max<size_t>(1, op->out_fields.size()), nullptr);
+  auto work = [&](int64_t n, B200Vector *v) -> int {
+    B200_CALL(ceedb200_vector_create(ceed, n, v));
+    owned.push_back(*v);
+    return B200_SUCCESS;
+  };
+  int ierr = B200_SUCCESS;
+  for (size_t i = 0; i < op->in_fields.size() && !ierr; i++) {
+    const B200OpField &f     = op->in_fields[i];
+    const int          emode = qf->inputs[i].eval_mode;
+    B200Vector         q     = nullptr;
+    if (f.is_active) {
+      if ((ierr = work(Qtot * qf->inputs[i].size, &q))) break;
+      if ((ierr = ceedb200_vector_set_value(q, 0.0))) break;
+      if ((ierr = b200_vector_device_write(q, &act_ptr[i], false))) break;
+      in_ptr[i] = act_ptr[i];
+      continue;
+    }
+    if (emode == B200_EVAL_WEIGHT) {
+      if ((ierr = work(Qtot, &q))) break;
+      if ((ierr = ceedb200_basis_apply(f.basis, num_elem, B200_NOTRANSPOSE, B200_EVAL_WEIGHT, B200_VECTOR_NONE, q))) break;
+    } else {
+      if (!f.vec || f.vec == B200_VECTOR_NONE) {
+        ierr = b200_error(ceed, B200_ERROR_INCOMPLETE, "missing passive input vector for field %zu", i);
+        break;
+      }
+      B200Vector e = nullptr;
+      if ((ierr = work((int64_t)f.rstr->num_elem * f.rstr->elem_size * f.rstr->num_comp, &e))) break;
+      if ((ierr = ceedb200_restriction_apply(f.rstr, B200_NOTRANSPOSE, f.vec, e))) break;
+      if (emode == B200_EVAL_NONE) q = e;
+      else {
+        if ((ierr = work(Qtot * qf->inputs[i].size, &q))) break;
+        if ((ierr = ceedb200_basis_apply(f.basis, num_elem, B200_NOTRANSPOSE, emode, e, q))) break;
+      }
+    }
+    if ((ierr = b200_vector_device_read(q, &in_ptr[i]))) break;
+  }
+  // passive outputs are computed into scratch space and dropped
+  for (size_t i = 0; i < op->out_fields.size() && !ierr; i++) {
+    if (op->out_fields[i].is_active) continue;
+    B200Vector q = nullptr;
+    if ((ierr = work(Qtot * qf->outputs[i].size, &q))) break;
+    ierr = b200_vector_device_write(q, &out_ptr[i], true);
+  }
+  // one QFunction sweep per active input component: unit input -> one block column of the assembled map
+  B200Vector unit = nullptr;
+  if (!ierr) ierr = work(0, &unit);
+  int a = 0;
+  for (size_t i = 0; i < op->in_fields.size() && !ierr; i++) {
+    if (!op->in_fields[i].is_active) continue;
+    for (int comp = 0; comp < qf->inputs[i].size && !ierr; comp++, a++) {
+      double *slice = act_ptr[i] + (int64_t)comp * Qtot;
+      ceedb200_vector_destroy(unit);
+      owned.pop_back();
+      if ((ierr = work(Qtot, &unit))) break;
+      if ((ierr = ceedb200_vector_set_array(unit, B200_MEM_DEVICE, B200_USE_POINTER, slice))) break;
+      if ((ierr = ceedb200_vector_set_value(unit, 1.0))) break;
+      int64_t off = (int64_t)a * size_out * Qtot;
+      for (size_t o = 0; o < op->out_fields.size(); o++) {
+        if (!op->out_fields[o].is_active) continue;
+        out_ptr[o] = d_asm + off;
+        off += (int64_t)qf->outputs[o].size * Qtot;
+      }
+      if ((ierr = ceedb200_qfunction_apply_ptr(qf, (b200_int)Qtot, in_ptr.data(), out_ptr.data()))) break;
+      if ((ierr = ceedb200_vector_set_value(unit, 0.0))) break;
+    }
+  }
+  if (!ierr && !b200_compile_only()) {
+    cudaError_t e = cudaStreamSynchronize(ceed->stream);  // the work vectors are released below
+    if (e != cudaSuccess) ierr = b200_error(ceed, B200_ERROR_BACKEND, "CUDA error in QFunction assembly: %s", cudaGetErrorString(e));
+  }
+  cleanup();
+  return ierr;
+}
+
 // ------------------------------------------------------------------------------------------------ autotuner
 // Opt-in (ceedb200_set_autotune / CEED_B200_AUTOTUNE): on the first overwrite-apply of a fused operator, time a small set
 // of kernel shapes on the caller's own vectors (Apply is idempotent) and keep the fastest.  Coordinate search: group width
@@ -436,16 +568,24 @@ static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
   bool       xline_ok = true;
   for (auto &g : op->plan->in_groups) xline_ok = xline_ok && !g.use_grad;
   for (auto &g : op->plan->out_groups) xline_ok = xline_ok && !g.use_grad;
-  // 1. group width / warps per CTA x QFunction layout (elements per group and occupancy target left to the heuristics)
-  const int shapes[][2] = {{1, 4}, {2, 2}, {2, 8}, {4, 4}, {1, 8}};
+  // 1. group width / warps per CTA x QFunction layout x plane layout (elements per group and occupancy target left to the heuristics)
+  bool swz_ok = op->plan->Q <= 8 && op->plan->scatter_mode != B200_SCATTER_ORDERED;
+  for (auto &b : op->plan->bases) swz_ok = swz_ok && b.P <= 8;
+  const bool full = ceed->autotune >= 3;  // level 3: also the rarely winning point-pair layout
+  const int  shapes[][2] = {{1, 4}, {2, 2}, {2, 8}, {4, 4}, {1, 8}};
   for (auto &sh : shapes)
     for (int qf = 0; qf < 4; qf++) {
-      if (qf == 2 && op->plan->Q % 2) continue;  // point pairs need an even number of points per row
-      if (qf == 3 && !xline_ok) continue;        // x-line fusion exists for gradient-free operators only
-      B200Tuning t  = base;
-      t.group_warps = sh[0], t.cta_warps = sh[1], t.qf_mode = qf;
-      if (qf == 2) t.qf_unroll = 2;
-      trial(t);
+      if (qf == 2 && (op->plan->Q % 2 || !full)) continue;  // point pairs need an even number of points per row
+      if (qf == 3 && !xline_ok) continue;                   // x-line fusion exists for gradient-free operators only
+      if (qf == 0 && xline_ok && !full) continue;           // gradient-free operators: the x-line layout wins
+      for (int swz = 0; swz < 2; swz++) {
+        if (swz && (!swz_ok || qf == 1 || qf == 2)) continue;  // the conflict-free swizzled planes exist for the z-line / x-line layouts
+        B200Tuning t  = base;
+        t.group_warps = sh[0], t.cta_warps = sh[1], t.qf_mode = qf;
+        if (swz) t.stage = 257;
+        if (qf == 2) t.qf_unroll = 2;
+        trial(t);
+      }
     }
   // 2. elements per group around the winner
   {
@@ -454,6 +594,7 @@ static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
       if (epw == win.epw) continue;
       B200Tuning t = base;
       t.group_warps = win.group_warps, t.cta_warps = win.cta_warps, t.qf_mode = win.qf_mode, t.epw = epw;
+      if (win.stage >= 0 && (win.stage & 256)) t.stage = win.stage;
       trial(t);
     }
   }
@@ -476,13 +617,14 @@ static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
       }
     }
   }
-  // 4. cp.async staging: scatter targets only (1), + gather offsets (9), nothing (0)
+  // 4. cp.async staging: scatter targets only (1), + gather offsets (9), nothing (0) -- keeping the winner's plane layout bit
   {
     const B200Tuning win = best;
+    const int        layout_bit = win.stage >= 0 ? (win.stage & 256) : 0;
     for (int stage : {9, 0}) {
-      if (stage == win.stage) continue;
+      if ((stage | layout_bit) == win.stage) continue;
       B200Tuning t = win;
-      t.stage      = stage;
+      t.stage      = stage | layout_bit;
       trial(t);
     }
   }

@@ -34,6 +34,8 @@ typedef std::ostringstream oss;
 namespace {
 
 int odd_pad(int n) { return (n % 2) ? n : n + 1; }
+// smallest m >= n with m = 8 (mod 16): the stride between z-layers of the conflict-free ("swizzled") shared-memory layouts
+int pad8(int n) { return n <= 8 ? 8 : ((n - 8 + 15) / 16) * 16 + 8; }
 
 string hexd(double v) {
   char buf[64];
@@ -94,6 +96,7 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
       g.is_active = f.is_active;
       g.rstr      = f.rstr;
       if (f.basis) {
+        if (!f.basis->is_tensor) return reject("non-tensor basis");
         if (dim == 0) {
           dim = f.basis->dim;
           Q   = f.basis->Q;
@@ -165,13 +168,6 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
   plan->Q        = Q;
   plan->Qs       = odd_pad(Q);
   plan->num_elem = num_elem;
-  // shared-memory planes
-  int plane_size = Q * Q * plan->Qs;
-  for (auto &b : plan->bases) {
-    plane_size = std::max(plane_size, Q * b.P * b.P);
-    plane_size = std::max(plane_size, Q * Q * odd_pad(b.P));
-  }
-  plan->plane_size = plane_size;
   // Kernel shape: explicit override (set_tuning / autotuner) > environment > tuning table > heuristic.
   {
     std::ostringstream sig;
@@ -239,6 +235,27 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     if (tn.qf_mode < 0 && no_grad && !getenv("CEED_B200_NO_XLINE")) tn.qf_mode = 3;
     plan->qf_xline = tn.qf_mode == 3;
   }
+  // Shared-memory layout of the contraction planes.  Default: rows padded to an odd pitch.  Swizzled (stage bit 256, Q <= 8,
+  // z-line / x-line QFunction stage): quadrature rows have pitch 8 with the x index XOR-ed by the row's y index, every
+  // z-stride is 8 (mod 16) and every stage enumerates its lanes with a fastest extent of 8 -- with that, all stages
+  // (x-, y- and z-lines) are free of shared-memory bank conflicts (scripts/model/swizzle_model.py), where the padded layout replays
+  // a third of its wavefronts (ncu, profiles/r01_ncu_full_summary.txt).
+  {
+    const int stage_req = tn.stage >= 0 ? tn.stage : 1;
+    bool      ok        = (stage_req & 256) && Q <= 8 && !getenv("CEED_B200_BLOCK_MODE") && !(tn.qf_mode == 1 || tn.qf_mode == 2) && !(stage_req & 16) &&
+              plan->scatter_mode != B200_SCATTER_ORDERED;
+    for (auto &b : plan->bases) ok = ok && b.P <= 8;
+    plan->swz = ok;
+  }
+  {
+    int plane_size = plan->swz ? Q * pad8(Q * 8) : Q * Q * plan->Qs;
+    for (auto &b : plan->bases) {
+      plane_size = std::max(plane_size, Q * (plan->swz ? pad8(b.P * b.P) : b.P * b.P));
+      plane_size = std::max(plane_size, Q * (plan->swz ? pad8(Q * odd_pad(b.P)) : Q * odd_pad(b.P)));
+    }
+    if (plan->swz) plane_size = (plane_size + 15) / 16 * 16;  // element / plane strides keep the bank residues
+    plan->plane_size = plane_size;
+  }
   plan->qf_pointwise = tn.qf_mode == 1 || tn.qf_mode == 2;
   plan->qf_pp        = (tn.qf_mode == 2 && Q % 2 == 0) ? 2 : 1;  // point pairs need x-adjacent points in one row
   plan->qf_unroll    = tn.qf_unroll > 0 ? tn.qf_unroll : 4;
@@ -260,7 +277,7 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
   // batch ahead (quadrature data, gathered inputs + their offsets, scatter targets).  Returns the total in bytes.
   plan->async_copy = !getenv("CEED_B200_NO_ASYNC");
   auto layout      = [&](int E) {
-    size_t off  = ((size_t)plan->num_planes * plane_size * 8 * E + 15) / 16 * 16;
+    size_t off  = ((size_t)plan->num_planes * plan->plane_size * 8 * E + 15) / 16 * 16;
     const int mask = plan->warp_mode ? plan->stage_mask : 7;
     auto   take = [&](size_t bytes) {
       size_t at = off;
@@ -421,6 +438,15 @@ struct Gen {
   int          TS        = 0;            // task-loop stride (threads that share a group)
   string       TID, SMBASE, SYNC;        // lane id expression, shared-memory base, barrier statement
   string       QLD = "__ldg";            // load intrinsic of streamed EVAL_NONE inputs (stage bit 128: __ldcs = evict-first in L2)
+  // plane layouts (see b200_opgen_plan): quadrature rows have pitch QP, z-layers are SZ apart, lanes enumerate the fastest
+  // quadrature index with extent LQ; swizzled: QP = LQ = 8 and the x index of a point is XOR-ed with its y index
+  bool         swz = false;
+  int          QP = 0, SZ = 0, LQ = 0;
+  int          lp(const B200GenBasis &b) const { return swz ? 8 : b.P; }                                     // lane extent of the fastest node index
+  int          sz1(const B200GenBasis &b) const { return swz ? pad8(b.P * b.P) : b.P * b.P; }                // z-stride of T1 [qz][j][i]
+  int          sz2(const B200GenBasis &b) const { return swz ? pad8(Q * odd_pad(b.P)) : Q * odd_pad(b.P); }  // z-stride of T2 [qz][qy][i]
+  string       xq(const string &x, const string &y) const { return swz ? "((" + x + ") ^ (" + y + "))" : "(" + x + ")"; }
+  string       xq(int x, const string &y) const { return swz ? "(" + std::to_string(x) + " ^ (" + y + "))" : std::to_string(x); }
   string       smw_expr() const {
     return warp_mode ? "sm + (threadIdx.x / " + std::to_string(TS) + ") * " + std::to_string(plan->group_smem_bytes / 8) : "sm";
   }
@@ -693,16 +719,16 @@ struct Gen {
     auto emit_compute_store = [&](const string &sfx, const string &ind) {
       // u<k><sfx> -> z-contraction -> T1 plane (or straight into the Uq plane for collocated bases)
       if (b.collocated) {
-        c << ind << "double *dst = " << plane(g.plane0, "le" + sfx) << " + cc" << sfx << " * " << E * S << " + (ij" << sfx << " / " << P << ") * " << Qs
-          << " + (ij" << sfx << " % " << P << ");\n";
-        for (int k = 0; k < P; k++) c << ind << "dst[" << k * Q * Qs << "] = u" << k << sfx << ";\n";
+        c << ind << "double *dst = " << plane(g.plane0, "le" + sfx) << " + cc" << sfx << " * " << E * S << " + (ij" << sfx << " / " << P << ") * " << QP
+          << " + " << xq("ij" + sfx + " % " + std::to_string(P), "ij" + sfx + " / " + std::to_string(P)) << ";\n";
+        for (int k = 0; k < P; k++) c << ind << "dst[" << k * SZ << "] = u" << k << sfx << ";\n";
       } else {
         c << ind << "double *dst = " << plane(g.plane0, "le" + sfx) << " + cc" << sfx << " * " << E * S << " + ij" << sfx << ";\n";  // T1 [qz][j][i]
         for (int o = 0; o < Q; o++) {
           c << ind << "double r" << o << " = cB" << g.basis_id << "[" << o * P << "] * u0" << sfx << ";\n";
           for (int i = 1; i < P; i++) c << ind << "r" << o << " = fma(cB" << g.basis_id << "[" << o * P + i << "], u" << i << sfx << ", r" << o << ");\n";
         }
-        for (int q = 0; q < Q; q++) c << ind << "dst[" << q * P * P << "] = r" << q << ";\n";
+        for (int q = 0; q < Q; q++) c << ind << "dst[" << q * sz1(b) << "] = r" << q << ";\n";
       }
     };
     const int rounds = (ntasks + TS - 1) / TS;
@@ -780,11 +806,13 @@ struct Gen {
     if (b.collocated) return;
     const int P = b.P, Ps = odd_pad(P);
     comment("y-contraction, input group slot " + std::to_string(g.slot));
-    task_loop_begin(std::to_string(E * g.nc * Q * P));
-    c << "      const int i = t % " << P << ", qz = (t / " << P << ") % " << Q << ", cc = (t / " << P * Q << ") % " << g.nc << ", le = t / "
-      << P * Q * g.nc << ";\n";
-    c << "      const double *src = " << plane(g.plane0, "le") << " + cc * " << E * S << " + qz * " << P * P << " + i;\n";
-    c << "      double *dst = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + qz * " << Q * Ps << " + i;\n";  // T2 in plane B
+    const int LP = lp(b);
+    task_loop_begin(std::to_string(E * g.nc * Q * LP));
+    c << "      const int i = t % " << LP << ", qz = (t / " << LP << ") % " << Q << ", cc = (t / " << LP * Q << ") % " << g.nc << ", le = t / "
+      << LP * Q * g.nc << ";\n";
+    if (LP != P) c << "      if (i >= " << P << ") continue;\n";
+    c << "      const double *src = " << plane(g.plane0, "le") << " + cc * " << E * S << " + qz * " << sz1(b) << " + i;\n";
+    c << "      double *dst = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + qz * " << sz2(b) << " + i;\n";  // T2 in plane B
     for (int j = 0; j < P; j++) c << "      const double u" << j << " = src[" << j * P << "];\n";
     contract("cB" + std::to_string(g.basis_id), P, Q, false, "u", "r", "      ");
     for (int q = 0; q < Q; q++) c << "      dst[" << q * Ps << "] = r" << q << ";\n";
@@ -796,21 +824,23 @@ struct Gen {
     const int           P = b.P, Ps = odd_pad(P);
     if (b.collocated && !g.use_grad) return;
     comment("x-contraction (+ d/dx), input group slot " + std::to_string(g.slot));
-    task_loop_begin(std::to_string(E * g.nc * Q * Q));
-    c << "      const int row = t % " << Q * Q << ", cc = (t / " << Q * Q << ") % " << g.nc << ", le = t / " << Q * Q * g.nc << ";\n";
-    c << "      double *uq = " << plane(g.plane0, "le") << " + cc * " << E * S << " + row * " << Qs << ";\n";
+    task_loop_begin(std::to_string(E * g.nc * Q * LQ));
+    c << "      const int qy = t % " << LQ << ", qz = (t / " << LQ << ") % " << Q << ", cc = (t / " << Q * LQ << ") % " << g.nc << ", le = t / " << Q * LQ * g.nc
+      << ";\n";
+    if (LQ != Q) c << "      if (qy >= " << Q << ") continue;\n";
+    c << "      double *uq = " << plane(g.plane0, "le") << " + cc * " << E * S << " + qz * " << SZ << " + qy * " << QP << ";\n";
     if (b.collocated) {
-      for (int q = 0; q < Q; q++) c << "      const double r" << q << " = uq[" << q << "];\n";
+      for (int q = 0; q < Q; q++) c << "      const double r" << q << " = uq[" << xq(q, "qy") << "];\n";
     } else {
-      c << "      const double *src = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + row * " << Ps << ";\n";
+      c << "      const double *src = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + qz * " << sz2(b) << " + qy * " << Ps << ";\n";
       for (int i = 0; i < P; i++) c << "      const double u" << i << " = src[" << i << "];\n";
       contract("cB" + std::to_string(g.basis_id), P, Q, false, "u", "r", "      ");
-      for (int q = 0; q < Q; q++) c << "      uq[" << q << "] = r" << q << ";\n";
+      for (int q = 0; q < Q; q++) c << "      uq[" << xq(q, "qy") << "] = r" << q << ";\n";
     }
     if (g.use_grad) {
-      c << "      double *gx = " << plane(g.plane0 + 2 * g.nc, "le") << " + cc * " << E * S << " + row * " << Qs << ";\n";
+      c << "      double *gx = " << plane(g.plane0 + 2 * g.nc, "le") << " + cc * " << E * S << " + qz * " << SZ << " + qy * " << QP << ";\n";
       contract("cG" + std::to_string(g.basis_id), Q, Q, false, "r", "d", "      ");
-      for (int q = 0; q < Q; q++) c << "      gx[" << q << "] = d" << q << ";\n";
+      for (int q = 0; q < Q; q++) c << "      gx[" << xq(q, "qy") << "] = d" << q << ";\n";
     }
     task_loop_end();
   }
@@ -818,14 +848,17 @@ struct Gen {
   void emit_grad_y(const B200GenGroup &g) {
     if (!g.use_grad) return;
     comment("d/dy, input group slot " + std::to_string(g.slot));
-    task_loop_begin(std::to_string(E * g.nc * Q * Q));
-    c << "      const int qx = t % " << Q << ", qz = (t / " << Q << ") % " << Q << ", cc = (t / " << Q * Q << ") % " << g.nc << ", le = t / "
-      << Q * Q * g.nc << ";\n";
-    c << "      const double *src = " << plane(g.plane0, "le") << " + cc * " << E * S << " + qz * " << Q * Qs << " + qx;\n";
-    c << "      double *dst = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + qz * " << Q * Qs << " + qx;\n";
-    for (int m = 0; m < Q; m++) c << "      const double u" << m << " = src[" << m * Qs << "];\n";
+    task_loop_begin(std::to_string(E * g.nc * Q * LQ));
+    c << "      const int qx = t % " << LQ << ", qz = (t / " << LQ << ") % " << Q << ", cc = (t / " << Q * LQ << ") % " << g.nc << ", le = t / "
+      << Q * LQ * g.nc << ";\n";
+    if (LQ != Q) c << "      if (qx >= " << Q << ") continue;\n";
+    // swizzled rows: point (qx, m) of the line sits at m * QP + (qx ^ m)
+    c << "      const double *src = " << plane(g.plane0, "le") << " + cc * " << E * S << " + qz * " << SZ << (swz ? "" : " + qx") << ";\n";
+    c << "      double *dst = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + qz * " << SZ << (swz ? "" : " + qx") << ";\n";
+    auto at = [&](int m) { return swz ? std::to_string(m * QP) + " + (qx ^ " + std::to_string(m) + ")" : std::to_string(m * QP); };
+    for (int m = 0; m < Q; m++) c << "      const double u" << m << " = src[" << at(m) << "];\n";
     contract("cG" + std::to_string(g.basis_id), Q, Q, false, "u", "d", "      ");
-    for (int q = 0; q < Q; q++) c << "      dst[" << q * Qs << "] = d" << q << ";\n";
+    for (int q = 0; q < Q; q++) c << "      dst[" << at(q) << "] = d" << q << ";\n";
     task_loop_end();
   }
 
@@ -969,11 +1002,11 @@ struct Gen {
   void emit_qf_stage() {
     B200QFunction qf = op->qf;
     comment("quadrature points: one z-line per thread; d/dz, QFunction, (d/dz)^T in registers");
-    task_loop_begin(std::to_string(E * Q * Q));
-    c << "      const int qx = t % " << Q << ", qy = (t / " << Q << ") % " << Q << ", le = t / " << Q * Q << ";\n";
+    task_loop_begin(std::to_string(E * Q * LQ));
+    c << "      const int qx = t % " << LQ << ", qy = (t / " << LQ << ") % " << Q << ", le = t / " << Q * LQ << ";\n";
     c << "      const long long e = e0 + le;\n";
-    c << "      if (e < b200_ne) {\n";
-    c << "      const int pxy = qy * " << Qs << " + qx;\n";
+    c << "      if (e < b200_ne" << (LQ != Q ? " && qx < " + std::to_string(Q) : "") << ") {\n";
+    c << "      const int pxy = qy * " << QP << " + " << xq("qx", "qy") << ";\n";
     // z-lines of input groups that need gradients (and their d/dz)
     for (size_t gi = 0; gi < plan->in_groups.size(); gi++) {
       const B200GenGroup &g = plan->in_groups[gi];
@@ -981,7 +1014,7 @@ struct Gen {
       for (int cc = 0; cc < g.nc; cc++) {
         const string tag = "g" + std::to_string(gi) + "c" + std::to_string(cc) + "_";
         c << "      const double *uq_" << tag << " = " << plane(g.plane0 + cc, "le") << " + pxy;\n";
-        for (int m = 0; m < Q; m++) c << "      const double uz_" << tag << m << " = uq_" << tag << "[" << m * Q * Qs << "];\n";
+        for (int m = 0; m < Q; m++) c << "      const double uz_" << tag << m << " = uq_" << tag << "[" << m * SZ << "];\n";
         contract("cG" + std::to_string(g.basis_id), Q, Q, false, "uz_" + tag, "dz_" + tag, "      ");
       }
     }
@@ -1023,7 +1056,7 @@ struct Gen {
         }
     for (int qz = 0; qz < Q; qz++) {
       c << "      {  // qz = " << qz << "\n";
-      c << "        const int p = pxy + " << qz * Q * Qs << ";\n";
+      c << "        const int p = pxy + " << qz * SZ << ";\n";
       c << "        const int pt = pt0 + " << qz * Q * Q << ";\n";
       for (size_t f = 0; f < plan->in_fields.size(); f++) {
         const B200GenField &fd = plan->in_fields[f];
@@ -1107,7 +1140,7 @@ struct Gen {
       for (int cc = 0; cc < g.nc; cc++) {
         c << "      { double *vq = " << plane(g.plane0 + cc, "le") << " + pxy;\n";
         for (int m = 0; m < Q; m++)
-          c << "        vq[" << m * Q * Qs << "] " << (g.use_interp ? "+=" : "=") << " vz_g" << gi << "c" << cc << "_" << m << ";\n";
+          c << "        vq[" << m * SZ << "] " << (g.use_interp ? "+=" : "=") << " vz_g" << gi << "c" << cc << "_" << m << ";\n";
         c << "      }\n";
       }
     }
@@ -1119,9 +1152,10 @@ struct Gen {
   void emit_xline_qf() {
     B200QFunction qf = op->qf;
     comment("x-lines: x-contraction, QFunction on the Q points of the line, x-contraction^T (all components of one line per lane)");
-    task_loop_begin(std::to_string(E * Q * Q));
-    c << "      const int row = t % " << Q * Q << ", le = t / " << Q * Q << ";\n";
-    c << "      const int qy = row % " << Q << ", qz = row / " << Q << ";\n";
+    task_loop_begin(std::to_string(E * Q * LQ));
+    c << "      const int qy = t % " << LQ << ", qz = (t / " << LQ << ") % " << Q << ", le = t / " << Q * LQ << ";\n";
+    if (LQ != Q) c << "      if (qy >= " << Q << ") continue;\n";
+    c << "      const int row = qz * " << Q << " + qy;\n";
     c << "      const long long e_real = e0 + le;\n";
     c << "      const long long e = e_real < b200_ne ? e_real : b200_ne - 1;\n      (void)qy; (void)qz; (void)e;\n";
     c << "      const CeedScalar *in[" << std::max<size_t>(1, qf->inputs.size()) << "];\n";
@@ -1155,7 +1189,7 @@ struct Gen {
       const B200GenBasis &b = basis(g.basis_id);
       const int           P = b.P, Ps = odd_pad(P);
       for (int cc = 0; cc < fd.nc; cc++) {
-        c << "      { const double *src = " << plane(g.plane0 + g.nc + cc, "le") << " + row * " << Ps << ";\n";
+        c << "      { const double *src = " << plane(g.plane0 + g.nc + cc, "le") << " + qz * " << sz2(b) << " + qy * " << Ps << ";\n";
         for (int i = 0; i < P; i++) c << "        const double u" << i << " = src[" << i << "];\n";
         contract("cB" + std::to_string(g.basis_id), P, Q, false, "u", "r", "        ");
         for (int q = 0; q < Q; q++) c << "        in_" << f << "[" << cc * Q + q << "] = r" << q << ";\n";
@@ -1178,7 +1212,7 @@ struct Gen {
           c << "        const double v" << q << " = " << val << ";\n";
         }
         contract("cB" + std::to_string(g.basis_id), Q, P, true, "v", "r", "        ");
-        c << "        double *dst = " << plane(g.plane0 + g.nc + cc, "le") << " + row * " << Ps << ";\n";
+        c << "        double *dst = " << plane(g.plane0 + g.nc + cc, "le") << " + qz * " << sz2(b) << " + qy * " << Ps << ";\n";
         for (int i = 0; i < P; i++) c << "        dst[" << i << "] = r" << i << ";\n";
         c << "      }\n";
       }
@@ -1432,14 +1466,16 @@ struct Gen {
   void emit_gradT_y(const B200GenGroup &g) {
     if (!g.use_grad) return;
     comment("(d/dy)^T, output group slot " + std::to_string(g.slot));
-    task_loop_begin(std::to_string(E * g.nc * Q * Q));
-    c << "      const int qx = t % " << Q << ", qz = (t / " << Q << ") % " << Q << ", cc = (t / " << Q * Q << ") % " << g.nc << ", le = t / "
-      << Q * Q * g.nc << ";\n";
-    c << "      const double *src = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + qz * " << Q * Qs << " + qx;\n";
-    c << "      double *vq = " << plane(g.plane0, "le") << " + cc * " << E * S << " + qz * " << Q * Qs << " + qx;\n";
-    for (int m = 0; m < Q; m++) c << "      const double u" << m << " = src[" << m * Qs << "];\n";
+    task_loop_begin(std::to_string(E * g.nc * Q * LQ));
+    c << "      const int qx = t % " << LQ << ", qz = (t / " << LQ << ") % " << Q << ", cc = (t / " << Q * LQ << ") % " << g.nc << ", le = t / "
+      << Q * LQ * g.nc << ";\n";
+    if (LQ != Q) c << "      if (qx >= " << Q << ") continue;\n";
+    c << "      const double *src = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + qz * " << SZ << (swz ? "" : " + qx") << ";\n";
+    c << "      double *vq = " << plane(g.plane0, "le") << " + cc * " << E * S << " + qz * " << SZ << (swz ? "" : " + qx") << ";\n";
+    auto at = [&](int m) { return swz ? std::to_string(m * QP) + " + (qx ^ " + std::to_string(m) + ")" : std::to_string(m * QP); };
+    for (int m = 0; m < Q; m++) c << "      const double u" << m << " = src[" << at(m) << "];\n";
     contract("cG" + std::to_string(g.basis_id), Q, Q, true, "u", "d", "      ");
-    for (int q = 0; q < Q; q++) c << "      vq[" << q * Qs << "] += d" << q << ";\n";
+    for (int q = 0; q < Q; q++) c << "      vq[" << at(q) << "] += d" << q << ";\n";
     task_loop_end();
   }
 
@@ -1448,21 +1484,23 @@ struct Gen {
     const int           P = b.P, Ps = odd_pad(P);
     if (b.collocated && !g.use_grad) return;
     comment("(d/dx)^T + x-contraction^T, output group slot " + std::to_string(g.slot));
-    task_loop_begin(std::to_string(E * g.nc * Q * Q));
-    c << "      const int row = t % " << Q * Q << ", cc = (t / " << Q * Q << ") % " << g.nc << ", le = t / " << Q * Q * g.nc << ";\n";
-    c << "      double *vq = " << plane(g.plane0, "le") << " + cc * " << E * S << " + row * " << Qs << ";\n";
+    task_loop_begin(std::to_string(E * g.nc * Q * LQ));
+    c << "      const int qy = t % " << LQ << ", qz = (t / " << LQ << ") % " << Q << ", cc = (t / " << Q * LQ << ") % " << g.nc << ", le = t / " << Q * LQ * g.nc
+      << ";\n";
+    if (LQ != Q) c << "      if (qy >= " << Q << ") continue;\n";
+    c << "      double *vq = " << plane(g.plane0, "le") << " + cc * " << E * S << " + qz * " << SZ << " + qy * " << QP << ";\n";
     if (g.use_grad) {
-      c << "      const double *vx = " << plane(g.plane0 + 2 * g.nc, "le") << " + cc * " << E * S << " + row * " << Qs << ";\n";
-      for (int m = 0; m < Q; m++) c << "      const double u" << m << " = vx[" << m << "];\n";
+      c << "      const double *vx = " << plane(g.plane0 + 2 * g.nc, "le") << " + cc * " << E * S << " + qz * " << SZ << " + qy * " << QP << ";\n";
+      for (int m = 0; m < Q; m++) c << "      const double u" << m << " = vx[" << xq(m, "qy") << "];\n";
       contract("cG" + std::to_string(g.basis_id), Q, Q, true, "u", "d", "      ");
-      for (int q = 0; q < Q; q++) c << "      const double v" << q << " = vq[" << q << "] + d" << q << ";\n";
+      for (int q = 0; q < Q; q++) c << "      const double v" << q << " = vq[" << xq(q, "qy") << "] + d" << q << ";\n";
     } else {
-      for (int q = 0; q < Q; q++) c << "      const double v" << q << " = vq[" << q << "];\n";
+      for (int q = 0; q < Q; q++) c << "      const double v" << q << " = vq[" << xq(q, "qy") << "];\n";
     }
     if (b.collocated) {
-      for (int q = 0; q < Q; q++) c << "      vq[" << q << "] = v" << q << ";\n";
+      for (int q = 0; q < Q; q++) c << "      vq[" << xq(q, "qy") << "] = v" << q << ";\n";
     } else {
-      c << "      double *dst = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + row * " << Ps << ";\n";
+      c << "      double *dst = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + qz * " << sz2(b) << " + qy * " << Ps << ";\n";
       contract("cB" + std::to_string(g.basis_id), Q, P, true, "v", "r", "      ");
       for (int i = 0; i < P; i++) c << "      dst[" << i << "] = r" << i << ";\n";
     }
@@ -1476,11 +1514,13 @@ struct Gen {
     // T1' goes to plane C when the group has a gradient (plane A still holds nothing live, but keep A/B/C rotation simple)
     const int t1_plane = g.plane0;  // Vq is dead after the x-stage
     comment("y-contraction^T, output group slot " + std::to_string(g.slot));
-    task_loop_begin(std::to_string(E * g.nc * Q * P));
-    c << "      const int i = t % " << P << ", qz = (t / " << P << ") % " << Q << ", cc = (t / " << P * Q << ") % " << g.nc << ", le = t / "
-      << P * Q * g.nc << ";\n";
-    c << "      const double *src = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + qz * " << Q * Ps << " + i;\n";
-    c << "      double *dst = " << plane(t1_plane, "le") << " + cc * " << E * S << " + qz * " << P * P << " + i;\n";
+    const int LP = lp(b);
+    task_loop_begin(std::to_string(E * g.nc * Q * LP));
+    c << "      const int i = t % " << LP << ", qz = (t / " << LP << ") % " << Q << ", cc = (t / " << LP * Q << ") % " << g.nc << ", le = t / "
+      << LP * Q * g.nc << ";\n";
+    if (LP != P) c << "      if (i >= " << P << ") continue;\n";
+    c << "      const double *src = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + qz * " << sz2(b) << " + i;\n";
+    c << "      double *dst = " << plane(t1_plane, "le") << " + cc * " << E * S << " + qz * " << sz1(b) << " + i;\n";
     for (int q = 0; q < Q; q++) c << "      const double u" << q << " = src[" << q * Ps << "];\n";
     contract("cB" + std::to_string(g.basis_id), Q, P, true, "u", "r", "      ");
     for (int j = 0; j < P; j++) c << "      dst[" << j * P << "] = r" << j << ";\n";
@@ -1576,11 +1616,12 @@ struct Gen {
     c << "      const int ij = t % " << P * P << ", cc = (t / " << P * P << ") % " << g.nc << ", le = t / " << P * P * g.nc << ";\n";
     c << "      const long long e = e0 + le;\n";
     if (b.collocated) {
-      c << "      const double *src = " << plane(g.plane0, "le") << " + cc * " << E * S << " + (ij / " << P << ") * " << Qs << " + (ij % " << P << ");\n";
-      for (int k = 0; k < P; k++) c << "      const double r" << k << " = src[" << k * Q * Qs << "];\n";
+      c << "      const double *src = " << plane(g.plane0, "le") << " + cc * " << E * S << " + (ij / " << P << ") * " << QP << " + "
+        << xq("ij % " + std::to_string(P), "ij / " + std::to_string(P)) << ";\n";
+      for (int k = 0; k < P; k++) c << "      const double r" << k << " = src[" << k * SZ << "];\n";
     } else {
       c << "      const double *src = " << plane(g.plane0, "le") << " + cc * " << E * S << " + ij;\n";
-      for (int q = 0; q < Q; q++) c << "      const double u" << q << " = src[" << q * P * P << "];\n";
+      for (int q = 0; q < Q; q++) c << "      const double u" << q << " = src[" << q * sz1(b) << "];\n";
       contract("cB" + std::to_string(g.basis_id), Q, P, true, "u", "r", "      ");
     }
     c << "      if (e < b200_ne) {\n";
@@ -1636,7 +1677,11 @@ struct Gen {
     if (!warp_mode || NT == TS) SYNC = "__syncthreads();";
     else if (plan->group_warps == 1) SYNC = "__syncwarp();";
     else SYNC = "asm volatile(\"bar.sync %0, " + std::to_string(TS) + ";\" ::\"r\"((int)(threadIdx.x / " + std::to_string(TS) + ") + 1) : \"memory\");";
-    S  = plan->plane_size;
+    S   = plan->plane_size;
+    swz = plan->swz;
+    QP  = swz ? 8 : Qs;
+    SZ  = swz ? pad8(Q * 8) : Q * Qs;
+    LQ  = swz ? 8 : Q;
     // quadrature data is read exactly once per apply: mark it evict-first so that u, v, the halo buffer and the offsets keep the L2
     if (plan->stage_mask & 128) QLD = "__ldcs";
     emit_header();

@@ -222,6 +222,7 @@ extern "C" int ceedb200_destroy(B200Ceed ceed) {
     delete kv.second;
   }
   b200_dfree(ceed, ceed->d_scratch);
+  for (int i = 0; i < 3; i++) b200_dfree(ceed, ceed->d_basis_tmp[i]);
   delete ceed;
   return B200_SUCCESS;
 }

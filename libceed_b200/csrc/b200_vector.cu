@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <algorithm>
+
 #include "b200_internal.h"
 
 namespace {
@@ -358,9 +360,11 @@ extern "C" int ceedb200_vector_norm(B200Vector vec, int norm_type, b200_scalar *
   B200_CHECK(!b200_compile_only(), ceed, B200_ERROR_BACKEND, "CEED_B200_COMPILE_ONLY is set; kernels cannot run");
   unsigned grid = grid_for(ceed, vec->length, 8);
   if (ceed->scratch_len < grid) {
+    const size_t want = std::max<size_t>((size_t)ceed->num_sms * 16, grid);
     B200_CALL(b200_dfree(ceed, ceed->d_scratch));
-    B200_CALL(b200_dmalloc(ceed, (void **)&ceed->d_scratch, (size_t)ceed->num_sms * 16 * sizeof(double)));
-    ceed->scratch_len = (size_t)ceed->num_sms * 16;
+    ceed->d_scratch = nullptr, ceed->scratch_len = 0;
+    B200_CALL(b200_dmalloc(ceed, (void **)&ceed->d_scratch, want * sizeof(double)));
+    ceed->scratch_len = want;
   }
   int mode = norm_type == B200_NORM_1 ? 0 : (norm_type == B200_NORM_2 ? 1 : 2);
   k_norm_partial<<<grid, kThreads, 0, ceed->stream>>>(d, vec->length, mode, ceed->d_scratch);
@@ -622,10 +626,13 @@ __global__ void k_cg_direction(double *__restrict__ p, const double *__restrict_
 }
 
 int cg_scratch(B200Ceed ceed) {
-  if (ceed->scratch_len < (size_t)ceed->num_sms * 16) {
+  // the partial sums use a FIXED grid of kCgBlocks CTAs (reproducible whatever the SM count): the buffer must hold them all
+  const size_t want = std::max<size_t>((size_t)ceed->num_sms * 16, (size_t)kCgBlocks);
+  if (ceed->scratch_len < want) {
     B200_CALL(b200_dfree(ceed, ceed->d_scratch));
-    B200_CALL(b200_dmalloc(ceed, (void **)&ceed->d_scratch, (size_t)ceed->num_sms * 16 * sizeof(double)));
-    ceed->scratch_len = (size_t)ceed->num_sms * 16;
+    ceed->d_scratch = nullptr, ceed->scratch_len = 0;
+    B200_CALL(b200_dmalloc(ceed, (void **)&ceed->d_scratch, want * sizeof(double)));
+    ceed->scratch_len = want;
   }
   return B200_SUCCESS;
 }

@@ -96,6 +96,35 @@ elif mode == "tma":
                 for stage in (33,):
                     env = {"CEED_B200_STAGE": str(stage), "CEED_B200_GROUP_WARPS": str(gw), "CEED_B200_WARPS": str(gw * groups), "CEED_B200_QF_POINTWISE": "0"}
                     run(f"tma stage={stage} gw={gw} groups={groups} epw={epw}", env, epb=epw)
+elif mode == "tma2":
+    # everything asynchronous: bulk-copied quadrature data (32) + cp.async gather of the next group's inputs (2) / offsets only (8)
+    run("table", {})
+    Q = base.Q
+    for gw, groups in ((2, 1), (2, 2), (4, 1), (1, 2), (1, 4)):
+        lanes = 32 * gw
+        for epw in (1, 2, 3):
+            tasks = epw * Q * Q
+            util = tasks / (lanes * ((tasks + lanes - 1) // lanes))
+            if util < 0.7 or tasks > 2 * lanes:
+                continue
+            for stage in (33, 35, 41):
+                env = {"CEED_B200_STAGE": str(stage), "CEED_B200_GROUP_WARPS": str(gw), "CEED_B200_WARPS": str(gw * groups), "CEED_B200_QF_POINTWISE": "0"}
+                run(f"stage={stage} gw={gw} groups={groups} epw={epw}", env, epb=epw)
+elif mode == "swz":
+    # conflict-free swizzled plane layout (stage bit 256) on the table shape and a few neighbours
+    run("table", {})
+    run("table + swz", {"CEED_B200_STAGE": "257"})
+    run("table + swz + idx", {"CEED_B200_STAGE": "265"})
+    Q = base.Q
+    for gw, groups in ((1, 4), (2, 1), (2, 2), (2, 4), (4, 1), (4, 2)):
+        lanes = 32 * gw
+        for epw in (1, 2, 3, 4, 5, 8):
+            tasks = epw * Q * 8
+            util = tasks / (lanes * ((tasks + lanes - 1) // lanes))
+            if util < 0.74 or tasks > 3 * lanes:
+                continue
+            env = {"CEED_B200_STAGE": "257", "CEED_B200_GROUP_WARPS": str(gw), "CEED_B200_WARPS": str(gw * groups), "CEED_B200_MINB": "0"}
+            run(f"swz gw={gw} groups={groups} epw={epw}", env, epb=epw)
 elif mode == "pf":
     # bulk L2 prefetch of the next batch's quadrature data (stage bit 64) on top of the table shape
     run("table", {})
