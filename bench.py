@@ -389,6 +389,51 @@ def run_case(args, ceed, cm, bp, p, dofs, rank, world, local_rank, dev, steps, w
         out["e2e_cabi"] = dict(value=total_dofs / e2e_s / 1e9, unit="GDoF/s", h2d_bytes_per_step=8 * n_local, d2h_bytes_per_step=8 * n_local, ms_per_step=e2e_s * 1e3,
                                mode="C ABI, pinned host buffers: H2D(u), step (apply + interface sum), D2H(v) one after the other, per rank; max over ranks")
         del uh, vh
+        # The same end-to-end step software-pipelined over steps (single GPU): every step still copies its own u from pinned host
+        # memory and its own v back, but on separate copy streams with double-buffered device vectors, so the H2D of step i+1 and the
+        # D2H of step i-1 overlap the kernels of step i (PCIe is full duplex).  Results must be bitwise equal to the serial path.
+        if world == 1 and not args.no_e2e_pipeline:
+            try:
+                nbuf = 2
+                s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+                u_d = [torch.empty(n_local, dtype=torch.float64, device=dev) for _ in range(nbuf)]
+                v_d = [torch.empty(n_local, dtype=torch.float64, device=dev) for _ in range(nbuf)]
+                v_h = [torch.empty(n_local, dtype=torch.float64).pin_memory() for _ in range(nbuf)]
+                uvec, vvec = [ceed.Vector(n_local) for _ in range(nbuf)], [ceed.Vector(n_local) for _ in range(nbuf)]
+                for k in range(nbuf):
+                    uvec[k].set_array(u_d[k], cm.MEM_DEVICE, cm.USE_POINTER)
+                    vvec[k].set_array(v_d[k], cm.MEM_DEVICE, cm.USE_POINTER)
+                ev_in, ev_done, ev_out = ([torch.cuda.Event() for _ in range(nbuf)] for _ in range(3))
+
+                def pipelined(nsteps):
+                    for i in range(nsteps):
+                        k = i % nbuf
+                        if i >= nbuf:
+                            s_in.wait_event(ev_out[k])            # buffer k is free once the D2H of step i - nbuf has finished
+                        with torch.cuda.stream(s_in):
+                            u_d[k].copy_(u_host, non_blocking=True)
+                            ev_in[k].record(s_in)
+                        stream.wait_event(ev_in[k])
+                        prob.op.apply(uvec[k], vvec[k])           # on the backend's stream (= `stream`)
+                        ev_done[k].record(stream)
+                        s_out.wait_event(ev_done[k])
+                        with torch.cuda.stream(s_out):
+                            v_h[k].copy_(v_d[k], non_blocking=True)
+                            ev_out[k].record(s_out)
+                    s_out.synchronize()
+                    stream.synchronize()
+
+                pipelined(2)
+                barrier()
+                t0 = time.perf_counter()
+                pipelined(e2e_steps * 2)
+                pipe_s = (time.perf_counter() - t0) / (e2e_steps * 2)
+                out["e2e_cabi"].update(pipelined_value=total_dofs / pipe_s / 1e9, pipelined_ms_per_step=pipe_s * 1e3,
+                                       pipelined_matches_serial=bool(torch.equal(v_h[0], v_host)),
+                                       pipelined_mode="C ABI, double-buffered: H2D of step i+1 and D2H of step i-1 overlap the kernels of step i; every step moves its own u and v")
+                del uvec, vvec
+            except Exception as exc:  # noqa: BLE001
+                out["e2e_cabi"]["pipelined_error"] = str(exc)[:200]
     out["prob"], out["dop"], out["part"], out["u_loc"], out["v_dev"], out["owned_mask"] = prob, dop, part, u_loc, v_dev, owned_mask
     return out
 
@@ -517,9 +562,14 @@ def main():
                 extra["libceed_matches_host_path"] = bool(np.array_equal(v_b200, v_host))
                 value, ms_per_step = dev_res["value"], dev_res["ms_per_step"]
                 config["boundary"] = "CeedOperatorApply on /gpu/cuda/b200 through libCEED's public C API (oracle/_ref/lib-cuda/libceed.so + plugin), eager launches"
+                cabi = e2e
                 e2e = dict(value=host_res["value"], unit="GDoF/s", h2d_bytes_per_step=8 * n_local, d2h_bytes_per_step=8 * n_local, ms_per_step=host_res["ms_per_step"],
                            mode="through libCEED: CeedVectorSetArray(u, HOST, USE_POINTER) -> CeedOperatorApply -> CeedVectorSyncArray(v, HOST), pinned host buffers, "
-                                "strictly serial", cabi=e2e)
+                                "strictly serial", serial_through_libceed=host_res["value"], cabi=cabi)
+                if cabi.get("pipelined_matches_serial") and cabi.get("pipelined_value", 0) > e2e["value"]:
+                    # headline = the software-pipelined figure (every step still moves its own u and v over PCIe inside the timed region,
+                    # results bitwise equal); the strictly serial through-libCEED figure stays next to it
+                    e2e.update(value=cabi["pipelined_value"], ms_per_step=cabi["pipelined_ms_per_step"], mode=cabi["pipelined_mode"])
                 extra["libceed_checksum_norm2"] = dev_res["checksum"]
                 try:
                     gen_res, v_gen = through_libceed("/gpu/cuda/gen", bp, p, nel, args.steps, args.warmup)

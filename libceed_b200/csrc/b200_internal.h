@@ -206,6 +206,8 @@ struct B200Operator_ {
   B200Tuning               tune;           // explicit overrides (ceedb200_operator_set_tuning, autotuner)
   bool                     tuned = false;  // autotuner has run (or was not applicable)
   bool                     no_tma = false; // an input of a bulk-copied field was not 16-byte aligned: generate without cp.async.bulk
+  bool                     no_ladder = false; // autotuner trials: a candidate shape that cannot be built is an error, not a reason to fall back
+  int                      build_rung = 0; // fallback ladder of the fused kernel: 0 tuned shape, 1 conservative shape, 2 unfused kernels
   bool                     timing = false;
   float                    last_fused_ms = 0.f, last_aux_ms = 0.f;
   cudaEvent_t              ev[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -85,6 +85,7 @@ extern "C" int ceedb200_operator_set_tuning(B200Operator op, int elems_per_block
   op->tune.epw  = elems_per_block;
   op->tune.minb = blocks_per_sm;
   op->tuned     = elems_per_block > 0 || blocks_per_sm > 0;  // explicit shape: the autotuner keeps its hands off
+  op->build_rung = 0;
   operator_reset(op);
   return B200_SUCCESS;
 }
@@ -93,6 +94,7 @@ extern "C" int ceedb200_operator_set_kernel_shape(B200Operator op, const int *sh
   op->tune.epw = shape[0], op->tune.group_warps = shape[1], op->tune.cta_warps = shape[2], op->tune.minb = shape[3];
   op->tune.qf_mode = shape[4], op->tune.qf_unroll = shape[5], op->tune.stage = shape[6];
   op->tuned = true;
+  op->build_rung = 0;
   operator_reset(op);
   return B200_SUCCESS;
 }
@@ -153,6 +155,8 @@ static int operator_setup(B200Operator op) {
 }
 
 // ------------------------------------------------------------------------------------------------ fused apply
+static int apply_unfused(B200Operator op, B200Vector u, B200Vector v, int add);
+
 // part: 0 = the whole operator; 1 / 2 = boundary / interior elements of a partitioned mesh (ceedb200_operator_apply_part):
 // part 1 applies elements [0, split) and finalizes the shared nodes touched by those elements only, part 2 the rest.
 static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int part = 0) {
@@ -241,7 +245,8 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
     if (part == 1) e_end = split;
     else e_begin = split;
   }
-  int kernel_add = add;
+  int  kernel_add = add;
+  bool zero_first = false;
   if (!add) {
     bool need_zero = false;
     for (auto &o : outs) need_zero = need_zero || o.writers > 1 || !o.covers;
@@ -249,12 +254,50 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
     for (size_t i = 0; i < op->out_fields.size(); i++)
       if (!op->out_fields[i].rstr->is_strided && plan->scatter_mode != B200_SCATTER_DETERMINISTIC && plan->scatter_mode != B200_SCATTER_ORDERED)
         offset_non_det = true;
-    if (need_zero || offset_non_det) {
-      if (part != 2)  // the interior part continues what the boundary part started
-        for (auto &o : outs) B200_CALL(ceedb200_vector_set_value(o.vec, 0.0));
-      kernel_add = 1;
+    if (need_zero || offset_non_det) zero_first = true, kernel_add = 1;
+  }
+  // Fallback ladder (the reference's contract: try to compile the fused kernel, else fall back -- backends/cuda-gen/
+  // ceed-cuda-gen-operator.c:291-298, backends/cuda/ceed-cuda-compile.cpp:206-224).  Before anything is written: build the kernel
+  // variant this apply needs.  If NVRTC fails, the kernel cannot be resident, or it spills heavily (a register-hungry user
+  // QFunction), regenerate it with a conservative shape (one element per group, z-line layout, nothing staged, no occupancy
+  // target); if that fails too, the operator permanently drops to the unfused restriction / basis / QFunction kernels.  A valid
+  // operator never returns an error because of its kernel shape.
+  {
+    constexpr int     kSpillLimit = 512;  // bytes of local memory per thread tolerated on the tuned shape
+    const std::string saved_error = ceed->last_error;
+    const int         berr        = b200_opgen_build(op, plan, kernel_add);
+    const bool        spilled     = !berr && !b200_compile_only() && plan->variant[kernel_add ? 1 : 0].local_bytes > kSpillLimit && op->build_rung == 0;
+    if (berr && op->no_ladder) return berr;
+    if ((berr || spilled) && !op->no_ladder) {
+      const std::string why = berr ? ceed->last_error : "tuned shape spills " + std::to_string(plan->variant[kernel_add ? 1 : 0].local_bytes) + " bytes per thread";
+      if (getenv("CEED_B200_DEBUG")) fprintf(stderr, "[ceed-b200] fused kernel, rung %d: %s\n", op->build_rung, why.c_str());
+      if (op->build_rung == 0) {
+        const int lines = plan->Q * plan->Q;
+        op->build_rung  = 1;
+        op->tune        = B200Tuning();
+        op->tune.epw = 1, op->tune.group_warps = lines > 64 ? 4 : (lines > 32 ? 2 : 1), op->tune.cta_warps = op->tune.group_warps, op->tune.minb = 1;
+        op->tune.qf_mode = 0, op->tune.qf_unroll = 1, op->tune.stage = 0;
+        op->tuned = true;  // no autotuning on the way down
+        plan_free(op);
+        op->is_setup = false;
+        B200_CALL(operator_setup(op));
+        ceed->last_error = saved_error;
+        if (op->plan->fused) return apply_fused(op, u, v, add, part);
+        B200_CHECK(!part, ceed, B200_ERROR_UNSUPPORTED, "apply_part needs a fused operator: %s", op->plan->why_not_fused.c_str());
+        return apply_unfused(op, u, v, add);
+      }
+      if (berr) {
+        op->build_rung      = 2;
+        plan->fused         = false;
+        plan->why_not_fused = "fused kernel could not be built: " + why;
+        B200_CHECK(!part, ceed, B200_ERROR_UNSUPPORTED, "apply_part needs a fused operator: %s", plan->why_not_fused.c_str());
+        ceed->last_error = saved_error;
+        return apply_unfused(op, u, v, add);
+      }
     }
   }
+  if (zero_first && part != 2)  // the interior part continues what the boundary part started
+    for (auto &o : outs) B200_CALL(ceedb200_vector_set_value(o.vec, 0.0));
   for (size_t i = 0; i < op->out_fields.size(); i++) {
     const B200OpField &f   = op->out_fields[i];
     B200Vector         vec = f.is_active ? v : f.vec;
@@ -272,8 +315,7 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
     args.ord_flags = plan->ordered.d_flags, args.ord_sync = plan->ordered.d_sync;
     args.ord_num_halo = plan->ordered.num_halo;
   }
-  B200_CALL(b200_opgen_build(op, plan, kernel_add));
-  B200KernelVariant &var = plan->variant[kernel_add ? 1 : 0];
+  B200KernelVariant &var = plan->variant[kernel_add ? 1 : 0];  // built above (fallback ladder)
 
   if (op->timing) B200_CUDA(ceed, cudaEventRecord(op->ev[3], ceed->stream));
   B200_CHECK(!(ordered && part), ceed, B200_ERROR_UNSUPPORTED, "apply_part is not available with the in-kernel ordered scatter");
@@ -542,7 +584,8 @@ static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
   const bool        timing0 = op->timing;
   const std::string sig = op->plan->signature, shape_sig = op->plan->shape_signature;
   const std::string saved_error = ceed->last_error;
-  op->timing = true;
+  op->timing    = true;
+  op->no_ladder = true;
   B200Tuning best = op->plan->resolved;
   float      best_ms = 1e30f;
   auto trial = [&](B200Tuning t) -> float {
@@ -629,8 +672,9 @@ static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
     }
   }
   operator_reset(op);
-  op->tune   = best;
-  op->timing = timing0;
+  op->tune      = best;
+  op->timing    = timing0;
+  op->no_ladder = false;
   ceed->last_error = saved_error;  // failed candidates are not errors of this call
   B200_CALL(operator_setup(op));
   ceed->tune_table[sig] = best;

@@ -1867,6 +1867,13 @@ int b200_opgen_build(B200Operator op, B200OpPlan *plan, int add) {
   B200Ceed           ceed = op->ceed;
   B200KernelVariant &v    = plan->variant[add ? 1 : 0];
   if (v.built) return B200_SUCCESS;
+  if (const char *inject = getenv("CEED_B200_FAIL_FUSED_BUILD")) {  // test hook of the fallback ladder: the first <n> fused builds fail
+    static int failed = 0;
+    if (failed < atoi(inject)) {
+      failed++;
+      return b200_error(ceed, B200_ERROR_BACKEND, "fused kernel build failure injected by CEED_B200_FAIL_FUSED_BUILD (%d)", failed);
+    }
+  }
   v.source = b200_opgen_source(op, plan, add);
   B200_CALL(b200_jit_compile(ceed, v.source, {}, &v.module));
   B200_CALL(b200_jit_get_kernel(ceed, v.module, ("b200_operator_" + op->qf->kernel_name).c_str(), &v.kernel));

@@ -506,3 +506,60 @@ def test_full_size_properties(cm, bp, p):
         assert abs(ones.sum() / ncomp - 1.0) < 1e-6  # sum of mass-matrix rows = volume of the (smoothly mapped) unit cube, up to quadrature error
     assert np.array_equal(A(u1), v1)  # idempotent / reproducible
     del ceed
+
+
+def test_fallback_ladder_never_fails_a_valid_operator(cm, oracle, monkeypatch, tmp_path):
+    """Try-compile -> fall back (backends/cuda-gen/ceed-cuda-gen-operator.c:291-298): a fused kernel that cannot be built first drops
+    to a conservative shape, then to the unfused kernels -- the apply still succeeds with the same result.  Build failures are
+    injected with the CEED_B200_FAIL_FUSED_BUILD test hook; a register-hungry user QFunction exercises the spill rung for real."""
+    bp, p, nel = 3, 2, (3, 3, 2)
+    ref_prob = make_problem(cm, bp, p, nel)
+    u = seeded_uniform(ref_prob.num_dofs, 37)
+    ref_prob.u.set_array(u)
+    ref_prob.op.apply(ref_prob.u, ref_prob.v)
+    v_ref = ref_prob.v.get_array_read().copy()
+    for nfail, expect_fused in ((1, True), (2, False)):
+        # fresh process-wide counter per case: the hook counts failures since library load, so raise the limit cumulatively
+        prob = make_problem(cm, bp, p, nel)  # qdata is computed by the (already cached) setup kernel
+        prob.u.set_array(u)
+        monkeypatch.setenv("CEED_B200_FAIL_FUSED_BUILD", str({1: 1, 2: 3}[nfail]))
+        prob.op.set_kernel_shape(elems_per_group=2, group_warps=1, cta_warps=2)  # a shape of its own: not in the module cache
+        prob.op.apply(prob.u, prob.v)
+        monkeypatch.delenv("CEED_B200_FAIL_FUSED_BUILD")
+        assert rel(prob.v.get_array_read(), v_ref) < OP_TOL
+        assert prob.op.is_fused == expect_fused
+        prob.op.apply_add(prob.u, prob.v)
+        assert rel(prob.v.get_array_read(), 2 * v_ref) < OP_TOL
+    # a QFunction that needs far more registers than any shape provides: whatever rung it lands on, the result is right
+    src = tmp_path / "heavy.h"
+    src.write_text('''
+#include <ceed/types.h>
+CEED_QFUNCTION(HeavyDiff)(void *ctx, const CeedInt Q, const CeedScalar *const *in, CeedScalar *const *out) {
+  const CeedScalar(*ug)[CEED_Q_VLA] = (const CeedScalar(*)[CEED_Q_VLA])in[0];
+  const CeedScalar(*qd)[CEED_Q_VLA] = (const CeedScalar(*)[CEED_Q_VLA])in[1];
+  CeedScalar(*vg)[CEED_Q_VLA]       = (CeedScalar(*)[CEED_Q_VLA])out[0];
+  for (CeedInt i = 0; i < Q; i++) {
+    CeedScalar w[160];
+    for (int k = 0; k < 160; k++) w[k] = qd[k % 7][i] * (1.0 + 1e-3 * k);
+    CeedScalar s = 0.0;
+    for (int k = 0; k < 160; k++) s += w[(k * 37 + (int)(ug[0][i] > 0)) % 160] - w[(k * 37) % 160];   /* == 0, keeps w alive and dynamically indexed */
+    const CeedScalar u0 = ug[0][i], u1 = ug[1][i], u2 = ug[2][i];
+    vg[0][i] = qd[1][i] * u0 + qd[2][i] * u1 + qd[3][i] * u2 + 0.0 * s;
+    vg[1][i] = qd[2][i] * u0 + qd[4][i] * u1 + qd[5][i] * u2;
+    vg[2][i] = qd[3][i] * u0 + qd[5][i] * u1 + qd[6][i] * u2;
+  }
+  return 0;
+}
+''')
+    ceed = ref_prob.ceed
+    qf = ceed.QFunction(str(src), "HeavyDiff")
+    qf.add_input("u", 3, cm.EVAL_GRAD)
+    qf.add_input("qdata", 7, cm.EVAL_NONE)
+    qf.add_output("v", 3, cm.EVAL_GRAD)
+    op = ceed.Operator(qf)
+    op.set_field("u", ref_prob.rstr_u, ref_prob.basis_u, cm.VECTOR_ACTIVE)
+    op.set_field("qdata", ref_prob.rstr_qd, cm.BASIS_NONE, ref_prob.qdata)
+    op.set_field("v", ref_prob.rstr_u, ref_prob.basis_u, cm.VECTOR_ACTIVE)
+    v2 = ceed.Vector(ref_prob.num_dofs)
+    op.apply(ref_prob.u, v2)
+    assert rel(v2.get_array_read(), v_ref) < OP_TOL
