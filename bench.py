@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--no-scaling-case", action="store_true", help="skip the second timed case (BP3 p=6, 50M DoFs per GPU: BASELINE configs[4])")
     ap.add_argument("--scaling-dofs", type=float, default=50e6, help="DoFs per GPU of the second timed case")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: apply, then exchange (no boundary-first overlap)")
+    ap.add_argument("--timeline", action="store_true", help="N > 1: add per-rank phase timestamps of the overlapped step (`timeline_ms`)")
     ap.add_argument("--transport", default="auto", choices=["auto", "peer", "nccl"], help="N > 1: interface exchange over NVLink peer memory or NCCL send/recv")
     return ap.parse_args()
 
@@ -326,8 +327,13 @@ def run_case(args, ceed, cm, bp, p, dofs, rank, world, local_rank, dev, steps, w
             ms = float(t.item())
         return ms / nsteps
 
-    out["sampler_fn"] = step
     ms_eager = timed(step, steps)
+    if dop is not None and args.timeline:
+        # per-rank event timeline of the overlapped step, gathered on rank 0
+        tl = dop.record_timeline()
+        rows = [None] * world
+        dist.all_gather_object(rows, tl)
+        out["timeline_ms"] = rows
     out.update(ms_per_step=ms_eager, value=total_dofs / ms_eager / 1e6, total_dofs=total_dofs, n_local=n_local, launches_per_step=launches_per_step)
     # verified checksum of the distributed result: ||v||_2 over owned DoFs
     vv = v_dev if owned_mask is None else v_dev * owned_mask
@@ -536,6 +542,8 @@ def main():
                  graph_replay_ms_per_step=case.get("graph_replay_ms_per_step"), checksum_norm2=case["checksum_norm2"])
     if world > 1:
         extra.update(transport=case["transport"], overlap=case["overlap"])
+        if "timeline_ms" in case:
+            extra["timeline_ms"] = case["timeline_ms"]
         # verified checksum: the same operator on the whole global mesh on ONE GPU (rank 0)
         if rank == 0 and total_dofs <= 110e6:
             try:
@@ -604,7 +612,7 @@ def main():
             scaling_case = dict(workload=f"BP3 diffusion p=6 q=8, {args.scaling_dofs / 1e6:.0f}M DoFs per GPU (weak scaling)", value=sc["value"], unit="GDoF/s",
                                 ms_per_step=sc["ms_per_step"], total_dofs=sc["total_dofs"], kernel_ms=k, kernel_share_of_step=k / sc["ms_per_step"],
                                 roofline_frac=sc["alg_bytes"] / (k * 1e-3) / 1e9 / peak, checksum_norm2=sc["checksum_norm2"], transport=sc.get("transport"),
-                                overlap=sc.get("overlap"))
+                                overlap=sc.get("overlap"), timeline_ms=sc.get("timeline_ms"))
             if world > 1 and rank == 0 and sc["total_dofs"] <= 110e6:
                 ref = verify_against_single_gpu(ceed, cm, 3, 6, sc, dev)
                 scaling_case["checksum_single_gpu_norm2"] = ref

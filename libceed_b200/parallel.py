@@ -255,6 +255,7 @@ class DistributedOperator:
                 self.exchange = InterfaceExchange(part, ncomp, self.prob.num_nodes, device, ceed=ceed, group=group)
         self.comm_stream = torch.cuda.Stream(device=device, priority=-1) if (overlap and self.exchange is not None) else None
         self.ev_boundary, self.ev_comm = torch.cuda.Event(), torch.cuda.Event()
+        self.timeline = None  # set to a dict of timing events by record_timeline()
 
     @property
     def transport(self):
@@ -273,12 +274,41 @@ class DistributedOperator:
             self.exchange.end(v_t)
         else:
             main = torch.cuda.current_stream(self.device)
+            tl = self.timeline
+            if tl is not None:
+                tl["start"].record(main)
             prob.op.apply_part(u_vec, v_vec, 1)        # boundary elements: interface values are complete after this
             self.ev_boundary.record(main)
+            if tl is not None:
+                tl["boundary_done"].record(main)
             self.comm_stream.wait_event(self.ev_boundary)
             self.exchange.begin(v_t, stream=self.comm_stream)
             self.ev_comm.record(self.comm_stream)
+            if tl is not None:
+                tl["send_done"].record(self.comm_stream)
             prob.op.apply_part(u_vec, v_vec, 2)        # interior elements, concurrently with the exchange
+            if tl is not None:
+                tl["interior_done"].record(main)
             main.wait_event(self.ev_comm)
             self.exchange.end(v_t)
+            if tl is not None:
+                tl["sum_done"].record(main)
         return v_t
+
+    def record_timeline(self, steps=5):
+        """Per-phase device timestamps (ms since the start of the step, median over `steps` steps) of the overlapped step on this
+        rank: end of the boundary elements (+ their finalize), end of the interface send on the communication stream, end of the
+        interior elements, end of the rank-ordered sum.  send_done < interior_done means the exchange was hidden."""
+        if not (self.overlap and self.exchange is not None):
+            return None
+        names = ("start", "boundary_done", "send_done", "interior_done", "sum_done")
+        rows = []
+        for _ in range(steps):
+            self.timeline = {n: torch.cuda.Event(enable_timing=True) for n in names}
+            torch.cuda.synchronize(self.device)
+            self.apply()
+            torch.cuda.synchronize(self.device)
+            rows.append([self.timeline["start"].elapsed_time(self.timeline[n]) for n in names[1:]])
+        self.timeline = None
+        med = np.median(np.array(rows), axis=0)
+        return dict(zip(names[1:], [float(x) for x in med]))

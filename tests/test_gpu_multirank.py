@@ -83,4 +83,4 @@ def test_partitioned_apply_on_gpus(tmp_path, world, bp, p, n_global, cg):
     if cg:
         for d in ranks:
             assert d["cg_r"] < 1e-8 * d["cg_r0"], (float(d["cg_r0"]), float(d["cg_r"]))
-            assert np.abs(d["cg_x"] - d["u"]).max() < 1e-6 * np.abs(d["u"]).max()
+            assert np.abs(d["cg_x"] - d["u"]).max() < 1e-5 * np.abs(d["u"]).max()
