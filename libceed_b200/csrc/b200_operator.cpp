@@ -612,6 +612,7 @@ static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
   for (auto &g : op->plan->in_groups) xline_ok = xline_ok && !g.use_grad;
   for (auto &g : op->plan->out_groups) xline_ok = xline_ok && !g.use_grad;
   // 1. group width / warps per CTA x QFunction layout x plane layout (elements per group and occupancy target left to the heuristics)
+  // (16-wide rows for Q = 9, 10 exist and are tested, but need 160-lane groups to pay: measured 2-3x slower with 128 lanes)
   bool swz_ok = op->plan->Q <= 8 && op->plan->scatter_mode != B200_SCATTER_ORDERED;
   for (auto &b : op->plan->bases) swz_ok = swz_ok && b.P <= 8;
   const bool full = ceed->autotune >= 3;  // level 3: also the rarely winning point-pair layout

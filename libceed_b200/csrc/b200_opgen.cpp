@@ -36,6 +36,9 @@ namespace {
 int odd_pad(int n) { return (n % 2) ? n : n + 1; }
 // smallest m >= n with m = 8 (mod 16): the stride between z-layers of the conflict-free ("swizzled") shared-memory layouts
 int pad8(int n) { return n <= 8 ? 8 : ((n - 8 + 15) / 16) * 16 + 8; }
+// Strides of the swizzled layouts for row width w (8: Q, P <= 8; 16: larger).  With w = 16 a half-warp is exactly one row, so the
+// z-strides need no residue and only the quadrature planes widen (pitch 16).
+int swz_sz(int w, int n) { return w == 8 ? pad8(n) : n; }
 
 string hexd(double v) {
   char buf[64];
@@ -242,16 +245,23 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
   // a third of its wavefronts (ncu, profiles/r01_ncu_full_summary.txt).
   {
     const int stage_req = tn.stage >= 0 ? tn.stage : 1;
-    bool      ok        = (stage_req & 256) && Q <= 8 && !getenv("CEED_B200_BLOCK_MODE") && !(tn.qf_mode == 1 || tn.qf_mode == 2) && !(stage_req & 16) &&
+    bool      ok        = (stage_req & 256) && Q <= 16 && !getenv("CEED_B200_BLOCK_MODE") && !(tn.qf_mode == 1 || tn.qf_mode == 2) && !(stage_req & 16) &&
               plan->scatter_mode != B200_SCATTER_ORDERED;
-    for (auto &b : plan->bases) ok = ok && b.P <= 8;
-    plan->swz = ok;
+    int w = Q <= 8 ? 8 : 16;
+    for (auto &b : plan->bases) {
+      ok = ok && b.P <= 16;
+      if (b.P > 8) w = 16;
+    }
+    plan->swz   = ok;
+    plan->swz_w = ok ? w : 0;
   }
   {
-    int plane_size = plan->swz ? Q * pad8(Q * 8) : Q * Q * plan->Qs;
+    const int w          = plan->swz_w;
+    int       plane_size = plan->swz ? Q * swz_sz(w, Q * w) : Q * Q * plan->Qs;
     for (auto &b : plan->bases) {
-      plane_size = std::max(plane_size, Q * (plan->swz ? pad8(b.P * b.P) : b.P * b.P));
-      plane_size = std::max(plane_size, Q * (plan->swz ? pad8(Q * odd_pad(b.P)) : Q * odd_pad(b.P)));
+      const int wp = b.P <= 8 ? 8 : 16;  // lane width of the node-indexed (y) stages of this basis
+      plane_size   = std::max(plane_size, Q * (plan->swz ? swz_sz(wp, b.P * b.P) : b.P * b.P));
+      plane_size   = std::max(plane_size, Q * (plan->swz ? swz_sz(wp, Q * odd_pad(b.P)) : Q * odd_pad(b.P)));
     }
     if (plan->swz) plane_size = (plane_size + 15) / 16 * 16;  // element / plane strides keep the bank residues
     plan->plane_size = plane_size;
@@ -442,9 +452,10 @@ struct Gen {
   // quadrature index with extent LQ; swizzled: QP = LQ = 8 and the x index of a point is XOR-ed with its y index
   bool         swz = false;
   int          QP = 0, SZ = 0, LQ = 0;
-  int          lp(const B200GenBasis &b) const { return swz ? 8 : b.P; }                                     // lane extent of the fastest node index
-  int          sz1(const B200GenBasis &b) const { return swz ? pad8(b.P * b.P) : b.P * b.P; }                // z-stride of T1 [qz][j][i]
-  int          sz2(const B200GenBasis &b) const { return swz ? pad8(Q * odd_pad(b.P)) : Q * odd_pad(b.P); }  // z-stride of T2 [qz][qy][i]
+  int          W = 0;                                                                                        // row width of the swizzled layouts (8 or 16)
+  int          lp(const B200GenBasis &b) const { return swz ? (b.P <= 8 ? 8 : 16) : b.P; }                   // lane extent of the fastest node index
+  int          sz1(const B200GenBasis &b) const { return swz ? swz_sz(lp(b), b.P * b.P) : b.P * b.P; }       // z-stride of T1 [qz][j][i]
+  int          sz2(const B200GenBasis &b) const { return swz ? swz_sz(lp(b), Q * odd_pad(b.P)) : Q * odd_pad(b.P); }  // z-stride of T2 [qz][qy][i]
   string       xq(const string &x, const string &y) const { return swz ? "((" + x + ") ^ (" + y + "))" : "(" + x + ")"; }
   string       xq(int x, const string &y) const { return swz ? "(" + std::to_string(x) + " ^ (" + y + "))" : std::to_string(x); }
   string       smw_expr() const {
@@ -1679,9 +1690,10 @@ struct Gen {
     else SYNC = "asm volatile(\"bar.sync %0, " + std::to_string(TS) + ";\" ::\"r\"((int)(threadIdx.x / " + std::to_string(TS) + ") + 1) : \"memory\");";
     S   = plan->plane_size;
     swz = plan->swz;
-    QP  = swz ? 8 : Qs;
-    SZ  = swz ? pad8(Q * 8) : Q * Qs;
-    LQ  = swz ? 8 : Q;
+    W   = plan->swz_w;
+    QP  = swz ? W : Qs;
+    SZ  = swz ? swz_sz(W, Q * W) : Q * Qs;
+    LQ  = swz ? W : Q;
     // quadrature data is read exactly once per apply: mark it evict-first so that u, v, the halo buffer and the offsets keep the L2
     if (plan->stage_mask & 128) QLD = "__ldcs";
     emit_header();

@@ -29,6 +29,8 @@ def parts(P, Q, Qs, Ps, Sz1, Sz2, SZ, collocated, TS):
         c1 += cost_stage(P * P, TS, [(lambda t, q=q: q * Sz1 + t, 2) for q in range(Q)])
     else:
         c3 += cost_stage(P * P, TS, [(lambda t, k=k: k * SZ + (t // P) * Qs + t % P, 2) for k in range(P)])
+        dr = lambda t: (t % Q, t // Q)  # d/dx on rows: read the values, write the derivative (and the transpose)
+        c3 += 2 * cost_stage(Q * Q, TS, [(lambda t, q=q: dr(t)[1] * SZ + dr(t)[0] * Qs + q, 2) for q in range(Q)])
     d = lambda t: (t % Q, t // Q)
     c3 += 2 * cost_stage(Q * Q, TS, [(lambda t, m=m: d(t)[1] * SZ + m * Qs + d(t)[0], 2) for m in range(Q)])
     c3 += cost_stage(Q * Q, TS, [(lambda t, m=m: m * SZ + d(t)[1] * Qs + d(t)[0], 6) for m in range(Q)])

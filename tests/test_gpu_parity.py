@@ -563,3 +563,27 @@ CEED_QFUNCTION(HeavyDiff)(void *ctx, const CeedInt Q, const CeedScalar *const *i
     v2 = ceed.Vector(ref_prob.num_dofs)
     op.apply(ref_prob.u, v2)
     assert rel(v2.get_array_read(), v_ref) < OP_TOL
+
+
+@pytest.mark.parametrize("bp,p,nel", [(3, 7, (2, 1, 1)), (3, 8, (1, 1, 2)), (1, 7, (1, 2, 1)), (4, 7, (1, 1, 1))])
+def test_swizzled_layout_row_width_16(cm, oracle, monkeypatch, bp, p, nel):
+    """Q = 9, 10: the conflict-free swizzled planes with 16-wide rows (stage bit 256) against the oracle and the padded layout."""
+    monkeypatch.setenv("CEED_B200_NO_TUNE_TABLE", "1")
+    prob = make_problem(cm, bp, p, nel)
+    u = seeded_uniform(prob.num_dofs, 43)
+    prob.u.set_array(u)
+    qd = oracle.bp_qdata(bp, p, prob.offsets, prob.coords)
+    ref = oracle.bp_apply(bp, p, prob.offsets, prob.num_nodes, qd, u)
+    prob.op.apply(prob.u, prob.v)
+    v0 = prob.v.get_array_read().copy()
+    assert rel(v0, ref) < OP_TOL
+    for shape in (dict(stage_mask=257), dict(stage_mask=257, group_warps=4, cta_warps=4), dict(stage_mask=265, group_warps=2, cta_warps=2),
+                  dict(stage_mask=256, group_warps=1, cta_warps=2)):
+        prob.op.set_kernel_shape(**shape)
+        prob.v.set_value(-7.0)
+        prob.op.apply(prob.u, prob.v)
+        assert prob.op.is_fused and prob.op.get_kernel_shape()["stage_mask"] == shape["stage_mask"]
+        assert rel(prob.v.get_array_read(), ref) < OP_TOL, shape
+        assert rel(prob.v.get_array_read(), v0) < 1e-13, shape
+        prob.op.apply_add(prob.u, prob.v)
+        assert rel(prob.v.get_array_read(), 2 * ref) < OP_TOL, shape
