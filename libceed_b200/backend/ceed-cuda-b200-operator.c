@@ -293,7 +293,8 @@ static int CeedOperatorLinearAssembleQFunctionCore_B200(CeedOperator op, bool bu
       if (vec == CEED_VECTOR_ACTIVE && r != CEED_ELEMRESTRICTION_NONE) CeedCallBackend(CeedElemRestrictionGetNumComponents(r, &num_comp));
       CeedCallBackend(CeedVectorDestroy(&vec));
       CeedCallBackend(CeedElemRestrictionDestroy(&r));
-      CeedCheck(num_comp == 1, ceed, CEED_ERROR_UNSUPPORTED, "Backend does not implement assembly of operators with multi-component active fields");
+      CeedCheck(num_comp == 1 || getenv("CEED_B200_ASSEMBLE_MULTICOMP"), ceed, CEED_ERROR_UNSUPPORTED,
+                "Backend does not implement assembly of operators with multi-component active fields");
     }
   }
   CeedCallB200(ceed, core, ceedb200_operator_assemble_qfunction_sizes(impl->core, &num_elem, &num_qpts, &size_in, &size_out));

@@ -182,20 +182,33 @@ static int CeedQFunctionApply_B200(CeedQFunction qf, CeedInt Q, CeedVector *U, C
   CeedCallBackend(CeedGetCore_B200(ceed, &core));
   CeedCallBackend(CeedQFunctionGetCore_B200(qf, &core_qf));
   CeedCallBackend(CeedQFunctionGetNumArgs(qf, &num_in, &num_out));
-  for (CeedInt i = 0; i < num_in; i++) CeedCallBackend(CeedVectorGetArrayRead(U[i], CEED_MEM_DEVICE, &d_in[i]));
-  for (CeedInt i = 0; i < num_out; i++) CeedCallBackend(CeedVectorGetArrayWrite(V[i], CEED_MEM_DEVICE, &d_out[i]));
   {
-    void *held;
-    int   ierr;
+    // the first error is recorded; every array and the context acquired before it are restored before it is reported
+    int     status = CEED_ERROR_SUCCESS, ierr2;
+    CeedInt got_in = 0, got_out = 0;
+    void   *held = NULL;
+    bool    ctx_held = false;
 
-    CeedCallBackend(CeedQFunctionContextAcquire_B200(qf, &held));
-    ierr = ceedb200_qfunction_apply_ptr(core_qf, Q, d_in, d_out);
-    CeedCallBackend(CeedQFunctionContextRelease_B200(qf, &held));
-    if (ierr) return CeedError(ceed, CEED_ERROR_BACKEND, "%s", ceedb200_last_error(core));
+    for (CeedInt i = 0; i < num_in && !status; i++) {
+      status = CeedVectorGetArrayRead(U[i], CEED_MEM_DEVICE, &d_in[i]);
+      if (!status) got_in = i + 1;
+    }
+    for (CeedInt i = 0; i < num_out && !status; i++) {
+      status = CeedVectorGetArrayWrite(V[i], CEED_MEM_DEVICE, &d_out[i]);
+      if (!status) got_out = i + 1;
+    }
+    if (!status) {
+      status   = CeedQFunctionContextAcquire_B200(qf, &held);
+      ctx_held = !status;
+    }
+    if (!status && ceedb200_qfunction_apply_ptr(core_qf, Q, d_in, d_out)) status = CeedError(ceed, CEED_ERROR_BACKEND, "%s", ceedb200_last_error(core));
+    if (ctx_held && (ierr2 = CeedQFunctionContextRelease_B200(qf, &held)) && !status) status = ierr2;
+    for (CeedInt i = 0; i < got_in; i++)
+      if ((ierr2 = CeedVectorRestoreArrayRead(U[i], &d_in[i])) && !status) status = ierr2;
+    for (CeedInt i = 0; i < got_out; i++)
+      if ((ierr2 = CeedVectorRestoreArray(V[i], &d_out[i])) && !status) status = ierr2;
+    return status;
   }
-  for (CeedInt i = 0; i < num_in; i++) CeedCallBackend(CeedVectorRestoreArrayRead(U[i], &d_in[i]));
-  for (CeedInt i = 0; i < num_out; i++) CeedCallBackend(CeedVectorRestoreArray(V[i], &d_out[i]));
-  return CEED_ERROR_SUCCESS;
 }
 
 static int CeedQFunctionDestroy_B200(CeedQFunction qf) {

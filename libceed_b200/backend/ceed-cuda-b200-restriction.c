@@ -1,5 +1,6 @@
 // ceed-cuda-b200-restriction.c -- CeedElemRestriction slots -> ceedb200_restriction_*
 // (replaces the wiring of backends/cuda-ref/ceed-cuda-ref-restriction.c:498-661; standard and strided restrictions)
+#include <stdbool.h>
 #include <stdlib.h>
 
 #include "ceed-cuda-b200.h"
@@ -13,14 +14,24 @@ static int CeedElemRestrictionApply_B200(CeedElemRestriction rstr, CeedTranspose
 
   CeedCallBackend(CeedGetCore_B200(ceed, &core));
   CeedCallBackend(CeedElemRestrictionGetData(rstr, &impl));
-  // device arrays through the interface, so vectors of any CUDA-family backend are accepted
-  CeedCallBackend(CeedVectorGetArrayRead(u, CEED_MEM_DEVICE, &d_u));
-  if (t_mode == CEED_TRANSPOSE) CeedCallBackend(CeedVectorGetArray(v, CEED_MEM_DEVICE, &d_v));  // sums into v
-  else CeedCallBackend(CeedVectorGetArrayWrite(v, CEED_MEM_DEVICE, &d_v));                      // overwrites the E-vector
-  CeedCallB200(ceed, core, ceedb200_restriction_apply_ptr(impl->core, t_mode, d_u, d_v));
-  CeedCallBackend(CeedVectorRestoreArrayRead(u, &d_u));
-  CeedCallBackend(CeedVectorRestoreArray(v, &d_v));
-  return CEED_ERROR_SUCCESS;
+  // device arrays through the interface, so vectors of any CUDA-family backend are accepted; whatever was acquired is restored
+  // on every path (libCEED's access locks), the first error is reported
+  {
+    int  status, ierr2;
+    bool got_u = false, got_v = false;
+
+    status = CeedVectorGetArrayRead(u, CEED_MEM_DEVICE, &d_u);
+    got_u  = !status;
+    if (!status) {
+      status = t_mode == CEED_TRANSPOSE ? CeedVectorGetArray(v, CEED_MEM_DEVICE, &d_v)        // sums into v
+                                        : CeedVectorGetArrayWrite(v, CEED_MEM_DEVICE, &d_v);  // overwrites the E-vector
+      got_v  = !status;
+    }
+    if (!status && ceedb200_restriction_apply_ptr(impl->core, t_mode, d_u, d_v)) status = CeedError(ceed, CEED_ERROR_BACKEND, "%s", ceedb200_last_error(core));
+    if (got_u && (ierr2 = CeedVectorRestoreArrayRead(u, &d_u)) && !status) status = ierr2;
+    if (got_v && (ierr2 = CeedVectorRestoreArray(v, &d_v)) && !status) status = ierr2;
+    return status;
+  }
 }
 
 static int CeedElemRestrictionGetOffsets_B200(CeedElemRestriction rstr, CeedMemType mem_type, const CeedInt **offsets) {

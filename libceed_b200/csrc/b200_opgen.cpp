@@ -360,7 +360,7 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     plan->stage_mask = stage;
     // warps that share one element group (1, 2 or 4): more resident warps per byte of shared memory for large Q
     int gw = tn.group_warps;
-    if (gw != 1 && gw != 2 && gw != 4) gw = 1;
+    if (gw < 1 || gw > 8) gw = 1;  // any width up to 8 warps (3 and 5 fit Q = 9, 10: 81 lines on 96 lanes, 160 swizzled tasks on 160)
     plan->group_warps = gw;
     plan->stage_mask  = stage;
     const int lanes = 32 * gw;
@@ -1682,7 +1682,7 @@ struct Gen {
     NT = plan->threads;
     warp_mode = plan->warp_mode;
     TS        = warp_mode ? 32 * plan->group_warps : NT;
-    TID       = warp_mode ? "(threadIdx.x & " + std::to_string(TS - 1) + ")" : "threadIdx.x";
+    TID       = !warp_mode ? "threadIdx.x" : ((TS & (TS - 1)) == 0 ? "(threadIdx.x & " + std::to_string(TS - 1) + ")" : "(threadIdx.x % " + std::to_string(TS) + ")");
     SMBASE    = warp_mode ? "smw" : "sm";
     // a group of one warp synchronises with __syncwarp(); wider groups meet at their own named barrier (ids 1..15)
     if (!warp_mode || NT == TS) SYNC = "__syncthreads();";

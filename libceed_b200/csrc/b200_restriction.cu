@@ -10,7 +10,8 @@
 // In addition, an "owner/halo" decomposition of the transpose is built for the fused operator kernel (see
 // b200_restriction_build_owner): the first E-entry of every L-node owns the store, the remaining entries go through
 // a compact halo buffer that a finalize kernel folds in, again in ascending E-order.
-// All index arithmetic on E-/Q-sized ranges is 64-bit (CeedInt overflows at 100M DoFs).
+// Index arithmetic on E-/Q-sized ranges in the kernels is 64-bit (CeedInt overflows at 100M DoFs); the setup
+// tables (CSR rows, scatter targets, halo slots) hold E-entry indices in int32 and refuse restrictions with >= 2^31 - 1 entries.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -195,6 +196,13 @@ extern "C" int ceedb200_restriction_destroy(B200Restriction r) {
   return B200_SUCCESS;
 }
 
+// The setup tables hold E-entry indices, CSR row starts and halo slots in int32.
+static int check_table_range(B200Restriction r) {
+  B200_CHECK((int64_t)r->num_elem * r->elem_size < INT32_MAX, r->ceed, B200_ERROR_UNSUPPORTED,
+             "Backend does not implement restrictions with more than 2^31 - 1 E-vector entries (%lld)", (long long)r->num_elem * r->elem_size);
+  return B200_SUCCESS;
+}
+
 // Host-side transpose CSR (counting sort by L-index; stable => ascending E-order inside each row).
 struct HostTranspose {
   std::vector<int32_t> lvec_indices, t_offsets, t_indices;
@@ -228,6 +236,7 @@ static void build_host_transpose(B200Restriction r, HostTranspose &t) {
 int b200_restriction_build_transpose(B200Restriction r) {
   if (r->transpose_built || r->is_strided) return B200_SUCCESS;
   B200Ceed      ceed = r->ceed;
+  B200_CALL(check_table_range(r));  // the CSR tables hold E-entry indices in int32
   HostTranspose t;
   build_host_transpose(r, t);
   r->num_nodes = (int64_t)t.lvec_indices.size();
@@ -250,12 +259,11 @@ int b200_restriction_build_transpose(B200Restriction r) {
 int b200_restriction_build_owner(B200Restriction r) {
   if (r->owner_built || r->is_strided) return B200_SUCCESS;
   B200Ceed      ceed = r->ceed;
+  B200_CALL(check_table_range(r));
   HostTranspose t;
   build_host_transpose(r, t);
   const int64_t        n         = (int64_t)r->num_elem * r->elem_size;
   const int64_t        num_nodes = (int64_t)t.lvec_indices.size();
-  B200_CHECK(n < INT32_MAX, ceed, B200_ERROR_UNSUPPORTED, "Backend does not implement restrictions with more than 2^31 - 1 E-vector entries (%lld)",
-             (long long)n);
   std::vector<int32_t> tgt(n), halo_node, halo_ptr;
   int64_t              slot = 0;
   // two passes over the shared nodes: first those touched by boundary elements only (see split_elem), then the rest
@@ -299,11 +307,13 @@ __global__ void k_ordered_write_ids(double *__restrict__ halo, const int32_t *__
 
 int b200_restriction_build_ordered(B200Restriction r, int group_elems, B200OrderedScatter *out) {
   B200Ceed      ceed = r->ceed;
+  B200_CALL(check_table_range(r));
   HostTranspose t;
   build_host_transpose(r, t);
   const int64_t n          = (int64_t)r->num_elem * r->elem_size;
   const int64_t num_nodes  = (int64_t)t.lvec_indices.size();
   const int64_t num_groups = ((int64_t)r->num_elem + group_elems - 1) / group_elems;
+
   int64_t       num_halo = 0, num_shared = 0;
   int32_t       max_cnt = 0;
   for (int64_t row = 0; row < num_nodes; row++) {

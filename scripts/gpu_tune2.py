@@ -125,6 +125,16 @@ elif mode == "swz":
                 continue
             env = {"CEED_B200_STAGE": "257", "CEED_B200_GROUP_WARPS": str(gw), "CEED_B200_WARPS": str(gw * groups), "CEED_B200_MINB": "0"}
             run(f"swz gw={gw} groups={groups} epw={epw}", env, epb=epw)
+elif mode == "gw35":
+    # odd group widths (3 / 5 warps) for Q = 9, 10, padded and swizzled (16-wide rows) planes
+    run("table", {})
+    for gw in (3, 5, 6):
+        for groups in (1, 2, 3):
+            for stage in (1, 257):
+                for epw in (1, 2):
+                    env = {"CEED_B200_STAGE": str(stage), "CEED_B200_GROUP_WARPS": str(gw), "CEED_B200_WARPS": str(gw * groups), "CEED_B200_MINB": "0",
+                           "CEED_B200_QF_POINTWISE": "0"}
+                    run(f"stage={stage} gw={gw} groups={groups} epw={epw}", env, epb=epw)
 elif mode == "pf":
     # bulk L2 prefetch of the next batch's quadrature data (stage bit 64) on top of the table shape
     run("table", {})

@@ -41,7 +41,7 @@ def main():
     u_loc = np.concatenate([u_glob[gid + c * n_glob] for c in range(ncomp)])
     res = {}
     for overlap in (False, True):
-        dop = DistributedOperator(ceed, bp, p, part, dev, overlap=overlap)
+        dop = DistributedOperator(ceed, bp, p, part, dev, overlap=overlap, transport=os.environ.get("CEED_B200_TEST_TRANSPORT", "auto"))
         dop.u_t.copy_(torch.from_numpy(u_loc))
         dop.apply()
         torch.cuda.synchronize()
