@@ -275,28 +275,6 @@ static int CeedOperatorLinearAssembleQFunctionCore_B200(CeedOperator op, bool bu
   CeedCallBackend(CeedOperatorSetup_B200(op));
   CeedCallBackend(CeedOperatorGetData(op, &impl));
   CeedCheck(!impl->use_fallback, ceed, CEED_ERROR_UNSUPPORTED, "Backend does not implement QFunction assembly with objects of other backends");
-  {
-    // The interface's host-side diagonal / full assembly built on top of this slot writes element matrices in the CPU E-vector
-    // layout [elem][comp][node] (interface/ceed-preconditioning.c:361-377); this backend's E-vectors are [comp][elem][node] like
-    // the reference GPU backends, which is only the same thing for single-component fields.
-    CeedInt            num_in, num_out;
-    CeedOperatorField *in, *out;
-
-    CeedCallBackend(CeedOperatorGetFields(op, &num_in, &in, &num_out, &out));
-    for (CeedInt i = 0; i < num_in + num_out; i++) {
-      CeedVector          vec;
-      CeedElemRestriction r;
-      CeedInt             num_comp = 1;
-
-      CeedCallBackend(CeedOperatorFieldGetVector(i < num_in ? in[i] : out[i - num_in], &vec));
-      CeedCallBackend(CeedOperatorFieldGetElemRestriction(i < num_in ? in[i] : out[i - num_in], &r));
-      if (vec == CEED_VECTOR_ACTIVE && r != CEED_ELEMRESTRICTION_NONE) CeedCallBackend(CeedElemRestrictionGetNumComponents(r, &num_comp));
-      CeedCallBackend(CeedVectorDestroy(&vec));
-      CeedCallBackend(CeedElemRestrictionDestroy(&r));
-      CeedCheck(num_comp == 1 || getenv("CEED_B200_ASSEMBLE_MULTICOMP"), ceed, CEED_ERROR_UNSUPPORTED,
-                "Backend does not implement assembly of operators with multi-component active fields");
-    }
-  }
   CeedCallB200(ceed, core, ceedb200_operator_assemble_qfunction_sizes(impl->core, &num_elem, &num_qpts, &size_in, &size_out));
   if (build_objects) {
     Ceed           ceed_parent;
@@ -374,6 +352,9 @@ int CeedOperatorCreate_B200(CeedOperator op) {
     if (!data->has_fallback) {  // with a fallback Ceed the interface routes assembly to the fallback operator by itself
       CeedCallBackend(CeedSetBackendFunction(ceed, "Operator", op, "LinearAssembleQFunction", CeedOperatorLinearAssembleQFunction_B200));
       CeedCallBackend(CeedSetBackendFunction(ceed, "Operator", op, "LinearAssembleQFunctionUpdate", CeedOperatorLinearAssembleQFunctionUpdate_B200));
+      // layout-aware twins of the interface's diagonal assembly (ceed-cuda-b200-assemble.c)
+      CeedCallBackend(CeedSetBackendFunction(ceed, "Operator", op, "LinearAssembleAddDiagonal", CeedOperatorLinearAssembleAddDiagonal_B200));
+      CeedCallBackend(CeedSetBackendFunction(ceed, "Operator", op, "LinearAssembleAddPointBlockDiagonal", CeedOperatorLinearAssembleAddPointBlockDiagonal_B200));
     }
   }
   CeedCallBackend(CeedSetBackendFunction(ceed, "Operator", op, "Destroy", CeedOperatorDestroy_B200));

@@ -74,6 +74,8 @@ CEED_INTERN int CeedBasisCreateH1_B200(CeedElemTopology topo, CeedInt dim, CeedI
 CEED_INTERN int CeedQFunctionCreate_B200(CeedQFunction qf);
 CEED_INTERN int CeedQFunctionContextCreate_B200(CeedQFunctionContext ctx);
 CEED_INTERN int CeedOperatorCreate_B200(CeedOperator op);
+CEED_INTERN int CeedOperatorLinearAssembleAddDiagonal_B200(CeedOperator op, CeedVector assembled, CeedRequest *request);
+CEED_INTERN int CeedOperatorLinearAssembleAddPointBlockDiagonal_B200(CeedOperator op, CeedVector assembled, CeedRequest *request);
 CEED_INTERN int CeedQFunctionContextAcquire_B200(CeedQFunction qf, void **held);
 CEED_INTERN int CeedQFunctionContextRelease_B200(CeedQFunction qf, void **held);
 CEED_INTERN int CeedQFunctionGetCore_B200(CeedQFunction qf, B200QFunction *core);
