@@ -631,10 +631,19 @@ static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
         trial(t);
       }
     }
+  // 1b. gradient-free operators: the lean in-place-plane kernel (layout 4; one warp per group, E elements per warp and iteration)
+  if (xline_ok)
+    for (int warps : {4, 8})
+      for (int epw : {4, 6, 8}) {
+        B200Tuning t  = base;
+        t.group_warps = 1, t.cta_warps = warps, t.qf_mode = 4, t.epw = epw, t.stage = 0;
+        trial(t);
+      }
   // 2. elements per group around the winner
   {
     const B200Tuning win = best;
-    for (int epw : {1, 2, 3, 4, 6, 8, 12}) {
+    for (int epw : {1, 2, 3, 4, 5, 6, 7, 8, 10, 12}) {
+      if (win.qf_mode != 4 && (epw == 5 || epw == 7 || epw == 10)) continue;
       if (epw == win.epw) continue;
       B200Tuning t = base;
       t.group_warps = win.group_warps, t.cta_warps = win.cta_warps, t.qf_mode = win.qf_mode, t.epw = epw;
@@ -651,7 +660,7 @@ static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
       t.minb       = minb;
       trial(t);
     }
-    if (best.qf_mode >= 1) {
+    if (best.qf_mode >= 1 && best.qf_mode <= 3) {
       const B200Tuning win2 = best;
       for (int unroll : {1, 2, 4, 8}) {
         if (unroll == win2.qf_unroll || (win2.qf_mode == 2 && unroll > 4)) continue;
@@ -666,7 +675,7 @@ static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
     const B200Tuning win = best;
     const int        layout_bit = win.stage >= 0 ? (win.stage & 256) : 0;
     for (int stage : {9, 0}) {
-      if ((stage | layout_bit) == win.stage) continue;
+      if ((stage | layout_bit) == win.stage || win.qf_mode == 4) continue;
       B200Tuning t = win;
       t.stage      = stage | layout_bit;
       trial(t);

@@ -234,9 +234,12 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     for (auto &g : plan->out_groups) no_grad = no_grad && !g.use_grad && !plan->bases[g.basis_id].collocated;
     for (auto &f : plan->in_fields) no_grad = no_grad && !(f.emode == B200_EVAL_NONE && !f.rstr->is_strided);
     for (auto &f : plan->out_fields) no_grad = no_grad && f.emode != B200_EVAL_NONE;
-    if (tn.qf_mode == 3 && !no_grad) tn.qf_mode = 0;
+    if ((tn.qf_mode == 3 || tn.qf_mode == 4) && !no_grad) tn.qf_mode = 0;
     if (tn.qf_mode < 0 && no_grad && !getenv("CEED_B200_NO_XLINE")) tn.qf_mode = 3;
-    plan->qf_xline = tn.qf_mode == 3;
+    // layout 4: the lean in-place-plane kernel (b200_opgen_lean.cpp); operators it does not cover run the general x-line layout
+    if (tn.qf_mode == 4 && (!b200_opgen_lean_eligible(plan) || getenv("CEED_B200_BLOCK_MODE"))) tn.qf_mode = 3;
+    plan->lean     = tn.qf_mode == 4;
+    plan->qf_xline = tn.qf_mode == 3 || plan->lean;
   }
   // Shared-memory layout of the contraction planes.  Default: rows padded to an odd pitch.  Swizzled (stage bit 256, Q <= 8,
   // z-line / x-line QFunction stage): quadrature rows have pitch 8 with the x index XOR-ed by the row's y index, every
@@ -354,7 +357,27 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
   };
   plan->warp_mode = !getenv("CEED_B200_BLOCK_MODE");
   int epb, threads;
-  if (plan->warp_mode) {
+  if (plan->lean) {
+    // one warp per element group, nothing staged by cp.async; E elements per warp and iteration (default 8)
+    // stage bit 32: offsets, scatter targets and quadrature data through cp.async.bulk + mbarrier, one batch ahead
+    plan->stage_mask = (tn.stage >= 0 && (tn.stage & 32) && plan->async_copy && !plan->no_tma) ? 32 : 0;
+    plan->swz = false, plan->swz_w = 0, plan->group_warps = 1;
+    plan->qd_tma = false, plan->mbar_off = -1, plan->ring_off = -1;
+    for (auto &f : plan->in_fields) f.qd_off = -1, f.qd_tma = false, f.ring_k = -1;
+    for (auto &g : plan->in_groups) g.uin_off = g.idx_off = -1;
+    for (auto &g : plan->out_groups) g.tgt_off = -1;
+    epb = tn.epw > 0 ? tn.epw : 8;
+    if (epb > std::max(1, num_elem)) epb = std::max(1, num_elem);
+    while (epb > 1 && b200_opgen_lean_layout(plan, epb) > (size_t)48 * 1024) epb--;
+    if (b200_opgen_lean_layout(plan, epb) > ceed->smem_optin) return reject("element working set exceeds shared memory");
+    int w = tn.cta_warps > 0 ? tn.cta_warps : 4;
+    while (w > 1 && (size_t)w * b200_opgen_lean_layout(plan, epb) > ceed->smem_optin) w--;
+    threads                = 32 * w;
+    plan->group_smem_bytes = (int)b200_opgen_lean_layout(plan, epb);
+    plan->epb              = epb;
+    plan->threads          = threads;
+    plan->smem_bytes       = w * plan->group_smem_bytes;
+  } else if (plan->warp_mode) {
     // staging defaults in warp mode: offsets + scatter targets only (small); CEED_B200_STAGE=<bitmask 1 idx/tgt, 2 gather, 4 qdata>
     const int stage = tn.stage >= 0 ? tn.stage : 1;
     plan->stage_mask = stage;
@@ -425,7 +448,7 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     minb = std::min(minb, std::max(1, 2048 / threads));
     plan->blocks_per_sm = std::max(1, minb);
     tn.epw = plan->epb, tn.group_warps = plan->group_warps, tn.cta_warps = plan->threads / 32, tn.minb = plan->blocks_per_sm;
-    tn.qf_mode = plan->qf_xline ? 3 : (plan->qf_pointwise ? plan->qf_pp : 0), tn.qf_unroll = plan->qf_unroll, tn.stage = plan->stage_mask;
+    tn.qf_mode = plan->lean ? 4 : (plan->qf_xline ? 3 : (plan->qf_pointwise ? plan->qf_pp : 0)), tn.qf_unroll = plan->qf_unroll, tn.stage = plan->stage_mask;
     plan->resolved = tn;
   }
   plan->fused      = true;
@@ -1868,6 +1891,7 @@ struct Gen {
 }  // namespace
 
 std::string b200_opgen_source(B200Operator op, B200OpPlan *plan, int add) {
+  if (plan->lean) return b200_opgen_lean_source(op, plan, add);
   Gen g;
   g.op   = op;
   g.plan = plan;

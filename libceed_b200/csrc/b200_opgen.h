@@ -89,6 +89,10 @@ struct B200OpPlan {
   // ring_slots - 1 steps are always in flight, ACROSS the other stages and across element groups.
   int                       ring_off = -1, ring_slots = 0, ring_comps = 0, ring_rounds = 0;
   bool                      qf_xline = false;    // gradient-free operators: QFunction on x-lines inside the x-contraction stage
+  bool                      lean = false;        // gradient-free operators on the lean in-place-plane kernel (b200_opgen_lean.cpp, QFunction layout 4)
+  int                       lean_es = 0;         // its element stride in shared memory (doubles)
+  int                       lean_tg_off = 0;     // byte offset of the parked (or bulk-copied) scatter targets in a warp's shared-memory slice
+  int                       lean_off_off = -1;   // bulk pipeline (stage bit 32): byte offset of the element offsets of the batch
   int                       qf_pp = 1;           // pointwise QFunction stage: points per lane (2 = x-adjacent pair, 16-byte loads)
   int                       qf_ahead = 1;        // z-line QFunction stage: z-layers of streamed inputs in flight per lane
   int                       qf_unroll = 4;       // pointwise QFunction stage: points in flight per lane
@@ -110,4 +114,8 @@ struct B200OpPlan {
 int b200_opgen_plan(B200Operator op, B200OpPlan *plan);
 int b200_opgen_build(B200Operator op, B200OpPlan *plan, int add);
 std::string b200_opgen_source(B200Operator op, B200OpPlan *plan, int add);
+// lean kernel of gradient-free operators (b200_opgen_lean.cpp)
+bool        b200_opgen_lean_eligible(const B200OpPlan *plan);
+size_t      b200_opgen_lean_layout(B200OpPlan *plan, int E);
+std::string b200_opgen_lean_source(B200Operator op, B200OpPlan *plan, int add);
 int b200_opgen_grid(B200Ceed ceed, const B200OpPlan *plan, const B200KernelVariant &v, long long num_elem);
