@@ -191,6 +191,23 @@ struct B200OrderedScatter {
   int32_t *d_sync = nullptr;      // {epoch of the last finished launch, CTAs finished in the running launch}
   int64_t  num_shared = 0, num_halo = 0, num_groups = 0, num_pred = 0;
 };
+// Tables of the RUN scatter (deterministic, b200_restriction_build_runs): the elements of a launch are cut into one contiguous run
+// per element group (warp); a group walks its run in nb = ceil(len / E) iterations, iteration i holding the E elements
+// s + i + k * nb (k < E).  An E-entry whose L-node was first touched by the SAME group, with every earlier toucher processed in an
+// earlier iteration of that group, is added straight into v (read-modify-write in program order: still the ascending E-order of
+// the serial reference); only the other non-owner entries go through the halo buffer and the finalize pass.
+//   tgt >= 0: L-index, bit 30 set = read-modify-write (clear = plain store of the owner entry);  tgt < 0: ~halo slot
+struct B200RunScatter {
+  int32_t *d_tgt = nullptr, *d_halo_node = nullptr, *d_halo_ptr = nullptr;
+  int64_t  num_shared = 0, num_halo = 0, num_rmw = 0;
+  int      num_groups = 0, group_elems = 0;  // key: the launch shape the tables were built for
+  bool     built = false;
+};
+constexpr int32_t B200_RUN_RMW_BIT = 1 << 30;
+int  b200_restriction_build_runs(B200Restriction r, int num_groups, int group_elems, B200RunScatter *out);
+void b200_run_scatter_free(B200Ceed ceed, B200RunScatter *t);
+int  b200_halo_finalize_lists(B200Restriction r, const int32_t *d_halo_node, const int32_t *d_halo_ptr, int64_t num_shared, int64_t num_halo, const double *d_halo,
+                              double *d_v);
 int  b200_restriction_build_ordered(B200Restriction r, int group_elems, B200OrderedScatter *out);
 int  b200_ordered_init_halo(B200Restriction r, const B200OrderedScatter *t, double *d_halo);
 void b200_ordered_scatter_free(B200Ceed ceed, B200OrderedScatter *t);

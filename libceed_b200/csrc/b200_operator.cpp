@@ -30,6 +30,8 @@ static void plan_free(B200Operator op) {
   if (!plan) return;
   for (int i = 0; i < 16; i++) b200_dfree(op->ceed, plan->aux[i]);
   b200_ordered_scatter_free(op->ceed, &plan->ordered);
+  for (int v = 0; v < 2; v++)
+    for (int i = 0; i < 16; i++) b200_run_scatter_free(op->ceed, &plan->run[v][i]);
   for (auto *vecs : {&plan->e_in, &plan->q_in, &plan->e_out, &plan->q_out})
     for (auto v : *vecs) ceedb200_vector_destroy(v);
   delete plan;
@@ -316,6 +318,24 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
     args.ord_num_halo = plan->ordered.num_halo;
   }
   B200KernelVariant &var = plan->variant[kernel_add ? 1 : 0];  // built above (fallback ladder)
+  // Lean kernel, deterministic scatter, whole-mesh launch: every warp owns one contiguous run of elements, and E-entries whose earlier
+  // touchers were all processed earlier by the same warp are added straight into v (B200RunScatter) -- fewer halo entries, a smaller
+  // finalize pass, same ascending E-order.  The tables depend on the launch shape (warps of the grid, elements per iteration).
+  int             run_mode = 0;
+  B200RunScatter *run      = nullptr;
+  if (plan->lean && plan->scatter_mode == B200_SCATTER_DETERMINISTIC) {
+    const int             slot = plan->out_groups[0].slot;
+    const B200Restriction r    = op->out_fields[slot].rstr;
+    args.ord_num_halo          = r->num_halo;
+    if (plan->lean_runs && !part && !(plan->stage_mask & 40) && r->l_size < (int64_t)B200_RUN_RMW_BIT && !getenv("CEED_B200_NO_RUNS") && e_end > e_begin) {
+      const int groups = b200_opgen_grid(ceed, plan, var, e_end - e_begin) * (plan->threads / 32);
+      run              = &plan->run[kernel_add ? 1 : 0][slot];
+      B200_CALL(b200_restriction_build_runs(r, groups, plan->epb, run));
+      args.out_idx[slot] = run->d_tgt;
+      args.ord_num_halo  = run->num_halo;
+      run_mode           = 1;
+    }
+  }
 
   if (op->timing) B200_CUDA(ceed, cudaEventRecord(op->ev[3], ceed->stream));
   B200_CHECK(!(ordered && part), ceed, B200_ERROR_UNSUPPORTED, "apply_part is not available with the in-kernel ordered scatter");
@@ -327,7 +347,7 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
       B200_CUDA(ceed, cudaMemcpyAsync((void *)mod->args_dptr, mod->last_args.data(), sizeof(args), cudaMemcpyHostToDevice, ceed->stream));
     }
     // element groups of the ordered scatter wait for each other: all CTAs must be resident (cooperative launch)
-    void *params[2] = {&e_begin, &e_end};
+    void *params[3] = {&e_begin, &e_end, &run_mode};  // (the general kernel takes the first two)
     B200_CALL(b200_launch(ceed, var.kernel, b200_opgen_grid(ceed, plan, var, e_end - e_begin), plan->threads, plan->smem_bytes, params, ordered));
   }
   if (op->timing) B200_CUDA(ceed, cudaEventRecord(op->ev[1], ceed->stream));
@@ -338,7 +358,9 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
     bool is_writer = plan->out_fields[i].emode == B200_EVAL_NONE || plan->out_groups[plan->out_fields[i].group].slot == (int)i;
     if (!is_writer) continue;
     if (ordered && (int)i == plan->ordered_slot) continue;  // completed inside the kernel
-    if (plan->scatter_mode == B200_SCATTER_DETERMINISTIC || ordered) B200_CALL(b200_halo_finalize(f.rstr, plan->aux[i], args.out_ptr[i], part));
+    if (run && (int)i == plan->out_groups[0].slot)
+      B200_CALL(b200_halo_finalize_lists(f.rstr, run->d_halo_node, run->d_halo_ptr, run->num_shared, run->num_halo, plan->aux[i], args.out_ptr[i]));
+    else if (plan->scatter_mode == B200_SCATTER_DETERMINISTIC || ordered) B200_CALL(b200_halo_finalize(f.rstr, plan->aux[i], args.out_ptr[i], part));
     else if (plan->scatter_mode == B200_SCATTER_EVECTOR) B200_CALL(b200_restriction_apply_raw(f.rstr, B200_TRANSPOSE, plan->aux[i], args.out_ptr[i]));
   }
   if (op->timing) {

@@ -239,6 +239,7 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     // layout 4: the lean in-place-plane kernel (b200_opgen_lean.cpp); operators it does not cover run the general x-line layout
     if (tn.qf_mode == 4 && (!b200_opgen_lean_eligible(plan) || getenv("CEED_B200_BLOCK_MODE"))) tn.qf_mode = 3;
     plan->lean     = tn.qf_mode == 4;
+    plan->lean_runs = plan->lean && getenv("CEED_B200_RUNS") != nullptr && plan->scatter_mode == B200_SCATTER_DETERMINISTIC;
     plan->qf_xline = tn.qf_mode == 3 || plan->lean;
   }
   // Shared-memory layout of the contraction planes.  Default: rows padded to an odd pitch.  Swizzled (stage bit 256, Q <= 8,
@@ -360,7 +361,9 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
   if (plan->lean) {
     // one warp per element group, nothing staged by cp.async; E elements per warp and iteration (default 8)
     // stage bit 32: offsets, scatter targets and quadrature data through cp.async.bulk + mbarrier, one batch ahead
-    plan->stage_mask = (tn.stage >= 0 && (tn.stage & 32) && plan->async_copy && !plan->no_tma) ? 32 : 0;
+    // (bit 8: element offsets + scatter targets, bit 32: quadrature data)
+    // bit 64: bulk L2 prefetch of the next batch's quadrature data
+    plan->stage_mask = (tn.stage >= 0 && plan->async_copy && !plan->no_tma) ? (tn.stage & (8 | 32 | 64)) : 0;
     plan->swz = false, plan->swz_w = 0, plan->group_warps = 1;
     plan->qd_tma = false, plan->mbar_off = -1, plan->ring_off = -1;
     for (auto &f : plan->in_fields) f.qd_off = -1, f.qd_tma = false, f.ring_k = -1;

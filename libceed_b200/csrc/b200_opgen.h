@@ -90,6 +90,7 @@ struct B200OpPlan {
   int                       ring_off = -1, ring_slots = 0, ring_comps = 0, ring_rounds = 0;
   bool                      qf_xline = false;    // gradient-free operators: QFunction on x-lines inside the x-contraction stage
   bool                      lean = false;        // gradient-free operators on the lean in-place-plane kernel (b200_opgen_lean.cpp, QFunction layout 4)
+  bool                      lean_runs = false;   // lean kernel generated with run-scatter support (experimental, CEED_B200_RUNS)
   int                       lean_es = 0;         // its element stride in shared memory (doubles)
   int                       lean_tg_off = 0;     // byte offset of the parked (or bulk-copied) scatter targets in a warp's shared-memory slice
   int                       lean_off_off = -1;   // bulk pipeline (stage bit 32): byte offset of the element offsets of the batch
@@ -106,6 +107,7 @@ struct B200OpPlan {
   double *aux[16]       = {nullptr};
   size_t  aux_bytes[16] = {0};
   B200OrderedScatter ordered;     // ordered scatter tables (scatter_mode == B200_SCATTER_ORDERED)
+  B200RunScatter     run[2][16];  // run scatter tables of the lean kernel, per kernel variant (their grids may differ) and output slot
   int                ordered_slot = -1;
   // unfused fallback scratch
   std::vector<B200Vector> e_in, q_in, e_out, q_out;

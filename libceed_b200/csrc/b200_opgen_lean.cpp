@@ -24,6 +24,9 @@
 //     offsets after the gather stage, quadrature data after the x-line stage, targets after the scatter stage.  Every stream is
 //     then in flight for most of a batch period with no registers held and no load instructions issued; the only demand loads
 //     left are the gathers of u.  Sources are aligned down to 16 bytes at run time (readers add the shift).
+//   * CEED_B200_RUNS (experimental, off): run scatter -- every warp owns a contiguous run of elements and adds E-entries whose earlier
+//     touchers it processed itself straight into v (B200RunScatter).  Bitwise equal results, finalize pass 20-30 % shorter, but the
+//     fused kernel loses its streaming locality (2x slower on B200): kept as a tested option, see DESIGN.md.
 //   * Full batches run code without any tail clamps; the (at most one) partial batch of a launch runs a second instantiation.
 #include <algorithm>
 #include <cstdlib>
@@ -49,9 +52,12 @@ struct LeanGen {
   int          add;
   oss          c;
   int          P, Q, E, nc, PS, ES, P2, P3, bid;
-  bool         staged = false;  // bulk pipeline (stage bit 32)
+  bool         staged = false;  // bulk pipeline: st_idx (stage bit 8: offsets + targets) and / or st_qd (bit 32: quadrature data)
+  bool         st_idx = false, st_qd = false;
+  bool         pf_qd = false;   // stage bit 64: bulk L2 prefetch (cp.async.bulk.prefetch.L2) of the directly loaded quadrature data of the NEXT batch
+  bool         runs   = false;  // run scatter (experimental, CEED_B200_RUNS): per-warp element runs, read-modify-write entries
   const B200GenGroup *gin, *gout;
-  bool qd_staged(const B200GenField &fd) const { return staged && fd.emode == B200_EVAL_NONE && fd.qd_off >= 0; }
+  bool qd_staged(const B200GenField &fd) const { return st_qd && fd.emode == B200_EVAL_NONE && fd.qd_off >= 0; }
 
   void contract(const string &mat, int n_in, int n_out, bool transposed, const string &in, const string &out, const string &ind) {
     for (int o = 0; o < n_out; o++) {
@@ -68,7 +74,7 @@ struct LeanGen {
     c << "// Fused operator kernel (lean, in-place plane) generated by ceed-b200 for QFunction " << qf->kernel_name << "\n";
     c << "#define CEED_Q_VLA " << Q << "  // the QFunction is called on whole x-lines (Q = " << Q << " points)\n";
     c << "#include <b200-jit.h>\n";
-    if (staged) c << "#include <b200-tma.h>\n";
+    if (staged || pf_qd) c << "#include <b200-tma.h>\n";
     c << "#include \"" << qf->source_path << "\"\n\n";
     for (size_t b = 0; b < plan->bases.size(); b++) {
       const B200Basis bs = plan->bases[b].basis;
@@ -89,7 +95,7 @@ struct LeanGen {
     c << "#define B200_SMW (sm + (threadIdx.x >> 5) * " << plan->group_smem_bytes / 8 << ")\n";
     c << "#define B200_TGS ((int *)(B200_SMW + " << plan->lean_tg_off / 8 << "))\n";
     if (staged) {
-      c << "#define B200_OFS ((int *)(B200_SMW + " << plan->lean_off_off / 8 << "))\n";
+      if (st_idx) c << "#define B200_OFS ((int *)(B200_SMW + " << plan->lean_off_off / 8 << "))\n";
       c << "#define B200_BAR(s) (b200_smem_u32((char *)B200_SMW + " << plan->mbar_off << " + 8 * (s)))  // 0 offsets, 1 quadrature data, 2 targets\n";
       // run-time shift (in elements) of a bulk-copied block whose source was aligned down to 16 bytes
       c << "#define B200_SHIFT(ptr, esize) ((int)(((unsigned long long)(ptr) & 15ULL) / (esize)))\n";
@@ -97,10 +103,12 @@ struct LeanGen {
       c << "static __device__ __forceinline__ void b200_lean_copy(void *dst, const void *src, unsigned bytes, unsigned bar) {\n"
         << "  b200_bulk_g2s(b200_smem_u32(dst), (const void *)((unsigned long long)src & ~15ULL), b200_lean_nb(src, bytes), bar);\n}\n";
       // issue functions (lane 0 of the warp; ne = elements of the batch starting at e0)
+      if (st_idx)
       c << "static __device__ __noinline__ void b200_lean_issue_off(const long long e0, const int ne) {\n"
         << "  const int *src = b200a.in_idx[" << gin->slot << "] + e0 * " << P3 << ";\n  const unsigned bar = B200_BAR(0);\n"
         << "  b200_fence_proxy_async();\n  b200_mbar_expect_tx(bar, b200_lean_nb(src, ne * " << P3 * 4 << "));\n"
         << "  b200_lean_copy(B200_OFS, src, ne * " << P3 * 4 << ", bar);\n}\n";
+      if (st_idx)
       c << "static __device__ __noinline__ void b200_lean_issue_tg(const long long e0, const int ne) {\n"
         << "  const int *src = b200a.out_idx[" << gout->slot << "] + e0 * " << P3 << ";\n  const unsigned bar = B200_BAR(2);\n"
         << "  b200_fence_proxy_async();\n  b200_mbar_expect_tx(bar, b200_lean_nb(src, ne * " << P3 * 4 << "));\n"
@@ -128,11 +136,29 @@ struct LeanGen {
         c << "}\n";
       }
     }
+    if (pf_qd) {
+      const int Q3 = Q * Q * Q;
+      c << "static __device__ __noinline__ void b200_lean_prefetch_qd(const long long e0, const int ne) {\n";
+      for (auto &fd : plan->in_fields) {
+        const bool contiguous = fd.emode == B200_EVAL_NONE && fd.rstr->is_strided && fd.rstr->strides[0] == 1 && fd.rstr->strides[2] == fd.rstr->elem_size;
+        if (!contiguous) continue;
+        for (int cc = 0; cc < fd.nc; cc++) {
+          c << "  { const unsigned long long a = (unsigned long long)(b200a.in_ptr[" << fd.slot << "] + " << (long long)cc * fd.rstr->strides[1] << "LL + e0 * " << Q3 << "LL);\n";
+          c << "    b200_bulk_prefetch_l2((const void *)(a & ~15ULL), (unsigned)(((a & 15ULL) + (unsigned long long)ne * " << Q3 * 8 << " + 15) & ~15ULL)); }\n";
+        }
+      }
+      c << "}\n";
+    }
     c << "\n";
   }
 
   // element number of local element `le` (tail batches clamp to the last element of the launch)
-  string elem(const string &le) const { return "(TAIL ? ((e0 + " + le + " < b200_ne) ? e0 + " + le + " : b200_ne - 1) : e0 + " + le + ")"; }
+  string elem(const string &le) const { return "(TAIL ? ((e0 + " + le + " * st < lim) ? e0 + " + le + " * st : e0) : e0 + " + le + " * st)"; }
+  // trailing parameters of the stage functions: element stride inside a batch and end of the warp's element range (run mode), or the
+  // parity of the mbarrier phase (bulk pipeline: batches are contiguous)
+  string stage_params() const { return staged ? ", const int par" : (runs ? ", const int st, const long long lim" : ""); }
+  string stage_locals() const { return runs ? "" : "  const int st = 1;\n  const long long lim = b200_ne;\n  (void)st; (void)lim;\n"; }
+  string stage_args() const { return staged ? ", par" : (runs ? ", st, lim" : ""); }
 
   // ---- gather + Z ----------------------------------------------------------------------------------
   void emit_z() {
@@ -141,11 +167,11 @@ struct LeanGen {
     const bool same_table = !det && gin->rstr == gout->rstr;  // atomic scatter through the gather offsets themselves
     const long long cs = gin->rstr->comp_stride;
     c << "// gather + z-contraction; the scatter targets of the batch are loaded here and parked in shared memory\n";
-    c << "template <bool TAIL> static __device__ __noinline__ void b200_lean_z(const long long e0" << (staged ? ", const int par" : "") << ") {\n";
+    c << "template <bool TAIL> static __device__ __noinline__ void b200_lean_z(const long long e0" << stage_params() << ") {\n" << stage_locals();
     c << "  double *const smw = B200_SMW;\n  int *const tgs = B200_TGS;\n  const int lane = threadIdx.x & 31;\n  (void)tgs;\n";
     c << "  const int *const ixb = b200a.in_idx[" << gin->slot << "];\n  const int *const txb = b200a.out_idx[" << gout->slot << "];\n";
     c << "  const double *const ub = b200a.in_ptr[" << gin->slot << "];\n  (void)txb;\n";
-    if (staged) {
+    if (st_idx) {
       c << "  const int nel = TAIL ? (int)(b200_ne - e0) : " << E << ";\n  (void)nel;\n";
       c << "  const int *const ofs = B200_OFS + B200_SHIFT(ixb + e0 * " << P3 << ", 4);\n";
       c << "  b200_mbar_wait(B200_BAR(0), par);\n";
@@ -160,7 +186,7 @@ struct LeanGen {
         c << "    const int t" << x << " = lane + " << 32 * r << ", tc" << x << " = " << ((r + 1) * 32 > T ? "t" + x + " < " + S(T) + " ? t" + x + " : " + S(T - 1) : "t" + x)
           << ";\n";
         c << "    const int ij" << x << " = tc" << x << " % " << P2 << ", le" << x << " = tc" << x << " / " << P2 << ";\n";
-        if (staged) {
+        if (st_idx) {
           c << "    const int *const ix" << x << " = ofs + (TAIL ? (le" << x << " < nel ? le" << x << " : nel - 1) : le" << x << ") * " << P3 << " + ij" << x << ";\n";
           for (int k = 0; k < P; k++) c << "    const int o" << k << x << " = ix" << x << "[" << k * P2 << "];\n";
         } else {
@@ -169,7 +195,7 @@ struct LeanGen {
           for (int k = 0; k < P; k++) c << "    const int o" << k << x << " = __ldg(ix" << x << " + " << k * P2 << ");\n";
         }
       }
-      if (!same_table && !staged) {
+      if (!same_table && !st_idx) {
         for (int r = r0; r < r1; r++) {
           const string x = "_" + S(r);
           c << "    const int *const tx" << x << " = txb + e" << x << " * " << P3 << " + ij" << x << ";\n";
@@ -181,7 +207,7 @@ struct LeanGen {
         for (int cc = 0; cc < nc; cc++)
           for (int k = 0; k < P; k++) c << "    const double u" << cc << "_" << k << x << " = __ldg(ub + o" << k << x << " + " << cc * cs << "LL);\n";
       }
-      for (int r = r0; r < r1 && !staged; r++) {
+      for (int r = r0; r < r1 && !st_idx; r++) {
         const string x = "_" + S(r), g = same_table ? "o" : "g";
         int k = 0;
         while (k < P) {
@@ -250,7 +276,7 @@ struct LeanGen {
     const int     TX = E * Q * Q, RX = (TX + 31) / 32;
     const int     TY = E * nc * P * Q, RY = (TY + 31) / 32;
     c << "// y-contraction in place, then x-lines: X, QFunction on the Q points of the line, X^T (all components of a line per lane)\n";
-    c << "template <bool TAIL> static __device__ __noinline__ void b200_lean_yx(const long long e0" << (staged ? ", const int par" : "") << ") {\n";
+    c << "template <bool TAIL> static __device__ __noinline__ void b200_lean_yx(const long long e0" << stage_params() << ") {\n" << stage_locals();
     c << "  double *const smw = B200_SMW;\n  const int lane = threadIdx.x & 31;\n";
     bool any_staged_qd = false;
     for (auto &fd : plan->in_fields) any_staged_qd = any_staged_qd || qd_staged(fd);
@@ -378,12 +404,13 @@ struct LeanGen {
   // ---- Z^T + scatter ---------------------------------------------------------------------------------------
   void emit_zt() {
     const int       T = E * P2, R = (T + 31) / 32;
-    const long long cs = gout->rstr->comp_stride, nh = gout->rstr->num_halo;
+    const long long cs = gout->rstr->comp_stride;
     const string    sl = S(gout->slot);
+    const bool      rmw = runs;  // the tables may carry the read-modify-write bit
     c << "// z-contraction^T + scatter (targets from the per-lane shared-memory slots the gather stage filled)\n";
-    c << "template <bool TAIL> static __device__ __noinline__ void b200_lean_zt(const long long e0" << (staged ? ", const int par" : "") << ") {\n";
+    c << "template <bool TAIL> static __device__ __noinline__ void b200_lean_zt(const long long e0" << stage_params() << ") {\n" << stage_locals();
     c << "  double *const smw = B200_SMW;\n  const int lane = threadIdx.x & 31;\n";
-    if (staged) {
+    if (st_idx) {
       c << "  const int nel = TAIL ? (int)(b200_ne - e0) : " << E << ";\n  (void)nel;\n";
       c << "  const int *const tgs = B200_TGS + B200_SHIFT(b200a.out_idx[" << sl << "] + e0 * " << P3 << ", 4);\n";
       c << "  b200_mbar_wait(B200_BAR(2), par);\n";
@@ -391,12 +418,13 @@ struct LeanGen {
       c << "  const int *const tgs = B200_TGS;\n";
     }
     c << "  double *const vb = b200a.out_ptr[" << sl << "];\n  double *const hb = b200a.out_aux[" << sl << "];\n  (void)hb;\n";
+    c << "  const long long hd = ((long long)hb - (long long)vb) >> 3;  // halo buffer relative to v, in doubles\n  (void)hd;\n";
     for (int r = 0; r < R; r++) {
       const bool partial = (r + 1) * 32 > T;
       c << "  {\n";
       c << "    const int t = lane + " << 32 * r << ", tc = " << (partial ? "t < " + S(T) + " ? t : " + S(T - 1) : string("t")) << ";\n";
       c << "    const int ij = tc % " << P2 << ", le = tc / " << P2 << ";\n";
-      if (staged) {
+      if (st_idx) {
         c << "    const int *const tx = tgs + (TAIL ? (le < nel ? le : nel - 1) : le) * " << P3 << " + ij;\n";
         for (int k = 0; k < P; k++) c << "    const int g" << k << " = tx[" << k * P2 << "];\n";
       } else {
@@ -416,18 +444,38 @@ struct LeanGen {
           k += w;
         }
       }
-      c << "    const bool live = " << (partial ? "(t < " + S(T) + ")" : string("true")) << " && (!TAIL || e0 + le < b200_ne);\n";
+      c << "    const bool live = " << (partial ? "(t < " + S(T) + ")" : string("true")) << " && (!TAIL || e0 + le * st < lim);\n";
+      const bool det = plan->scatter_mode != B200_SCATTER_ATOMIC;
+      const bool one_store = det && !rmw && !add;  // owner entries and halo entries through ONE store: halo slots addressed relative to v
+      if (one_store) {
+        for (int k = 0; k < P; k++)
+          c << "    const long long a" << k << " = (long long)(g" << k << " ^ (g" << k << " >> 31)) + (g" << k << " < 0 ? hd : 0LL);  // g >= 0: L-index; g < 0: ~g = halo slot\n";
+      } else if (det) {
+        // direct entries: bit 30 = read-modify-write of a value this warp stored in an earlier iteration (run scatter); the old values are
+        // requested (L2, ld.cg) before the contraction so that their latency overlaps it
+        for (int k = 0; k < P; k++) {
+          if (rmw) c << "    const bool m" << k << " = g" << k << " >= 0 && (" << (add ? "true" : "(g" + S(k) + " & " + S(B200_RUN_RMW_BIT) + ") != 0") << ");\n";
+          else c << "    const bool m" << k << " = g" << k << " >= 0 && " << (add ? "true" : "false") << ";\n";
+          c << "    const long long a" << k << " = g" << k << (rmw ? " & " + S(B200_RUN_RMW_BIT - 1) : "") << ";\n";
+        }
+        if (rmw || add)
+          for (int cc = 0; cc < nc; cc++)
+            for (int k = 0; k < P; k++) c << "    const double old" << cc << "_" << k << " = m" << k << " ? __ldcg(vb + a" << k << " + " << cc * cs << "LL) : 0.0;\n";
+      }
       for (int cc = 0; cc < nc; cc++) {
         c << "    {\n      const double *const src = smw + le * " << ES << " + " << cc * PS << " + ij;\n";
         for (int q = 0; q < Q; q++) c << "      const double u" << q << " = src[" << q * Q * P << "];\n";
         contract("cB" + S(bid), Q, P, true, "u", "r", "      ");
         c << "      if (live) {\n";
         for (int k = 0; k < P; k++) {
-          if (plan->scatter_mode == B200_SCATTER_ATOMIC) {
+          if (!det) {
             c << "        atomicAdd(vb + g" << k << " + " << cc * cs << "LL, r" << k << ");\n";
+          } else if (one_store) {
+            if (cc == 0) c << "        vb[a" << k << "] = r" << k << ";\n";
+            else c << "        vb[a" << k << " + (g" << k << " < 0 ? " << cc << " * b200a.ord_num_halo : " << cc * cs << "LL)] = r" << k << ";\n";
           } else {
-            c << "        if (g" << k << " >= 0) vb[g" << k << " + " << cc * cs << "LL] " << (add ? "+=" : "=") << " r" << k << ";\n";
-            c << "        else hb[(long long)(~g" << k << ") + " << cc * nh << "LL] = r" << k << ";\n";
+            c << "        if (g" << k << " >= 0) vb[a" << k << " + " << cc * cs << "LL] = " << ((rmw || add) ? "m" + S(k) + " ? old" + S(cc) + "_" + S(k) + " + r" + S(k) + " : r" + S(k) : "r" + S(k)) << ";\n";
+            c << "        else hb[(long long)(~g" << k << ") + " << cc << " * b200a.ord_num_halo] = r" << k << ";\n";
           }
         }
         c << "      }\n    }\n";
@@ -449,7 +497,11 @@ struct LeanGen {
     P3   = P2 * P;
     PS   = Q * Q * P;
     ES   = plan->lean_es;
-    staged = (plan->stage_mask & 32) != 0;
+    st_idx = (plan->stage_mask & 8) != 0;
+    st_qd  = (plan->stage_mask & 32) != 0;
+    staged = st_idx || st_qd;
+    pf_qd  = (plan->stage_mask & 64) != 0 && !st_qd;
+    runs   = plan->lean_runs && !staged;
     emit_header();
     emit_z();
     emit_yx();
@@ -457,19 +509,38 @@ struct LeanGen {
     emit_zt();
     const int NT = plan->threads, W = NT / 32;
     c << "extern \"C\" __global__ void __launch_bounds__(" << NT << ", " << std::max(1, plan->blocks_per_sm) << ") b200_operator_" << op->qf->kernel_name
-      << "(const long long e_begin, const long long e_end) {\n";
+      << "(const long long e_begin, const long long e_end, const int run_mode) {\n";
     c << "  if (threadIdx.x == 0) b200_ne = e_end;\n  __syncthreads();\n";
-    c << "  const long long num_batches = (e_end - e_begin + " << E - 1 << ") / " << E << ";\n";
+    if (staged) c << "  const long long num_batches = (e_end - e_begin + " << E - 1 << ") / " << E << ";\n  (void)run_mode;\n";
     const string first = "(long long)blockIdx.x * " + S(W) + " + (threadIdx.x >> 5)", stride = "(long long)gridDim.x * " + S(W);
     if (!staged) {
-      c << "  for (long long batch = " << first << "; batch < num_batches; batch += " << stride << ") {\n";
-      c << "    const long long e0 = e_begin + batch * " << E << ";\n";
-      c << "    if (e0 + " << E << " <= e_end) {\n";
-      c << "      b200_lean_z<false>(e0);\n      __syncwarp();\n      b200_lean_yx<false>(e0);\n      __syncwarp();\n      b200_lean_yt();\n      __syncwarp();\n"
-        << "      b200_lean_zt<false>(e0);\n      __syncwarp();\n";
+      const string a = stage_args();
+      if (runs) {
+        // run mode (run_mode != 0, deterministic scatter with run tables): the warp owns one contiguous run of elements and walks it
+        // in nb iterations, iteration i holding elements s + i + k * nb; otherwise grid-stride over contiguous batches of E elements
+        c << "  const long long ne = e_end - e_begin, gw = " << first << ", ng = " << stride << ";\n";
+        c << "  long long base0, step, lim;\n  int st, n_it;\n";
+        c << "  if (run_mode) {\n    base0 = e_begin + gw * ne / ng;\n    lim = e_begin + (gw + 1) * ne / ng;\n"
+          << "    n_it = (int)((lim - base0 + " << E - 1 << ") / " << E << ");\n    st = n_it;\n    step = 1;\n  } else {\n"
+          << "    const long long num_batches = (ne + " << E - 1 << ") / " << E << ";\n    n_it = gw < num_batches ? (int)((num_batches - gw + ng - 1) / ng) : 0;\n"
+          << "    base0 = e_begin + gw * " << E << ";\n    step = ng * " << E << ";\n    st = 1;\n    lim = e_end;\n  }\n";
+        c << "  for (int it = 0; it < n_it; it++) {\n";
+        c << "    const long long e0 = base0 + it * step;\n";
+        c << "    if (e0 + " << E - 1 << "LL * st < lim) {\n";
+      } else {
+        c << "  (void)run_mode;\n  const long long num_batches = (e_end - e_begin + " << E - 1 << ") / " << E << ";\n";
+        c << "  for (long long batch = " << first << "; batch < num_batches; batch += " << stride << ") {\n";
+        c << "    const long long e0 = e_begin + batch * " << E << ";\n";
+        if (pf_qd)
+          c << "    { const long long e0n = e_begin + (batch + " << stride << ") * " << E << ";\n"
+            << "      if ((threadIdx.x & 31) == 0 && e0n < e_end) b200_lean_prefetch_qd(e0n, (int)(e_end - e0n < " << E << " ? e_end - e0n : " << E << ")); }\n";
+        c << "    if (e0 + " << E << " <= e_end) {\n";
+      }
+      c << "      b200_lean_z<false>(e0" << a << ");\n      __syncwarp();\n      b200_lean_yx<false>(e0" << a << ");\n      __syncwarp();\n      b200_lean_yt();\n      __syncwarp();\n"
+        << "      b200_lean_zt<false>(e0" << a << ");\n      __syncwarp();\n";
       c << "    } else {\n";
-      c << "      b200_lean_z<true>(e0);\n      __syncwarp();\n      b200_lean_yx<true>(e0);\n      __syncwarp();\n      b200_lean_yt();\n      __syncwarp();\n"
-        << "      b200_lean_zt<true>(e0);\n      __syncwarp();\n";
+      c << "      b200_lean_z<true>(e0" << a << ");\n      __syncwarp();\n      b200_lean_yx<true>(e0" << a << ");\n      __syncwarp();\n      b200_lean_yt();\n      __syncwarp();\n"
+        << "      b200_lean_zt<true>(e0" << a << ");\n      __syncwarp();\n";
       c << "    }\n  }\n}\n";
       return c.str();
     }
@@ -481,17 +552,18 @@ struct LeanGen {
     c << "  long long batch = " << first << ";\n";
     c << "  if (lead && batch < num_batches) {\n    const long long e0 = e_begin + batch * " << E << ";\n"
       << "    const int ne = (int)(e_end - e0 < " << E << " ? e_end - e0 : " << E << ");\n"
-      << "    b200_lean_issue_off(e0, ne);\n" << (any_qd ? "    b200_lean_issue_qd(e0, ne);\n" : "") << "    b200_lean_issue_tg(e0, ne);\n  }\n";
+      << (st_idx ? "    b200_lean_issue_off(e0, ne);\n" : "") << (any_qd ? "    b200_lean_issue_qd(e0, ne);\n" : "") << (st_idx ? "    b200_lean_issue_tg(e0, ne);\n" : "") << "  }\n";
     c << "  for (int it = 0; batch < num_batches; batch += " << stride << ", it++) {\n";
     c << "    const long long e0 = e_begin + batch * " << E << ", e0n = e_begin + (batch + " << stride << ") * " << E << ";\n";
     c << "    const int nen = e0n >= e_end ? 0 : (int)(e_end - e0n < " << E << " ? e_end - e0n : " << E << "), par = it & 1;\n";
+    if (pf_qd) c << "    if (lead && nen) b200_lean_prefetch_qd(e0n, nen);\n";
     for (int tail = 0; tail < 2; tail++) {
       const string T = tail ? "true" : "false";
       c << (tail ? "    } else {\n" : "    if (e0 + " + S(E) + " <= e_end) {\n");
-      c << "      b200_lean_z<" << T << ">(e0, par);\n      __syncwarp();\n      if (lead && nen) b200_lean_issue_off(e0n, nen);\n";
+      c << "      b200_lean_z<" << T << ">(e0, par);\n      __syncwarp();\n" << (st_idx ? "      if (lead && nen) b200_lean_issue_off(e0n, nen);\n" : "");
       c << "      b200_lean_yx<" << T << ">(e0, par);\n      __syncwarp();\n" << (any_qd ? "      if (lead && nen) b200_lean_issue_qd(e0n, nen);\n" : "");
       c << "      b200_lean_yt();\n      __syncwarp();\n";
-      c << "      b200_lean_zt<" << T << ">(e0, par);\n      __syncwarp();\n      if (lead && nen) b200_lean_issue_tg(e0n, nen);\n";
+      c << "      b200_lean_zt<" << T << ">(e0, par);\n      __syncwarp();\n" << (st_idx ? "      if (lead && nen) b200_lean_issue_tg(e0n, nen);\n" : "");
     }
     c << "    }\n  }\n}\n";
     return c.str();
@@ -531,10 +603,16 @@ size_t b200_opgen_lean_layout(B200OpPlan *plan, int E) {
   };
   plan->mbar_off = -1, plan->lean_off_off = -1;
   for (auto &f : plan->in_fields) f.qd_off = -1, f.qd_tma = false;
-  if (plan->stage_mask & 32) {
-    // bulk pipeline: single buffers for the offsets, the targets and every contiguous EVAL_NONE component (+16 bytes: aligned-down sources)
+  // bulk pipeline: single buffers for the offsets and the targets (bit 8) and every contiguous EVAL_NONE component (bit 32), each
+  // + 16 bytes for the aligned-down sources
+  if (plan->stage_mask & 8) {
     plan->lean_off_off = take((size_t)E * P * P * P * 4 + 16);
     plan->lean_tg_off  = take((size_t)E * P * P * P * 4 + 16);
+  } else {
+    const int rounds  = (E * P * P + 31) / 32;
+    plan->lean_tg_off = take((size_t)rounds * P * 32 * 4);
+  }
+  if (plan->stage_mask & 32) {
     for (auto &f : plan->in_fields) {
       const bool contiguous = f.emode == B200_EVAL_NONE && f.rstr->is_strided && f.rstr->strides[0] == 1 && f.rstr->strides[2] == f.rstr->elem_size;
       if (!contiguous) continue;
@@ -542,11 +620,8 @@ size_t b200_opgen_lean_layout(B200OpPlan *plan, int E) {
       f.qd_off = take((size_t)f.nc * f.qd_cs * 8);
       f.qd_tma = true;
     }
-    plan->mbar_off = take(32);
-  } else {
-    const int rounds  = (E * P * P + 31) / 32;
-    plan->lean_tg_off = take((size_t)rounds * P * 32 * 4);
   }
+  if (plan->stage_mask & 40) plan->mbar_off = take(32);
   return off;
 }
 

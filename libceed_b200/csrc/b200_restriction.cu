@@ -294,6 +294,73 @@ int b200_restriction_build_owner(B200Restriction r) {
   return B200_SUCCESS;
 }
 
+// Run scatter tables (see B200RunScatter): run of group w = elements [w * ne / G, (w + 1) * ne / G), walked in nb = ceil(len / E)
+// iterations; element e of the run sits in iteration (e - s) % nb.  Host-side, O(E-entries).
+int b200_restriction_build_runs(B200Restriction r, int num_groups, int group_elems, B200RunScatter *out) {
+  B200Ceed ceed = r->ceed;
+  if (out->built && out->num_groups == num_groups && out->group_elems == group_elems) return B200_SUCCESS;
+  b200_run_scatter_free(ceed, out);
+  B200_CALL(check_table_range(r));
+  B200_CHECK(r->l_size < (int64_t)B200_RUN_RMW_BIT, ceed, B200_ERROR_UNSUPPORTED, "run scatter tables need L-vectors shorter than 2^30");
+  B200_CHECK(num_groups > 0 && group_elems > 0, ceed, B200_ERROR_DIMENSION, "invalid run shape");
+  HostTranspose t;
+  build_host_transpose(r, t);
+  const int64_t        ne = r->num_elem, es = r->elem_size, n = ne * es, num_nodes = (int64_t)t.lvec_indices.size();
+  std::vector<int32_t> grp(ne), iter(ne);
+  for (int64_t w = 0; w < num_groups; w++) {
+    const int64_t s = w * ne / num_groups, s1 = (w + 1) * ne / num_groups, len = s1 - s;
+    if (len <= 0) continue;
+    const int64_t nb = (len + group_elems - 1) / group_elems;
+    for (int64_t e = s; e < s1; e++) grp[e] = (int32_t)w, iter[e] = (int32_t)((e - s) % nb);
+  }
+  std::vector<int32_t> tgt(n), halo_node, halo_ptr;
+  int64_t              slot = 0, num_rmw = 0;
+  for (int64_t row = 0; row < num_nodes; row++) {
+    const int32_t begin = t.t_offsets[row], end = t.t_offsets[row + 1];
+    const int32_t l     = t.lvec_indices[row];
+    tgt[t.t_indices[begin]] = l;  // owner: plain store
+    bool    chain = true, any_halo = false;
+    int64_t prev  = t.t_indices[begin] / es;
+    const int32_t owner_group = grp[prev];
+    for (int32_t j = begin + 1; j < end; j++) {
+      const int64_t e = t.t_indices[j] / es;
+      chain           = chain && grp[e] == owner_group && iter[e] > iter[prev];
+      prev            = e;
+      if (chain) {
+        tgt[t.t_indices[j]] = l | B200_RUN_RMW_BIT;
+        num_rmw++;
+      } else {
+        if (!any_halo) {
+          halo_node.push_back(l);
+          halo_ptr.push_back((int32_t)slot);
+          any_halo = true;
+        }
+        tgt[t.t_indices[j]] = ~(int32_t)(slot++);
+      }
+    }
+  }
+  halo_ptr.push_back((int32_t)slot);
+  out->num_shared = (int64_t)halo_node.size();
+  out->num_halo   = slot;
+  out->num_rmw    = num_rmw;
+  B200_CALL(b200_dmalloc(ceed, (void **)&out->d_tgt, n * sizeof(int32_t)));
+  B200_CALL(b200_dmalloc(ceed, (void **)&out->d_halo_node, (halo_node.size() + 1) * sizeof(int32_t)));
+  B200_CALL(b200_dmalloc(ceed, (void **)&out->d_halo_ptr, halo_ptr.size() * sizeof(int32_t)));
+  B200_CALL(b200_h2d(ceed, out->d_tgt, tgt.data(), n * sizeof(int32_t)));
+  if (!halo_node.empty()) B200_CALL(b200_h2d(ceed, out->d_halo_node, halo_node.data(), halo_node.size() * sizeof(int32_t)));
+  B200_CALL(b200_h2d(ceed, out->d_halo_ptr, halo_ptr.data(), halo_ptr.size() * sizeof(int32_t)));
+  out->num_groups = num_groups, out->group_elems = group_elems;
+  out->built = true;
+  return B200_SUCCESS;
+}
+
+void b200_run_scatter_free(B200Ceed ceed, B200RunScatter *t) {
+  b200_dfree(ceed, t->d_tgt);
+  b200_dfree(ceed, t->d_halo_node);
+  b200_dfree(ceed, t->d_halo_ptr);
+  *t = B200RunScatter();
+}
+
 // Ordered scatter tables for element groups of `group_elems` consecutive elements (see B200OrderedScatter).
 // Halo image of one shared node: [node id (as a 64-bit integer)][contribution of toucher 0]...[contribution of the last toucher].
 // tgt of an E-entry: >= 0 plain L-index; < 0: x = ~tgt, bits 0..26 = slot of this entry's contribution, bit 27 = "last toucher:
@@ -399,6 +466,12 @@ extern "C" int ceedb200_restriction_debug_scatter_tables(B200Restriction r, int 
       if (pred_idx && t.num_pred <= pred_capacity && t.num_pred > 0) B200_CALL(b200_d2h(ceed, pred_idx, t.d_pred_idx, t.num_pred * sizeof(int32_t)));
       b200_ordered_scatter_free(ceed, &t);
     }
+  } else if (mode == 4) {  // run scatter: group_elems = elements per iteration, pred_capacity = number of groups (warps) of the launch
+    B200RunScatter t;
+    B200_CALL(b200_restriction_build_runs(r, (int)pred_capacity, group_elems, &t));
+    counts[0] = t.num_shared, counts[1] = t.num_halo, counts[2] = t.num_groups, counts[3] = t.num_rmw, counts[4] = 1;
+    B200_CALL(b200_d2h(ceed, tgt, t.d_tgt, n * sizeof(int32_t)));
+    b200_run_scatter_free(ceed, &t);
   } else {
     B200_CALL(b200_restriction_build_owner(r));
     counts[0] = r->num_shared, counts[1] = r->num_halo, counts[2] = 0, counts[3] = 0, counts[4] = 1;
@@ -440,6 +513,14 @@ int b200_halo_finalize(B200Restriction r, const double *d_halo, double *d_v, int
   const int64_t count = part == 1 ? r->num_shared_first : r->num_shared - first;
   if (count <= 0) return B200_SUCCESS;
   LAUNCH(ceed, k_halo_finalize, count, r->d_halo_node + first, r->d_halo_ptr + first, d_halo, d_v, count, r->num_halo, r->num_comp, r->comp_stride);
+  return B200_SUCCESS;
+}
+
+int b200_halo_finalize_lists(B200Restriction r, const int32_t *d_halo_node, const int32_t *d_halo_ptr, int64_t num_shared, int64_t num_halo, const double *d_halo,
+                             double *d_v) {
+  B200Ceed ceed = r->ceed;
+  if (num_shared <= 0) return B200_SUCCESS;
+  LAUNCH(ceed, k_halo_finalize, num_shared, d_halo_node, d_halo_ptr, d_halo, d_v, num_shared, num_halo, r->num_comp, r->comp_stride);
   return B200_SUCCESS;
 }
 
