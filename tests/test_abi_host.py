@@ -230,6 +230,40 @@ def check(nel, p, group_elems, scramble):
         got = sorted(int(x) for x in pred_idx[pred_ptr[g]:pred_ptr[g + 1]])
         assert got == sorted(expect_pred[g]) and all(q < g for q in got), g   # waits only ever point to earlier groups
     out["ordered"] = [int(x) for x in cnt[:4]]
+    # ---- run scatter tables (B200RunScatter): simulate the warps walking their runs and check that every direct entry (store / read-modify-
+    # write) finds exactly the ascending-E prefix of its node already in v, and that the halo entries are the remaining suffix in order
+    RMW = 1 << 30
+    out["runs"] = []
+    for num_groups, E in ((1, 2), (3, 1), (4, 3), (7, 2)):
+        assert lib.ceedb200_restriction_debug_scatter_tables(r._ptr, 4, E, tgt.ctypes.data, cnt.ctypes.data, None, None, num_groups) == 0
+        applied = {}                                          # node -> list of E-entries already added into v, in order of arrival
+        for w in range(num_groups):                           # groups are independent: a direct entry only ever follows entries of its own group
+            s0, s1 = w * num_elem // num_groups, (w + 1) * num_elem // num_groups
+            nb = (s1 - s0 + E - 1) // E if s1 > s0 else 0
+            for it in range(nb):
+                batch = [s0 + it + k * nb for k in range(E) if s0 + it + k * nb < s1]
+                touched = set()
+                for e in batch:
+                    for n in range(es):
+                        g = int(tgt[e * es + n])
+                        if g < 0: continue
+                        node = g & (RMW - 1)
+                        assert node == flat[e * es + n]
+                        assert node not in touched, "two direct entries of one node in the same iteration would race"
+                        touched.add(node)
+                        if g & RMW: assert node in applied
+                        else: assert node not in applied
+                        applied.setdefault(node, []).append(e * es + n)
+        n_rmw = 0; next_slot = 0
+        for node, s, c in zip(nodes, starts, counts):
+            entries = [int(x) for x in order[s:s + c]]
+            direct = applied[int(node)]
+            assert direct == entries[:len(direct)]             # ascending E-order prefix, owner first
+            n_rmw += len(direct) - 1
+            for e in entries[len(direct):]:                    # halo suffix: consecutive slots in ascending E-order
+                assert ~int(tgt[e]) == next_slot; next_slot += 1
+        assert next_slot == cnt[1] and n_rmw == cnt[3] and cnt[2] == num_groups
+        out["runs"].append([int(cnt[1]), int(cnt[3])])
     return out
 
 res = {"%%dx%%dx%%d p%%d g%%d s%%d" %% (*nel, p, ge, sc): check(nel, p, ge, sc)
@@ -246,6 +280,43 @@ def test_scatter_tables_match_serial_order_model_without_gpu():
     assert r.returncode == 0, r.stderr[-3000:]
     res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][0][6:])
     assert len(res) == 4 and all(v["det"][1] > 0 and v["ordered"][2] > 0 for v in res.values())
+    for v in res.values():  # one group walking everything one element at a time needs no halo at all; more groups need more
+        assert len(v["runs"]) == 4 and all(h + m == v["det"][1] for h, m in v["runs"]) and v["runs"][1][0] >= 0
+
+
+LEAN_SHAPES = r"""
+import json, sys
+sys.path.insert(0, %r)
+from libceed_b200 import Ceed
+from libceed_b200.bp import BPProblem
+ceed = Ceed()
+out = {}
+for bp, p in ((1, 3), (2, 2), (1, 4), (1, 1), (3, 3)):
+    prob = BPProblem(ceed, bp, p, (3, 3, 2), build_qdata=False)
+    for E, warps, stage in ((6, 4, 0), (3, 2, 40), (4, 4, 8), (5, 1, 96)):
+        prob.op.set_kernel_shape(qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=stage)
+        src = prob.op.kernel_source()
+        got = prob.op.get_kernel_shape()
+        out["bp%%d p%%d E%%d s%%d" %% (bp, p, E, stage)] = dict(layout=got["qf_mode"], stage=got["stage_mask"], lean="b200_lean_z" in src, bulk="b200_lean_copy" in src,
+                                                               prefetch="b200_lean_prefetch_qd" in src, smem=prob.op.kernel_info()["smem_bytes"])
+print("RESULT" + json.dumps(out))
+""" % ROOT
+
+
+def test_lean_kernel_generates_and_compiles_without_gpu():
+    """The lean in-place-plane kernel (layout 4) is generated and NVRTC-compiled for sm_100a for BP1 / BP2 shapes incl. the bulk pipelines;
+    operators with gradients keep their own layout."""
+    env = dict(os.environ, CEED_B200_COMPILE_ONLY="1", CEED_B200_NO_TUNE_TABLE="1")
+    r = subprocess.run([sys.executable, "-c", LEAN_SHAPES], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][0][6:])
+    for key, v in res.items():
+        if key.startswith("bp3"):
+            assert v["layout"] != 4 and not v["lean"], (key, v)
+            continue
+        assert v["layout"] == 4 and v["lean"], (key, v)
+        want = int(key.rsplit("s", 1)[1]) & (8 | 32 | 64)
+        assert v["stage"] == want and v["bulk"] == bool(want & 40) and v["prefetch"] == bool((want & 64) and not (want & 32)), (key, v)
 
 
 VECTOR_STATE = r"""

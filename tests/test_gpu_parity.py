@@ -356,7 +356,9 @@ SHAPES = [dict(group_warps=2, cta_warps=2), dict(group_warps=2, cta_warps=8), di
           dict(stage_mask=32, group_warps=4, cta_warps=4, elems_per_group=2),
           # conflict-free swizzled plane layout (stage bit 256), alone and with the other staging options
           dict(stage_mask=257), dict(stage_mask=257, group_warps=2, cta_warps=4, elems_per_group=2), dict(stage_mask=289, group_warps=2, cta_warps=2),
-          dict(stage_mask=265, group_warps=4, cta_warps=4, elems_per_group=3), dict(stage_mask=256, qf_mode=0, cta_warps=2)]
+          dict(stage_mask=265, group_warps=4, cta_warps=4, elems_per_group=3), dict(stage_mask=256, qf_mode=0, cta_warps=2),
+          # lean in-place-plane kernel of gradient-free operators (layout 4; other operators fall back to their own layouts)
+          dict(qf_mode=4, group_warps=1, cta_warps=4, elems_per_group=6, stage_mask=0), dict(qf_mode=4, group_warps=1, cta_warps=2, elems_per_group=3, stage_mask=40)]
 
 
 @pytest.mark.parametrize("bp,p,nel", [(3, 2, (5, 3, 2)), (5, 3, (3, 3, 2)), (1, 3, (4, 3, 3)), (6, 2, (3, 2, 2)), (3, 4, (3, 2, 2)), (3, 6, (2, 2, 1)), (5, 7, (2, 1, 2)),
@@ -379,14 +381,79 @@ def test_kernel_shapes_give_identical_results(cm, oracle, monkeypatch, bp, p, ne
         prob.op.apply(prob.u, prob.v)
         got = prob.op.get_kernel_shape()
         for k, val in shape.items():
-            if k == "qf_mode" and val in (2, 3):
-                continue  # point pairs need an even Q, x-line fusion a gradient-free operator: otherwise they fall back
+            if (k == "qf_mode" and val in (2, 3, 4)) or shape.get("qf_mode") == 4:
+                continue  # point pairs need an even Q, x-line fusion / the lean kernel a gradient-free operator: otherwise they fall back
             if k == "cta_warps":
                 assert got[k] <= val, (shape, got)  # groups per CTA are reduced when their shared memory would not fit
                 continue
             assert got[k] == val, (shape, got)
         assert rel(prob.v.get_array_read(), ref) < OP_TOL, shape
         assert rel(prob.v.get_array_read(), v0) < 1e-13, shape
+
+
+LEAN_CASES = [(1, 3, (5, 3, 3)), (1, 3, (7, 5, 3)), (2, 3, (3, 2, 3)), (1, 1, (5, 4, 3)), (1, 2, (3, 3, 3)), (1, 4, (3, 2, 3)), (1, 5, (2, 3, 2)), (2, 2, (3, 3, 2)),
+              (2, 1, (4, 4, 3)), (2, 4, (2, 2, 1))]
+
+
+@pytest.mark.parametrize("bp,p,nel", LEAN_CASES)
+def test_lean_kernel_matches_oracle(cm, oracle, monkeypatch, bp, p, nel):
+    """The lean in-place-plane kernel (QFunction layout 4, b200_opgen_lean.cpp) on BP1 / BP2: every batch width incl. partial tail
+    batches, deterministic and atomic scatter, Apply and ApplyAdd, direct loads and the bulk-copy (cp.async.bulk + mbarrier) pipelines
+    for the index tables (stage bit 8) and the quadrature data (bit 32) and the bulk L2 prefetch (bit 64), lexicographic and Morton
+    element order -- against the oracle; the deterministic variants also bitwise against each other."""
+    from libceed_b200 import mesh as M
+    monkeypatch.setenv("CEED_B200_NO_TUNE_TABLE", "1")
+    perm = M.morton_permutation(*nel) if (bp + p) % 2 else None
+    v_det = None
+    for mode in (0, 1):
+        prob = make_problem(cm, bp, p, nel, mode=mode, elem_perm=perm)
+        u = seeded_uniform(prob.num_dofs, 31)
+        prob.u.set_array(u)
+        qd = oracle.bp_qdata(bp, p, prob.offsets, prob.coords)
+        ref = oracle.bp_apply(bp, p, prob.offsets, prob.num_nodes, qd, u)
+        for E, warps, stage in ((1, 1, 0), (3, 2, 0), (6, 4, 0), (8, 8, 0), (3, 1, 32), (6, 4, 40), (5, 2, 8), (4, 4, 64), (2, 2, 72)):
+            prob.op.set_kernel_shape(qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=stage)
+            prob.v.set_value(-3.0)
+            prob.op.apply(prob.u, prob.v)
+            got = prob.op.get_kernel_shape()
+            assert got["qf_mode"] == 4 and got["stage_mask"] == stage and got["elems_per_group"] == min(E, prob.num_elem), (got, E, stage)
+            v = prob.v.get_array_read().copy()
+            assert rel(v, ref) < OP_TOL, (mode, E, warps, stage)
+            if mode == 0:
+                v_det = v if v_det is None else v_det
+                assert np.array_equal(v, v_det), (E, warps, stage)  # same ascending E-order whatever the shape
+            w0 = seeded_uniform(prob.num_dofs, 5)
+            prob.v.set_array(w0)
+            prob.op.apply_add(prob.u, prob.v)
+            assert np.abs(prob.v.get_array_read() - w0 - ref).max() < 1e-12 * max(1.0, np.abs(ref).max()), (mode, E, warps, stage)
+
+
+@pytest.mark.parametrize("bp,p,nel,morton", [(1, 3, (32, 31, 31), True), (1, 3, (33, 30, 29), False), (2, 2, (30, 29, 28), True)])
+def test_lean_kernel_run_scatter_is_bitwise_equal(cm, oracle, monkeypatch, bp, p, nel, morton):
+    """Experimental run scatter (CEED_B200_RUNS; B200RunScatter): warps own contiguous element runs and add the E-entries whose earlier
+    touchers they processed themselves straight into v.  Same ascending E-order: bitwise equal to the owner/halo tables."""
+    from libceed_b200 import mesh as M
+    monkeypatch.setenv("CEED_B200_NO_TUNE_TABLE", "1")
+    perm = M.morton_permutation(*nel) if morton else None
+    prob = make_problem(cm, bp, p, nel, elem_perm=perm)
+    u = seeded_uniform(prob.num_dofs, 37)
+    prob.u.set_array(u)
+    qd = oracle.bp_qdata(bp, p, prob.offsets, prob.coords)
+    ref = oracle.bp_apply(bp, p, prob.offsets, prob.num_nodes, qd, u)
+    prob.op.set_kernel_shape(qf_mode=4, elems_per_group=4, cta_warps=4, group_warps=1, stage_mask=0)
+    prob.op.apply(prob.u, prob.v)
+    v_classic = prob.v.get_array_read().copy()
+    assert rel(v_classic, ref) < OP_TOL
+    monkeypatch.setenv("CEED_B200_RUNS", "1")
+    for E, warps in ((1, 4), (2, 4), (6, 4), (8, 2)):
+        prob.op.set_kernel_shape(qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=0)
+        prob.v.set_value(-3.0)
+        prob.op.apply(prob.u, prob.v)
+        assert np.array_equal(prob.v.get_array_read(), v_classic), (E, warps)
+        w0 = seeded_uniform(prob.num_dofs, 5)
+        prob.v.set_array(w0)
+        prob.op.apply_add(prob.u, prob.v)
+        assert np.abs(prob.v.get_array_read() - w0 - ref).max() < 1e-12 * max(1.0, np.abs(ref).max()), (E, warps)
 
 
 def test_autotuner_picks_a_shape_and_keeps_results(cm, oracle, tmp_path, monkeypatch):
