@@ -85,6 +85,8 @@ CEEDB200_EXPORT int ceedb200_vector_destroy(B200Vector vec);
 CEEDB200_EXPORT int ceedb200_vector_length(B200Vector vec, b200_size *length);
 CEEDB200_EXPORT int ceedb200_vector_has_valid_array(B200Vector vec, int *has_valid);
 CEEDB200_EXPORT int ceedb200_vector_has_borrowed_array_of_type(B200Vector vec, int mem_type, int *has_borrowed);
+/* which mirrors currently hold valid data (the lazy-sync state of backends/cuda-ref/ceed-cuda-ref-vector.c:20-38 CeedVectorNeedSync_Cuda) */
+CEEDB200_EXPORT int ceedb200_vector_valid_sides(B200Vector vec, int *host_valid, int *device_valid);
 CEEDB200_EXPORT int ceedb200_vector_set_array(B200Vector vec, int mem_type, int copy_mode, b200_scalar *array);
 CEEDB200_EXPORT int ceedb200_vector_take_array(B200Vector vec, int mem_type, b200_scalar **array);
 CEEDB200_EXPORT int ceedb200_vector_set_value(B200Vector vec, b200_scalar value);
@@ -223,6 +225,16 @@ CEEDB200_EXPORT int ceedb200_operator_assemble_qfunction(B200Operator op, B200Ve
  * ceedb200_restriction_set_split -- plus the finalize pass of the nodes only they touch; part 2 = the interior elements.
  * part 1 followed by part 2 produces exactly the bits of ceedb200_operator_apply. */
 CEEDB200_EXPORT int ceedb200_operator_apply_part(B200Operator op, B200Vector u, B200Vector v, int part);
+/* v = A u for an application that keeps its vectors in HOST memory: u valid on the host only, v with a host array (pinned memory both).
+ * Replaces the sequence the reference performs for CeedVectorSetArray(HOST) -> CeedOperatorApply -> CeedVectorSyncArray(HOST): a whole-
+ * vector host-to-device copy when the operator asks for the device array (backends/cuda-ref/ceed-cuda-ref-vector.c:40-76
+ * CeedVectorSyncH2D_Cuda), the apply (backends/cuda-gen/ceed-cuda-gen-operator.c:99-300), and a whole-vector copy back
+ * (ceed-cuda-ref-vector.c:101-130 CeedVectorSyncD2H_Cuda), one after the other.  Here the elements are cut into num_chunks (0 = default)
+ * contiguous chunks; a chunk is applied as soon as the part of u it gathers has arrived and the part of v that no later chunk touches
+ * is copied back while the next chunks run (two copy streams, PCIe is full duplex).  Bitwise the result of ceedb200_operator_apply; on
+ * return v is valid on BOTH sides.  Falls back to ceedb200_operator_apply (*streamed = 0) when a precondition does not hold (operator not
+ * fused, other scatter mode, u already valid on the device, pageable host memory, partially covered output, fewer than 4096 elements). */
+CEEDB200_EXPORT int ceedb200_operator_apply_streamed(B200Operator op, B200Vector u, B200Vector v, int num_chunks, int *streamed);
 CEEDB200_EXPORT int ceedb200_operator_set_timing(B200Operator op, int enabled);
 CEEDB200_EXPORT int ceedb200_operator_last_kernel_ms(B200Operator op, float *fused_ms, float *aux_ms);
 /* tuning override: elems_per_block (0 = heuristic), blocks_per_sm (0 = heuristic) */

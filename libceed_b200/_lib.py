@@ -129,7 +129,9 @@ def load(path=LIB_PATH):
         "ceedb200_ipc_open": [handle, C.c_char_p, P(C.c_void_p)],
         "ceedb200_ipc_close": [handle, C.c_void_p],
         "ceedb200_ipc_free": [handle, C.c_void_p],
+        "ceedb200_vector_valid_sides": [handle, C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "ceedb200_operator_apply_part": [handle, handle, handle, C.c_int],
+        "ceedb200_operator_apply_streamed": [handle, handle, handle, C.c_int, C.POINTER(C.c_int)],
         "ceedb200_restriction_set_split": [handle, C.c_int32],
     }
     for name, argtypes in sigs.items():

@@ -137,6 +137,26 @@ static int CeedOperatorApplyCore_B200(CeedOperator op, CeedVector in_vec, CeedVe
     return CeedOperatorApplyAdd(op_fallback, in_vec, out_vec, CEED_REQUEST_IMMEDIATE);
   }
 
+  // Host-resident application (CeedVectorSetArray(HOST) -> CeedOperatorApply -> CeedVectorSyncArray(HOST)): the input is valid on the
+  // host only and the output has a caller-owned host array.  The core then pipelines copy-in, apply and copy-out chunk by chunk
+  // (ceedb200_operator_apply_streamed) instead of the reference's whole-vector copies around the apply; it falls back to the plain apply
+  // by itself when a precondition does not hold.  Only when both vectors belong to this backend and there are no passive fields to bind
+  // differently (their device arrays are bound below as usual).
+  bool try_streamed = false;
+  if (!add && in_vec != CEED_VECTOR_NONE && out_vec != CEED_VECTOR_NONE && in_vec != out_vec && !getenv("CEED_B200_NO_STREAMED") &&
+      CeedVectorReturnCeed(in_vec) == ceed && CeedVectorReturnCeed(out_vec) == ceed) {
+    CeedVector_B200 *vi, *vo;
+    int              h_valid = 0, d_valid = 0, out_borrowed = 0;
+    bool             passive_out = false;
+
+    CeedCallBackend(CeedVectorGetData(in_vec, &vi));
+    CeedCallBackend(CeedVectorGetData(out_vec, &vo));
+    CeedCallB200(ceed, core, ceedb200_vector_valid_sides(vi->core, &h_valid, &d_valid));
+    CeedCallB200(ceed, core, ceedb200_vector_has_borrowed_array_of_type(vo->core, B200_MEM_HOST, &out_borrowed));
+    for (CeedInt i = 0; i < impl->num_out; i++) passive_out = passive_out || impl->passive_out_vec[i];
+    try_streamed = h_valid && !d_valid && out_borrowed && !passive_out;
+  }
+
   // Device arrays of every vector involved, through the interface.  From here on no early return: the first error is recorded,
   // every array that was acquired is restored (libCEED's access locks must be released whatever happens) and the error is
   // reported at the end.
@@ -155,7 +175,14 @@ static int CeedOperatorApplyCore_B200(CeedOperator op, CeedVector in_vec, CeedVe
     if (!status && !core_err) core_err = (call); \
   } while (0)
 
-    if (in_vec != CEED_VECTOR_NONE) {
+    if (try_streamed) {
+      // interface bookkeeping only (access locks, state counters): the host arrays are valid, nothing is copied here
+      B200_TRY(CeedVectorGetArrayRead(in_vec, CEED_MEM_HOST, &d_in));
+      got_in = !status;
+      B200_TRY(CeedVectorGetArrayWrite(out_vec, CEED_MEM_HOST, &d_out));
+      got_out = !status;
+    }
+    if (in_vec != CEED_VECTOR_NONE && !try_streamed) {
       B200_TRY(CeedVectorGetLength(in_vec, &len));
       B200_TRY(CeedVectorGetArrayRead(in_vec, CEED_MEM_DEVICE, &d_in));
       got_in = !status;
@@ -167,7 +194,7 @@ static int CeedOperatorApplyCore_B200(CeedOperator op, CeedVector in_vec, CeedVe
       }
       B200_TRY_CORE(ceedb200_vector_set_array(impl->view_in, B200_MEM_DEVICE, B200_USE_POINTER, (CeedScalar *)d_in));
     }
-    if (out_vec != CEED_VECTOR_NONE) {
+    if (out_vec != CEED_VECTOR_NONE && !try_streamed) {
       B200_TRY(CeedVectorGetLength(out_vec, &len));
       if (add) B200_TRY(CeedVectorGetArray(out_vec, CEED_MEM_DEVICE, &d_out));
       else B200_TRY(CeedVectorGetArrayWrite(out_vec, CEED_MEM_DEVICE, &d_out));
@@ -203,7 +230,14 @@ static int CeedOperatorApplyCore_B200(CeedOperator op, CeedVector in_vec, CeedVe
       B200_TRY(CeedQFunctionContextAcquire_B200(qf, &held_ctx));
       ctx_held = !status;
     }
-    if (!status && !core_err) {
+    if (!status && !core_err && try_streamed) {
+      CeedVector_B200 *vi, *vo;
+      int              used = 0;
+
+      B200_TRY(CeedVectorGetData(in_vec, &vi));
+      B200_TRY(CeedVectorGetData(out_vec, &vo));
+      if (!status) core_err = ceedb200_operator_apply_streamed(impl->core, vi->core, vo->core, 0, &used);
+    } else if (!status && !core_err) {
       // overwrite semantics can only be used when every output is the active vector
       if (!add && !has_passive_out) core_err = ceedb200_operator_apply(impl->core, in_vec != CEED_VECTOR_NONE ? impl->view_in : NULL, impl->view_out);
       else {

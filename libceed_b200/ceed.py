@@ -349,6 +349,13 @@ class Operator(_Object):
         (ElemRestriction.set_split); 1 followed by 2 equals apply()."""
         self._chk(self._ceed._lib.ceedb200_operator_apply_part(self._ptr, u._ptr, v._ptr, part))
 
+    def apply_streamed(self, u, v, num_chunks=0):
+        """v = A u with u valid on the (pinned) host only and v wanted on the host: chunked H2D / apply / D2H pipeline
+        (ceedb200_operator_apply_streamed).  Returns True when the streamed path ran, False when it fell back to apply()."""
+        used = C.c_int(0)
+        self._chk(self._ceed._lib.ceedb200_operator_apply_streamed(self._ptr, u._ptr, v._ptr, num_chunks, C.byref(used)))
+        return bool(used.value)
+
     def set_tuning(self, elems_per_block=0, blocks_per_sm=0):
         self._chk(self._ceed._lib.ceedb200_operator_set_tuning(self._ptr, elems_per_block, blocks_per_sm))
 

@@ -50,6 +50,9 @@ struct B200Ceed_ {
   int                                 autotune = 0;  // 0 off, 1 tune operators missing from the table, 2 always
   // scratch for norms
   double *d_scratch = nullptr;
+  // copy streams + events of the streamed host-buffer apply (ceedb200_operator_apply_streamed), created on first use
+  cudaStream_t             s_h2d = nullptr, s_d2h = nullptr;
+  std::vector<cudaEvent_t> ev_stream;
   size_t  scratch_len = 0;
   // grow-only work buffers of the standalone basis kernels (stream-ordered reuse: no allocation, no synchronisation per apply)
   double *d_basis_tmp[3]     = {nullptr, nullptr, nullptr};
@@ -134,6 +137,11 @@ struct B200Restriction_ {
   // the boundary part of the scatter can be finalized -- and sent -- while the interior elements are still being applied.
   int      split_elem = -1;
   int64_t  num_shared_first = 0;
+  // Generalisation to K element parts (streamed host-buffer apply, ceedb200_operator_apply_streamed): part p = elements
+  // [part_ends[p - 1], part_ends[p]) (part_ends[-1] = 0); shared nodes are ordered by the part of their LAST toucher, shared_prefix[p]
+  // = number of shared nodes completed by parts <= p.  The split above is the two-part case {split_elem, num_elem}.
+  std::vector<int32_t> part_ends;
+  std::vector<int64_t> shared_prefix;
   bool     transpose_built = false, owner_built = false;
 };
 
@@ -238,5 +246,9 @@ int b200_restriction_build_owner(B200Restriction rstr);
 int b200_restriction_e_size(B200Restriction rstr, int64_t *e_size);
 // raw device-pointer restriction kernels (used by the unfused operator path and EVECTOR scatter mode)
 int b200_restriction_apply_raw(B200Restriction rstr, int t_mode, const double *d_u, double *d_v);
-int b200_halo_finalize(B200Restriction rstr, const double *d_halo, double *d_v, int part = 0);  // part 0 all, 1 boundary-only nodes, 2 the rest
+// streamed apply: device side of `vec` handed out WITHOUT the host-to-device copy (the caller copies chunk by chunk); both sides valid after
+int b200_vector_streamed_input(B200Vector vec, const double **h, double **d);
+int b200_vector_streamed_output(B200Vector vec, double **h);  // host array the chunks of the result are copied into; valid on both sides after
+int b200_halo_finalize(B200Restriction rstr, const double *d_halo, double *d_v, int part = 0);  // part 0 all; p >= 1: the shared nodes completed by element part p
+int b200_restriction_set_parts(B200Restriction rstr, const std::vector<int32_t> &part_ends);     // K element parts (rebuilds the owner/halo tables if they change)
 int b200_memset_async(B200Ceed ceed, void *d, size_t bytes);

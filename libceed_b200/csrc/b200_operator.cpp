@@ -233,19 +233,21 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
   // element range of this launch
   long long e_begin = 0, e_end = plan->num_elem;
   if (part) {
-    int split = -1;
+    // element part `part` (1-based) of the output restriction's part table: the two parts of a partitioned mesh
+    // (ceedb200_restriction_set_split) or the K chunks of a streamed host-buffer apply (ceedb200_operator_apply_streamed)
+    const std::vector<int32_t> *ends = nullptr;
     for (size_t i = 0; i < op->out_fields.size(); i++) {
       const B200Restriction r = op->out_fields[i].rstr;
-      B200_CHECK(r->is_strided || r->split_elem >= 0, ceed, B200_ERROR_INCOMPLETE, "apply_part needs ceedb200_restriction_set_split on the output restriction");
-      if (!r->is_strided) {
-        B200_CHECK(split < 0 || split == r->split_elem, ceed, B200_ERROR_INCOMPATIBLE, "output restrictions with different element splits");
-        split = r->split_elem;
-      }
+      if (r->is_strided) continue;
+      B200_CHECK(!r->part_ends.empty(), ceed, B200_ERROR_INCOMPLETE, "apply_part needs ceedb200_restriction_set_split on the output restriction");
+      B200_CHECK(!ends || *ends == r->part_ends, ceed, B200_ERROR_INCOMPATIBLE, "output restrictions with different element splits");
+      ends = &r->part_ends;
     }
-    B200_CHECK(split >= 0, ceed, B200_ERROR_INCOMPLETE, "apply_part needs an offset-restricted output");
+    B200_CHECK(ends, ceed, B200_ERROR_INCOMPLETE, "apply_part needs an offset-restricted output");
+    B200_CHECK(part <= (int)ends->size(), ceed, B200_ERROR_DIMENSION, "element part %d of %d", part, (int)ends->size());
     B200_CHECK(plan->scatter_mode == B200_SCATTER_DETERMINISTIC, ceed, B200_ERROR_UNSUPPORTED, "apply_part needs the deterministic scatter mode");
-    if (part == 1) e_end = split;
-    else e_begin = split;
+    e_begin = part >= 2 ? (*ends)[part - 2] : 0;
+    e_end   = (*ends)[part - 1];
   }
   int  kernel_add = add;
   bool zero_first = false;
@@ -298,13 +300,13 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
       }
     }
   }
-  if (zero_first && part != 2)  // the interior part continues what the boundary part started
+  if (zero_first && part <= 1)  // later parts continue what the first part started
     for (auto &o : outs) B200_CALL(ceedb200_vector_set_value(o.vec, 0.0));
   for (size_t i = 0; i < op->out_fields.size(); i++) {
     const B200OpField &f   = op->out_fields[i];
     B200Vector         vec = f.is_active ? v : f.vec;
     // discard previous contents only when the kernel overwrites everything
-    B200_CALL(b200_vector_device_write(vec, &args.out_ptr[i], !kernel_add && part != 2));
+    B200_CALL(b200_vector_device_write(vec, &args.out_ptr[i], !kernel_add && part <= 1));
     if (!f.rstr->is_strided) {
       if (plan->scatter_mode == B200_SCATTER_ORDERED && (int)i == plan->ordered_slot) args.out_idx[i] = plan->ordered.d_tgt;
       else args.out_idx[i] = plan->scatter_mode == B200_SCATTER_DETERMINISTIC ? f.rstr->d_tgt : f.rstr->d_offsets;
@@ -744,6 +746,152 @@ extern "C" int ceedb200_operator_apply_part(B200Operator op, B200Vector u, B200V
   return apply_fused(op, u, v, 0, part);
 }
 extern "C" int ceedb200_operator_apply_add(B200Operator op, B200Vector u, B200Vector v) { return operator_apply(op, u, v, 1); }
+
+// ------------------------------------------------------------------------------------------------ streamed host-buffer apply
+// v = A u with u valid on the HOST only and v wanted on the host (the end-to-end call of an application that keeps its vectors in host
+// memory: CeedVectorSetArray(HOST) -> CeedOperatorApply -> CeedVectorSyncArray(HOST)).  Instead of copy-in, apply, copy-out one after
+// the other, the elements are cut into K contiguous chunks: chunk c is applied (fused kernel + the finalize pass of the shared nodes it
+// completes) as soon as the part of u it gathers has arrived, and the part of v no later chunk touches is copied back while the next
+// chunks run.  PCIe is full duplex, so the step costs about one transfer instead of two plus the kernels.  Which part of u a chunk
+// needs / which part of v it completes comes from the offsets (prefix maximum / suffix minimum of the L-indices per chunk): element
+// orders with locality (lexicographic, space-filling curves) stream well, a random order degenerates to copy-then-apply -- always
+// correct.  Results are bitwise those of ceedb200_operator_apply.  Falls back to the plain apply (returns *streamed = 0) whenever a
+// precondition does not hold: not fused, other scatter mode, u already on the device, pageable host memory, partial coverage, ...
+namespace {
+bool is_pinned_host(const void *p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
+extern "C" int ceedb200_operator_apply_streamed(B200Operator op, B200Vector u, B200Vector v, int num_chunks, int *streamed) {
+  B200Ceed ceed = op->ceed;
+  if (streamed) *streamed = 0;
+  B200_CALL(operator_setup(op));
+  B200OpPlan *plan = op->plan;
+  // ---- preconditions
+  B200Restriction rin = nullptr, rout = nullptr;
+  bool            ok  = plan->fused && !b200_compile_only() && plan->scatter_mode == B200_SCATTER_DETERMINISTIC && u && v && u != v &&
+            u != B200_VECTOR_NONE && v != B200_VECTOR_NONE && !(ceed->autotune && !op->tuned);
+  for (size_t i = 0; ok && i < op->in_fields.size(); i++) {
+    const B200OpField &f = op->in_fields[i];
+    if (!f.is_active || !f.rstr) continue;
+    ok  = ok && !f.rstr->is_strided && (!rin || rin == f.rstr);
+    rin = f.rstr;
+  }
+  for (size_t i = 0; ok && i < op->out_fields.size(); i++) {
+    const B200OpField &f = op->out_fields[i];
+    ok   = ok && f.is_active && !f.rstr->is_strided && (!rout || rout == f.rstr);
+    rout = f.rstr;
+  }
+  ok = ok && rin && rout && rout->split_elem < 0 && u->h_array && !u->d_array && (v->h_borrowed || v->h_owned) && u->length == rin->l_size && v->length == rout->l_size;
+  ok = ok && rout->num_elem >= 4096 && is_pinned_host(u->h_array) && is_pinned_host(v->h_borrowed ? v->h_borrowed : v->h_owned);
+  if (ok) {
+    B200_CALL(b200_restriction_build_owner(rout));
+    ok = rout->num_nodes * rout->num_comp == v->length;  // every entry of v is written: no zero-first pass
+  }
+  if (!ok) return operator_apply(op, u, v, 0);
+  B200_CUDA(ceed, cudaSetDevice(ceed->device_id));
+  // ---- chunk tables (cached in the plan)
+  const int K  = std::max(2, std::min(num_chunks > 0 ? num_chunks : 12, 64));
+  const int ne = rout->num_elem;
+  B200StreamPlan &sp = plan->stream;
+  if (sp.num_chunks != K) {
+    sp = B200StreamPlan();
+    for (int c = 1; c <= K; c++) sp.ends.push_back((int32_t)((int64_t)ne * c / K));
+    auto ranges = [&](B200Restriction r, std::vector<int64_t> &lo, std::vector<int64_t> &hi) {
+      lo.assign(K, INT64_MAX), hi.assign(K, -1);
+      for (int c = 0; c < K; c++) {
+        const int64_t b = (c ? sp.ends[c - 1] : 0) * (int64_t)r->elem_size, e = sp.ends[c] * (int64_t)r->elem_size;
+        for (int64_t i = b; i < e; i++) {
+          const int64_t l = r->h_offsets[i];
+          lo[c] = std::min(lo[c], l), hi[c] = std::max(hi[c], l);
+        }
+      }
+    };
+    std::vector<int64_t> in_lo, in_hi, out_lo, out_hi;
+    ranges(rin, in_lo, in_hi);
+    ranges(rout, out_lo, out_hi);
+    const auto blocked = [&](B200Restriction r, const std::vector<int64_t> &hi) {
+      return r->comp_stride >= *std::max_element(hi.begin(), hi.end()) + 1 && (int64_t)r->num_comp * r->comp_stride == r->l_size;
+    };
+    sp.per_comp = rin->num_comp > 1 && rin->num_comp == rout->num_comp && blocked(rin, in_hi) && blocked(rout, out_hi);
+    sp.in_hi.resize(K), sp.out_done.resize(K);
+    for (int c = 0; c < K; c++) sp.in_hi[c] = std::max(c ? sp.in_hi[c - 1] : (int64_t)0, in_hi[c] + 1);
+    int64_t later = INT64_MAX;  // lowest offset touched by a later chunk: everything below it is complete
+    for (int c = K - 1; c >= 0; c--) {
+      sp.out_done[c] = later;
+      later          = std::min(later, out_lo[c]);
+    }
+    sp.num_chunks = K;
+  }
+  B200_CALL(b200_restriction_set_parts(rout, sp.ends));
+  // ---- streams and events
+  if (!ceed->s_h2d) {
+    B200_CUDA(ceed, cudaStreamCreateWithFlags(&ceed->s_h2d, cudaStreamNonBlocking));
+    B200_CUDA(ceed, cudaStreamCreateWithFlags(&ceed->s_d2h, cudaStreamNonBlocking));
+  }
+  while ((int)ceed->ev_stream.size() < 2 * K + 2) {
+    cudaEvent_t ev;
+    B200_CUDA(ceed, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ceed->ev_stream.push_back(ev);
+  }
+  const double *h_u = nullptr;
+  double       *d_u = nullptr, *h_v = nullptr;
+  B200_CALL(b200_vector_streamed_input(u, &h_u, &d_u));
+  // range [b, e) of L-indices of one component block (or of the whole vector) -> byte ranges to copy
+  const int     ncb    = sp.per_comp ? rin->num_comp : 1;
+  const int64_t in_len = sp.per_comp ? rin->comp_stride : rin->l_size, out_len = sp.per_comp ? rout->comp_stride : rout->l_size;
+  const int64_t in_top = sp.per_comp ? 0 : (int64_t)(rin->num_comp - 1) * rin->comp_stride;  // one range: the other components sit above the offsets
+  // everything queued on the copy-in stream must follow what the caller already queued on the backend's stream (e.g. a previous apply)
+  cudaEvent_t ev_start = ceed->ev_stream[2 * K], ev_end = ceed->ev_stream[2 * K + 1];
+  B200_CUDA(ceed, cudaEventRecord(ev_start, ceed->stream));
+  B200_CUDA(ceed, cudaStreamWaitEvent(ceed->s_h2d, ev_start, 0));
+  int64_t copied = 0;
+  for (int c = 0; c < K; c++) {
+    const int64_t upto = c == K - 1 ? in_len : std::min(in_len, sp.in_hi[c] + in_top);
+    if (upto > copied)
+      for (int cc = 0; cc < ncb; cc++)
+        B200_CUDA(ceed, cudaMemcpyAsync(d_u + cc * rin->comp_stride + copied, h_u + cc * rin->comp_stride + copied, (upto - copied) * sizeof(double),
+                                        cudaMemcpyHostToDevice, ceed->s_h2d));
+    copied = std::max(copied, upto);
+    B200_CUDA(ceed, cudaEventRecord(ceed->ev_stream[c], ceed->s_h2d));
+  }
+  int64_t done = 0;
+  int     err  = B200_SUCCESS;
+  double *d_v  = nullptr;
+  for (int c = 0; c < K && !err; c++) {
+    B200_CUDA(ceed, cudaStreamWaitEvent(ceed->stream, ceed->ev_stream[c], 0));
+    err = apply_fused(op, u, v, 0, c + 1);
+    if (err) break;
+    if (c == 0) {
+      d_v = v->d_array;
+      B200_CALL(b200_vector_streamed_output(v, &h_v));
+    }
+    B200_CUDA(ceed, cudaEventRecord(ceed->ev_stream[K + c], ceed->stream));
+    B200_CUDA(ceed, cudaStreamWaitEvent(ceed->s_d2h, ceed->ev_stream[K + c], 0));
+    const int64_t upto = c == K - 1 ? out_len : std::min(out_len, sp.out_done[c]);
+    if (upto > done)
+      for (int cc = 0; cc < ncb; cc++)
+        B200_CUDA(ceed, cudaMemcpyAsync(h_v + cc * rout->comp_stride + done, d_v + cc * rout->comp_stride + done, (upto - done) * sizeof(double),
+                                        cudaMemcpyDeviceToHost, ceed->s_d2h));
+    done = std::max(done, upto);
+  }
+  // the result is on the host when the call returns (the caller's CeedVectorSyncArray(HOST) is then a no-op), and later work on the
+  // backend's stream is ordered after the copies
+  B200_CUDA(ceed, cudaEventRecord(ev_end, ceed->s_d2h));
+  B200_CUDA(ceed, cudaStreamWaitEvent(ceed->stream, ev_end, 0));
+  B200_CUDA(ceed, cudaStreamSynchronize(ceed->s_d2h));
+  B200_CUDA(ceed, cudaStreamSynchronize(ceed->s_h2d));
+  if (err) return err;
+  B200_CALL(b200_vector_streamed_output(v, &h_v));  // (every part re-marked the host side stale when it took the device array)
+  if (streamed) *streamed = 1;
+  return B200_SUCCESS;
+}
 
 extern "C" int ceedb200_operator_is_fused(B200Operator op, int *is_fused) {
   B200_CALL(operator_setup(op));

@@ -65,6 +65,14 @@ struct B200KernelVariant {
   bool        built = false;
 };
 
+// chunk tables of the streamed host-buffer apply (ceedb200_operator_apply_streamed), cached per operator
+struct B200StreamPlan {
+  int                  num_chunks = 0;
+  std::vector<int32_t> ends;             // element chunk ends
+  std::vector<int64_t> in_hi, out_done;  // per chunk: (highest offset gathered by chunks <= c) + 1; offsets below out_done[c] are complete after chunk c
+  bool                 per_comp = false; // components are blocks of comp_stride (each streams its own range); else one range over L-indices
+};
+
 struct B200OpPlan {
   bool                      fused = false;
   std::string               why_not_fused;
@@ -107,6 +115,7 @@ struct B200OpPlan {
   double *aux[16]       = {nullptr};
   size_t  aux_bytes[16] = {0};
   B200OrderedScatter ordered;     // ordered scatter tables (scatter_mode == B200_SCATTER_ORDERED)
+  B200StreamPlan     stream;      // streamed host-buffer apply
   B200RunScatter     run[2][16];  // run scatter tables of the lean kernel, per kernel variant (their grids may differ) and output slot
   int                ordered_slot = -1;
   // unfused fallback scratch

@@ -266,20 +266,40 @@ int b200_restriction_build_owner(B200Restriction r) {
   const int64_t        num_nodes = (int64_t)t.lvec_indices.size();
   std::vector<int32_t> tgt(n), halo_node, halo_ptr;
   int64_t              slot = 0;
-  // two passes over the shared nodes: first those touched by boundary elements only (see split_elem), then the rest
-  for (int pass = 0; pass < 2; pass++) {
-    for (int64_t row = 0; row < num_nodes; row++) {
+  // shared nodes ordered by the element part of their last toucher (see part_ends; one part when no split is set), L-index order inside
+  // a part: the nodes completed by part p can be finalized -- and sent, or copied to the host -- while later parts are still applied
+  std::vector<int32_t> ends = r->part_ends;
+  if (ends.empty() || ends.back() != r->num_elem) ends.push_back(r->num_elem);
+  const int num_parts = (int)ends.size();
+  auto part_of = [&](int64_t elem) { return (int)(std::upper_bound(ends.begin(), ends.end(), (int32_t)elem) - ends.begin()); };
+  std::vector<int32_t> node_part(num_nodes, -1);
+  std::vector<int64_t> count(num_parts + 1, 0);
+  for (int64_t row = 0; row < num_nodes; row++) {
+    const int32_t begin = t.t_offsets[row], end = t.t_offsets[row + 1];
+    tgt[t.t_indices[begin]] = t.lvec_indices[row];
+    if (end - begin <= 1) continue;
+    node_part[row] = std::min(num_parts - 1, part_of(t.t_indices[end - 1] / r->elem_size));  // last toucher = highest element
+    count[node_part[row] + 1]++;
+  }
+  for (int p = 0; p < num_parts; p++) count[p + 1] += count[p];
+  r->shared_prefix.assign(count.begin(), count.end());  // shared_prefix[p] = shared nodes completed by parts < p ... [num_parts] = all
+  {
+    const int64_t        num_shared = count[num_parts];
+    std::vector<int64_t> fill(count.begin(), count.end() - 1);
+    std::vector<int32_t> row_at(num_shared);
+    for (int64_t row = 0; row < num_nodes; row++)
+      if (node_part[row] >= 0) row_at[fill[node_part[row]]++] = (int32_t)row;
+    halo_node.resize(num_shared);
+    halo_ptr.resize(num_shared);
+    for (int64_t i = 0; i < num_shared; i++) {
+      const int32_t row   = row_at[i];
       const int32_t begin = t.t_offsets[row], end = t.t_offsets[row + 1];
-      if (pass == 0) tgt[t.t_indices[begin]] = t.lvec_indices[row];
-      if (end - begin <= 1) continue;
-      const bool boundary_only = r->split_elem > 0 && t.t_indices[end - 1] / r->elem_size < r->split_elem;  // last toucher = highest element
-      if (boundary_only != (pass == 0)) continue;
-      halo_node.push_back(t.lvec_indices[row]);
-      halo_ptr.push_back((int32_t)slot);
+      halo_node[i]        = t.lvec_indices[row];
+      halo_ptr[i]         = (int32_t)slot;
       for (int32_t j = begin + 1; j < end; j++) tgt[t.t_indices[j]] = ~(int32_t)(slot++);
     }
-    if (pass == 0) r->num_shared_first = (int64_t)halo_node.size();
   }
+  r->num_shared_first = r->shared_prefix.size() > 1 ? r->shared_prefix[1] : 0;
   halo_ptr.push_back((int32_t)slot);
   r->num_shared = (int64_t)halo_node.size();
   r->num_halo   = slot;
@@ -466,6 +486,15 @@ extern "C" int ceedb200_restriction_debug_scatter_tables(B200Restriction r, int 
       if (pred_idx && t.num_pred <= pred_capacity && t.num_pred > 0) B200_CALL(b200_d2h(ceed, pred_idx, t.d_pred_idx, t.num_pred * sizeof(int32_t)));
       b200_ordered_scatter_free(ceed, &t);
     }
+  } else if (mode == 5) {  // owner/halo tables with K = group_elems equal element parts (streamed apply): pred_ptr receives shared_prefix, pred_idx halo_node
+    std::vector<int32_t> ends;
+    for (int c = 1; c <= group_elems; c++) ends.push_back((int32_t)((int64_t)r->num_elem * c / group_elems));
+    B200_CALL(b200_restriction_set_parts(r, ends));
+    B200_CALL(b200_restriction_build_owner(r));
+    counts[0] = r->num_shared, counts[1] = r->num_halo, counts[2] = (int64_t)r->shared_prefix.size(), counts[3] = 0, counts[4] = 1;
+    B200_CALL(b200_d2h(ceed, tgt, r->d_tgt, n * sizeof(int32_t)));
+    for (size_t i = 0; i < r->shared_prefix.size() && pred_ptr; i++) pred_ptr[i] = (int32_t)r->shared_prefix[i];
+    if (pred_idx && r->num_shared <= pred_capacity && r->num_shared > 0) B200_CALL(b200_d2h(ceed, pred_idx, r->d_halo_node, r->num_shared * sizeof(int32_t)));
   } else if (mode == 4) {  // run scatter: group_elems = elements per iteration, pred_capacity = number of groups (warps) of the launch
     B200RunScatter t;
     B200_CALL(b200_restriction_build_runs(r, (int)pred_capacity, group_elems, &t));
@@ -509,8 +538,12 @@ int b200_restriction_apply_raw(B200Restriction r, int t_mode, const double *d_u,
 
 int b200_halo_finalize(B200Restriction r, const double *d_halo, double *d_v, int part) {
   B200Ceed      ceed  = r->ceed;
-  const int64_t first = part == 2 ? r->num_shared_first : 0;
-  const int64_t count = part == 1 ? r->num_shared_first : r->num_shared - first;
+  int64_t first = 0, count = r->num_shared;
+  if (part >= 1) {
+    B200_CHECK(part < (int)r->shared_prefix.size(), ceed, B200_ERROR_DIMENSION, "element part %d of %d", part, (int)r->shared_prefix.size() - 1);
+    first = r->shared_prefix[part - 1];
+    count = r->shared_prefix[part] - first;
+  }
   if (count <= 0) return B200_SUCCESS;
   LAUNCH(ceed, k_halo_finalize, count, r->d_halo_node + first, r->d_halo_ptr + first, d_halo, d_v, count, r->num_halo, r->num_comp, r->comp_stride);
   return B200_SUCCESS;
@@ -530,14 +563,23 @@ extern "C" int ceedb200_restriction_set_split(B200Restriction r, b200_int split_
   B200Ceed ceed = r->ceed;
   B200_CHECK(!r->is_strided, ceed, B200_ERROR_UNSUPPORTED, "element split applies to offset restrictions");
   B200_CHECK(split_elem >= 0 && split_elem <= r->num_elem, ceed, B200_ERROR_DIMENSION, "element split %d outside [0, %d]", split_elem, r->num_elem);
-  if (r->owner_built && r->split_elem != split_elem) {
+  B200_CALL(b200_restriction_set_parts(r, {(int32_t)split_elem, (int32_t)r->num_elem}));  // (either part may be empty)
+  r->split_elem = split_elem;
+  return B200_SUCCESS;
+}
+
+int b200_restriction_set_parts(B200Restriction r, const std::vector<int32_t> &part_ends) {
+  B200Ceed ceed = r->ceed;
+  if (r->part_ends == part_ends) return B200_SUCCESS;
+  if (r->owner_built) {
     b200_dfree(ceed, r->d_tgt);
     b200_dfree(ceed, r->d_halo_node);
     b200_dfree(ceed, r->d_halo_ptr);
     r->d_tgt = r->d_halo_node = r->d_halo_ptr = nullptr;
     r->owner_built = false;
   }
-  r->split_elem = split_elem;
+  r->part_ends  = part_ends;
+  r->split_elem = -1;
   return B200_SUCCESS;
 }
 

@@ -152,6 +152,20 @@ int b200_vector_device_read(B200Vector vec, const double **d) {
   *d = vec->d_array;
   return B200_SUCCESS;
 }
+int b200_vector_streamed_input(B200Vector vec, const double **h, double **d) {
+  B200_CHECK(vec->h_array && !vec->d_array, vec->ceed, B200_ERROR_BACKEND, "streamed input needs a vector that is valid on the host only");
+  B200_CALL(device_alloc(vec));
+  *h           = vec->h_array;
+  *d           = device_ptr(vec);
+  vec->d_array = device_ptr(vec);  // filled chunk by chunk on the copy stream; kernels wait for the chunk events
+  return B200_SUCCESS;
+}
+int b200_vector_streamed_output(B200Vector vec, double **h) {
+  B200_CHECK(host_ptr(vec), vec->ceed, B200_ERROR_BACKEND, "streamed output needs a vector with a host array");
+  *h           = host_ptr(vec);
+  vec->h_array = host_ptr(vec);
+  return B200_SUCCESS;
+}
 int b200_vector_device_write(B200Vector vec, double **d, bool discard) {
   if (discard || (!vec->h_array && !vec->d_array)) {  // nothing valid to preserve: (allocate and) hand out the device side
     B200_CALL(device_alloc(vec));
@@ -198,6 +212,12 @@ extern "C" int ceedb200_vector_has_borrowed_array_of_type(B200Vector vec, int me
 }
 
 // CeedVectorSetArray_Cuda (ceed-cuda-ref-vector.c:177-228): the given side becomes the only valid one.
+extern "C" int ceedb200_vector_valid_sides(B200Vector vec, int *host_valid, int *device_valid) {
+  if (host_valid) *host_valid = vec->h_array != nullptr;
+  if (device_valid) *device_valid = vec->d_array != nullptr;
+  return B200_SUCCESS;
+}
+
 extern "C" int ceedb200_vector_set_array(B200Vector vec, int mem_type, int copy_mode, b200_scalar *array) {
   B200Ceed ceed  = vec->ceed;
   size_t   bytes = vec->length * sizeof(double);

@@ -138,8 +138,8 @@ def sweep():
             run(f"{order} general kernel (table)")
         return
     run("table (general kernel)")
-    for stage in (0, 64, 72):
-        for E, warps, minb in ((6, 4, 0), (6, 4, 6), (6, 2, 0), (6, 2, 12), (6, 3, 7), (5, 4, 0), (4, 4, 6), (4, 4, 7)):
+    for stage in (0, 32):
+        for E, warps, minb in ((6, 4, 0), (6, 3, 6), (6, 2, 9), (6, 1, 18), (5, 3, 7), (5, 2, 10), (5, 2, 11), (4, 3, 8), (4, 2, 12), (6, 3, 5), (6, 2, 8)):
             run(f"lean stage={stage} E={E} warps={warps} minb={minb}", qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=stage, min_blocks_per_sm=minb)
     return
     for stage in (0, 8, 32, 40):

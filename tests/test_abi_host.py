@@ -230,6 +230,31 @@ def check(nel, p, group_elems, scramble):
         got = sorted(int(x) for x in pred_idx[pred_ptr[g]:pred_ptr[g + 1]])
         assert got == sorted(expect_pred[g]) and all(q < g for q in got), g   # waits only ever point to earlier groups
     out["ordered"] = [int(x) for x in cnt[:4]]
+    # ---- owner/halo tables with K element parts (streamed host-buffer apply / multi-GPU split): shared nodes ordered by the part of their
+    # last toucher, halo slots consecutive in that node order and ascending E-order inside a node
+    out["parts"] = []
+    for K in (1, 2, 3, 5):
+        prefix = np.zeros(K + 2, dtype=np.int32); hnode = np.zeros(flat.size, dtype=np.int32)
+        assert lib.ceedb200_restriction_debug_scatter_tables(r._ptr, 5, K, tgt.ctypes.data, cnt.ctypes.data, prefix.ctypes.data, hnode.ctypes.data, hnode.size) == 0
+        assert cnt[2] == K + 1 and prefix[0] == 0 and prefix[K] == cnt[0]
+        ends = [num_elem * c // K for c in range(1, K + 1)]
+        last_part = {}
+        for node, s, c in zip(nodes, starts, counts):
+            entries = order[s:s + c]
+            assert tgt[entries[0]] == node
+            if c > 1:
+                e_last = int(entries[-1]) // es
+                last_part[int(node)] = min(K - 1, int(np.searchsorted(ends, e_last, side="right")))
+        slot = 0
+        for k in range(K):
+            seg = [int(x) for x in hnode[prefix[k]:prefix[k + 1]]]
+            assert seg == sorted(seg) and all(last_part[x] == k for x in seg), (K, k)
+            for node in seg:
+                i = int(np.searchsorted(nodes, node)); entries = order[starts[i]:starts[i] + counts[i]]
+                for e in entries[1:]:
+                    assert ~int(tgt[e]) == slot; slot += 1
+        assert slot == cnt[1] and len(last_part) == cnt[0]
+        out["parts"].append([int(x) for x in prefix[:K + 1]])
     # ---- run scatter tables (B200RunScatter): simulate the warps walking their runs and check that every direct entry (store / read-modify-
     # write) finds exactly the ascending-E prefix of its node already in v, and that the halo entries are the remaining suffix in order
     RMW = 1 << 30
@@ -280,6 +305,7 @@ def test_scatter_tables_match_serial_order_model_without_gpu():
     assert r.returncode == 0, r.stderr[-3000:]
     res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][0][6:])
     assert len(res) == 4 and all(v["det"][1] > 0 and v["ordered"][2] > 0 for v in res.values())
+    assert all(len(v["parts"]) == 4 and v["parts"][0][-1] == v["det"][0] for v in res.values())
     for v in res.values():  # one group walking everything one element at a time needs no halo at all; more groups need more
         assert len(v["runs"]) == 4 and all(h + m == v["det"][1] for h, m in v["runs"]) and v["runs"][1][0] >= 0
 
