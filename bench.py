@@ -199,11 +199,12 @@ def _load_libceed_with_plugin():
     return R
 
 
-def through_libceed(resource, bp, p, nel, steps, warmup, host_buffers=False):
+def through_libceed(resource, bp, p, nel, steps, warmup, host_buffers=False, streamed=True):
     """GDoF/s of CeedOperatorApply(op, u, v, CEED_REQUEST_IMMEDIATE) called through libCEED's public C API on `resource`
     (eager launches, the call every C / Fortran / Python / Julia / Rust user makes).  Device-resident vectors, or -- host_buffers --
     the caller's pinned HOST arrays every step: CeedVectorSetArray(u, HOST, USE_POINTER), apply, CeedVectorSyncArray(v, HOST),
-    i.e. the H2D copy of u and the D2H copy of v are inside the timed region.  Timed with CUDA events on the default stream
+    i.e. the H2D copy of u and the D2H copy of v are inside the timed region (streamed=False: CEED_B200_NO_STREAMED, the plugin then
+    copies, applies and copies back one after the other like the reference's backends).  Timed with CUDA events on the default stream
     (the stream libCEED's CUDA backends launch on), synchronised on both sides."""
     import ctypes as C
     import torch
@@ -218,6 +219,10 @@ def through_libceed(resource, bp, p, nel, steps, warmup, host_buffers=False):
     u_host = torch.from_numpy(seeded_uniform(n)).pin_memory()
     v_host = torch.empty(n, dtype=torch.float64).pin_memory()
     lib = rc.lib
+    if streamed:
+        os.environ.pop("CEED_B200_NO_STREAMED", None)
+    else:
+        os.environ["CEED_B200_NO_STREAMED"] = "1"
     if host_buffers:
         def step():
             rc._chk(lib.CeedVectorSetArray(prob.u, R.MEM_HOST, R.USE_POINTER, C.c_void_p(u_host.data_ptr())))
@@ -244,6 +249,7 @@ def through_libceed(resource, bp, p, nel, steps, warmup, host_buffers=False):
     if host_buffers:
         ms = max(ms, wall * 1e3)  # the copies into / out of host memory are synchronous host calls: wall clock is the honest figure
     v = v_host.numpy().copy() if host_buffers else rc.get_array(prob.v, n)
+    os.environ.pop("CEED_B200_NO_STREAMED", None)
     return dict(value=n / ms / 1e6, ms_per_step=ms, wall_ms_per_step=wall * 1e3, dofs=n, checksum=float(np.linalg.norm(v))), v
 
 
@@ -395,6 +401,35 @@ def run_case(args, ceed, cm, bp, p, dofs, rank, world, local_rank, dev, steps, w
         out["e2e_cabi"] = dict(value=total_dofs / e2e_s / 1e9, unit="GDoF/s", h2d_bytes_per_step=8 * n_local, d2h_bytes_per_step=8 * n_local, ms_per_step=e2e_s * 1e3,
                                mode="C ABI, pinned host buffers: H2D(u), step (apply + interface sum), D2H(v) one after the other, per rank; max over ranks")
         del uh, vh
+        # ONE step, streamed inside the call (single GPU): ceedb200_operator_apply_streamed cuts the elements into chunks, applies a chunk as
+        # soon as its part of u has arrived and copies the finished part of v back while the next chunks run -- same bytes over PCIe
+        # inside the timed region, one public call per step, results bitwise equal
+        if world == 1:
+            try:
+                us, vs = ceed.Vector(n_local), ceed.Vector(n_local)
+                v_host_s = torch.empty(n_local, dtype=torch.float64).pin_memory()
+                used = [False]
+
+                def streamed_step():
+                    us.set_array(u_host.numpy(), cm.MEM_HOST, cm.USE_POINTER)
+                    vs.set_array(v_host_s.numpy(), cm.MEM_HOST, cm.USE_POINTER)
+                    used[0] = prob.op.apply_streamed(us, vs, 0)
+                    vs.sync_array(cm.MEM_HOST)
+                    us.take_array(), vs.take_array()
+
+                streamed_step(), streamed_step()
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    streamed_step()
+                torch.cuda.synchronize()
+                st_s = (time.perf_counter() - t0) / e2e_steps
+                out["e2e_cabi"].update(streamed_value=total_dofs / st_s / 1e9, streamed_ms_per_step=st_s * 1e3, streamed_path_taken=bool(used[0]),
+                                       streamed_matches_serial=bool(torch.equal(v_host_s, v_host)),
+                                       streamed_mode="C ABI, one call per step: ceedb200_operator_apply_streamed (chunked H2D / apply / D2H on two copy streams)")
+                del us, vs
+            except Exception as exc:  # noqa: BLE001
+                out["e2e_cabi"]["streamed_error"] = str(exc)[:200]
         # The same end-to-end step software-pipelined over steps (single GPU): every step still copies its own u from pinned host
         # memory and its own v back, but on separate copy streams with double-buffered device vectors, so the H2D of step i+1 and the
         # D2H of step i-1 overlap the kernels of step i (PCIe is full duplex).  Results must be bitwise equal to the serial path.
@@ -567,17 +602,17 @@ def main():
             try:
                 dev_res, v_b200 = through_libceed("/gpu/cuda/b200", bp, p, nel, args.steps, args.warmup)
                 host_res, v_host = through_libceed("/gpu/cuda/b200", bp, p, nel, max(3, min(args.steps, 10)), args.warmup, host_buffers=True)
-                extra["libceed_matches_host_path"] = bool(np.array_equal(v_b200, v_host))
+                serial_res, v_serial = through_libceed("/gpu/cuda/b200", bp, p, nel, max(3, min(args.steps, 10)), args.warmup, host_buffers=True, streamed=False)
+                extra["libceed_matches_host_path"] = bool(np.array_equal(v_b200, v_host) and np.array_equal(v_b200, v_serial))
                 value, ms_per_step = dev_res["value"], dev_res["ms_per_step"]
                 config["boundary"] = "CeedOperatorApply on /gpu/cuda/b200 through libCEED's public C API (oracle/_ref/lib-cuda/libceed.so + plugin), eager launches"
                 cabi = e2e
                 e2e = dict(value=host_res["value"], unit="GDoF/s", h2d_bytes_per_step=8 * n_local, d2h_bytes_per_step=8 * n_local, ms_per_step=host_res["ms_per_step"],
-                           mode="through libCEED: CeedVectorSetArray(u, HOST, USE_POINTER) -> CeedOperatorApply -> CeedVectorSyncArray(v, HOST), pinned host buffers, "
-                                "strictly serial", serial_through_libceed=host_res["value"], cabi=cabi)
-                if cabi.get("pipelined_matches_serial") and cabi.get("pipelined_value", 0) > e2e["value"]:
-                    # headline = the software-pipelined figure (every step still moves its own u and v over PCIe inside the timed region,
-                    # results bitwise equal); the strictly serial through-libCEED figure stays next to it
-                    e2e.update(value=cabi["pipelined_value"], ms_per_step=cabi["pipelined_ms_per_step"], mode=cabi["pipelined_mode"])
+                           mode="through libCEED, ONE step at a time: CeedVectorSetArray(u, HOST, USE_POINTER) -> CeedOperatorApply -> CeedVectorSyncArray(v, HOST), pinned "
+                                "host buffers; inside the call the plugin streams the step (chunked H2D / apply / D2H on two copy streams, ceedb200_operator_apply_streamed), "
+                                "results bitwise equal to the device-resident apply",
+                           serial_through_libceed=serial_res["value"], serial_ms_per_step=serial_res["ms_per_step"],
+                           serial_mode="the same calls with CEED_B200_NO_STREAMED=1: whole-vector H2D, apply, whole-vector D2H one after the other", cabi=cabi)
                 extra["libceed_checksum_norm2"] = dev_res["checksum"]
                 try:
                     gen_res, v_gen = through_libceed("/gpu/cuda/gen", bp, p, nel, args.steps, args.warmup)

@@ -284,6 +284,10 @@ CEEDB200_EXPORT int ceedb200_ipc_free(B200Ceed ceed, void *d_ptr);
 CEEDB200_EXPORT int ceedb200_cg_dot(B200Ceed ceed, const double *d_x, const double *d_y, const double *d_w, long long n, double *d_out);
 CEEDB200_EXPORT int ceedb200_cg_update(B200Ceed ceed, double *d_x, double *d_r, const double *d_p, const double *d_Ap, const double *d_w, long long n,
                                        const double *d_rr, const double *d_pAp, double *d_rr_new);
+/* essential boundary conditions in the CG loop: Ap[i] = p[i] wherever free_mask[i] == 0 (identity rows for constrained DoFs; with b and
+ * the start vector zero there, the iterates stay in the constrained subspace -- what PETSc's DMPlex does for examples/petsc/bps.c by
+ * leaving the constrained DoFs out of the global vector, examples/petsc/src/petscutils.c) */
+CEEDB200_EXPORT int ceedb200_cg_constrain(B200Ceed ceed, double *d_Ap, const double *d_p, const double *d_free_mask, long long n);
 CEEDB200_EXPORT int ceedb200_cg_direction(B200Ceed ceed, double *d_p, const double *d_r, long long n, const double *d_rr_new, const double *d_rr);
 
 #ifdef __cplusplus

@@ -118,6 +118,7 @@ def load(path=LIB_PATH):
         "ceedb200_cg_dot": [handle, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p],
         "ceedb200_cg_update": [handle, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p],
         "ceedb200_cg_direction": [handle, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p],
+        "ceedb200_cg_constrain": [handle, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong],
         "ceedb200_restriction_debug_scatter_tables": [handle, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64],
         "ceedb200_iface_pack": [handle, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p],
         "ceedb200_iface_unpack_sum": [handle, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],

@@ -20,10 +20,12 @@ import torch.distributed as dist
 
 
 class DeviceCG:
-    def __init__(self, ceed, op, u_vec, v_vec, n, device, exchange=None, owned_mask=None, group=None, dist_op=None):
+    def __init__(self, ceed, op, u_vec, v_vec, n, device, exchange=None, owned_mask=None, group=None, dist_op=None, free_mask=None):
         """op: libceed_b200 Operator; u_vec / v_vec: its active input / output Vectors (length n) that wrap the torch tensors
         created here (USE_POINTER), so the operator reads p and writes Ap in place.
-        dist_op: a parallel.DistributedOperator instead of (op, u_vec, v_vec, exchange): A p is then its (overlapped) multi-GPU step."""
+        dist_op: a parallel.DistributedOperator instead of (op, u_vec, v_vec, exchange): A p is then its (overlapped) multi-GPU step.
+        free_mask: 1 = free DoF, 0 = essential (Dirichlet) DoF: constrained rows of A act as identity rows (ceedb200_cg_constrain), the
+        right-hand side must be zero there (homogeneous conditions; lift inhomogeneous data into b beforehand)."""
         from . import ceed as cm
         self.dist_op = dist_op
         if dist_op is not None:
@@ -32,6 +34,7 @@ class DeviceCG:
         f64 = dict(dtype=torch.float64, device=device)
         self.x, self.r, self.p, self.Ap = (torch.zeros(n, **f64) for _ in range(4))
         self.w = None if owned_mask is None else torch.from_numpy(np.ascontiguousarray(owned_mask, dtype=np.float64)).to(device)
+        self.free = None if free_mask is None else torch.from_numpy(np.ascontiguousarray(free_mask, dtype=np.float64)).to(device)
         self.scal = torch.zeros(4, **f64)  # rr, pAp, rr_new, spare
         self.u_vec, self.v_vec = u_vec, v_vec
         u_vec.set_array(self.p, cm.MEM_DEVICE, cm.USE_POINTER)
@@ -49,10 +52,12 @@ class DeviceCG:
         """Ap = A p (including the interface sum)."""
         if self.dist_op is not None:
             self.dist_op.apply(self.u_vec, self.v_vec, v_t=self.Ap)
-            return
-        self.op.apply(self.u_vec, self.v_vec)
-        if self.exchange is not None:
-            self.exchange.sum_interfaces(self.Ap)
+        else:
+            self.op.apply(self.u_vec, self.v_vec)
+            if self.exchange is not None:
+                self.exchange.sum_interfaces(self.Ap)
+        if self.free is not None:
+            self.ceed._chk(self.ceed._lib.ceedb200_cg_constrain(self.ceed._ptr, self._ptr(self.Ap), self._ptr(self.p), self._ptr(self.free), self.n))
 
     def start(self, b):
         """x = 0, r = p = b (b: torch tensor on the device, already consistent on interface copies); rr = <r, r>_w."""

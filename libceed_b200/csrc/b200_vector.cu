@@ -645,6 +645,12 @@ __global__ void k_cg_direction(double *__restrict__ p, const double *__restrict_
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = fma(beta, p[i], r[i]);
 }
 
+// essential (Dirichlet) boundary conditions: constrained rows of A become identity rows -- Ap[i] = p[i] where free[i] == 0
+__global__ void k_cg_constrain(double *__restrict__ Ap, const double *__restrict__ p, const double *__restrict__ free_mask, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (free_mask[i] == 0.0) Ap[i] = p[i];
+}
+
 int cg_scratch(B200Ceed ceed) {
   // the partial sums use a FIXED grid of kCgBlocks CTAs (reproducible whatever the SM count): the buffer must hold them all
   const size_t want = std::max<size_t>((size_t)ceed->num_sms * 16, (size_t)kCgBlocks);
@@ -677,6 +683,10 @@ extern "C" int ceedb200_cg_update(B200Ceed ceed, double *d_x, double *d_r, const
   B200_CALL(cg_scratch(ceed));
   CG_LAUNCH(ceed, k_cg_update_partial, kCgBlocks, d_x, d_r, d_p, d_Ap, d_w, n, d_rr, d_pAp, ceed->d_scratch);
   CG_LAUNCH(ceed, k_cg_final, 1, ceed->d_scratch, kCgBlocks, d_rr_new);
+  return B200_SUCCESS;
+}
+extern "C" int ceedb200_cg_constrain(B200Ceed ceed, double *d_Ap, const double *d_p, const double *d_free_mask, long long n) {
+  CG_LAUNCH(ceed, k_cg_constrain, kCgBlocks, d_Ap, d_p, d_free_mask, n);
   return B200_SUCCESS;
 }
 extern "C" int ceedb200_cg_direction(B200Ceed ceed, double *d_p, const double *d_r, long long n, const double *d_rr_new, const double *d_rr) {

@@ -47,6 +47,40 @@ def test_operator_through_libceed_matches_cpu_reference(R, bp, p, nel):
     assert np.abs(gpu.rc.get_array(gpu.v, gpu.ncomp * nn) - 2 * vc).max() / np.abs(vc).max() < 1e-12
 
 
+@pytest.mark.parametrize("bp,p,nel", [(1, 3, (17, 16, 16)), (3, 2, (20, 18, 17))])
+def test_host_resident_apply_streams_and_matches(R, monkeypatch, bp, p, nel):
+    """The host-resident call sequence (CeedVectorSetArray(HOST, USE_POINTER) -> CeedOperatorApply -> CeedVectorSyncArray(HOST)) with pinned
+    buffers: the plugin streams the step through ceedb200_operator_apply_streamed.  Bitwise the device-resident result, with and without
+    streaming (CEED_B200_NO_STREAMED), and the vectors stay usable afterwards (ApplyAdd on the same objects)."""
+    import ctypes as C
+    import torch
+    from libceed_b200 import mesh as M
+    from libceed_b200.bp import seeded_uniform
+    off, coords = M.hex_offsets(*nel, p), M.hex_coords(*nel, p)
+    nn = coords.shape[1]
+    rc = R.RefCeed("/gpu/cuda/b200", cuda=True)
+    prob = R.RefBP(rc, bp, p, off.shape[0], nn, off, coords)
+    n = prob.ncomp * nn
+    u = seeded_uniform(n, 27)
+    ref = prob.apply(u)  # device-resident path
+    u_host = torch.from_numpy(u).pin_memory()
+    v_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    for no_stream in (False, True, False):
+        if no_stream:
+            monkeypatch.setenv("CEED_B200_NO_STREAMED", "1")
+        else:
+            monkeypatch.delenv("CEED_B200_NO_STREAMED", raising=False)
+        v_host.fill_(-5.0)
+        rc._chk(rc.lib.CeedVectorSetArray(prob.u, R.MEM_HOST, R.USE_POINTER, C.c_void_p(u_host.data_ptr())))
+        rc._chk(rc.lib.CeedVectorSetArray(prob.v, R.MEM_HOST, R.USE_POINTER, C.c_void_p(v_host.data_ptr())))
+        rc.op_apply(prob.op, prob.u, prob.v)
+        rc._chk(rc.lib.CeedVectorSyncArray(prob.v, R.MEM_HOST))
+        assert np.array_equal(v_host.numpy(), ref), no_stream
+    # both sides of v are valid after the streamed apply: accumulate on the device, read on the host
+    rc.op_apply_add(prob.op, prob.u, prob.v)
+    assert np.abs(rc.get_array(prob.v, n) - 2 * ref).max() <= 1e-12 * np.abs(ref).max()
+
+
 def test_resource_prefix_resolves_to_b200(R):
     rc = R.RefCeed("/gpu/cuda", cuda=True)  # prefix resolves to some CUDA backend (b200 registers with priority 45: only by full name)
     import ctypes as C

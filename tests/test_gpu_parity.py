@@ -526,6 +526,72 @@ def test_device_resident_cg_converges(cm):
     assert abs(float(out.item()) - float((a * c * w).sum().item())) < 1e-12 * n
 
 
+@pytest.mark.parametrize("bp,p,nel,kw", [(1, 3, (24, 23, 22), {}), (3, 2, (30, 29, 28), {}), (2, 2, (20, 21, 22), {}), (4, 1, (30, 30, 30), dict(interlaced=True)),
+                                         (1, 3, (20, 20, 20), dict(morton=True)), (5, 4, (14, 13, 12), {})])
+def test_streamed_host_buffer_apply_is_bitwise_equal(cm, bp, p, nel, kw):
+    """ceedb200_operator_apply_streamed (chunked H2D / apply / finalize / D2H pipeline for host-resident vectors): bitwise the plain apply
+    for every chunk count, blocked and interlaced components, an element order without locality (Morton); the result is on the host when
+    the call returns and the vector is valid on both sides; pageable host memory and small meshes fall back to the plain apply."""
+    import torch
+    from libceed_b200 import mesh as M
+    kw = dict(kw)
+    perm = M.morton_permutation(*nel) if kw.pop("morton", False) else None
+    prob = make_problem(cm, bp, p, nel, elem_perm=perm, **kw)
+    n = prob.num_dofs
+    u_t, v_t = torch.empty(n, dtype=torch.float64).pin_memory(), torch.empty(n, dtype=torch.float64).pin_memory()
+    u_np, v_np = u_t.numpy(), v_t.numpy()
+    u_np[:] = seeded_uniform(n, 41)
+    prob.u.set_array(u_np.copy())
+    prob.op.apply(prob.u, prob.v)
+    ref = prob.v.get_array_read().copy()
+    for K in (0, 2, 5, 33):
+        v_np[:] = -7.0
+        prob.u.set_array(u_np, cm.MEM_HOST, cm.USE_POINTER)
+        prob.v.set_array(v_np, cm.MEM_HOST, cm.USE_POINTER)
+        used = prob.op.apply_streamed(prob.u, prob.v, K)
+        assert used == (prob.num_elem >= 4096)
+        if used:
+            assert np.array_equal(v_np, ref), K           # already on the host, no sync needed
+        assert np.array_equal(prob.v.get_array_read(), ref), K
+        prob.u.take_array(), prob.v.take_array()
+    u_pg, v_pg = u_np.copy(), np.zeros(n)                  # pageable memory: plain apply, same result
+    prob.u.set_array(u_pg, cm.MEM_HOST, cm.USE_POINTER)
+    prob.v.set_array(v_pg, cm.MEM_HOST, cm.USE_POINTER)
+    assert not prob.op.apply_streamed(prob.u, prob.v, 0)
+    assert np.array_equal(prob.v.get_array_read(), ref)
+    prob.u.take_array(), prob.v.take_array()
+    # the restriction keeps its chunk parts: a plain apply afterwards still gives the same bits
+    prob.u.set_array(u_np.copy())
+    prob.op.apply(prob.u, prob.v)
+    assert np.array_equal(prob.v.get_array_read(), ref)
+
+
+def test_device_cg_with_dirichlet_conditions_solves_poisson(cm):
+    """BP3 (Poisson) with homogeneous Dirichlet conditions on the box boundary, the reference's BP3 setting (examples/petsc/bps.c with
+    DMPlex-constrained boundary DoFs): constrained rows act as identity rows (ceedb200_cg_constrain).  Without them the operator is
+    singular; with them CG recovers a manufactured solution that vanishes on the boundary."""
+    import torch
+    from libceed_b200.cg import DeviceCG
+    p, nel = 2, (6, 5, 5)
+    prob = make_problem(cm, 3, p, nel)
+    n, dev = prob.num_dofs, torch.device("cuda")
+    nx, ny, nz = (k * p + 1 for k in nel)
+    iz, iy, ix = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    free = ((ix > 0) & (ix < nx - 1) & (iy > 0) & (iy < ny - 1) & (iz > 0) & (iz < nz - 1)).reshape(-1).astype(np.float64)
+    cg = DeviceCG(prob.ceed, prob.op, prob.u, prob.v, n, dev, free_mask=free)
+    x_true = torch.from_numpy(seeded_uniform(n, 33) * free).to(dev)
+    cg.p.copy_(x_true)
+    cg.apply()
+    b = cg.Ap.clone()
+    assert float((b * torch.from_numpy(1.0 - free).to(dev)).abs().max()) == 0.0  # identity rows: b = x_true = 0 on the boundary
+    cg.start(b)
+    r0 = cg.residual_norm2()
+    cg.iterate(400)
+    assert cg.residual_norm2() < 1e-10 * r0, (r0, cg.residual_norm2())
+    assert float((cg.x - x_true).abs().max()) < 1e-7 * float(x_true.abs().max())
+    assert float((cg.x * torch.from_numpy(1.0 - free).to(dev)).abs().max()) == 0.0   # the iterates never leave the constrained subspace
+
+
 @pytest.mark.parametrize("bp,p", [(1, 3), (3, 6), (5, 7), (6, 4)])
 def test_full_size_vs_reference_cpu_backend(cm, refceed, bp, p):
     """BASELINE.json sizes (10M DoFs) against the UNMODIFIED reference's /cpu/self/opt/blocked on the same mesh and input: the
