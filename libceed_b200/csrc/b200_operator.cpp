@@ -30,6 +30,8 @@ static void plan_free(B200Operator op) {
   if (!plan) return;
   for (int i = 0; i < 16; i++) b200_dfree(op->ceed, plan->aux[i]);
   b200_ordered_scatter_free(op->ceed, &plan->ordered);
+  b200_dfree(op->ceed, plan->d_fin_tab);
+  b200_dfree(op->ceed, plan->d_fin_done);
   for (int v = 0; v < 2; v++)
     for (int i = 0; i < 16; i++) b200_run_scatter_free(op->ceed, &plan->run[v][i]);
   for (auto *vecs : {&plan->e_in, &plan->q_in, &plan->e_out, &plan->q_out})
@@ -159,6 +161,16 @@ static int operator_setup(B200Operator op) {
 // ------------------------------------------------------------------------------------------------ fused apply
 static int apply_unfused(B200Operator op, B200Vector u, B200Vector v, int add);
 
+// K contiguous element parts with ends at multiples of the kernel's batch width (shared by the streamed apply and the in-kernel finalize)
+static std::vector<int32_t> chunk_ends(int num_elem, int epb, int K) {
+  const long long      num_batches = ((long long)num_elem + epb - 1) / epb;
+  std::vector<int32_t> ends;
+  for (int c = 1; c <= K; c++) ends.push_back((int32_t)std::min<long long>(num_elem, num_batches * c / K * epb));
+  ends.back() = num_elem;
+  return ends;
+}
+static int default_parts() { return getenv("CEED_B200_PARTS") ? std::max(2, std::min(atoi(getenv("CEED_B200_PARTS")), 64)) : 8; }
+
 // part: 0 = the whole operator; 1 / 2 = boundary / interior elements of a partitioned mesh (ceedb200_operator_apply_part):
 // part 1 applies elements [0, split) and finalizes the shared nodes touched by those elements only, part 2 the rest.
 static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int part = 0) {
@@ -170,6 +182,35 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
   if (op->qf->ctx) B200_CALL(ceedb200_qfcontext_get_data(op->qf->ctx, B200_MEM_DEVICE, &args.ctx));
   else args.ctx = op->qf->raw_ctx;
 
+  // In-kernel finalize (lean kernel, stage bit 128, whole-mesh launches with the deterministic scatter): the output restriction gets K
+  // batch-aligned element parts -- before its tables are used below -- and the kernel folds the shared nodes of a part into v itself.
+  bool fin_mode = false;
+  if (plan->lean && (plan->stage_mask & 128) && plan->scatter_mode == B200_SCATTER_DETERMINISTIC && !part && !b200_compile_only()) {
+    const B200Restriction r = op->out_fields[plan->out_groups[0].slot].rstr;
+    const int             K = default_parts();
+    const long long       num_batches = ((long long)plan->num_elem + plan->epb - 1) / plan->epb;
+    if (r->split_elem < 0 && num_batches >= 64LL * K) {
+      B200_CALL(b200_restriction_set_parts(r, chunk_ends(plan->num_elem, plan->epb, K)));
+      B200_CALL(b200_restriction_build_owner(r));
+      std::vector<int32_t> tab(2 * K + 3);
+      tab[0] = K;
+      for (int c = 0; c <= K; c++) tab[1 + c] = (int32_t)(c == K ? num_batches : num_batches * c / K);
+      for (int c = 0; c <= K; c++) tab[K + 2 + c] = (int32_t)r->shared_prefix[c];
+      if (tab != plan->fin_tab_host) {
+        if (!plan->d_fin_tab || plan->fin_parts < K) {
+          B200_CALL(b200_dfree(ceed, plan->d_fin_tab));
+          B200_CALL(b200_dfree(ceed, plan->d_fin_done));
+          plan->d_fin_tab = plan->d_fin_done = nullptr;
+          B200_CALL(b200_dmalloc(ceed, (void **)&plan->d_fin_tab, tab.size() * sizeof(int32_t)));
+          B200_CALL(b200_dmalloc(ceed, (void **)&plan->d_fin_done, K * sizeof(int32_t)));
+          plan->fin_parts = K;
+        }
+        B200_CALL(b200_h2d(ceed, plan->d_fin_tab, tab.data(), tab.size() * sizeof(int32_t)));
+        plan->fin_tab_host = tab;
+      }
+      fin_mode = true;
+    }
+  }
   // inputs
   for (size_t i = 0; i < op->in_fields.size(); i++) {
     const B200OpField &f = op->in_fields[i];
@@ -329,7 +370,11 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
     const int             slot = plan->out_groups[0].slot;
     const B200Restriction r    = op->out_fields[slot].rstr;
     args.ord_num_halo          = r->num_halo;
-    if (plan->lean_runs && !part && !(plan->stage_mask & 40) && r->l_size < (int64_t)B200_RUN_RMW_BIT && !getenv("CEED_B200_NO_RUNS") && e_end > e_begin) {
+    if (fin_mode) {
+      args.ord_pred_ptr = plan->d_fin_tab, args.ord_pred_idx = r->d_halo_node, args.ord_sync = r->d_halo_ptr, args.ord_flags = plan->d_fin_done;
+      run_mode          = 2;
+    }
+    if (plan->lean_runs && !fin_mode && !part && !(plan->stage_mask & 40) && r->l_size < (int64_t)B200_RUN_RMW_BIT && !getenv("CEED_B200_NO_RUNS") && e_end > e_begin) {
       const int groups = b200_opgen_grid(ceed, plan, var, e_end - e_begin) * (plan->threads / 32);
       run              = &plan->run[kernel_add ? 1 : 0][slot];
       B200_CALL(b200_restriction_build_runs(r, groups, plan->epb, run));
@@ -350,7 +395,9 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
     }
     // element groups of the ordered scatter wait for each other: all CTAs must be resident (cooperative launch)
     void *params[3] = {&e_begin, &e_end, &run_mode};  // (the general kernel takes the first two)
-    B200_CALL(b200_launch(ceed, var.kernel, b200_opgen_grid(ceed, plan, var, e_end - e_begin), plan->threads, plan->smem_bytes, params, ordered));
+    if (fin_mode) B200_CUDA(ceed, cudaMemsetAsync(plan->d_fin_done, 0, plan->fin_parts * sizeof(int32_t), ceed->stream));
+    // (in-kernel finalize: warps wait for each other's parts, so all CTAs must be resident -- cooperative launch)
+    B200_CALL(b200_launch(ceed, var.kernel, b200_opgen_grid(ceed, plan, var, e_end - e_begin), plan->threads, plan->smem_bytes, params, ordered || fin_mode));
   }
   if (op->timing) B200_CUDA(ceed, cudaEventRecord(op->ev[1], ceed->stream));
   // second phase of the scatter
@@ -360,6 +407,7 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
     bool is_writer = plan->out_fields[i].emode == B200_EVAL_NONE || plan->out_groups[plan->out_fields[i].group].slot == (int)i;
     if (!is_writer) continue;
     if (ordered && (int)i == plan->ordered_slot) continue;  // completed inside the kernel
+    if (fin_mode && (int)i == plan->out_groups[0].slot) continue;  // folded in by the kernel
     if (run && (int)i == plan->out_groups[0].slot)
       B200_CALL(b200_halo_finalize_lists(f.rstr, run->d_halo_node, run->d_halo_ptr, run->num_shared, run->num_halo, plan->aux[i], args.out_ptr[i]));
     else if (plan->scatter_mode == B200_SCATTER_DETERMINISTIC || ordered) B200_CALL(b200_halo_finalize(f.rstr, plan->aux[i], args.out_ptr[i], part));
@@ -797,12 +845,12 @@ extern "C" int ceedb200_operator_apply_streamed(B200Operator op, B200Vector u, B
   if (!ok) return operator_apply(op, u, v, 0);
   B200_CUDA(ceed, cudaSetDevice(ceed->device_id));
   // ---- chunk tables (cached in the plan)
-  const int K  = std::max(2, std::min(num_chunks > 0 ? num_chunks : 8, 64));
+  const int K  = std::max(2, std::min(num_chunks > 0 ? num_chunks : default_parts(), 64));
   const int ne = rout->num_elem;
   B200StreamPlan &sp = plan->stream;
   if (sp.num_chunks != K) {
     sp = B200StreamPlan();
-    for (int c = 1; c <= K; c++) sp.ends.push_back((int32_t)((int64_t)ne * c / K));  // (graded chunk sizes were measured: no gain, PCIe duplex rate is the bound)
+    sp.ends = chunk_ends(ne, plan->epb, K);  // (graded chunk sizes were measured: no gain, the PCIe duplex rate is the bound)
     auto ranges = [&](B200Restriction r, std::vector<int64_t> &lo, std::vector<int64_t> &hi) {
       lo.assign(K, INT64_MAX), hi.assign(K, -1);
       for (int c = 0; c < K; c++) {

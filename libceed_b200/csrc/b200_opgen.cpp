@@ -363,7 +363,9 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     // stage bit 32: offsets, scatter targets and quadrature data through cp.async.bulk + mbarrier, one batch ahead
     // (bit 8: element offsets + scatter targets, bit 32: quadrature data)
     // bit 64: bulk L2 prefetch of the next batch's quadrature data
-    plan->stage_mask = (tn.stage >= 0 && plan->async_copy && !plan->no_tma) ? (tn.stage & (8 | 32 | 64)) : 0;
+    // bit 128: in-kernel finalize of the deterministic scatter
+    plan->stage_mask = (tn.stage >= 0 && plan->async_copy && !plan->no_tma) ? (tn.stage & (8 | 32 | 64 | 128)) : 0;
+    if ((plan->stage_mask & 40) || plan->scatter_mode != B200_SCATTER_DETERMINISTIC || plan->lean_runs) plan->stage_mask &= ~128;
     plan->swz = false, plan->swz_w = 0, plan->group_warps = 1;
     plan->qd_tma = false, plan->mbar_off = -1, plan->ring_off = -1;
     for (auto &f : plan->in_fields) f.qd_off = -1, f.qd_tma = false, f.ring_k = -1;

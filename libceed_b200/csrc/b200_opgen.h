@@ -116,6 +116,10 @@ struct B200OpPlan {
   size_t  aux_bytes[16] = {0};
   B200OrderedScatter ordered;     // ordered scatter tables (scatter_mode == B200_SCATTER_ORDERED)
   B200StreamPlan     stream;      // streamed host-buffer apply
+  // in-kernel finalize of the lean kernel (stage bit 128): device part table {K, batch starts[K+1], shared prefix[K+1]} and per-part counters
+  int32_t           *d_fin_tab = nullptr, *d_fin_done = nullptr;
+  int                fin_parts = 0;
+  std::vector<int32_t> fin_tab_host;
   B200RunScatter     run[2][16];  // run scatter tables of the lean kernel, per kernel variant (their grids may differ) and output slot
   int                ordered_slot = -1;
   // unfused fallback scratch

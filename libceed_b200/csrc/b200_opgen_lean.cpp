@@ -24,6 +24,11 @@
 //     offsets after the gather stage, quadrature data after the x-line stage, targets after the scatter stage.  Every stream is
 //     then in flight for most of a batch period with no registers held and no load instructions issued; the only demand loads
 //     left are the gathers of u.  Sources are aligned down to 16 bytes at run time (readers add the shift).
+//   * Stage bit 128 = IN-KERNEL FINALIZE: the elements are cut into K contiguous parts (batch-aligned); a warp that has finished its
+//     batches of part c publishes that (release add on a per-part counter), and -- once every warp has done so for part c - 1 --
+//     folds its static slice of the shared nodes part c - 1 completed into v (the work of k_halo_finalize), while the halo values and
+//     the owner values it reads are still in L2.  One launch instead of two, no second pass over DRAM for the halo buffer.  All CTAs
+//     must be resident (cooperative launch); a warp only ever waits for parts that lie one part duration in the past.
 //   * CEED_B200_RUNS (experimental, off): run scatter -- every warp owns a contiguous run of elements and adds E-entries whose earlier
 //     touchers it processed itself straight into v (B200RunScatter).  Bitwise equal results, finalize pass 20-30 % shorter, but the
 //     fused kernel loses its streaming locality (2x slower on B200): kept as a tested option, see DESIGN.md.
@@ -54,6 +59,7 @@ struct LeanGen {
   int          P, Q, E, nc, PS, ES, P2, P3, bid;
   bool         staged = false;  // bulk pipeline: st_idx (stage bit 8: offsets + targets) and / or st_qd (bit 32: quadrature data)
   bool         st_idx = false, st_qd = false;
+  bool         fin   = false;   // stage bit 128: in-kernel finalize of the deterministic scatter (whole-mesh launches)
   bool         pf_qd = false;   // stage bit 64: bulk L2 prefetch (cp.async.bulk.prefetch.L2) of the directly loaded quadrature data of the NEXT batch
   bool         runs   = false;  // run scatter (experimental, CEED_B200_RUNS): per-warp element runs, read-modify-write entries
   const B200GenGroup *gin, *gout;
@@ -485,6 +491,43 @@ struct LeanGen {
     c << "}\n\n";
   }
 
+  // ---- in-kernel finalize (stage bit 128) ------------------------------------------------------------------
+  // part table b200a.ord_pred_ptr: [0] = K, [1 + c] = first batch of part c (c = 0..K), [K + 2 + c] = number of shared nodes completed by
+  // parts < c (c = 0..K); b200a.ord_flags = per-part counters of finished batches (zeroed before the launch); b200a.ord_pred_idx /
+  // b200a.ord_sync = halo_node / halo_ptr of the output restriction.
+  void emit_fin() {
+    const long long cs = gout->rstr->comp_stride;
+    const string    sl = S(gout->slot);
+    c << "// this warp has finished `mine` batches of part c: publish (release) -- its stores to v and to the halo buffer come first\n";
+    c << "static __device__ __forceinline__ void b200_fin_signal(const int c, const int mine) {\n  __syncwarp();\n"
+      << "  if ((threadIdx.x & 31) == 0 && mine) {\n    __threadfence();\n    atomicAdd(b200a.ord_flags + c, mine);\n  }\n}\n";
+    c << "// fold this warp's slice of the shared nodes completed by part c into v, once every batch of the part has been published\n";
+    c << "static __device__ __noinline__ void b200_fin_part(const int c, const long long gw, const long long ng) {\n";
+    c << "  const int *const tab = b200a.ord_pred_ptr;\n  const int K = tab[0], total = tab[2 + c] - tab[1 + c];\n  const int lane = threadIdx.x & 31;\n";
+    c << "  if (lane == 0) {\n    int seen;\n    do { asm volatile(\"ld.acquire.gpu.global.s32 %0, [%1];\" : \"=r\"(seen) : \"l\"(b200a.ord_flags + c) : \"memory\"); } while (seen < total);\n  }\n";
+    c << "  __syncwarp();\n";
+    c << "  const long long s0 = tab[K + 2 + c], cnt = tab[K + 3 + c] - s0;\n";
+    c << "  const long long b = s0 + gw * cnt / ng, e = s0 + (gw + 1) * cnt / ng;\n";
+    c << "  const int *const hn = b200a.ord_pred_idx;\n  const int *const hp = b200a.ord_sync;\n";
+    c << "  const double *const h = b200a.out_aux[" << sl << "];\n  double *const v = b200a.out_ptr[" << sl << "];\n";
+    // U nodes per lane in flight: the table loads of all of them first, then their owner values and first halo values, then the (short)
+    // tails -- the standalone finalize kernel gets its memory parallelism from 1.2 M threads, a persistent grid has to unroll for it
+    const int U = 8;
+    c << "  for (long long i0 = b + lane; i0 < e; i0 += " << 32 * U << ") {\n";
+    c << "    long long l[" << U << "];\n    int p0[" << U << "], p1[" << U << "];\n";
+    c << "#pragma unroll\n    for (int u = 0; u < " << U << "; u++) {\n      const long long i = i0 + 32 * u;\n      const bool ok = i < e;\n"
+      << "      l[u] = ok ? (long long)__ldg(hn + i) : -1LL;\n      p0[u] = ok ? __ldg(hp + i) : 0;\n      p1[u] = ok ? __ldg(hp + i + 1) : 0;\n    }\n";
+    for (int cc = 0; cc < nc; cc++) {
+      c << "    {\n      double acc[" << U << "], h0[" << U << "];\n";
+      c << "#pragma unroll\n      for (int u = 0; u < " << U << "; u++) acc[u] = l[u] >= 0 ? __ldcg(v + l[u] + " << cc * cs << "LL) : 0.0;\n";
+      c << "#pragma unroll\n      for (int u = 0; u < " << U << "; u++) h0[u] = l[u] >= 0 ? __ldcg(h + p0[u] + " << cc << " * b200a.ord_num_halo) : 0.0;\n";
+      c << "#pragma unroll\n      for (int u = 0; u < " << U << "; u++) {\n        double a = acc[u] + h0[u];\n"
+        << "        for (int j = p0[u] + 1; j < p1[u]; j++) a += __ldcg(h + j + " << cc << " * b200a.ord_num_halo);\n"
+        << "        if (l[u] >= 0) v[l[u] + " << cc * cs << "LL] = a;\n      }\n    }\n";
+    }
+    c << "  }\n}\n\n";
+  }
+
   string generate() {
     gin  = &plan->in_groups[0];
     gout = &plan->out_groups[0];
@@ -501,12 +544,14 @@ struct LeanGen {
     st_qd  = (plan->stage_mask & 32) != 0;
     staged = st_idx || st_qd;
     pf_qd  = (plan->stage_mask & 64) != 0 && !st_qd;
+    fin    = (plan->stage_mask & 128) != 0 && !staged && !runs && plan->scatter_mode == B200_SCATTER_DETERMINISTIC;
     runs   = plan->lean_runs && !staged;
     emit_header();
     emit_z();
     emit_yx();
     emit_yt();
     emit_zt();
+    if (fin) emit_fin();
     const int NT = plan->threads, W = NT / 32;
     c << "extern \"C\" __global__ void __launch_bounds__(" << NT << ", " << std::max(1, plan->blocks_per_sm) << ") b200_operator_" << op->qf->kernel_name
       << "(const long long e_begin, const long long e_end, const int run_mode) {\n";
@@ -529,7 +574,15 @@ struct LeanGen {
         c << "    if (e0 + " << E - 1 << "LL * st < lim) {\n";
       } else {
         c << "  (void)run_mode;\n  const long long num_batches = (e_end - e_begin + " << E - 1 << ") / " << E << ";\n";
+        if (fin) {
+          // run_mode == 2: in-kernel finalize (whole-mesh launch, e_begin == 0); parts are ranges of the global batch index
+          c << "  const long long gw = " << first << ", ng = " << stride << ";\n";
+          c << "  const int *const tab = b200a.ord_pred_ptr;\n  const int K = run_mode == 2 ? tab[0] : 0;\n  int part = 0, mine = 0;\n";
+        }
         c << "  for (long long batch = " << first << "; batch < num_batches; batch += " << stride << ") {\n";
+        if (fin)
+          c << "    while (part < K && batch >= tab[2 + part]) {  // this warp is done with part `part`\n      b200_fin_signal(part, mine);\n      mine = 0;\n"
+            << "      if (part >= 1) b200_fin_part(part - 1, gw, ng);\n      part++;\n    }\n    mine++;\n";
         c << "    const long long e0 = e_begin + batch * " << E << ";\n";
         if (pf_qd)
           c << "    { const long long e0n = e_begin + (batch + " << stride << ") * " << E << ";\n"
@@ -541,7 +594,11 @@ struct LeanGen {
       c << "    } else {\n";
       c << "      b200_lean_z<true>(e0" << a << ");\n      __syncwarp();\n      b200_lean_yx<true>(e0" << a << ");\n      __syncwarp();\n      b200_lean_yt();\n      __syncwarp();\n"
         << "      b200_lean_zt<true>(e0" << a << ");\n      __syncwarp();\n";
-      c << "    }\n  }\n}\n";
+      c << "    }\n  }\n";
+      if (fin && !runs)
+        c << "  for (; part < K; part++) {\n    b200_fin_signal(part, mine);\n    mine = 0;\n    if (part >= 1) b200_fin_part(part - 1, gw, ng);\n  }\n"
+          << "  if (K) b200_fin_part(K - 1, gw, ng);\n";
+      c << "}\n";
       return c.str();
     }
     bool any_qd = false;

@@ -71,8 +71,12 @@ def parity_runs():
         prob.op.apply(prob.u, prob.v)
         v_classic = prob.v.get_array_read().copy()
         os.environ.pop("CEED_B200_NO_RUNS")
-        for E, warps in ((1, 4), (2, 4), (6, 4), (8, 2)):
-            prob.op.set_kernel_shape(qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=0)
+        for E, warps, stage, parts in ((1, 4, 0, 0), (6, 4, 0, 0), (6, 4, 128, 8), (2, 4, 128, 3), (5, 2, 128, 16), (8, 8, 128, 5)):
+            if stage:
+                os.environ.pop("CEED_B200_RUNS", None); os.environ["CEED_B200_PARTS"] = str(parts)
+            else:
+                os.environ["CEED_B200_RUNS"] = "1"
+            prob.op.set_kernel_shape(qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=stage)
             prob.v.set_value(-3.0)
             prob.op.apply(prob.u, prob.v)
             v = prob.v.get_array_read().copy()
@@ -82,7 +86,7 @@ def parity_runs():
             e2 = rel(prob.v.get_array_read() - w0, ref)
             ok = rel(v, ref) < 1e-12 and np.array_equal(v, v_classic) and e2 < 1e-9
             bad += not ok
-            print(f"runs bp{bp} p={p} nel={nel} morton={morton} E={E} warps={warps}: vs oracle {rel(v, ref):.1e}, bitwise == classic tables {np.array_equal(v, v_classic)}, "
+            print(f"runs bp{bp} p={p} nel={nel} morton={morton} E={E} warps={warps} stage={prob.op.get_kernel_shape()['stage_mask']} parts={parts}: vs oracle {rel(v, ref):.1e}, bitwise == classic tables {np.array_equal(v, v_classic)}, "
                   f"add {e2:.1e} {'ok' if ok else 'FAIL'}", flush=True)
     print("parity_runs:", "all ok" if not bad else f"{bad} FAILED")
     return bad
@@ -138,8 +142,13 @@ def sweep():
             run(f"{order} general kernel (table)")
         return
     run("table (general kernel)")
-    for stage in (0, 32):
-        for E, warps, minb in ((6, 4, 0), (6, 3, 6), (6, 2, 9), (6, 1, 18), (5, 3, 7), (5, 2, 10), (5, 2, 11), (4, 3, 8), (4, 2, 12), (6, 3, 5), (6, 2, 8)):
+    for parts in (2, 3, 4, 6, 8, 12):
+        os.environ["CEED_B200_PARTS"] = str(parts)
+        for E, warps in ((6, 4), (4, 4)):
+            run(f"lean fin parts={parts} E={E} warps={warps}", qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=128)
+    os.environ.pop("CEED_B200_PARTS", None)
+    for stage in (0,):
+        for E, warps, minb in ((6, 4, 0),):
             run(f"lean stage={stage} E={E} warps={warps} minb={minb}", qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=stage, min_blocks_per_sm=minb)
     return
     for stage in (0, 8, 32, 40):

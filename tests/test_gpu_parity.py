@@ -431,7 +431,8 @@ def test_lean_kernel_matches_oracle(cm, oracle, monkeypatch, bp, p, nel):
 @pytest.mark.parametrize("bp,p,nel,morton", [(1, 3, (32, 31, 31), True), (1, 3, (33, 30, 29), False), (2, 2, (30, 29, 28), True)])
 def test_lean_kernel_run_scatter_is_bitwise_equal(cm, oracle, monkeypatch, bp, p, nel, morton):
     """Experimental run scatter (CEED_B200_RUNS; B200RunScatter): warps own contiguous element runs and add the E-entries whose earlier
-    touchers they processed themselves straight into v.  Same ascending E-order: bitwise equal to the owner/halo tables."""
+    touchers they processed themselves straight into v.  Same ascending E-order: bitwise equal to the owner/halo tables.  Also the in-kernel
+    finalize (stage bit 128): one cooperative launch instead of fused kernel + finalize kernel, same bits."""
     from libceed_b200 import mesh as M
     monkeypatch.setenv("CEED_B200_NO_TUNE_TABLE", "1")
     perm = M.morton_permutation(*nel) if morton else None
@@ -444,9 +445,15 @@ def test_lean_kernel_run_scatter_is_bitwise_equal(cm, oracle, monkeypatch, bp, p
     prob.op.apply(prob.u, prob.v)
     v_classic = prob.v.get_array_read().copy()
     assert rel(v_classic, ref) < OP_TOL
-    monkeypatch.setenv("CEED_B200_RUNS", "1")
-    for E, warps in ((1, 4), (2, 4), (6, 4), (8, 2)):
-        prob.op.set_kernel_shape(qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=0)
+    # (stage bit 128: in-kernel finalize -- warps fold the shared nodes of finished element parts into v themselves; cooperative launch)
+    for E, warps, stage, parts in ((1, 4, 0, 0), (2, 4, 0, 0), (6, 4, 0, 0), (8, 2, 0, 0), (6, 4, 128, 8), (2, 4, 128, 3), (5, 2, 128, 16), (8, 8, 128, 5)):
+        if stage:
+            monkeypatch.delenv("CEED_B200_RUNS", raising=False)
+            monkeypatch.setenv("CEED_B200_PARTS", str(parts))
+        else:
+            monkeypatch.setenv("CEED_B200_RUNS", "1")
+        prob.op.set_kernel_shape(qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=stage)
+        assert prob.op.get_kernel_shape()["stage_mask"] == stage
         prob.v.set_value(-3.0)
         prob.op.apply(prob.u, prob.v)
         assert np.array_equal(prob.v.get_array_read(), v_classic), (E, warps)
