@@ -453,9 +453,9 @@ def test_lean_kernel_run_scatter_is_bitwise_equal(cm, oracle, monkeypatch, bp, p
         else:
             monkeypatch.setenv("CEED_B200_RUNS", "1")
         prob.op.set_kernel_shape(qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=stage)
-        assert prob.op.get_kernel_shape()["stage_mask"] == stage
         prob.v.set_value(-3.0)
         prob.op.apply(prob.u, prob.v)
+        assert prob.op.get_kernel_shape()["stage_mask"] == stage
         assert np.array_equal(prob.v.get_array_read(), v_classic), (E, warps)
         w0 = seeded_uniform(prob.num_dofs, 5)
         prob.v.set_array(w0)
