@@ -689,7 +689,13 @@ struct Gen {
           c << "    const double *src" << k << " = b200a.in_ptr[" << f.slot << "] + " << (long long)cc * f.rstr->strides[1] << "LL + e0 * " << Q3 << "LL;\n";
           if (Q3 % 2) {
             c << "    const unsigned sh" << k << " = (unsigned)((" << (long long)cc * f.rstr->strides[1] << "LL + e0 * " << Q3 << "LL) & 1);\n";
-            c << "    const unsigned nb" << k << " = ((ne * " << Q3 << " + sh" << k << ") * 8 + 15) & ~15u;\n";
+            c << "    unsigned nb" << k << " = ((ne * " << Q3 << " + sh" << k << ") * 8 + 15) & ~15u;\n";
+            // the last block of the array: rounding up would read 8 bytes past its end -- copy up to the last 16-byte boundary and
+            // let this lane move the final double itself
+            c << "    { const double *end = b200a.in_ptr[" << f.slot << "] + " << (long long)cc * f.rstr->strides[1] << "LL + b200a.num_elem * " << Q3 << "LL;\n";
+            c << "      if ((const char *)(src" << k << " - sh" << k << ") + nb" << k << " > (const char *)end) {\n";
+            c << "        nb" << k << " -= 16;\n";
+            c << "        ((double *)((char *)" << SMBASE << " + " << f.qd_off + cc * f.qd_cs * 8 << "))[(end - 1) - (src" << k << " - sh" << k << ")] = end[-1];\n      } }\n";
           } else {
             c << "    const unsigned sh" << k << " = 0, nb" << k << " = ne * " << Q3 * 8 << ";\n";
           }

@@ -105,20 +105,30 @@ struct LeanGen {
       c << "#define B200_BAR(s) (b200_smem_u32((char *)B200_SMW + " << plan->mbar_off << " + 8 * (s)))  // 0 offsets, 1 quadrature data, 2 targets\n";
       // run-time shift (in elements) of a bulk-copied block whose source was aligned down to 16 bytes
       c << "#define B200_SHIFT(ptr, esize) ((int)(((unsigned long long)(ptr) & 15ULL) / (esize)))\n";
-      c << "static __device__ __forceinline__ unsigned b200_lean_nb(const void *src, unsigned bytes) { return (unsigned)(((unsigned long long)src & 15ULL) + bytes + 15u) & ~15u; }\n";
-      c << "static __device__ __forceinline__ void b200_lean_copy(void *dst, const void *src, unsigned bytes, unsigned bar) {\n"
-        << "  b200_bulk_g2s(b200_smem_u32(dst), (const void *)((unsigned long long)src & ~15ULL), b200_lean_nb(src, bytes), bar);\n}\n";
+      // Bytes of the bulk copy of [src, src + bytes): the source is aligned down to 16 bytes and the size rounded up to 16 -- except in
+      // the last block of the array (`end` = one past its last byte), where rounding up would read past the allocation: the copy then
+      // stops at the last 16-byte boundary inside the array and the few trailing elements are moved by the issuing lane itself.
+      c << "static __device__ __forceinline__ unsigned b200_lean_nb(const void *src, unsigned bytes, const void *end) {\n"
+        << "  const unsigned long long a0 = (unsigned long long)src & ~15ULL;\n  unsigned nb = (unsigned)(((unsigned long long)src & 15ULL) + bytes + 15u) & ~15u;\n"
+        << "  if (a0 + nb > (unsigned long long)end) nb = (unsigned)((unsigned long long)end - a0) & ~15u;\n  return nb;\n}\n";
+      c << "template <typename T> static __device__ __forceinline__ void b200_lean_copy(void *dst, const T *src, unsigned bytes, unsigned bar, const T *end) {\n"
+        << "  const unsigned long long a0 = (unsigned long long)src & ~15ULL;\n  const unsigned nb = b200_lean_nb(src, bytes, end);\n"
+        << "  for (const T *p = (const T *)(a0 + nb) < src ? src : (const T *)(a0 + nb); p < (const T *)((const char *)src + bytes); p++)\n"
+        << "    *(T *)((char *)dst + ((unsigned long long)p - a0)) = *p;  // (only ever runs for the last block of the array)\n"
+        << "  if (nb) b200_bulk_g2s(b200_smem_u32(dst), (const void *)a0, nb, bar);\n}\n";
       // issue functions (lane 0 of the warp; ne = elements of the batch starting at e0)
       if (st_idx)
       c << "static __device__ __noinline__ void b200_lean_issue_off(const long long e0, const int ne) {\n"
         << "  const int *src = b200a.in_idx[" << gin->slot << "] + e0 * " << P3 << ";\n  const unsigned bar = B200_BAR(0);\n"
-        << "  b200_fence_proxy_async();\n  b200_mbar_expect_tx(bar, b200_lean_nb(src, ne * " << P3 * 4 << "));\n"
-        << "  b200_lean_copy(B200_OFS, src, ne * " << P3 * 4 << ", bar);\n}\n";
+        << "  const int *end = b200a.in_idx[" << gin->slot << "] + b200a.num_elem * " << P3 << ";\n"
+        << "  b200_fence_proxy_async();\n  b200_mbar_expect_tx(bar, b200_lean_nb(src, ne * " << P3 * 4 << ", end));\n"
+        << "  b200_lean_copy(B200_OFS, src, ne * " << P3 * 4 << ", bar, end);\n}\n";
       if (st_idx)
       c << "static __device__ __noinline__ void b200_lean_issue_tg(const long long e0, const int ne) {\n"
         << "  const int *src = b200a.out_idx[" << gout->slot << "] + e0 * " << P3 << ";\n  const unsigned bar = B200_BAR(2);\n"
-        << "  b200_fence_proxy_async();\n  b200_mbar_expect_tx(bar, b200_lean_nb(src, ne * " << P3 * 4 << "));\n"
-        << "  b200_lean_copy(B200_TGS, src, ne * " << P3 * 4 << ", bar);\n}\n";
+        << "  const int *end = b200a.out_idx[" << gout->slot << "] + b200a.num_elem * " << P3 << ";\n"
+        << "  b200_fence_proxy_async();\n  b200_mbar_expect_tx(bar, b200_lean_nb(src, ne * " << P3 * 4 << ", end));\n"
+        << "  b200_lean_copy(B200_TGS, src, ne * " << P3 * 4 << ", bar, end);\n}\n";
       bool any_qd = false;
       for (auto &fd : plan->in_fields) any_qd = any_qd || qd_staged(fd);
       if (any_qd) {
@@ -127,17 +137,19 @@ struct LeanGen {
         int k = 0;
         for (auto &fd : plan->in_fields) {
           if (!qd_staged(fd)) continue;
-          for (int cc = 0; cc < fd.nc; cc++, k++)
+          for (int cc = 0; cc < fd.nc; cc++, k++) {
             c << "  const double *src" << k << " = b200a.in_ptr[" << fd.slot << "] + " << (long long)cc * fd.rstr->strides[1] << "LL + e0 * " << Q3 << "LL;\n";
+            c << "  const double *end" << k << " = b200a.in_ptr[" << fd.slot << "] + " << (long long)cc * fd.rstr->strides[1] << "LL + b200a.num_elem * " << Q3 << "LL;\n";
+          }
         }
         c << "  b200_fence_proxy_async();\n  b200_mbar_expect_tx(bar, 0u";
-        for (int i = 0; i < k; i++) c << " + b200_lean_nb(src" << i << ", ne * " << Q3 * 8 << ")";
+        for (int i = 0; i < k; i++) c << " + b200_lean_nb(src" << i << ", ne * " << Q3 * 8 << ", end" << i << ")";
         c << ");\n";
         k = 0;
         for (auto &fd : plan->in_fields) {
           if (!qd_staged(fd)) continue;
           for (int cc = 0; cc < fd.nc; cc++, k++)
-            c << "  b200_lean_copy((char *)B200_SMW + " << fd.qd_off + cc * fd.qd_cs * 8 << ", src" << k << ", ne * " << Q3 * 8 << ", bar);\n";
+            c << "  b200_lean_copy((char *)B200_SMW + " << fd.qd_off + cc * fd.qd_cs * 8 << ", src" << k << ", ne * " << Q3 * 8 << ", bar, end" << k << ");\n";
         }
         c << "}\n";
       }
@@ -150,7 +162,11 @@ struct LeanGen {
         if (!contiguous) continue;
         for (int cc = 0; cc < fd.nc; cc++) {
           c << "  { const unsigned long long a = (unsigned long long)(b200a.in_ptr[" << fd.slot << "] + " << (long long)cc * fd.rstr->strides[1] << "LL + e0 * " << Q3 << "LL);\n";
-          c << "    b200_bulk_prefetch_l2((const void *)(a & ~15ULL), (unsigned)(((a & 15ULL) + (unsigned long long)ne * " << Q3 * 8 << " + 15) & ~15ULL)); }\n";
+          c << "    const unsigned long long end = (unsigned long long)(b200a.in_ptr[" << fd.slot << "] + " << (long long)cc * fd.rstr->strides[1] << "LL + b200a.num_elem * " << Q3
+            << "LL);\n";
+          c << "    unsigned nb = (unsigned)(((a & 15ULL) + (unsigned long long)ne * " << Q3 * 8 << " + 15) & ~15ULL);\n";
+          c << "    if ((a & ~15ULL) + nb > end) nb = (unsigned)(end - (a & ~15ULL)) & ~15u;  // never past the end of the array\n";
+          c << "    if (nb) b200_bulk_prefetch_l2((const void *)(a & ~15ULL), nb); }\n";
         }
       }
       c << "}\n";
@@ -609,7 +625,8 @@ struct LeanGen {
     c << "  long long batch = " << first << ";\n";
     c << "  if (lead && batch < num_batches) {\n    const long long e0 = e_begin + batch * " << E << ";\n"
       << "    const int ne = (int)(e_end - e0 < " << E << " ? e_end - e0 : " << E << ");\n"
-      << (st_idx ? "    b200_lean_issue_off(e0, ne);\n" : "") << (any_qd ? "    b200_lean_issue_qd(e0, ne);\n" : "") << (st_idx ? "    b200_lean_issue_tg(e0, ne);\n" : "") << "  }\n";
+      << (st_idx ? "    b200_lean_issue_off(e0, ne);\n" : "") << (any_qd ? "    b200_lean_issue_qd(e0, ne);\n" : "") << (st_idx ? "    b200_lean_issue_tg(e0, ne);\n" : "") << "  }\n"
+      << "  __syncwarp();  // (trailing elements the issuing lane moved itself at the end of an array)\n";
     c << "  for (int it = 0; batch < num_batches; batch += " << stride << ", it++) {\n";
     c << "    const long long e0 = e_begin + batch * " << E << ", e0n = e_begin + (batch + " << stride << ") * " << E << ";\n";
     c << "    const int nen = e0n >= e_end ? 0 : (int)(e_end - e0n < " << E << " ? e_end - e0n : " << E << "), par = it & 1;\n";

@@ -223,6 +223,9 @@ extern "C" int ceedb200_destroy(B200Ceed ceed) {
   }
   b200_dfree(ceed, ceed->d_scratch);
   for (int i = 0; i < 3; i++) b200_dfree(ceed, ceed->d_basis_tmp[i]);
+  for (auto ev : ceed->ev_stream) cudaEventDestroy(ev);  // streamed apply: events and copy streams
+  if (ceed->s_h2d) cudaStreamDestroy(ceed->s_h2d);
+  if (ceed->s_d2h) cudaStreamDestroy(ceed->s_d2h);
   delete ceed;
   return B200_SUCCESS;
 }
