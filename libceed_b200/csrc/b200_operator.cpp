@@ -694,11 +694,13 @@ static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
       if (qf == 2 && (op->plan->Q % 2 || !full)) continue;  // point pairs need an even number of points per row
       if (qf == 3 && !xline_ok) continue;                   // x-line fusion exists for gradient-free operators only
       if (qf == 0 && xline_ok && !full) continue;           // gradient-free operators: the x-line layout wins
-      for (int swz = 0; swz < 2; swz++) {
-        if (swz && (!swz_ok || qf == 1 || qf == 2)) continue;  // the conflict-free swizzled planes exist for the z-line / x-line layouts
+      for (int swz = 0; swz < 3; swz++) {
+        if (swz == 1 && (!swz_ok || qf == 1 || qf == 2)) continue;  // the conflict-free swizzled planes exist for the z-line / x-line layouts
+        if (swz == 2 && (op->plan->Q % 2 || qf == 1 || qf == 2)) continue;  // even-Q linear layout (16-byte x-lines)
         B200Tuning t  = base;
         t.group_warps = sh[0], t.cta_warps = sh[1], t.qf_mode = qf;
-        if (swz) t.stage = 257;
+        if (swz == 1) t.stage = 257;
+        if (swz == 2) t.stage = 513;
         if (qf == 2) t.qf_unroll = 2;
         trial(t);
       }
@@ -719,7 +721,7 @@ static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
       if (epw == win.epw) continue;
       B200Tuning t = base;
       t.group_warps = win.group_warps, t.cta_warps = win.cta_warps, t.qf_mode = win.qf_mode, t.epw = epw;
-      if (win.stage >= 0 && (win.stage & 256)) t.stage = win.stage;
+      if (win.stage >= 0 && (win.stage & (256 | 512))) t.stage = win.stage;
       trial(t);
     }
   }
@@ -745,7 +747,7 @@ static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
   // 4. cp.async staging: scatter targets only (1), + gather offsets (9), nothing (0) -- keeping the winner's plane layout bit
   {
     const B200Tuning win = best;
-    const int        layout_bit = win.stage >= 0 ? (win.stage & 256) : 0;
+    const int        layout_bit = win.stage >= 0 ? (win.stage & (256 | 512)) : 0;
     for (int stage : {9, 0}) {
       if ((stage | layout_bit) == win.stage || win.qf_mode == 4) continue;
       B200Tuning t = win;

@@ -39,6 +39,14 @@ int pad8(int n) { return n <= 8 ? 8 : ((n - 8 + 15) / 16) * 16 + 8; }
 // Strides of the swizzled layouts for row width w (8: Q, P <= 8; 16: larger).  With w = 16 a half-warp is exactly one row, so the
 // z-strides need no residue and only the quadrature planes widen (pitch 16).
 int swz_sz(int w, int n) { return w == 8 ? pad8(n) : n; }
+// z-stride of the even-Q linear layout: smallest m >= Q^2 with m = Q (mod 16) -- y- and z-line stages then map consecutive lanes to
+// consecutive banks (lane (qx, qz) -> qx + Q qz (mod 16)), x-lines move as 16-byte accesses (2-way conflicts instead of clean, but the
+// y- and z-line stages carry 2.5x the traffic): scripts/model/lin_layout.py
+int lin_sz(int Q) {
+  int m = Q * Q;
+  while (m % 16 != Q % 16) m++;
+  return m;
+}
 
 string hexd(double v) {
   char buf[64];
@@ -258,16 +266,19 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     }
     plan->swz   = ok;
     plan->swz_w = ok ? w : 0;
+    plan->lin   = !ok && (stage_req & 512) && Q % 2 == 0 && !getenv("CEED_B200_BLOCK_MODE") && tn.qf_mode != 1 && tn.qf_mode != 2 && !(stage_req & 16) &&
+                plan->scatter_mode != B200_SCATTER_ORDERED;
   }
   {
     const int w          = plan->swz_w;
-    int       plane_size = plan->swz ? Q * swz_sz(w, Q * w) : Q * Q * plan->Qs;
+    int       plane_size = plan->swz ? Q * swz_sz(w, Q * w) : (plan->lin ? Q * lin_sz(Q) : Q * Q * plan->Qs);
     for (auto &b : plan->bases) {
       const int wp = b.P <= 8 ? 8 : 16;  // lane width of the node-indexed (y) stages of this basis
       plane_size   = std::max(plane_size, Q * (plan->swz ? swz_sz(wp, b.P * b.P) : b.P * b.P));
       plane_size   = std::max(plane_size, Q * (plan->swz ? swz_sz(wp, Q * odd_pad(b.P)) : Q * odd_pad(b.P)));
     }
     if (plan->swz) plane_size = (plane_size + 15) / 16 * 16;  // element / plane strides keep the bank residues
+    if (plan->lin) plane_size = (plane_size + 1) / 2 * 2;       // rows stay 16-byte aligned
     plan->plane_size = plane_size;
   }
   plan->qf_pointwise = tn.qf_mode == 1 || tn.qf_mode == 2;
@@ -479,6 +490,7 @@ struct Gen {
   // plane layouts (see b200_opgen_plan): quadrature rows have pitch QP, z-layers are SZ apart, lanes enumerate the fastest
   // quadrature index with extent LQ; swizzled: QP = LQ = 8 and the x index of a point is XOR-ed with its y index
   bool         swz = false;
+  bool         lin = false;  // even-Q linear layout: QP = Q, SZ = lin_sz(Q), x-lines through 16-byte accesses
   int          QP = 0, SZ = 0, LQ = 0;
   int          W = 0;                                                                                        // row width of the swizzled layouts (8 or 16)
   int          lp(const B200GenBasis &b) const { return swz ? (b.P <= 8 ? 8 : 16) : b.P; }                   // lane extent of the fastest node index
@@ -486,6 +498,25 @@ struct Gen {
   int          sz2(const B200GenBasis &b) const { return swz ? swz_sz(lp(b), Q * odd_pad(b.P)) : Q * odd_pad(b.P); }  // z-stride of T2 [qz][qy][i]
   string       xq(const string &x, const string &y) const { return swz ? "((" + x + ") ^ (" + y + "))" : "(" + x + ")"; }
   string       xq(int x, const string &y) const { return swz ? "(" + std::to_string(x) + " ^ (" + y + "))" : std::to_string(x); }
+  // Q consecutive doubles of an x-line of a quadrature plane: scalar accesses (swizzled: XOR-ed index), or -- even-Q linear layout --
+  // 16-byte accesses (every row starts at a 16-byte boundary there)
+  void row_load(const string &ptr, const string &name, const string &y, const string &ind) {
+    if (lin) {
+      for (int q = 0; q < Q; q += 2) {
+        c << ind << "const double2 " << name << "v" << q << " = *(const double2 *)(" << ptr << " + " << q << ");\n";
+        c << ind << "const double " << name << q << " = " << name << "v" << q << ".x, " << name << q + 1 << " = " << name << "v" << q << ".y;\n";
+      }
+    } else {
+      for (int q = 0; q < Q; q++) c << ind << "const double " << name << q << " = " << ptr << "[" << xq(q, y) << "];\n";
+    }
+  }
+  void row_store(const string &ptr, const string &name, const string &y, const string &ind) {
+    if (lin) {
+      for (int q = 0; q < Q; q += 2) c << ind << "*(double2 *)(" << ptr << " + " << q << ") = make_double2(" << name << q << ", " << name << q + 1 << ");\n";
+    } else {
+      for (int q = 0; q < Q; q++) c << ind << ptr << "[" << xq(q, y) << "] = " << name << q << ";\n";
+    }
+  }
   string       smw_expr() const {
     return warp_mode ? "sm + (threadIdx.x / " + std::to_string(TS) + ") * " + std::to_string(plan->group_smem_bytes / 8) : "sm";
   }
@@ -570,7 +601,7 @@ struct Gen {
       // the argument block lives in constant memory (written by the host before the launch): every stage function reads its
       // pointers with uniform constant loads instead of generic loads through a reference to the kernel parameter
       << "__constant__ B200OpArgs b200a;\n\n";
-    c << "extern __shared__ double sm[];\n";
+    c << "extern __shared__ __align__(16) double sm[];\n";
     // end of the element range of this launch (kernel parameter e_end, published by thread 0): stage functions clamp tail groups with it
     c << "__shared__ long long b200_ne;\n\n";
     // cp.async (LDGSTS): global -> shared without staging registers; completion tracked per thread with commit/wait groups
@@ -875,17 +906,17 @@ struct Gen {
     if (LQ != Q) c << "      if (qy >= " << Q << ") continue;\n";
     c << "      double *uq = " << plane(g.plane0, "le") << " + cc * " << E * S << " + qz * " << SZ << " + qy * " << QP << ";\n";
     if (b.collocated) {
-      for (int q = 0; q < Q; q++) c << "      const double r" << q << " = uq[" << xq(q, "qy") << "];\n";
+      row_load("uq", "r", "qy", "      ");
     } else {
       c << "      const double *src = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + qz * " << sz2(b) << " + qy * " << Ps << ";\n";
       for (int i = 0; i < P; i++) c << "      const double u" << i << " = src[" << i << "];\n";
       contract("cB" + std::to_string(g.basis_id), P, Q, false, "u", "r", "      ");
-      for (int q = 0; q < Q; q++) c << "      uq[" << xq(q, "qy") << "] = r" << q << ";\n";
+      row_store("uq", "r", "qy", "      ");
     }
     if (g.use_grad) {
       c << "      double *gx = " << plane(g.plane0 + 2 * g.nc, "le") << " + cc * " << E * S << " + qz * " << SZ << " + qy * " << QP << ";\n";
       contract("cG" + std::to_string(g.basis_id), Q, Q, false, "r", "d", "      ");
-      for (int q = 0; q < Q; q++) c << "      gx[" << xq(q, "qy") << "] = d" << q << ";\n";
+      row_store("gx", "d", "qy", "      ");
     }
     task_loop_end();
   }
@@ -1536,14 +1567,15 @@ struct Gen {
     c << "      double *vq = " << plane(g.plane0, "le") << " + cc * " << E * S << " + qz * " << SZ << " + qy * " << QP << ";\n";
     if (g.use_grad) {
       c << "      const double *vx = " << plane(g.plane0 + 2 * g.nc, "le") << " + cc * " << E * S << " + qz * " << SZ << " + qy * " << QP << ";\n";
-      for (int m = 0; m < Q; m++) c << "      const double u" << m << " = vx[" << xq(m, "qy") << "];\n";
+      row_load("vx", "u", "qy", "      ");
       contract("cG" + std::to_string(g.basis_id), Q, Q, true, "u", "d", "      ");
-      for (int q = 0; q < Q; q++) c << "      const double v" << q << " = vq[" << xq(q, "qy") << "] + d" << q << ";\n";
+      row_load("vq", "w", "qy", "      ");
+      for (int q = 0; q < Q; q++) c << "      const double v" << q << " = w" << q << " + d" << q << ";\n";
     } else {
-      for (int q = 0; q < Q; q++) c << "      const double v" << q << " = vq[" << xq(q, "qy") << "];\n";
+      row_load("vq", "v", "qy", "      ");
     }
     if (b.collocated) {
-      for (int q = 0; q < Q; q++) c << "      vq[" << xq(q, "qy") << "] = v" << q << ";\n";
+      row_store("vq", "v", "qy", "      ");
     } else {
       c << "      double *dst = " << plane(g.plane0 + g.nc, "le") << " + cc * " << E * S << " + qz * " << sz2(b) << " + qy * " << Ps << ";\n";
       contract("cB" + std::to_string(g.basis_id), Q, P, true, "v", "r", "      ");
@@ -1725,8 +1757,9 @@ struct Gen {
     S   = plan->plane_size;
     swz = plan->swz;
     W   = plan->swz_w;
-    QP  = swz ? W : Qs;
-    SZ  = swz ? swz_sz(W, Q * W) : Q * Qs;
+    lin = plan->lin;
+    QP  = swz ? W : (lin ? Q : Qs);
+    SZ  = swz ? swz_sz(W, Q * W) : (lin ? lin_sz(Q) : Q * Qs);
     LQ  = swz ? W : Q;
     // quadrature data is read exactly once per apply: mark it evict-first so that u, v, the halo buffer and the offsets keep the L2
     if (plan->stage_mask & 128) QLD = "__ldcs";

@@ -86,6 +86,7 @@ struct B200OpPlan {
                                                  // 16 per-lane qdata ring; 32 qdata through cp.async.bulk (TMA) + mbarrier
   bool                      swz = false;         // conflict-free swizzled plane layout (stage bit 256), see b200_opgen_plan
   int                       swz_w = 0;           // its row width: 8 (Q, P <= 8) or 16
+  bool                      lin = false;         // even-Q linear layout (stage bit 512): unpadded rows, z-stride = Q (mod 16), 16-byte x-line accesses
   bool                      qd_tma = false;      // some EVAL_NONE input is staged by bulk copies
   int                       mbar_off = -1;       // byte offset of the group's mbarrier (bulk-copy completion)
   bool                      no_tma = false;      // set by the host when an input pointer is not 16-byte aligned

@@ -13,6 +13,7 @@ CASES = [(1, 3, (3, 2, 2), dict(stage_mask=33)), (3, 2, (3, 3, 2), dict(stage_ma
          (3, 6, (2, 1, 1), dict(stage_mask=257)), (5, 7, (1, 2, 1), dict(stage_mask=257, group_warps=2, cta_warps=4)),
          (3, 6, (1, 2, 1), dict(stage_mask=289, group_warps=2, cta_warps=2)), (3, 5, (2, 1, 1), dict(stage_mask=297, group_warps=1, cta_warps=2)),
          (3, 3, (3, 2, 2), dict(stage_mask=65)), (6, 2, (2, 2, 1), dict(stage_mask=257)),
+         (3, 4, (3, 2, 2), dict(stage_mask=513)), (5, 5, (2, 2, 1), dict(stage_mask=513, group_warps=2, cta_warps=4, elems_per_group=2)), (4, 1, (3, 2, 2), dict(stage_mask=512)),
          # lean in-place-plane kernel (layout 4): direct loads with parked targets, bulk pipelines (odd Q^3: sources aligned down at run time),
          # partial tail batches, 3 components; in-kernel finalize with per-part release / acquire counters (needs >= 64 batches per part)
          (1, 3, (5, 3, 3), dict(qf_mode=4, group_warps=1, cta_warps=4, elems_per_group=6, stage_mask=0)),

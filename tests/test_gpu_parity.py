@@ -357,6 +357,8 @@ SHAPES = [dict(group_warps=2, cta_warps=2), dict(group_warps=2, cta_warps=8), di
           # conflict-free swizzled plane layout (stage bit 256), alone and with the other staging options
           dict(stage_mask=257), dict(stage_mask=257, group_warps=2, cta_warps=4, elems_per_group=2), dict(stage_mask=289, group_warps=2, cta_warps=2),
           dict(stage_mask=265, group_warps=4, cta_warps=4, elems_per_group=3), dict(stage_mask=256, qf_mode=0, cta_warps=2),
+          # even-Q linear layout (stage bit 512; Q odd: falls back to the padded layout): unpadded rows, z-stride = Q (mod 16), 16-byte x-lines
+          dict(stage_mask=513), dict(stage_mask=512, group_warps=2, cta_warps=4, elems_per_group=3), dict(stage_mask=521, group_warps=4, cta_warps=4, elems_per_group=2),
           # lean in-place-plane kernel of gradient-free operators (layout 4; other operators fall back to their own layouts)
           dict(qf_mode=4, group_warps=1, cta_warps=4, elems_per_group=6, stage_mask=0), dict(qf_mode=4, group_warps=1, cta_warps=2, elems_per_group=3, stage_mask=40)]
 
