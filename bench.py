@@ -676,6 +676,25 @@ def main():
                 sweep.append(dict(bp=sbp, p=sp, dofs=sprob.num_dofs, ms=ms, gdofs=sprob.num_dofs / ms / 1e6,
                                   frac=sprob.bytes_per_apply() / (ms * 1e-3) / 1e9 / peak))
                 del sprob
+        # the headline operator with the ATOMIC scatter (the reference's /gpu/cuda/gen semantics: not reproducible run to run), for comparison
+        # with the deterministic default: memset + fused kernel, no finalize pass
+        try:
+            aceed = cm.Ceed(f"/gpu/cuda/b200:device_id={local_rank}")
+            aceed.set_scatter_mode(1)
+            aprob = BPProblem(aceed, bp, p, M.choose_elements(args.dofs, p, ncomp))
+            aprob.u.set_array(seeded_uniform(aprob.num_dofs))
+            aprob.op.set_timing(True)
+            t = []
+            for i in range(8):
+                aprob.op.apply(aprob.u, aprob.v)
+                if i >= 3:
+                    t.append(sum(aprob.op.last_kernel_ms()))
+            ms = float(np.median(t))
+            extra["atomic_scatter"] = dict(ms=ms, gdofs=aprob.num_dofs / ms / 1e6, frac=aprob.bytes_per_apply() / (ms * 1e-3) / 1e9 / peak,
+                                           note="opt-in (CEED_B200_SCATTER=atomic): zero v, accumulate with red.global.add.f64; the default is the deterministic owner/halo scatter")
+            del aprob, aceed
+        except Exception as exc:  # noqa: BLE001
+            extra["atomic_scatter"] = dict(error=str(exc)[:200])
 
     if rank == 0:
         line = dict(metric="CeedOperatorApply throughput", value=value, unit="GDoF/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
