@@ -235,6 +235,10 @@ CEEDB200_EXPORT int ceedb200_operator_apply_part(B200Operator op, B200Vector u, 
  * return v is valid on BOTH sides.  Falls back to ceedb200_operator_apply (*streamed = 0) when a precondition does not hold (operator not
  * fused, other scatter mode, u already valid on the device, pageable host memory, partially covered output, fewer than 4096 elements). */
 CEEDB200_EXPORT int ceedb200_operator_apply_streamed(B200Operator op, B200Vector u, B200Vector v, int num_chunks, int *streamed);
+/* host-logic tests: the chunk tables of the streamed apply for num_chunks chunks -- element chunk ends, per chunk the number of leading
+ * L-indices of u that must have arrived before it runs, and the number of leading L-indices of v that are final after it (INT64_MAX for
+ * the last chunk); *per_comp = 1 when blocked components stream their own ranges */
+CEEDB200_EXPORT int ceedb200_operator_debug_stream_plan(B200Operator op, int num_chunks, int32_t *ends, int64_t *in_hi, int64_t *out_done, int *per_comp);
 CEEDB200_EXPORT int ceedb200_operator_set_timing(B200Operator op, int enabled);
 CEEDB200_EXPORT int ceedb200_operator_last_kernel_ms(B200Operator op, float *fused_ms, float *aux_ms);
 /* tuning override: elems_per_block (0 = heuristic), blocks_per_sm (0 = heuristic) */

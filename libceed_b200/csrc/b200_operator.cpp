@@ -797,6 +797,59 @@ extern "C" int ceedb200_operator_apply_part(B200Operator op, B200Vector u, B200V
 }
 extern "C" int ceedb200_operator_apply_add(B200Operator op, B200Vector u, B200Vector v) { return operator_apply(op, u, v, 1); }
 
+// Chunk tables of the streamed apply for K chunks (cached in the plan): element chunk ends, per chunk how much of u must have arrived
+// (prefix maximum of the gathered L-indices) and how much of v is final (suffix minimum of the L-indices later chunks still touch).
+static void build_stream_plan(B200OpPlan *plan, B200Restriction rin, B200Restriction rout, int K) {
+  const int ne = rout->num_elem;
+  B200StreamPlan &sp = plan->stream;
+  if (sp.num_chunks == K) return;
+  sp = B200StreamPlan();
+  sp.ends = chunk_ends(ne, plan->epb, K);  // (graded chunk sizes were measured: no gain, the PCIe duplex rate is the bound)
+  auto ranges = [&](B200Restriction r, std::vector<int64_t> &lo, std::vector<int64_t> &hi) {
+    lo.assign(K, INT64_MAX), hi.assign(K, -1);
+    for (int c = 0; c < K; c++) {
+      const int64_t b = (c ? sp.ends[c - 1] : 0) * (int64_t)r->elem_size, e = sp.ends[c] * (int64_t)r->elem_size;
+      for (int64_t i = b; i < e; i++) {
+        const int64_t l = r->h_offsets[i];
+        lo[c] = std::min(lo[c], l), hi[c] = std::max(hi[c], l);
+      }
+    }
+  };
+  std::vector<int64_t> in_lo, in_hi, out_lo, out_hi;
+  ranges(rin, in_lo, in_hi);
+  ranges(rout, out_lo, out_hi);
+  const auto blocked = [&](B200Restriction r, const std::vector<int64_t> &hi) {
+    return r->comp_stride >= *std::max_element(hi.begin(), hi.end()) + 1 && (int64_t)r->num_comp * r->comp_stride == r->l_size;
+  };
+  sp.per_comp = rin->num_comp > 1 && rin->num_comp == rout->num_comp && blocked(rin, in_hi) && blocked(rout, out_hi);
+  sp.in_hi.resize(K), sp.out_done.resize(K);
+  for (int c = 0; c < K; c++) sp.in_hi[c] = std::max(c ? sp.in_hi[c - 1] : (int64_t)0, in_hi[c] + 1);
+  int64_t later = INT64_MAX;  // lowest offset touched by a later chunk: everything below it is complete
+  for (int c = K - 1; c >= 0; c--) {
+    sp.out_done[c] = later;
+    later          = std::min(later, out_lo[c]);
+  }
+  sp.num_chunks = K;
+}
+
+// host-logic tests: the chunk tables for K chunks (arrays of K entries each); active input / output restrictions as the streamed apply picks them
+extern "C" int ceedb200_operator_debug_stream_plan(B200Operator op, int num_chunks, int32_t *ends, int64_t *in_hi, int64_t *out_done, int *per_comp) {
+  B200_CALL(operator_setup(op));
+  B200_CHECK(op->plan->fused, op->ceed, B200_ERROR_UNSUPPORTED, "operator is not fused");
+  B200Restriction rin = nullptr, rout = nullptr;
+  for (auto &f : op->in_fields)
+    if (f.is_active && f.rstr && !f.rstr->is_strided) rin = f.rstr;
+  for (auto &f : op->out_fields)
+    if (f.is_active && f.rstr && !f.rstr->is_strided) rout = f.rstr;
+  B200_CHECK(rin && rout, op->ceed, B200_ERROR_UNSUPPORTED, "no offset-restricted active input / output");
+  op->plan->stream.num_chunks = 0;
+  build_stream_plan(op->plan, rin, rout, num_chunks);
+  const B200StreamPlan &sp = op->plan->stream;
+  for (int c = 0; c < num_chunks; c++) ends[c] = sp.ends[c], in_hi[c] = sp.in_hi[c], out_done[c] = sp.out_done[c];
+  *per_comp = sp.per_comp;
+  return B200_SUCCESS;
+}
+
 // ------------------------------------------------------------------------------------------------ streamed host-buffer apply
 // v = A u with u valid on the HOST only and v wanted on the host (the end-to-end call of an application that keeps its vectors in host
 // memory: CeedVectorSetArray(HOST) -> CeedOperatorApply -> CeedVectorSyncArray(HOST)).  Instead of copy-in, apply, copy-out one after
@@ -848,37 +901,8 @@ extern "C" int ceedb200_operator_apply_streamed(B200Operator op, B200Vector u, B
   B200_CUDA(ceed, cudaSetDevice(ceed->device_id));
   // ---- chunk tables (cached in the plan)
   const int K  = std::max(2, std::min(num_chunks > 0 ? num_chunks : default_parts(), 64));
-  const int ne = rout->num_elem;
+  build_stream_plan(plan, rin, rout, K);
   B200StreamPlan &sp = plan->stream;
-  if (sp.num_chunks != K) {
-    sp = B200StreamPlan();
-    sp.ends = chunk_ends(ne, plan->epb, K);  // (graded chunk sizes were measured: no gain, the PCIe duplex rate is the bound)
-    auto ranges = [&](B200Restriction r, std::vector<int64_t> &lo, std::vector<int64_t> &hi) {
-      lo.assign(K, INT64_MAX), hi.assign(K, -1);
-      for (int c = 0; c < K; c++) {
-        const int64_t b = (c ? sp.ends[c - 1] : 0) * (int64_t)r->elem_size, e = sp.ends[c] * (int64_t)r->elem_size;
-        for (int64_t i = b; i < e; i++) {
-          const int64_t l = r->h_offsets[i];
-          lo[c] = std::min(lo[c], l), hi[c] = std::max(hi[c], l);
-        }
-      }
-    };
-    std::vector<int64_t> in_lo, in_hi, out_lo, out_hi;
-    ranges(rin, in_lo, in_hi);
-    ranges(rout, out_lo, out_hi);
-    const auto blocked = [&](B200Restriction r, const std::vector<int64_t> &hi) {
-      return r->comp_stride >= *std::max_element(hi.begin(), hi.end()) + 1 && (int64_t)r->num_comp * r->comp_stride == r->l_size;
-    };
-    sp.per_comp = rin->num_comp > 1 && rin->num_comp == rout->num_comp && blocked(rin, in_hi) && blocked(rout, out_hi);
-    sp.in_hi.resize(K), sp.out_done.resize(K);
-    for (int c = 0; c < K; c++) sp.in_hi[c] = std::max(c ? sp.in_hi[c - 1] : (int64_t)0, in_hi[c] + 1);
-    int64_t later = INT64_MAX;  // lowest offset touched by a later chunk: everything below it is complete
-    for (int c = K - 1; c >= 0; c--) {
-      sp.out_done[c] = later;
-      later          = std::min(later, out_lo[c]);
-    }
-    sp.num_chunks = K;
-  }
   B200_CALL(b200_restriction_set_parts(rout, sp.ends));
   // ---- streams and events
   if (!ceed->s_h2d) {

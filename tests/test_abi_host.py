@@ -329,6 +329,50 @@ print("RESULT" + json.dumps(out))
 """ % ROOT
 
 
+STREAM_PLAN = r"""
+import ctypes as C, json, sys
+import numpy as np
+sys.path.insert(0, %r)
+from libceed_b200 import Ceed, mesh as M
+from libceed_b200.bp import BPProblem
+ceed = Ceed(); lib = ceed._lib
+out = {}
+for name, bp, p, nel, kw in (("bp1", 1, 2, (6, 5, 7), {}), ("bp2 blocked", 2, 1, (5, 5, 6), {}), ("bp4 interlaced", 4, 1, (4, 5, 6), dict(interlaced=True)),
+                            ("bp3 morton", 3, 2, (6, 6, 6), dict(morton=True))):
+    morton = kw.pop("morton", False)
+    prob = BPProblem(ceed, bp, p, nel, build_qdata=False, elem_perm=M.morton_permutation(*nel) if morton else None, **kw)
+    off = prob.offsets.astype(np.int64) * (prob.ncomp if kw.get("interlaced") else 1)
+    for K in (2, 5, 8):
+        ends = np.zeros(K, dtype=np.int32); in_hi = np.zeros(K, dtype=np.int64); out_done = np.zeros(K, dtype=np.int64); pc = C.c_int()
+        assert lib.ceedb200_operator_debug_stream_plan(prob.op._ptr, K, ends.ctypes.data, in_hi.ctypes.data, out_done.ctypes.data, C.byref(pc)) == 0
+        assert ends[-1] == prob.num_elem and np.all(np.diff(ends) >= 0)
+        lo = 0
+        for c in range(K):
+            chunk = off[lo:ends[c]]
+            # everything chunk c gathers lies below in_hi[c]; nothing a later chunk touches lies below out_done[c]
+            assert chunk.size == 0 or chunk.max() < in_hi[c]
+            later = off[ends[c]:]
+            assert later.size == 0 or later.min() >= out_done[c] or c == K - 1
+            if c < K - 1 and later.size: assert out_done[c] == later.min()
+            lo = ends[c]
+        assert np.all(np.diff(in_hi) >= 0) and np.all(np.diff(out_done[:-1]) >= 0)
+        out["%%s K%%d" %% (name, K)] = dict(per_comp=pc.value, first_in=int(in_hi[0]), nodes=int(prob.num_nodes))
+print("RESULT" + json.dumps(out))
+""" % ROOT
+
+
+def test_streamed_apply_chunk_tables_without_gpu():
+    """Chunk tables of ceedb200_operator_apply_streamed against a numpy restatement: a chunk only gathers what has arrived, only final entries
+    of v are copied back; blocked components stream per component, a Morton element order needs (almost) the whole input up front."""
+    env = dict(os.environ, CEED_B200_COMPILE_ONLY="1")
+    r = subprocess.run([sys.executable, "-c", STREAM_PLAN], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][0][6:])
+    assert res["bp2 blocked K5"]["per_comp"] == 1 and res["bp1 K5"]["per_comp"] == 0 and res["bp4 interlaced K5"]["per_comp"] == 0
+    lex, mor = res["bp1 K8"]["first_in"] / res["bp1 K8"]["nodes"], res["bp3 morton K8"]["first_in"] / res["bp3 morton K8"]["nodes"]
+    assert lex < 0.3 and mor > 1.3 * lex, (lex, mor)  # lexicographic order streams; a space-filling order touches far-away nodes early
+
+
 def test_lean_kernel_generates_and_compiles_without_gpu():
     """The lean in-place-plane kernel (layout 4) is generated and NVRTC-compiled for sm_100a for BP1 / BP2 shapes incl. the bulk pipelines;
     operators with gradients keep their own layout."""
