@@ -235,6 +235,20 @@ CEEDB200_EXPORT int ceedb200_operator_apply_part(B200Operator op, B200Vector u, 
  * return v is valid on BOTH sides.  Falls back to ceedb200_operator_apply (*streamed = 0) when a precondition does not hold (operator not
  * fused, other scatter mode, u already valid on the device, pageable host memory, partially covered output, fewer than 4096 elements). */
 CEEDB200_EXPORT int ceedb200_operator_apply_streamed(B200Operator op, B200Vector u, B200Vector v, int num_chunks, int *streamed);
+/* Host-logic tests: description of the launch the fused apply would perform for (u, v) -- nothing is launched.  `args` is the kernel's
+   argument block (the __constant__ B200OpArgs object of the generated source, see ceedb200_operator_kernel_source); the halo_* / v fields
+   describe the second pass of the deterministic scatter (v[halo_node[i] + c comp_stride] += halo[j + c num_halo], j in
+   [halo_ptr[i], halo_ptr[i + 1]), ascending) for output field `fin_slot` (-1: none). */
+typedef struct {
+  unsigned char args[1024];
+  int           args_size, grid, threads, smem_bytes, run_mode, kernel_add, zero_first, fin_slot, num_comp;
+  long long     e_begin, e_end, comp_stride, num_shared, num_halo;
+  const int    *halo_node, *halo_ptr;
+  const double *halo;
+  double       *v;
+  const char   *source; /* generated source of the kernel variant (store / accumulate) this apply launches */
+} B200DebugLaunch;
+CEEDB200_EXPORT int ceedb200_operator_debug_launch(B200Operator op, B200Vector u, B200Vector v, int add, int part, B200DebugLaunch *desc);
 /* host-logic tests: the chunk tables of the streamed apply for num_chunks chunks -- element chunk ends, per chunk the number of leading
  * L-indices of u that must have arrived before it runs, and the number of leading L-indices of v that are final after it (INT64_MAX for
  * the last chunk); *per_comp = 1 when blocked components stream their own ranges */

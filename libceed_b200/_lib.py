@@ -133,6 +133,7 @@ def load(path=LIB_PATH):
         "ceedb200_vector_valid_sides": [handle, C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "ceedb200_operator_apply_part": [handle, handle, handle, C.c_int],
         "ceedb200_operator_apply_streamed": [handle, handle, handle, C.c_int, C.POINTER(C.c_int)],
+        "ceedb200_operator_debug_launch": [handle, handle, handle, C.c_int, C.c_int, C.c_void_p],
         "ceedb200_operator_debug_stream_plan": [handle, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)],
         "ceedb200_restriction_set_split": [handle, C.c_int32],
     }

@@ -173,7 +173,7 @@ static int default_parts() { return getenv("CEED_B200_PARTS") ? std::max(2, std:
 
 // part: 0 = the whole operator; 1 / 2 = boundary / interior elements of a partitioned mesh (ceedb200_operator_apply_part):
 // part 1 applies elements [0, split) and finalizes the shared nodes touched by those elements only, part 2 the rest.
-static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int part = 0) {
+static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int part = 0, B200DebugLaunch *desc = nullptr) {
   B200Ceed    ceed = op->ceed;
   B200OpPlan *plan = op->plan;
   B200OpArgs  args;
@@ -233,7 +233,7 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
       op->is_setup = false;
       B200_CALL(operator_setup(op));
       B200_CHECK(op->plan->fused && !op->plan->qd_tma, ceed, B200_ERROR_BACKEND, "could not regenerate the operator kernel without bulk copies");
-      return apply_fused(op, u, v, add, part);
+      return apply_fused(op, u, v, add, part, desc);
     }
   }
   // outputs.  Decide per distinct output vector whether the kernel can store (overwrite) or must accumulate.
@@ -327,7 +327,7 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
         op->is_setup = false;
         B200_CALL(operator_setup(op));
         ceed->last_error = saved_error;
-        if (op->plan->fused) return apply_fused(op, u, v, add, part);
+        if (op->plan->fused) return apply_fused(op, u, v, add, part, desc);
         B200_CHECK(!part, ceed, B200_ERROR_UNSUPPORTED, "apply_part needs a fused operator: %s", op->plan->why_not_fused.c_str());
         return apply_unfused(op, u, v, add);
       }
@@ -341,7 +341,7 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
       }
     }
   }
-  if (zero_first && part <= 1)  // later parts continue what the first part started
+  if (zero_first && part <= 1 && !desc)  // later parts continue what the first part started
     for (auto &o : outs) B200_CALL(ceedb200_vector_set_value(o.vec, 0.0));
   for (size_t i = 0; i < op->out_fields.size(); i++) {
     const B200OpField &f   = op->out_fields[i];
@@ -384,6 +384,33 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
     }
   }
 
+  if (desc) {
+    // host-logic tests (ceedb200_operator_debug_launch): describe the launch -- argument block, grid, element range, the second pass of
+    // the deterministic scatter -- instead of performing it
+    memset(desc, 0, sizeof(*desc));
+    static_assert(sizeof(args) <= sizeof(desc->args), "argument block larger than the debug copy");
+    memcpy(desc->args, &args, sizeof(args));
+    desc->args_size = (int)sizeof(args);
+    desc->source    = var.source.c_str();
+    desc->grid = b200_opgen_grid(ceed, plan, var, e_end - e_begin), desc->threads = plan->threads, desc->smem_bytes = plan->smem_bytes;
+    desc->run_mode = run_mode, desc->kernel_add = kernel_add, desc->zero_first = zero_first, desc->e_begin = e_begin, desc->e_end = e_end;
+    desc->fin_slot = -1;
+    for (size_t i = 0; i < op->out_fields.size() && plan->num_elem > 0; i++) {
+      const B200OpField &f = op->out_fields[i];
+      const bool is_writer = plan->out_fields[i].emode == B200_EVAL_NONE || plan->out_groups[plan->out_fields[i].group].slot == (int)i;
+      if (f.rstr->is_strided || !is_writer) continue;
+      B200_CHECK(!desc->v, ceed, B200_ERROR_UNSUPPORTED, "debug launch description holds one offset-restricted output");
+      desc->v = args.out_ptr[i], desc->num_comp = f.rstr->num_comp, desc->comp_stride = f.rstr->comp_stride;
+      if (!plan->aux[i] || run || fin_mode || plan->scatter_mode != B200_SCATTER_DETERMINISTIC) continue;
+      int64_t first = 0, count = f.rstr->num_shared;
+      if (part >= 1) first = f.rstr->shared_prefix[part - 1], count = f.rstr->shared_prefix[part] - first;
+      desc->fin_slot = (int)i, desc->num_comp = f.rstr->num_comp, desc->comp_stride = f.rstr->comp_stride;
+      desc->num_shared = count, desc->num_halo = f.rstr->num_halo;
+      desc->halo_node = f.rstr->d_halo_node + first, desc->halo_ptr = f.rstr->d_halo_ptr + first;
+      desc->halo = plan->aux[i], desc->v = args.out_ptr[i];
+    }
+    return B200_SUCCESS;
+  }
   if (op->timing) B200_CUDA(ceed, cudaEventRecord(op->ev[3], ceed->stream));
   B200_CHECK(!(ordered && part), ceed, B200_ERROR_UNSUPPORTED, "apply_part is not available with the in-kernel ordered scatter");
   if (e_end > e_begin) {
@@ -755,6 +782,18 @@ static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
       trial(t);
     }
   }
+  // 4b. lean kernel: element-interleaved columns (1), + padded element stride (3), 16-byte quadrature-data loads (4) and their unions,
+  //     at the winner's batch width and at 8 elements (one full node row of 8 elements per request when P = 4)
+  if (best.qf_mode == 4) {
+    const B200Tuning win = best;
+    for (int pass = 0; pass < (win.epw == 8 ? 1 : 2); pass++)
+      for (int stage : {1, 3, 4, 5, 7}) {
+        const int epw = pass ? 8 : win.epw;
+        B200Tuning t = win;
+        t.epw = epw, t.stage = (win.stage > 0 ? win.stage & ~7 : 0) | stage;
+        trial(t);
+      }
+  }
   operator_reset(op);
   op->tune      = best;
   op->timing    = timing0;
@@ -830,6 +869,16 @@ static void build_stream_plan(B200OpPlan *plan, B200Restriction rin, B200Restric
     later          = std::min(later, out_lo[c]);
   }
   sp.num_chunks = K;
+}
+
+// host-logic tests: everything the fused apply would launch for (u, v) -- the kernel's argument block, launch shape, element range and the
+// tables of the finalize pass -- without launching anything.  In compile-only mode (CEED_B200_COMPILE_ONLY: "device" memory is host memory)
+// tests/test_kernel_emulation.py runs the generated source of the same kernel on CPU threads against these arguments.
+extern "C" int ceedb200_operator_debug_launch(B200Operator op, B200Vector u, B200Vector v, int add, int part, B200DebugLaunch *desc) {
+  B200_CALL(operator_setup(op));
+  B200_CHECK(op->plan->fused, op->ceed, B200_ERROR_UNSUPPORTED, "operator is not fused: %s", op->plan->why_not_fused.c_str());
+  B200_CHECK(desc, op->ceed, B200_ERROR_MAJOR, "no description to fill");
+  return apply_fused(op, u, v, add, part, desc);
 }
 
 // host-logic tests: the chunk tables for K chunks (arrays of K entries each); active input / output restrictions as the streamed apply picks them

@@ -375,7 +375,10 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     // (bit 8: element offsets + scatter targets, bit 32: quadrature data)
     // bit 64: bulk L2 prefetch of the next batch's quadrature data
     // bit 128: in-kernel finalize of the deterministic scatter
+    // bit 1: element-interleaved node columns in the gather / scatter stages; bit 2: element stride of the planes = P (mod 16);
     plan->stage_mask = (tn.stage >= 0 && plan->async_copy && !plan->no_tma) ? (tn.stage & (8 | 32 | 64 | 128)) : 0;
+    // bit 4: directly loaded quadrature data of an x-line through 16-byte loads
+    if (tn.stage >= 0) plan->stage_mask |= tn.stage & 7;
     if ((plan->stage_mask & 40) || plan->scatter_mode != B200_SCATTER_DETERMINISTIC || plan->lean_runs) plan->stage_mask &= ~128;
     plan->swz = false, plan->swz_w = 0, plan->group_warps = 1;
     plan->qd_tma = false, plan->mbar_off = -1, plan->ring_off = -1;

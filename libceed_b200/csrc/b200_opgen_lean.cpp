@@ -32,6 +32,16 @@
 //   * CEED_B200_RUNS (experimental, off): run scatter -- every warp owns a contiguous run of elements and adds E-entries whose earlier
 //     touchers it processed itself straight into v (B200RunScatter).  Bitwise equal results, finalize pass 20-30 % shorter, but the
 //     fused kernel loses its streaming locality (2x slower on B200): kept as a tested option, see DESIGN.md.
+//   * Stage bit 1 = ELEMENT-INTERLEAVED COLUMNS: the gather + Z and Z^T + scatter stages enumerate their node columns as (i, element, j)
+//     instead of (i, j, element).  The E elements of a batch are x-neighbours on a lexicographically ordered mesh, so the lanes of one
+//     load / store then walk ONE node row across the whole batch (E p + 1 consecutive L-nodes, 200 B at p = 3, E = 8) instead of eight
+//     32-byte row segments in eight different 128-byte lines: every request of the gather and of the owner / halo stores touches 2-3 lines
+//     instead of 8-10.  The L1 data pipe processes one line per wavefront, and it is the unit that bounds this kernel (ncu: 91 % busy).
+//     Stage bit 2 pads the element stride of the planes to P (mod 16) doubles, which keeps those stages free of bank conflicts for every P.
+//   * Stage bit 4 = 16-BYTE QUADRATURE-DATA LOADS: a lane of the x-line stage reads Q consecutive doubles per component; as 8-byte loads
+//     with a lane stride of 8 Q bytes every one of the Q requests touches the same ~Q / 4 lines per 8 lanes again.  With this bit the
+//     lane reads the 16-byte aligned window around its line with ceil(Q / 2) 16-byte loads (the alignment is taken from the address at
+//     run time; the first / last line of an array and misaligned user arrays take scalar loads) and, for an odd Q, selects.
 //   * Full batches run code without any tail clamps; the (at most one) partial batch of a launch runs a second instantiation.
 #include <algorithm>
 #include <cstdlib>
@@ -61,9 +71,24 @@ struct LeanGen {
   bool         st_idx = false, st_qd = false;
   bool         fin   = false;   // stage bit 128: in-kernel finalize of the deterministic scatter (whole-mesh launches)
   bool         pf_qd = false;   // stage bit 64: bulk L2 prefetch (cp.async.bulk.prefetch.L2) of the directly loaded quadrature data of the NEXT batch
+  bool         vqd    = false;  // stage bit 4: directly loaded quadrature data of an x-line through 16-byte loads (aligned window)
+  bool         ilv    = false;  // stage bit 1: element-interleaved node columns in the gather / scatter stages
   bool         runs   = false;  // run scatter (experimental, CEED_B200_RUNS): per-warp element runs, read-modify-write entries
   const B200GenGroup *gin, *gout;
   bool qd_staged(const B200GenField &fd) const { return st_qd && fd.emode == B200_EVAL_NONE && fd.qd_off >= 0; }
+  // stage bit 4: the Q consecutive doubles a lane reads per (x-line, component) come in as ceil(Q / 2) 16-byte loads from the 16-byte
+  // aligned window around them (an odd Q makes every other line start 8 bytes off: those lanes pick their values one double later)
+  bool qd_vector(const B200GenField &fd) const { return vqd && !qd_staged(fd) && fd.emode == B200_EVAL_NONE && fd.rstr->is_strided && fd.rstr->strides[0] == 1 && Q >= 2; }
+  int  qd_nv() const { return (Q + 1) / 2; }
+  // value q of component cc of EVAL_NONE input f in round x
+  string qd_value(size_t f, int cc, int q, const string &x) const {
+    const B200GenField &fd = plan->in_fields[f];
+    if (!qd_vector(fd)) return "d" + S((long long)f) + "_" + S(cc * Q + q) + x;
+    const string w = "w" + S((long long)f) + "_" + S(cc) + "_";
+    auto at = [&](int j) { return w + S(j / 2) + x + (j % 2 ? ".y" : ".x"); };
+    if (Q % 2 == 0) return at(q);
+    return "(od" + S((long long)f) + "_" + S(cc) + x + " ? " + at(q + 1) + " : " + at(q) + ")";
+  }
 
   void contract(const string &mat, int n_in, int n_out, bool transposed, const string &in, const string &out, const string &ind) {
     for (int o = 0; o < n_out; o++) {
@@ -182,6 +207,13 @@ struct LeanGen {
   string stage_locals() const { return runs ? "" : "  const int st = 1;\n  const long long lim = b200_ne;\n  (void)st; (void)lim;\n"; }
   string stage_args() const { return staged ? ", par" : (runs ? ", st, lim" : ""); }
 
+  // node column (ij = i + P j, local element le) of task `t` of the gather / scatter stages: (i, j, element) by default, (i, element, j)
+  // with stage bit 1 -- consecutive lanes then walk one node row across the x-neighbouring elements of the batch
+  string column_decode(const string &t, const string &x) const {
+    if (!ilv) return "const int ij" + x + " = " + t + " % " + S(P2) + ", le" + x + " = " + t + " / " + S(P2) + ";";
+    return "const int le" + x + " = (" + t + " / " + S(P) + ") % " + S(E) + ", ij" + x + " = " + t + " % " + S(P) + " + (" + t + " / " + S(P * E) + ") * " + S(P) + ";";
+  }
+
   // ---- gather + Z ----------------------------------------------------------------------------------
   void emit_z() {
     const int  T = E * P2, R = (T + 31) / 32;
@@ -207,7 +239,7 @@ struct LeanGen {
         const string x = "_" + S(r);
         c << "    const int t" << x << " = lane + " << 32 * r << ", tc" << x << " = " << ((r + 1) * 32 > T ? "t" + x + " < " + S(T) + " ? t" + x + " : " + S(T - 1) : "t" + x)
           << ";\n";
-        c << "    const int ij" << x << " = tc" << x << " % " << P2 << ", le" << x << " = tc" << x << " / " << P2 << ";\n";
+        c << "    " << column_decode("tc" + x, x) << "\n";
         if (st_idx) {
           c << "    const int *const ix" << x << " = ofs + (TAIL ? (le" << x << " < nel ? le" << x << " : nel - 1) : le" << x << ") * " << P3 << " + ij" << x << ";\n";
           for (int k = 0; k < P; k++) c << "    const int o" << k << x << " = ix" << x << "[" << k * P2 << "];\n";
@@ -286,6 +318,34 @@ struct LeanGen {
       }
       c << "  const double *const qd" << f << x << " = b200a.in_ptr[" << fd.slot << "] + e" << x << " * " << rs->strides[2] << "LL + (long long)row" << x << " * "
         << (long long)Q * rs->strides[0] << "LL;\n";
+      if (qd_vector(fd)) {
+        // 16-byte loads from the aligned window [wp, wp + NV): the fast path needs the window inside the array (the first / last line of
+        // the array may stick out by one double) and, for an even Q, an aligned line; everything else takes scalar loads into the same slots
+        const int NV = qd_nv();
+        c << "  const unsigned long long qlo" << f << x << " = (unsigned long long)b200a.in_ptr[" << fd.slot << "], qhi" << f << x << " = qlo" << f << x << " + "
+          << (long long)rs->l_size * 8 << "ULL;\n";
+        for (int cc = 0; cc < fd.nc; cc++) {
+          const string t = S((long long)f) + "_" + S(cc), w = "w" + t + "_";
+          c << "  const unsigned long long qa" << t << x << " = (unsigned long long)(qd" << f << x << " + " << (long long)cc * rs->strides[1] << "LL);\n";
+          c << "  const bool od" << t << x << " = " << (Q % 2 ? "((qa" + t + x + " >> 3) & 1ULL) != 0" : "false") << ";\n  (void)od" << t << x << ";\n";
+          c << "  double2 ";
+          for (int j = 0; j < NV; j++) c << (j ? ", " : "") << w << j << x;
+          c << ";\n";
+          c << "  { const double2 *const wp = (const double2 *)(qa" << t << x << " & ~15ULL);\n";
+          c << "    if ((unsigned long long)wp >= qlo" << f << x << " && (unsigned long long)(wp + " << NV << ") <= qhi" << f << x
+            << (Q % 2 ? "" : " && (qa" + t + x + " & 15ULL) == 0") << ") {\n";
+          for (int j = 0; j < NV; j++) c << "      " << w << j << x << " = __ldg(wp + " << j << ");\n";
+          c << "    } else {\n      const double *const sp = (const double *)qa" << t << x << ";\n";
+          for (int q = 0; q < Q; q++) c << "      const double s" << q << " = __ldg(sp + " << q << ");\n";
+          // slot j of the window holds value j (even line) or value j - 1 (odd line)
+          for (int j = 0; j < 2 * NV; j++) {
+            const string ev = j < Q ? "s" + S(j) : string("0.0"), ov = (j >= 1 && j - 1 < Q) ? "s" + S(j - 1) : string("0.0");
+            c << "      " << w << j / 2 << x << (j % 2 ? ".y" : ".x") << " = " << (Q % 2 ? "od" + t + x + " ? " + ov + " : " + ev : ev) << ";\n";
+          }
+          c << "    }\n  }\n";
+        }
+        continue;
+      }
       for (int cc = 0; cc < fd.nc; cc++)
         for (int q = 0; q < Q; q++)
           c << "  const double d" << f << "_" << cc * Q + q << x << " = __ldg(qd" << f << x << " + " << (long long)cc * rs->strides[1] + (long long)q * rs->strides[0] << "LL);\n";
@@ -348,7 +408,7 @@ struct LeanGen {
       for (size_t f = 0; f < plan->in_fields.size(); f++) {
         const B200GenField &fd = plan->in_fields[f];
         if (fd.emode == B200_EVAL_NONE) {
-          for (int i = 0; i < fd.nc * Q; i++) c << "    in_" << f << "[" << i << "] = d" << f << "_" << i << x << ";\n";
+          for (int i = 0; i < fd.nc * Q; i++) c << "    in_" << f << "[" << i << "] = " << qd_value(f, i / Q, i % Q, x) << ";\n";
         } else if (fd.emode == B200_EVAL_WEIGHT) {
           c << "    { const double wyz = cW" << fd.basis_id << "[row" << x << " % " << Q << "] * cW" << fd.basis_id << "[row" << x << " / " << Q << "];\n";
           for (int q = 0; q < Q; q++) c << "      in_" << f << "[" << q << "] = cW" << fd.basis_id << "[" << q << "] * wyz;\n";
@@ -445,7 +505,7 @@ struct LeanGen {
       const bool partial = (r + 1) * 32 > T;
       c << "  {\n";
       c << "    const int t = lane + " << 32 * r << ", tc = " << (partial ? "t < " + S(T) + " ? t : " + S(T - 1) : string("t")) << ";\n";
-      c << "    const int ij = tc % " << P2 << ", le = tc / " << P2 << ";\n";
+      c << "    " << column_decode("tc", "") << "\n";
       if (st_idx) {
         c << "    const int *const tx = tgs + (TAIL ? (le < nel ? le : nel - 1) : le) * " << P3 << " + ij;\n";
         for (int k = 0; k < P; k++) c << "    const int g" << k << " = tx[" << k * P2 << "];\n";
@@ -556,6 +616,8 @@ struct LeanGen {
     P3   = P2 * P;
     PS   = Q * Q * P;
     ES   = plan->lean_es;
+    ilv    = (plan->stage_mask & 1) != 0;
+    vqd    = (plan->stage_mask & 4) != 0;
     st_idx = (plan->stage_mask & 8) != 0;
     st_qd  = (plan->stage_mask & 32) != 0;
     staged = st_idx || st_qd;
@@ -669,6 +731,10 @@ size_t b200_opgen_lean_layout(B200OpPlan *plan, int E) {
   const B200GenGroup &gi = plan->in_groups[0];
   const int           P  = plan->bases[gi.basis_id].P, Q = plan->Q;
   plan->lean_es          = gi.nc * Q * Q * P;
+  // stage bit 2: element stride = P (mod 16) doubles, so that the lanes (i, element) of an interleaved column stage hit consecutive banks
+  // (an even P keeps an even stride: x-lines stay 16-byte aligned)
+  if (plan->stage_mask & 2)
+    while (plan->lean_es % 16 != P % 16) plan->lean_es++;
   size_t off             = ((size_t)E * plan->lean_es * 8 + 15) / 16 * 16;
   auto   take            = [&](size_t bytes) {
     const size_t at = off;

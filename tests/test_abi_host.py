@@ -319,12 +319,13 @@ ceed = Ceed()
 out = {}
 for bp, p in ((1, 3), (2, 2), (1, 4), (1, 1), (3, 3)):
     prob = BPProblem(ceed, bp, p, (3, 3, 2), build_qdata=False)
-    for E, warps, stage in ((6, 4, 0), (3, 2, 40), (4, 4, 8), (5, 1, 96)):
+    for E, warps, stage in ((6, 4, 0), (3, 2, 40), (4, 4, 8), (5, 1, 96), (8, 4, 1), (6, 4, 7), (5, 2, 13), (4, 2, 38)):
         prob.op.set_kernel_shape(qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=stage)
         src = prob.op.kernel_source()
         got = prob.op.get_kernel_shape()
         out["bp%%d p%%d E%%d s%%d" %% (bp, p, E, stage)] = dict(layout=got["qf_mode"], stage=got["stage_mask"], lean="b200_lean_z" in src, bulk="b200_lean_copy" in src,
-                                                               prefetch="b200_lean_prefetch_qd" in src, smem=prob.op.kernel_info()["smem_bytes"])
+                                                               prefetch="b200_lean_prefetch_qd" in src, smem=prob.op.kernel_info()["smem_bytes"],
+                                                               interleaved=("/ %%d) %%%% %%d, ij" %% (p + 1, min(E, 18))) in src, vector_qd="const double2 *const wp" in src)
 print("RESULT" + json.dumps(out))
 """ % ROOT
 
@@ -385,8 +386,10 @@ def test_lean_kernel_generates_and_compiles_without_gpu():
             assert v["layout"] != 4 and not v["lean"], (key, v)
             continue
         assert v["layout"] == 4 and v["lean"], (key, v)
-        want = int(key.rsplit("s", 1)[1]) & (8 | 32 | 64)
+        want = int(key.rsplit("s", 1)[1]) & (1 | 2 | 4 | 8 | 32 | 64)
         assert v["stage"] == want and v["bulk"] == bool(want & 40) and v["prefetch"] == bool((want & 64) and not (want & 32)), (key, v)
+        # bit 1: (i, element, j) column decode; bit 4: 16-byte window loads of the directly loaded quadrature data (not with the bulk copy, bit 32)
+        assert v["interleaved"] == bool(want & 1) and v["vector_qd"] == bool((want & 4) and not (want & 32)), (key, v)
 
 
 VECTOR_STATE = r"""

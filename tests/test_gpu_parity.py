@@ -413,7 +413,9 @@ def test_lean_kernel_matches_oracle(cm, oracle, monkeypatch, bp, p, nel):
         prob.u.set_array(u)
         qd = oracle.bp_qdata(bp, p, prob.offsets, prob.coords)
         ref = oracle.bp_apply(bp, p, prob.offsets, prob.num_nodes, qd, u)
-        for E, warps, stage in ((1, 1, 0), (3, 2, 0), (6, 4, 0), (8, 8, 0), (3, 1, 32), (6, 4, 40), (5, 2, 8), (4, 4, 64), (2, 2, 72)):
+        # (bit 1: element-interleaved node columns, bit 2: element stride = P (mod 16), bit 4: quadrature data through 16-byte loads)
+        for E, warps, stage in ((1, 1, 0), (3, 2, 0), (6, 4, 0), (8, 8, 0), (3, 1, 32), (6, 4, 40), (5, 2, 8), (4, 4, 64), (2, 2, 72),
+                                (6, 4, 1), (8, 4, 3), (5, 2, 7), (8, 4, 4), (3, 2, 6), (6, 4, 13), (4, 2, 39), (7, 1, 5), (1, 2, 7)):
             prob.op.set_kernel_shape(qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=stage)
             prob.v.set_value(-3.0)
             prob.op.apply(prob.u, prob.v)
@@ -428,6 +430,39 @@ def test_lean_kernel_matches_oracle(cm, oracle, monkeypatch, bp, p, nel):
             prob.v.set_array(w0)
             prob.op.apply_add(prob.u, prob.v)
             assert np.abs(prob.v.get_array_read() - w0 - ref).max() < 1e-12 * max(1.0, np.abs(ref).max()), (mode, E, warps, stage)
+
+
+@pytest.mark.parametrize("bp,p,nel", [(1, 3, (5, 3, 3)), (1, 2, (4, 3, 3)), (2, 3, (3, 3, 2)), (1, 4, (3, 2, 2))])
+def test_lean_kernel_vector_qdata_loads_with_any_alignment(cm, oracle, monkeypatch, bp, p, nel):
+    """Stage bit 4 of the lean kernel reads the quadrature data of an x-line through 16-byte loads from the aligned window around the line.
+    A user array that starts 8 bytes off a 16-byte boundary flips which lines are aligned (odd Q) or misaligns all of them (even Q), and
+    puts the first line's window before the start of the array: same bits as the 8-byte loads in every case."""
+    import torch
+    monkeypatch.setenv("CEED_B200_NO_TUNE_TABLE", "1")
+    prob = make_problem(cm, bp, p, nel)
+    u = seeded_uniform(prob.num_dofs, 41)
+    prob.u.set_array(u)
+    qd = oracle.bp_qdata(bp, p, prob.offsets, prob.coords)
+    ref = oracle.bp_apply(bp, p, prob.offsets, prob.num_nodes, qd, u)
+    prob.op.set_kernel_shape(qf_mode=4, elems_per_group=4, cta_warps=2, group_warps=1, stage_mask=0)
+    prob.op.apply(prob.u, prob.v)
+    v0 = prob.v.get_array_read().copy()
+    assert rel(v0, ref) < OP_TOL
+    q_host = prob.qdata.get_array_read().copy()
+    n = q_host.size
+    buf = torch.full((n + 3,), float("nan"), dtype=torch.float64, device="cuda")
+    for shift in (0, 1):  # (torch allocations are 256-byte aligned: shift 1 = 8 bytes off)
+        view = buf[shift:shift + n]
+        view.copy_(torch.from_numpy(q_host))
+        assert view.data_ptr() % 16 == 8 * shift
+        prob.qdata.set_array(view, cm.MEM_DEVICE, cm.USE_POINTER)
+        for E, warps, stage in ((4, 2, 4), (6, 4, 5), (3, 1, 7), (8, 4, 4)):
+            prob.op.set_kernel_shape(qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=stage)
+            prob.v.set_value(-3.0)
+            prob.op.apply(prob.u, prob.v)
+            assert prob.op.get_kernel_shape()["stage_mask"] == stage
+            assert np.array_equal(prob.v.get_array_read(), v0), (shift, E, warps, stage)
+    prob.qdata.take_array(cm.MEM_DEVICE)
 
 
 @pytest.mark.parametrize("bp,p,nel,morton", [(1, 3, (32, 31, 31), True), (1, 3, (33, 30, 29), False), (2, 2, (30, 29, 28), True)])

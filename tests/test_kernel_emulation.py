@@ -1,0 +1,159 @@
+"""CPU emulation of the GENERATED fused-operator kernels against the oracle (no GPU): tests/kernel_emu.py compiles the very source NVRTC
+would compile with g++ (one OS thread per CUDA thread) and runs it on the argument block ceedb200_operator_debug_launch describes.
+What this covers that the compile-only tests cannot: lane -> task maps, shared-memory plane addressing, the owner / halo scatter tables
+as the kernel uses them, tail batches, element ranges of partitioned meshes, Apply vs ApplyAdd variants -- for every kernel shape
+without bulk copies.  (Performance and the asynchronous-copy pipelines need the GPU: tests/test_gpu_parity.py.)"""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+PRELUDE = r"""
+import json, os, sys
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import numpy as np
+from libceed_b200 import Ceed, ceed as cm, mesh as M
+from libceed_b200.bp import BPProblem, seeded_uniform
+from oracle import oracle as O
+import kernel_emu as KE
+out = {}
+def rel(a, b): return float(np.abs(a - b).max() / np.abs(b).max())
+def problem(ceed, bp, p, nel, **kw):
+    prob = BPProblem(ceed, bp, p, nel, build_qdata=False, **kw)
+    qd = O.bp_qdata(bp, p, prob.offsets, prob.coords)
+    prob.qdata.set_array(qd)
+    u = seeded_uniform(prob.num_dofs, 31)
+    prob.u.set_array(u)
+    return prob, qd, u, O.bp_apply(bp, p, prob.offsets, prob.num_nodes, qd, u, interlaced=kw.get("interlaced", False))
+""" % (ROOT, ROOT)
+
+
+def run(body, timeout=1500):
+    env = dict(os.environ, CEED_B200_COMPILE_ONLY="1", CEED_B200_NO_TUNE_TABLE="1")
+    r = subprocess.run([sys.executable, "-c", PRELUDE + body + '\nprint("RESULT" + json.dumps(out))\n'], capture_output=True, text=True, env=env, timeout=timeout)
+    assert r.returncode == 0, r.stderr[-4000:]
+    return json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][0][6:])
+
+
+LEAN = r"""
+for bp, p, nel, morton in ((1, 3, (5, 3, 3), False), (1, 2, (4, 3, 3), True), (2, 3, (3, 2, 3), False)):
+    for mode in (0, 1):
+        ceed = Ceed(); ceed.set_scatter_mode(mode)
+        prob, qd, u, ref = problem(ceed, bp, p, nel, elem_perm=M.morton_permutation(*nel) if morton else None)
+        v_det = None
+        # stage bits of the lean kernel: 1 element-interleaved columns, 2 element stride = P (mod 16), 4 quadrature data through 16-byte loads
+        for E, warps, stage in ((6, 4, 0), (6, 4, 1), (8, 4, 3), (5, 2, 7), (8, 2, 4), (7, 1, 5)):
+            if mode == 1 and stage not in (1, 7): continue   # (atomic scatter: two shapes)
+            prob.op.set_kernel_shape(qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=stage)
+            KE.emulated_apply(prob.op, prob.u, prob.v)
+            got = prob.op.get_kernel_shape()
+            v = prob.v.get_array_read().copy()
+            key = "bp%d p%d mode%d E%d w%d s%d" % (bp, p, mode, E, warps, stage)
+            v_det = v if (mode == 0 and v_det is None) else v_det
+            add_err = 0.0
+            if stage in (3, 7):   # the accumulating kernel variant (ApplyAdd)
+                w0 = seeded_uniform(prob.num_dofs, 5)
+                prob.v.set_array(w0)
+                KE.emulated_apply(prob.op, prob.u, prob.v, add=True)
+                add_err = float(np.abs(prob.v.get_array_read() - w0 - ref).max() / np.abs(ref).max())
+            out[key] = dict(layout=got["qf_mode"], stage=got["stage_mask"], err=rel(v, ref), bitwise=bool(mode == 1 or np.array_equal(v, v_det)), add_err=add_err)
+"""
+
+
+def test_lean_kernel_variants_emulated_against_the_oracle():
+    """Every lean-kernel shape incl. the element-interleaved column map (stage bit 1), the padded element stride (2) and the 16-byte
+    quadrature-data loads (4): oracle parity, bitwise equality of the deterministic variants, ApplyAdd, tails, Morton order, atomic scatter."""
+    res = run(LEAN)
+    assert len(res) == 3 * (6 + 2)
+    for key, v in res.items():
+        assert v["layout"] == 4 and v["stage"] == int(key.rsplit("s", 1)[1]), (key, v)
+        assert v["err"] < 1e-12 and v["add_err"] < 1e-12 and v["bitwise"], (key, v)
+
+
+MISALIGNED = r"""
+ceed = Ceed()
+for bp, p, nel in ((1, 3, (5, 3, 3)), (2, 2, (4, 3, 3))):
+    prob, qd, u, ref = problem(ceed, bp, p, nel)
+    prob.op.set_kernel_shape(qf_mode=4, elems_per_group=4, cta_warps=2, group_warps=1, stage_mask=0)
+    KE.emulated_apply(prob.op, prob.u, prob.v)
+    v0 = prob.v.get_array_read().copy()
+    raw = np.full(qd.size + 4, np.nan)
+    base = (-(raw.ctypes.data // 8)) % 2   # index of the first 16-byte aligned double
+    for shift in (0, 1):
+        view = raw[base + shift: base + shift + qd.size]
+        view[:] = qd
+        assert view.ctypes.data % 16 == 8 * shift
+        prob.qdata.set_array(view.ctypes.data, cm.MEM_DEVICE, cm.USE_POINTER)   # (compile-only mode: "device" memory is host memory)
+        for E, warps, stage in ((4, 2, 4), (3, 1, 7)):
+            prob.op.set_kernel_shape(qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=stage)
+            KE.emulated_apply(prob.op, prob.u, prob.v)
+            out["bp%d p%d shift%d E%d s%d" % (bp, p, shift, E, stage)] = dict(err=rel(prob.v.get_array_read(), ref), bitwise=bool(np.array_equal(prob.v.get_array_read(), v0)))
+    prob.qdata.take_array(cm.MEM_DEVICE)
+"""
+
+
+def test_lean_vector_qdata_loads_with_misaligned_arrays_emulated():
+    """16-byte window loads (stage bit 4) with a user array 8 bytes off a 16-byte boundary: the window of the first line starts before the
+    array, that of the last line may end after it, an even Q loses its alignment altogether -- all through the scalar path, same bits."""
+    res = run(MISALIGNED)
+    assert len(res) == 8
+    for key, v in res.items():
+        assert v["err"] < 1e-12 and v["bitwise"], (key, v)
+
+
+GENERAL = r"""
+ceed = Ceed()
+shapes = (dict(stage_mask=1), dict(stage_mask=257), dict(stage_mask=513), dict(stage_mask=9, qf_mode=1, qf_unroll=2), dict(stage_mask=0, qf_mode=2, qf_unroll=2),
+          dict(stage_mask=7, group_warps=2, cta_warps=4, elems_per_group=3), dict(qf_mode=3, stage_mask=17, group_warps=4, cta_warps=4))
+for bp, p, nel, kw in ((3, 2, (4, 3, 2), {}), (6, 2, (3, 2, 2), {}), (4, 1, (3, 3, 2), dict(interlaced=True)), (3, 6, (2, 1, 1), {}), (1, 5, (2, 2, 1), {})):
+    prob, qd, u, ref = problem(ceed, bp, p, nel, **kw)
+    v0 = None
+    for shape in shapes:
+        prob.op.set_kernel_shape(**shape)
+        KE.emulated_apply(prob.op, prob.u, prob.v)
+        v = prob.v.get_array_read().copy()
+        v0 = v if v0 is None else v0
+        out["bp%d p%d %s" % (bp, p, sorted(shape.items()))] = dict(err=rel(v, ref), same=rel(v, v0))
+"""
+
+
+def test_general_kernel_shapes_emulated_against_the_oracle():
+    """The general kernel (z-line / pointwise / point-pair / x-line QFunction stage; padded, swizzled and even-Q linear planes; one- to
+    four-warp element groups with named barriers; cp.async staging of targets, offsets, gathered inputs and quadrature data) on BP3-BP6."""
+    res = run(GENERAL)
+    assert len(res) == 35
+    for key, v in res.items():
+        assert v["err"] < 1e-12 and v["same"] < 1e-13, (key, v)
+
+
+PARTS = r"""
+from libceed_b200.mesh import Partition
+ceed = Ceed()
+for bp, p, nel, shape in ((1, 3, (6, 5, 4), dict(qf_mode=4, elems_per_group=6, cta_warps=2, group_warps=1, stage_mask=3)), (3, 2, (5, 4, 4), dict(stage_mask=1))):
+    prob, qd, u, ref = problem(ceed, bp, p, nel)
+    prob.op.set_kernel_shape(**shape)
+    KE.emulated_apply(prob.op, prob.u, prob.v)
+    whole = prob.v.get_array_read().copy()
+    # the same mesh with a boundary-first element order and a split: part 1 then part 2 = the whole apply on that order
+    ne = prob.num_elem
+    perm = np.roll(np.arange(ne), 7)
+    split = 2 * ne // 5
+    prob2, _, _, ref2 = problem(Ceed(), bp, p, nel, elem_perm=perm, split=split)
+    prob2.op.set_kernel_shape(**shape)
+    d1 = KE.emulated_apply(prob2.op, prob2.u, prob2.v, part=1)
+    d2 = KE.emulated_apply(prob2.op, prob2.u, prob2.v, part=2)
+    out["bp%d p%d" % (bp, p)] = dict(err=rel(whole, ref), part_err=rel(prob2.v.get_array_read(), ref2), ranges=[d1.e_begin, d1.e_end, d2.e_begin, d2.e_end], ne=ne, split=split)
+"""
+
+
+def test_element_parts_emulated():
+    """apply_part (boundary / interior element ranges of a partitioned mesh, also the chunks of the streamed apply): part 1 + part 2 of
+    the lean and the general kernel reproduce the operator."""
+    res = run(PARTS)
+    for key, v in res.items():
+        assert v["err"] < 1e-12 and v["part_err"] < 1e-12, (key, v)
+        assert v["ranges"] == [0, v["split"], v["split"], v["ne"]], (key, v)
