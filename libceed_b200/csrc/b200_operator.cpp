@@ -236,6 +236,19 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
       return apply_fused(op, u, v, add, part, desc);
     }
   }
+  // the vector loads that stage the offset table of the lean kernel's interleaved columns (stage bit 1) have the same requirement
+  // (the owner / halo target table is always the backend's own allocation)
+  if (plan->lean && (plan->stage_mask & 1)) {
+    const int slot = plan->in_groups[0].slot;
+    if ((uintptr_t)args.in_idx[slot] & 15) {
+      op->no_tma = true;
+      plan_free(op);
+      op->is_setup = false;
+      B200_CALL(operator_setup(op));
+      B200_CHECK(op->plan->fused && !(op->plan->lean && (op->plan->stage_mask & 1)), ceed, B200_ERROR_BACKEND, "could not regenerate the operator kernel without vector table loads");
+      return apply_fused(op, u, v, add, part, desc);
+    }
+  }
   // outputs.  Decide per distinct output vector whether the kernel can store (overwrite) or must accumulate.
   struct OutVec {
     B200Vector vec;

@@ -378,7 +378,9 @@ int b200_opgen_plan(B200Operator op, B200OpPlan *plan) {
     // bit 1: element-interleaved node columns in the gather / scatter stages; bit 2: element stride of the planes = P (mod 16);
     plan->stage_mask = (tn.stage >= 0 && plan->async_copy && !plan->no_tma) ? (tn.stage & (8 | 32 | 64 | 128)) : 0;
     // bit 4: directly loaded quadrature data of an x-line through 16-byte loads
-    if (tn.stage >= 0) plan->stage_mask |= tn.stage & 7;
+    if (tn.stage >= 0) plan->stage_mask |= tn.stage & (plan->no_tma ? 6 : 7);  // (no_tma: a caller-owned table is not 16-byte aligned)
+    if (plan->stage_mask & 1) plan->stage_mask &= ~8;  // (interleaved columns stage the index tables themselves)
+    if (plan->lean_runs) plan->stage_mask &= ~1;       // (run scatter: the elements of a batch are not contiguous)
     if ((plan->stage_mask & 40) || plan->scatter_mode != B200_SCATTER_DETERMINISTIC || plan->lean_runs) plan->stage_mask &= ~128;
     plan->swz = false, plan->swz_w = 0, plan->group_warps = 1;
     plan->qd_tma = false, plan->mbar_off = -1, plan->ring_off = -1;

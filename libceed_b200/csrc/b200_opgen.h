@@ -102,6 +102,7 @@ struct B200OpPlan {
   bool                      lean_runs = false;   // lean kernel generated with run-scatter support (experimental, CEED_B200_RUNS)
   int                       lean_es = 0;         // its element stride in shared memory (doubles)
   int                       lean_tg_off = 0;     // byte offset of the parked (or bulk-copied) scatter targets in a warp's shared-memory slice
+  int                       lean_ip = 0;         // stage bit 1 (element-interleaved columns): element pitch (ints) of the staged offset / target tables
   int                       lean_off_off = -1;   // bulk pipeline (stage bit 32): byte offset of the element offsets of the batch
   int                       qf_pp = 1;           // pointwise QFunction stage: points per lane (2 = x-adjacent pair, 16-byte loads)
   int                       qf_ahead = 1;        // z-line QFunction stage: z-layers of streamed inputs in flight per lane

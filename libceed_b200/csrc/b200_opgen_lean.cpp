@@ -37,6 +37,9 @@
 //     load / store then walk ONE node row across the whole batch (E p + 1 consecutive L-nodes, 200 B at p = 3, E = 8) instead of eight
 //     32-byte row segments in eight different 128-byte lines: every request of the gather and of the owner / halo stores touches 2-3 lines
 //     instead of 8-10.  The L1 data pipe processes one line per wavefront, and it is the unit that bounds this kernel (ncu: 91 % busy).
+//     The element-major offset and target tables would pay for that (a request would touch every element's block): the warp first copies
+//     the batch's two tables into shared memory with coalesced vector loads (element pitch = P (mod 32) ints: the interleaved reads are
+//     conflict-free) and both column stages read them from there -- which also replaces the parked targets (scripts/model/lean_columns.py).
 //     Stage bit 2 pads the element stride of the planes to P (mod 16) doubles, which keeps those stages free of bank conflicts for every P.
 //   * Stage bit 4 = 16-BYTE QUADRATURE-DATA LOADS: a lane of the x-line stage reads Q consecutive doubles per component; as 8-byte loads
 //     with a lane stride of 8 Q bytes every one of the Q requests touches the same ~Q / 4 lines per 8 lanes again.  With this bit the
@@ -125,6 +128,7 @@ struct LeanGen {
     c << "__shared__ long long b200_ne;\n\n";
     c << "#define B200_SMW (sm + (threadIdx.x >> 5) * " << plan->group_smem_bytes / 8 << ")\n";
     c << "#define B200_TGS ((int *)(B200_SMW + " << plan->lean_tg_off / 8 << "))\n";
+    if (ilv) c << "#define B200_OFS ((int *)(B200_SMW + " << plan->lean_off_off / 8 << "))\n";
     if (staged) {
       if (st_idx) c << "#define B200_OFS ((int *)(B200_SMW + " << plan->lean_off_off / 8 << "))\n";
       c << "#define B200_BAR(s) (b200_smem_u32((char *)B200_SMW + " << plan->mbar_off << " + 8 * (s)))  // 0 offsets, 1 quadrature data, 2 targets\n";
@@ -207,6 +211,12 @@ struct LeanGen {
   string stage_locals() const { return runs ? "" : "  const int st = 1;\n  const long long lim = b200_ne;\n  (void)st; (void)lim;\n"; }
   string stage_args() const { return staged ? ", par" : (runs ? ", st, lim" : ""); }
 
+  // vector width (ints) of the table staging loads of stage bit 1: element blocks and the padded pitch must be multiples of it
+  int ilv_width() const {
+    for (int w : {4, 2})
+      if (P3 % w == 0 && plan->lean_ip % w == 0) return w;
+    return 1;
+  }
   // node column (ij = i + P j, local element le) of task `t` of the gather / scatter stages: (i, j, element) by default, (i, element, j)
   // with stage bit 1 -- consecutive lanes then walk one node row across the x-neighbouring elements of the batch
   string column_decode(const string &t, const string &x) const {
@@ -230,6 +240,30 @@ struct LeanGen {
       c << "  const int *const ofs = B200_OFS + B200_SHIFT(ixb + e0 * " << P3 << ", 4);\n";
       c << "  b200_mbar_wait(B200_BAR(0), par);\n";
     }
+    if (ilv) {
+      // the batch's offsets and targets: coalesced vector loads of the two contiguous table blocks, stored with the padded element pitch
+      const int IP = plan->lean_ip, w = ilv_width(), nv = E * P3 / w, R_ld = (nv + 31) / 32;
+      const string vt = w == 4 ? "int4" : (w == 2 ? "int2" : "int");
+      c << "  const int nel = TAIL ? (int)(lim - e0) : " << E << ";\n  (void)nel;\n";
+      c << "  int *const ofs = B200_OFS;\n";
+      c << "  {\n    const " << vt << " *const isrc = (const " << vt << " *)(ixb + e0 * " << P3 << ");\n";
+      if (!same_table) c << "    const " << vt << " *const tsrc = (const " << vt << " *)(txb + e0 * " << P3 << ");\n";
+      c << "    const int nvec = TAIL ? nel * " << P3 / w << " : " << nv << ";\n";
+      for (int m = 0; m < R_ld; m++) {
+        c << "    const int q" << m << " = lane + " << 32 * m << ";\n";
+        c << "    " << vt << " a" << m << " = {}" << (same_table ? "" : ", b" + S(m) + " = {}") << ";\n";
+        c << "    if (q" << m << " < nvec) {\n      a" << m << " = __ldg(isrc + q" << m << ");\n";
+        if (!same_table) c << "      b" << m << " = __ldg(tsrc + q" << m << ");\n";
+        c << "    }\n";
+      }
+      for (int m = 0; m < R_ld; m++) {
+        c << "    if (q" << m << " < nvec) {\n      const int at = (q" << m << " / " << P3 / w << ") * " << IP << " + (q" << m << " % " << P3 / w << ") * " << w << ";\n";
+        c << "      *(" << vt << " *)(ofs + at) = a" << m << ";\n";
+        if (!same_table) c << "      *(" << vt << " *)(tgs + at) = b" << m << ";\n";
+        c << "    }\n";
+      }
+      c << "  }\n  __syncwarp();\n";
+    }
     // rounds are processed in chunks so that at most ~16 index pairs are in flight per lane
     const int chunk = std::max(1, 16 / P);
     for (int r0 = 0; r0 < R; r0 += chunk) {
@@ -240,8 +274,9 @@ struct LeanGen {
         c << "    const int t" << x << " = lane + " << 32 * r << ", tc" << x << " = " << ((r + 1) * 32 > T ? "t" + x + " < " + S(T) + " ? t" + x + " : " + S(T - 1) : "t" + x)
           << ";\n";
         c << "    " << column_decode("tc" + x, x) << "\n";
-        if (st_idx) {
-          c << "    const int *const ix" << x << " = ofs + (TAIL ? (le" << x << " < nel ? le" << x << " : nel - 1) : le" << x << ") * " << P3 << " + ij" << x << ";\n";
+        if (st_idx || ilv) {
+          c << "    const int *const ix" << x << " = ofs + (TAIL ? (le" << x << " < nel ? le" << x << " : nel - 1) : le" << x << ") * " << (ilv ? plan->lean_ip : P3) << " + ij" << x
+            << ";\n";
           for (int k = 0; k < P; k++) c << "    const int o" << k << x << " = ix" << x << "[" << k * P2 << "];\n";
         } else {
           c << "    const long long e" << x << " = " << elem("le" + x) << ";\n";
@@ -249,7 +284,7 @@ struct LeanGen {
           for (int k = 0; k < P; k++) c << "    const int o" << k << x << " = __ldg(ix" << x << " + " << k * P2 << ");\n";
         }
       }
-      if (!same_table && !st_idx) {
+      if (!same_table && !st_idx && !ilv) {
         for (int r = r0; r < r1; r++) {
           const string x = "_" + S(r);
           c << "    const int *const tx" << x << " = txb + e" << x << " * " << P3 << " + ij" << x << ";\n";
@@ -261,7 +296,7 @@ struct LeanGen {
         for (int cc = 0; cc < nc; cc++)
           for (int k = 0; k < P; k++) c << "    const double u" << cc << "_" << k << x << " = __ldg(ub + o" << k << x << " + " << cc * cs << "LL);\n";
       }
-      for (int r = r0; r < r1 && !st_idx; r++) {
+      for (int r = r0; r < r1 && !st_idx && !ilv; r++) {
         const string x = "_" + S(r), g = same_table ? "o" : "g";
         int k = 0;
         while (k < P) {
@@ -496,6 +531,10 @@ struct LeanGen {
       c << "  const int nel = TAIL ? (int)(b200_ne - e0) : " << E << ";\n  (void)nel;\n";
       c << "  const int *const tgs = B200_TGS + B200_SHIFT(b200a.out_idx[" << sl << "] + e0 * " << P3 << ", 4);\n";
       c << "  b200_mbar_wait(B200_BAR(2), par);\n";
+    } else if (ilv) {
+      const bool same_table = plan->scatter_mode != B200_SCATTER_DETERMINISTIC && gin->rstr == gout->rstr;
+      c << "  const int nel = TAIL ? (int)(lim - e0) : " << E << ";\n  (void)nel;\n";
+      c << "  const int *const tgs = " << (same_table ? "B200_OFS" : "B200_TGS") << ";  // staged by the gather stage of this batch\n";
     } else {
       c << "  const int *const tgs = B200_TGS;\n";
     }
@@ -506,8 +545,8 @@ struct LeanGen {
       c << "  {\n";
       c << "    const int t = lane + " << 32 * r << ", tc = " << (partial ? "t < " + S(T) + " ? t : " + S(T - 1) : string("t")) << ";\n";
       c << "    " << column_decode("tc", "") << "\n";
-      if (st_idx) {
-        c << "    const int *const tx = tgs + (TAIL ? (le < nel ? le : nel - 1) : le) * " << P3 << " + ij;\n";
+      if (st_idx || ilv) {
+        c << "    const int *const tx = tgs + (TAIL ? (le < nel ? le : nel - 1) : le) * " << (ilv ? plan->lean_ip : P3) << " + ij;\n";
         for (int k = 0; k < P; k++) c << "    const int g" << k << " = tx[" << k * P2 << "];\n";
       } else {
         int k = 0;
@@ -745,7 +784,14 @@ size_t b200_opgen_lean_layout(B200OpPlan *plan, int E) {
   for (auto &f : plan->in_fields) f.qd_off = -1, f.qd_tma = false;
   // bulk pipeline: single buffers for the offsets and the targets (bit 8) and every contiguous EVAL_NONE component (bit 32), each
   // + 16 bytes for the aligned-down sources
-  if (plan->stage_mask & 8) {
+  if (plan->stage_mask & 1) {
+    // interleaved columns: both tables of the batch staged with an element pitch = P (mod 32) ints
+    int ip = P * P * P;
+    while (ip % 32 != P % 32) ip++;
+    plan->lean_ip      = ip;
+    plan->lean_off_off = take((size_t)E * ip * 4);
+    plan->lean_tg_off  = take((size_t)E * ip * 4);
+  } else if (plan->stage_mask & 8) {
     plan->lean_off_off = take((size_t)E * P * P * P * 4 + 16);
     plan->lean_tg_off  = take((size_t)E * P * P * P * 4 + 16);
   } else {

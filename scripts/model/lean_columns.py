@@ -44,7 +44,7 @@ for E in Es:
             if pad:
                 while ES % 16 != P % 16: ES += 1
             T = E * P * P
-            lines = reqs = sw = sreq = 0
+            lines = reqs = sw = sreq = ilines = 0
             for e0 in range(nx * ny * 3 + 5, nx * ny * 3 + 5 + 40 * E, E):
                 offs = [offsets(e0 + le) for le in range(E)]
                 for r in range((T + 31) // 32):
@@ -54,9 +54,12 @@ for E in Es:
                         a = np.array([offs[l][ii, jj, k] for ii, jj, l in zip(i, j, le)]) * 8
                         lines += len(set((a // 128).tolist()))
                         reqs += 1
+                        # the int32 offsets (and, identically, the scatter targets) of the same request: element-major table
+                        ia = ((e0 + le) * P ** 3 + k * P * P + j * P + i) * 4
+                        ilines += len(set((ia // 128).tolist()))
                     sa = le * ES + j * P + i
                     sw += smem_wavefronts(sa) * Q
                     sreq += Q
             nelem = 40 * E
-            print(f"  E={E} interleaved={ilv} pad={pad} ES={ES}: gather lines/request {lines/reqs:5.2f}, lines/element {lines/nelem:6.2f}; "
+            print(f"  E={E} interleaved={ilv} pad={pad} ES={ES}: gather lines/request {lines/reqs:5.2f}, lines/element {lines/nelem:6.2f}, offset-table lines/element {ilines/nelem:5.2f}; "
                   f"plane-store wavefronts/request {sw/sreq:4.2f} (ideal 2), per element {sw/nelem:5.2f}")
