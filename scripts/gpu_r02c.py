@@ -108,7 +108,7 @@ def sweep(patch):
         for E in e_list:
             for warps in ((4, 8) if first else (4,)):
                 for stage in (0, 4, 1, 5, 3, 7):
-                    if not first and stage in (1, 3): continue
+                    if (not first and stage in (1, 3)) or (warps == 8 and stage not in (0, 7)): continue
                     # (occupancy target as the heuristics would set it -- fields left open would come from the table entry)
                     run(f"lean E={E} warps={warps} stage={stage}", qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=stage,
                         min_blocks_per_sm=max(1, 65536 // (warps * 32 * 96)), qf_unroll=4)
