@@ -157,3 +157,35 @@ def test_element_parts_emulated():
     for key, v in res.items():
         assert v["err"] < 1e-12 and v["part_err"] < 1e-12, (key, v)
         assert v["ranges"] == [0, v["split"], v["split"], v["ne"]], (key, v)
+
+
+GUARD = r"""
+import ctypes as C
+ceed = Ceed(); lib = ceed._lib
+prob, qd, u, ref = problem(ceed, 1, 3, (5, 3, 3))
+off = np.ascontiguousarray(prob.offsets, dtype=np.int32).reshape(-1)
+raw = np.zeros(off.size + 8, dtype=np.int32)
+first = (-(raw.ctypes.data // 4)) % 4
+for shift in (0, 1):   # a caller-owned "device" offset array (compile-only mode: host memory), 16-byte aligned and 4 bytes off
+    view = raw[first + shift: first + shift + off.size]; view[:] = off
+    assert view.ctypes.data % 16 == 4 * shift
+    ptr = C.c_void_p()
+    ceed._chk(lib.ceedb200_restriction_create(ceed._ptr, prob.num_elem, 64, 1, prob.num_nodes, prob.num_nodes, cm.MEM_DEVICE, cm.USE_POINTER, C.c_void_p(view.ctypes.data), C.byref(ptr)))
+    rs = cm.ElemRestriction.__new__(cm.ElemRestriction); cm._Object.__init__(rs, ceed, ptr)
+    op = ceed.Operator(prob.qf)
+    op.set_field("u", rs, prob.basis_u, cm.VECTOR_ACTIVE)
+    op.set_field("qdata", prob.rstr_qd, cm.BASIS_NONE, prob.qdata)
+    op.set_field("v", rs, prob.basis_u, cm.VECTOR_ACTIVE)
+    op.set_kernel_shape(qf_mode=4, elems_per_group=6, cta_warps=2, group_warps=1, stage_mask=7)
+    KE.emulated_apply(op, prob.u, prob.v)
+    out["shift%d" % shift] = dict(stage=op.get_kernel_shape()["stage_mask"], err=rel(prob.v.get_array_read(), ref))
+    del op, rs
+"""
+
+
+def test_misaligned_offset_table_drops_the_vector_table_loads():
+    """Stage bit 1 stages the offset table with 16-byte loads: a caller-owned offset array that is not 16-byte aligned makes the apply
+    regenerate the kernel without that bit (same mechanism as the bulk copies of misaligned quadrature data) -- never a misaligned access."""
+    res = run(GUARD)
+    assert res["shift0"]["stage"] == 7 and res["shift1"]["stage"] == 6, res
+    assert res["shift0"]["err"] < 1e-12 and res["shift1"]["err"] < 1e-12, res
