@@ -746,9 +746,12 @@ static int operator_autotune(B200Operator op, B200Vector u, B200Vector v) {
       }
     }
   // 1b. gradient-free operators: the lean in-place-plane kernel (layout 4; one warp per group, E elements per warp and iteration)
+  //     -- batch widths by order: the planes of E elements must leave room for 16-20 resident warps (profiles/r02c_lean_sweep2.txt)
   if (xline_ok)
     for (int warps : {4, 8})
-      for (int epw : {4, 6, 8}) {
+      for (int k = 0; k < 3; k++) {
+        const int Pmax = op->plan->bases.empty() ? 4 : op->plan->bases[0].P;
+        const int epw  = Pmax >= 6 ? 1 + k : (Pmax == 5 ? 2 + k : 4 + 2 * k);
         B200Tuning t  = base;
         t.group_warps = 1, t.cta_warps = warps, t.qf_mode = 4, t.epw = epw, t.stage = 0;
         trial(t);

@@ -9,7 +9,7 @@ from libceed_b200 import Ceed, ceed as cm
 from libceed_b200.bp import BP_TABLE, BPProblem, seeded_uniform
 from libceed_b200.mesh import choose_elements
 OUT = os.path.join(ROOT, "gpurun_out"); os.makedirs(OUT, exist_ok=True)
-log = open(os.path.join(OUT, "r02c_lean_sweep2.txt"), "w")
+log = open(os.path.join(OUT, "r02c_lean_sweep3.txt" if "high" in sys.argv else "r02c_lean_sweep2.txt"), "w")
 T0 = time.time()
 BUDGET = float(os.environ.get("R02C_SWEEP_BUDGET", "200"))
 
@@ -57,11 +57,16 @@ def lean(E, warps, stage, minb=0):
     return (f"lean E={E} warps={warps} stage={stage} minb={mb}", dict(qf_mode=4, elems_per_group=E, cta_warps=warps, group_warps=1, stage_mask=stage, min_blocks_per_sm=mb, qf_unroll=4))
 
 
-c13 = [lean(6, 4, s, mb) for s in (0, 1) for mb in (4, 6)]
-c13 += [lean(E, w, s) for E in (4, 5, 7, 3) for w in (4, 2) for s in (0, 1)]
-c13 += [lean(4, 4, 3), lean(4, 8, 1), lean(5, 4, 3), lean(4, 4, 1, 4), lean(4, 4, 1, 6)]
-sweep(1, 3, c13)
-sweep(2, 4, [lean(E, w, s) for E in (2, 3, 4) for w in (4, 8) for s in (0, 1, 5)])
-sweep(1, 5, [lean(E, w, s) for E in (2, 3, 4) for w in (4, 8) for s in (0, 1, 5)])
-sweep(2, 5, [lean(E, w, s) for E in (1, 2, 3) for w in (4, 8) for s in (0, 1)])
+if "high" in sys.argv:
+    # third session: lean kernel with one or two elements per warp against the shipped general x-line entries at p = 6..8
+    for bp, p in ((1, 6), (2, 6), (1, 7), (2, 7), (1, 8)):
+        sweep(bp, p, [lean(E, w, s) for E in (1, 2) for w in (4, 8) for s in (0, 1)])
+else:
+    c13 = [lean(6, 4, s, mb) for s in (0, 1) for mb in (4, 6)]
+    c13 += [lean(E, w, s) for E in (4, 5, 7, 3) for w in (4, 2) for s in (0, 1)]
+    c13 += [lean(4, 4, 3), lean(4, 8, 1), lean(5, 4, 3), lean(4, 4, 1, 4), lean(4, 4, 1, 6)]
+    sweep(1, 3, c13)
+    sweep(2, 4, [lean(E, w, s) for E in (2, 3, 4) for w in (4, 8) for s in (0, 1, 5)])
+    sweep(1, 5, [lean(E, w, s) for E in (2, 3, 4) for w in (4, 8) for s in (0, 1, 5)])
+    sweep(2, 5, [lean(E, w, s) for E in (1, 2, 3) for w in (4, 8) for s in (0, 1)])
 say(f"done ({time.time() - T0:.0f} s)")

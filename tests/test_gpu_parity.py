@@ -502,8 +502,10 @@ def test_lean_kernel_run_scatter_is_bitwise_equal(cm, oracle, monkeypatch, bp, p
         assert np.abs(prob.v.get_array_read() - w0 - ref).max() < 1e-12 * max(1.0, np.abs(ref).max()), (E, warps)
 
 
-def test_autotuner_picks_a_shape_and_keeps_results(cm, oracle, tmp_path, monkeypatch):
-    bp, p, nel = 3, 3, (12, 12, 12)
+@pytest.mark.parametrize("bp,p,nel", [(3, 3, (12, 12, 12)), (1, 2, (20, 20, 20))])
+def test_autotuner_picks_a_shape_and_keeps_results(cm, oracle, tmp_path, monkeypatch, bp, p, nel):
+    """The core's autotuner on a diffusion operator (general kernel) and on a mass operator (lean kernel candidates incl. the
+    interleaved-column / vector-load stage bits): the tuned operator still matches the oracle and the table line is written."""
     monkeypatch.setenv("CEED_B200_TUNE_SAVE", str(tmp_path / "t.tune"))
     monkeypatch.setenv("CEED_B200_NO_TUNE_TABLE", "1")
     prob = make_problem(cm, bp, p, nel)
