@@ -5,8 +5,9 @@ entry point ceedb200_operator_debug_launch describes the launch the fused apply 
 element range, the generated source of the variant and the tables of the finalize pass.  This module compiles that very source for the
 host with g++ (tests/emu/b200-jit.h maps the CUDA constructs: one OS thread per CUDA thread, barriers for __syncwarp / __syncthreads),
 runs it against the argument block and performs the finalize pass in numpy -- so the code generator's lane maps, table use, tail
-handling and scatter are checked against the oracle on a machine without a GPU.  Kernels with asynchronous-copy stages (cp.async,
-cp.async.bulk + mbarrier, named barriers) are not emulated.  Nothing of this is reachable from the product."""
+handling and scatter are checked against the oracle on a machine without a GPU.  cp.async is emulated as an immediate copy, cp.async.bulk +
+mbarrier by tests/emu/b200-tma.h (copy at once, byte-counted completion, phase parity), named barriers as pthread barriers; the in-kernel
+ordered completion / in-kernel finalize (acquire / release flags between CTAs) are not emulated.  Nothing of this is reachable from the product."""
 import ctypes as C
 import hashlib
 import os
@@ -43,8 +44,8 @@ def build(source):
     source = re.sub(r'asm volatile\("cp\.async\.(commit_group|wait_group \d+);"[^;]*;', "", source)
     source = re.sub(r'asm volatile\("bar\.sync %0, (\d+);" ::"r"\((.*?)\) : "memory"\);', r"b200_emu_named_barrier(\2, \1);", source)
     source = re.sub(r'asm volatile\("prefetch\.global\.L2 \[%0\];"[^;]*;', "", source)
-    if "asm volatile" in source or "b200-tma.h" in source:
-        raise NotImplementedError("kernel uses inline PTX that is not emulated (bulk copies / mbarrier / acquire-release flags)")
+    if "asm volatile" in source:
+        raise NotImplementedError("kernel uses inline PTX that is not emulated (acquire / release flags of the in-kernel ordered completion)")
     name = re.search(r"__global__ void\s+(?:__launch_bounds__\([^)]*\)\s*)?(b200_operator_\w+)\s*\(", source).group(1)
     d = tempfile.mkdtemp(prefix="b200emu_")
     cu = os.path.join(d, "kernel.cpp")
