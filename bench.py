@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--no-e2e-pipeline", action="store_true", help="skip the software-pipelined end-to-end measurement")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a captured CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--no-sweep", action="store_true", help="skip the `sweep` key (kernel numbers of BP1 p=3, BP3 p=1..8, BP5 p=4..7, BP6 p=4,6)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the `sweep` key (kernel numbers of BP1 p=2..5, BP2 p=3, BP3 p=1..8, BP5 p=4..7, BP6 p=4,6)")
     ap.add_argument("--no-libceed", action="store_true", help="do not measure through libCEED's public API (oracle/_ref/lib-cuda + plugin)")
     ap.add_argument("--no-scaling-case", action="store_true", help="skip the second timed case (BP3 p=6, 50M DoFs per GPU: BASELINE configs[4])")
     ap.add_argument("--scaling-dofs", type=float, default=50e6, help="DoFs per GPU of the second timed case")
@@ -661,7 +661,7 @@ def main():
     sweep = None
     if not args.no_sweep and rank == 0 and world == 1:
         sweep = []
-        for sbp, ps in ((1, (3,)), (3, range(1, 9)), (5, range(4, 8)), (6, (4, 6))):
+        for sbp, ps in ((1, (2, 3, 4, 5)), (2, (3,)), (3, range(1, 9)), (5, range(4, 8)), (6, (4, 6))):
             for sp in ps:
                 sc = BP_TABLE[sbp][0]
                 sprob = BPProblem(ceed, sbp, sp, M.choose_elements(args.dofs, sp, sc))
