@@ -214,3 +214,46 @@ def test_bulk_copy_pipelines_emulated():
     assert len(res) == 13
     for key, v in res.items():
         assert v["err"] < 1e-12 and v["stage"] == v["want"], (key, v)
+
+
+TABLE = r"""
+import re
+ceed = Ceed()   # (the subprocess of this test runs WITHOUT CEED_B200_NO_TUNE_TABLE: the context carries the shipped table)
+table = {}
+for ln in open(os.path.join(%r, "libceed_b200", "tuned", "sm_100a.tune")):
+    if ln.strip() and not ln.startswith("#"):
+        tok = ln.split("#")[0].split()
+        table[tok[0]] = [int(x) for x in tok[1:8]]
+for bp in (1, 2, 3, 4, 5, 6):
+    for p in range(1, 9):
+        if bp in (5, 6) and p == 1: continue
+        nel = (3, 2, 2) if p <= 3 else ((2, 2, 1) if p <= 5 else (2, 1, 1))
+        prob, qd, u, ref = problem(ceed, bp, p, nel)
+        d = KE.emulated_apply(prob.op, prob.u, prob.v)
+        got = prob.op.get_kernel_shape()
+        entry = table.get(got["signature"])
+        out["bp%%d p%%d" %% (bp, p)] = dict(err=rel(prob.v.get_array_read(), ref), in_table=entry is not None, entry=entry,
+                                         got=[got[k] for k in ("elems_per_group", "group_warps", "cta_warps", "min_blocks_per_sm", "qf_mode", "qf_unroll", "stage_mask")],
+                                         num_elem=prob.num_elem)
+""" % ROOT
+
+
+def test_every_shipped_tuning_table_entry_generates_a_correct_kernel():
+    """BP1-BP6, p = 1..8 with the shipped tuning table active: the kernel each entry selects (layout, batch width, staging bits incl. the
+    bulk-copy ones) is generated, emulated on the CPU and compared with the oracle; the resolved shape is the table's (the batch width is
+    capped by the small mesh, the occupancy target by what shared memory allows)."""
+    env = dict(os.environ, CEED_B200_COMPILE_ONLY="1")
+    env.pop("CEED_B200_NO_TUNE_TABLE", None)
+    r = subprocess.run([sys.executable, "-c", PRELUDE + TABLE + '\nprint("RESULT" + json.dumps(out))\n'], capture_output=True, text=True, env=env, timeout=1500)
+    assert r.returncode == 0, r.stderr[-4000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][0][6:])
+    assert len(res) == 46
+    hits = 0
+    for key, v in res.items():
+        assert v["err"] < 1e-12, (key, v)
+        if v["in_table"]:
+            hits += 1
+            e, g = v["entry"], v["got"]
+            assert g[0] == min(e[0], v["num_elem"]) and g[1] == e[1] and g[2] <= e[2] and g[4] == e[4] and g[5] == e[5], (key, v)
+            assert g[6] == e[6] or g[4] == 4, (key, v)  # (the lean kernel masks the stage bits it does not read)
+    assert hits >= 30, hits
