@@ -48,4 +48,5 @@ BP_CASES = [
     (4, 2, (2, 1, 2), False, True), (6, 2, (2, 2, 1), False, False), (6, 3, (1, 2, 1), False, True), (1, 2, (2, 2, 2), True, False),
     (3, 2, (2, 2, 2), True, False), (3, 5, (2, 1, 1), False, False), (3, 7, (1, 1, 1), False, False), (5, 5, (1, 2, 1), False, False),
     (5, 6, (1, 1, 2), False, False), (6, 4, (2, 1, 1), False, False), (6, 6, (1, 1, 1), False, False), (4, 3, (2, 1, 1), False, False),
+    (1, 2, (2, 2, 2), False, False), (1, 4, (2, 1, 1), False, False), (1, 5, (1, 1, 2), False, False), (2, 3, (2, 1, 1), False, False),
 ]
