@@ -21,6 +21,8 @@ from libceed_b200.bp import BPProblem, seeded_uniform
 from oracle import oracle as O
 import kernel_emu as KE
 out = {}
+SHARD, NSHARD = int(os.environ.get("EMU_SHARD", "0")), int(os.environ.get("EMU_NSHARD", "1"))
+def mine(i): return i %% NSHARD == SHARD   # (the larger tests split their cases over a few concurrent processes)
 def rel(a, b): return float(np.abs(a - b).max() / np.abs(b).max())
 def problem(ceed, bp, p, nel, **kw):
     prob = BPProblem(ceed, bp, p, nel, build_qdata=False, **kw)
@@ -32,15 +34,23 @@ def problem(ceed, bp, p, nel, **kw):
 """ % (ROOT, ROOT)
 
 
-def run(body, timeout=1500):
-    env = dict(os.environ, CEED_B200_COMPILE_ONLY="1", CEED_B200_NO_TUNE_TABLE="1")
-    r = subprocess.run([sys.executable, "-c", PRELUDE + body + '\nprint("RESULT" + json.dumps(out))\n'], capture_output=True, text=True, env=env, timeout=timeout)
-    assert r.returncode == 0, r.stderr[-4000:]
-    return json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][0][6:])
+def run(body, timeout=1500, shards=1, table=False):
+    env = dict(os.environ, CEED_B200_COMPILE_ONLY="1", CEED_B200_NO_TUNE_TABLE="1", EMU_NSHARD=str(shards))
+    if table:
+        env.pop("CEED_B200_NO_TUNE_TABLE")
+    procs = [subprocess.Popen([sys.executable, "-c", PRELUDE + body + '\nprint("RESULT" + json.dumps(out))\n'], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                              env=dict(env, EMU_SHARD=str(i))) for i in range(shards)]
+    res = {}
+    for pr in procs:
+        so, se = pr.communicate(timeout=timeout)
+        assert pr.returncode == 0, se[-4000:]
+        res.update(json.loads([ln for ln in so.splitlines() if ln.startswith("RESULT")][0][6:]))
+    return res
 
 
 LEAN = r"""
-for bp, p, nel, morton in ((1, 3, (5, 3, 3), False), (1, 2, (4, 3, 3), True), (2, 3, (3, 2, 3), False)):
+for k, (bp, p, nel, morton) in enumerate(((1, 3, (5, 3, 3), False), (1, 2, (4, 3, 3), True), (2, 3, (3, 2, 3), False))):
+    if not mine(k): continue
     for mode in (0, 1):
         ceed = Ceed(); ceed.set_scatter_mode(mode)
         prob, qd, u, ref = problem(ceed, bp, p, nel, elem_perm=M.morton_permutation(*nel) if morton else None)
@@ -67,7 +77,7 @@ for bp, p, nel, morton in ((1, 3, (5, 3, 3), False), (1, 2, (4, 3, 3), True), (2
 def test_lean_kernel_variants_emulated_against_the_oracle():
     """Every lean-kernel shape incl. the element-interleaved column map (stage bit 1), the padded element stride (2) and the 16-byte
     quadrature-data loads (4): oracle parity, bitwise equality of the deterministic variants, ApplyAdd, tails, Morton order, atomic scatter."""
-    res = run(LEAN)
+    res = run(LEAN, shards=3)
     assert len(res) == 3 * (6 + 2)
     for key, v in res.items():
         assert v["layout"] == 4 and v["stage"] == int(key.rsplit("s", 1)[1]), (key, v)
@@ -109,7 +119,8 @@ GENERAL = r"""
 ceed = Ceed()
 shapes = (dict(stage_mask=1), dict(stage_mask=257), dict(stage_mask=513), dict(stage_mask=9, qf_mode=1, qf_unroll=2), dict(stage_mask=0, qf_mode=2, qf_unroll=2),
           dict(stage_mask=7, group_warps=2, cta_warps=4, elems_per_group=3), dict(qf_mode=3, stage_mask=17, group_warps=4, cta_warps=4))
-for bp, p, nel, kw in ((3, 2, (4, 3, 2), {}), (6, 2, (3, 2, 2), {}), (4, 1, (3, 3, 2), dict(interlaced=True)), (3, 6, (2, 1, 1), {}), (1, 5, (2, 2, 1), {})):
+for k, (bp, p, nel, kw) in enumerate(((3, 2, (4, 3, 2), {}), (6, 2, (3, 2, 2), {}), (4, 1, (3, 3, 2), dict(interlaced=True)), (3, 6, (2, 1, 1), {}), (1, 5, (2, 2, 1), {}))):
+    if not mine(k): continue
     prob, qd, u, ref = problem(ceed, bp, p, nel, **kw)
     v0 = None
     for shape in shapes:
@@ -124,7 +135,7 @@ for bp, p, nel, kw in ((3, 2, (4, 3, 2), {}), (6, 2, (3, 2, 2), {}), (4, 1, (3, 
 def test_general_kernel_shapes_emulated_against_the_oracle():
     """The general kernel (z-line / pointwise / point-pair / x-line QFunction stage; padded, swizzled and even-Q linear planes; one- to
     four-warp element groups with named barriers; cp.async staging of targets, offsets, gathered inputs and quadrature data) on BP3-BP6."""
-    res = run(GENERAL)
+    res = run(GENERAL, shards=3)
     assert len(res) == 35
     for key, v in res.items():
         assert v["err"] < 1e-12 and v["same"] < 1e-13, (key, v)
@@ -226,7 +237,7 @@ for ln in open(os.path.join(%r, "libceed_b200", "tuned", "sm_100a.tune")):
         table[tok[0]] = [int(x) for x in tok[1:8]]
 for bp in (1, 2, 3, 4, 5, 6):
     for p in range(1, 9):
-        if bp in (5, 6) and p == 1: continue
+        if (bp in (5, 6) and p == 1) or not mine(bp * 8 + p): continue
         nel = (3, 2, 2) if p <= 3 else ((2, 2, 1) if p <= 5 else (2, 1, 1))
         prob, qd, u, ref = problem(ceed, bp, p, nel)
         d = KE.emulated_apply(prob.op, prob.u, prob.v)
@@ -242,11 +253,7 @@ def test_every_shipped_tuning_table_entry_generates_a_correct_kernel():
     """BP1-BP6, p = 1..8 with the shipped tuning table active: the kernel each entry selects (layout, batch width, staging bits incl. the
     bulk-copy ones) is generated, emulated on the CPU and compared with the oracle; the resolved shape is the table's (the batch width is
     capped by the small mesh, the occupancy target by what shared memory allows)."""
-    env = dict(os.environ, CEED_B200_COMPILE_ONLY="1")
-    env.pop("CEED_B200_NO_TUNE_TABLE", None)
-    r = subprocess.run([sys.executable, "-c", PRELUDE + TABLE + '\nprint("RESULT" + json.dumps(out))\n'], capture_output=True, text=True, env=env, timeout=1500)
-    assert r.returncode == 0, r.stderr[-4000:]
-    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][0][6:])
+    res = run(TABLE, shards=4, table=True)
     assert len(res) == 46
     hits = 0
     for key, v in res.items():
