@@ -131,6 +131,12 @@ struct B200Restriction_ {
   int32_t *d_tgt = nullptr;         // per E-entry: >=0 L-index to store into (owner), <0: ~slot in halo buffer
   int32_t *d_halo_node = nullptr;   // per shared node: L-index
   int32_t *d_halo_ptr = nullptr;    // per shared node: start slot (CSR), size num_shared+1
+  // dense form of the same tables for whole-mesh applies of an unpartitioned restriction (halo slots are then in ascending L-index
+  // order): one BYTE per L-index (number of halo slots of that node, 0 for unshared nodes) + the first slot of every block of
+  // kDenseBlockNodes L-indices -- 1 byte per node of table traffic in the finalize pass instead of 8 bytes per shared node
+  uint8_t *d_halo_cnt = nullptr;
+  int32_t *d_halo_block_base = nullptr;
+  int64_t  dense_n = 0;             // L-indices covered by d_halo_cnt (0: dense form not available)
   int64_t  num_shared = 0, num_halo = 0;
   // element split of a partitioned mesh (multi-GPU overlap): elements [0, split_elem) touch the rank interface and are applied first.
   // Shared nodes all of whose touchers lie in that range come first in halo_node / halo_ptr (num_shared_first of them), so that

@@ -90,6 +90,48 @@ __global__ void k_halo_finalize(const int32_t *__restrict__ halo_node, const int
   }
 }
 
+// Dense form of the finalize pass: thread t of block b handles the 4 consecutive L-indices b * 1024 + 4 t ... + 3.  Their halo-slot
+// counts come in as one 4-byte load, the first slot of the thread's nodes is the block's base + an exclusive block scan of the counts
+// (no per-node pointer table, no node list); same additions in the same order as k_halo_finalize.
+constexpr int kDenseThreads = 256, kDenseBlockNodes = 4 * kDenseThreads;
+__global__ void __launch_bounds__(kDenseThreads) k_halo_finalize_dense(const uint8_t *__restrict__ cnt, const int32_t *__restrict__ block_base,
+                                                                        const double *__restrict__ halo, double *__restrict__ v, int64_t num_halo, int num_comp,
+                                                                        int64_t comp_stride) {
+  __shared__ int warp_sum[kDenseThreads / 32];
+  const int     lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n0 = (int64_t)blockIdx.x * kDenseBlockNodes + 4 * threadIdx.x;
+  const uchar4  c4 = reinterpret_cast<const uchar4 *>(cnt)[n0 >> 2];  // (the table is zero-padded to a whole number of blocks)
+  const int     c[4] = {c4.x, c4.y, c4.z, c4.w};
+  const int     mine = c[0] + c[1] + c[2] + c[3];
+  int           incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += up;
+  }
+  if (lane == 31) warp_sum[warp] = incl;
+  __syncthreads();
+  int before = 0;
+#pragma unroll
+  for (int w = 0; w < kDenseThreads / 32; w++) before += w < warp ? warp_sum[w] : 0;
+  if (!mine) return;
+  int64_t slot = (int64_t)block_base[blockIdx.x] + before + incl - mine;
+  for (int comp = 0; comp < num_comp; comp++) {
+    const double *h = halo + (int64_t)comp * num_halo;
+    double       *w = v + (int64_t)comp * comp_stride + n0;
+    int64_t       s = slot;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (c[k]) {
+        double acc = w[k];
+        for (int j = 0; j < c[k]; j++) acc += h[s + j];
+        w[k] = acc;
+        s += c[k];
+      }
+    }
+  }
+}
+
 }  // namespace
 
 #define LAUNCH(ceed, kernel, n, ...)                                                                                  \
@@ -192,6 +234,8 @@ extern "C" int ceedb200_restriction_destroy(B200Restriction r) {
   b200_dfree(ceed, r->d_tgt);
   b200_dfree(ceed, r->d_halo_node);
   b200_dfree(ceed, r->d_halo_ptr);
+  b200_dfree(ceed, r->d_halo_cnt);
+  b200_dfree(ceed, r->d_halo_block_base);
   delete r;
   return B200_SUCCESS;
 }
@@ -310,6 +354,32 @@ int b200_restriction_build_owner(B200Restriction r) {
   B200_CALL(b200_h2d(ceed, r->d_tgt, tgt.data(), n * sizeof(int32_t)));
   if (!halo_node.empty()) B200_CALL(b200_h2d(ceed, r->d_halo_node, halo_node.data(), halo_node.size() * sizeof(int32_t)));
   B200_CALL(b200_h2d(ceed, r->d_halo_ptr, halo_ptr.data(), halo_ptr.size() * sizeof(int32_t)));
+  // dense form (see B200Restriction_::d_halo_cnt): only for an unpartitioned restriction -- the slots are then numbered in ascending
+  // L-index order -- whose nodes have at most 255 halo slots each
+  r->dense_n = 0;
+  if (num_parts == 1 && r->num_shared > 0 && !getenv("CEED_B200_NO_DENSE_FINALIZE")) {
+    const int64_t dense_n = (int64_t)halo_node.back() + 1, padded = (dense_n + kDenseBlockNodes - 1) / kDenseBlockNodes * kDenseBlockNodes;
+    std::vector<uint8_t> cnt(padded, 0);
+    std::vector<int32_t> base(padded / kDenseBlockNodes, 0);
+    bool                 ok = true;
+    for (int64_t i = 0; i < r->num_shared && ok; i++) {
+      const int32_t k = halo_ptr[i + 1] - halo_ptr[i];
+      ok              = k <= 255 && (i == 0 || halo_node[i] > halo_node[i - 1]);
+      cnt[halo_node[i]] = (uint8_t)k;
+    }
+    if (ok) {
+      int64_t run = 0;
+      for (int64_t b = 0; b < (int64_t)base.size(); b++) {
+        base[b] = (int32_t)run;
+        for (int64_t l = b * kDenseBlockNodes; l < (b + 1) * kDenseBlockNodes; l++) run += cnt[l];
+      }
+      B200_CALL(b200_dmalloc(ceed, (void **)&r->d_halo_cnt, cnt.size()));
+      B200_CALL(b200_dmalloc(ceed, (void **)&r->d_halo_block_base, base.size() * sizeof(int32_t)));
+      B200_CALL(b200_h2d(ceed, r->d_halo_cnt, cnt.data(), cnt.size()));
+      B200_CALL(b200_h2d(ceed, r->d_halo_block_base, base.data(), base.size() * sizeof(int32_t)));
+      r->dense_n = padded;
+    }
+  }
   r->owner_built = true;
   return B200_SUCCESS;
 }
@@ -536,6 +606,12 @@ int b200_restriction_apply_raw(B200Restriction r, int t_mode, const double *d_u,
   return B200_SUCCESS;
 }
 
+// CEED_B200_DENSE_FINALIZE=0|1: the dense form of the finalize pass for whole-mesh applies (read at every apply: the tuning scripts toggle it)
+static bool b200_dense_finalize_enabled() {
+  const char *e = getenv("CEED_B200_DENSE_FINALIZE");
+  return e ? atoi(e) != 0 : false;
+}
+
 int b200_halo_finalize(B200Restriction r, const double *d_halo, double *d_v, int part) {
   B200Ceed      ceed  = r->ceed;
   int64_t first = 0, count = r->num_shared;
@@ -545,6 +621,15 @@ int b200_halo_finalize(B200Restriction r, const double *d_halo, double *d_v, int
     count = r->shared_prefix[part] - first;
   }
   if (count <= 0) return B200_SUCCESS;
+  if (part == 0 && r->dense_n > 0 && b200_dense_finalize_enabled()) {
+    // whole mesh, unpartitioned restriction: dense tables (v must cover the padded index range only where counts are non-zero)
+    B200_CHECK(!b200_compile_only(), ceed, B200_ERROR_BACKEND, "CEED_B200_COMPILE_ONLY is set; kernels cannot run");
+    k_halo_finalize_dense<<<(unsigned)(r->dense_n / kDenseBlockNodes), kDenseThreads, 0, ceed->stream>>>(r->d_halo_cnt, r->d_halo_block_base, d_halo, d_v, r->num_halo,
+                                                                                                   r->num_comp, r->comp_stride);
+    ceed->launch_count++;
+    B200_CUDA(ceed, cudaGetLastError());
+    return B200_SUCCESS;
+  }
   LAUNCH(ceed, k_halo_finalize, count, r->d_halo_node + first, r->d_halo_ptr + first, d_halo, d_v, count, r->num_halo, r->num_comp, r->comp_stride);
   return B200_SUCCESS;
 }
@@ -575,7 +660,10 @@ int b200_restriction_set_parts(B200Restriction r, const std::vector<int32_t> &pa
     b200_dfree(ceed, r->d_tgt);
     b200_dfree(ceed, r->d_halo_node);
     b200_dfree(ceed, r->d_halo_ptr);
+    b200_dfree(ceed, r->d_halo_cnt);
+    b200_dfree(ceed, r->d_halo_block_base);
     r->d_tgt = r->d_halo_node = r->d_halo_ptr = nullptr;
+    r->d_halo_cnt = nullptr, r->d_halo_block_base = nullptr, r->dense_n = 0;
     r->owner_built = false;
   }
   r->part_ends  = part_ends;
