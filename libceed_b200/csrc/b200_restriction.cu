@@ -357,7 +357,7 @@ int b200_restriction_build_owner(B200Restriction r) {
   // dense form (see B200Restriction_::d_halo_cnt): only for an unpartitioned restriction -- the slots are then numbered in ascending
   // L-index order -- whose nodes have at most 255 halo slots each
   r->dense_n = 0;
-  if (num_parts == 1 && r->num_shared > 0 && !getenv("CEED_B200_NO_DENSE_FINALIZE")) {
+  if (num_parts == 1 && r->num_shared > 0 && getenv("CEED_B200_DENSE_FINALIZE")) {  // (built only when the option is in play: measured slower)
     const int64_t dense_n = (int64_t)halo_node.back() + 1, padded = (dense_n + kDenseBlockNodes - 1) / kDenseBlockNodes * kDenseBlockNodes;
     std::vector<uint8_t> cnt(padded, 0);
     std::vector<int32_t> base(padded / kDenseBlockNodes, 0);
