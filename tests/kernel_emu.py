@@ -70,8 +70,9 @@ def emulated_apply(op, u, v, add=False, part=0, grid=3):
     desc = DebugLaunch()
     op._chk(lib.ceedb200_operator_debug_launch(op._ptr, u._ptr, v._ptr, int(bool(add)), int(part), C.byref(desc)))
     n = len(v)
-    out = np.ctypeslib.as_array(desc.v, shape=(n,))
+    out = np.ctypeslib.as_array(desc.v, shape=(n,)) if desc.v else None  # (NULL: no offset-restricted output, e.g. a setup operator)
     if desc.zero_first and part <= 1:
+        assert out is not None
         out[:] = 0.0
     if desc.e_end > desc.e_begin:
         kernel = build(desc.source.decode())

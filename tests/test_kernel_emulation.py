@@ -240,24 +240,26 @@ for bp in (1, 2, 3, 4, 5, 6):
         if (bp in (5, 6) and p == 1) or not mine(bp * 8 + p): continue
         nel = (3, 2, 2) if p <= 3 else ((2, 2, 1) if p <= 5 else (2, 1, 1))
         prob, qd, u, ref = problem(ceed, bp, p, nel)
-        d = KE.emulated_apply(prob.op, prob.u, prob.v)
+        KE.emulated_apply(prob.op_setup, prob.x, prob.qdata)   # the setup operator's fused kernel (x INTERP + GRAD, weights -> strided qdata)
+        qd_err = rel(prob.qdata.get_array_read(), qd)
+        d = KE.emulated_apply(prob.op, prob.u, prob.v)         # ... whose output the apply operator then reads
         got = prob.op.get_kernel_shape()
         entry = table.get(got["signature"])
-        out["bp%%d p%%d" %% (bp, p)] = dict(err=rel(prob.v.get_array_read(), ref), in_table=entry is not None, entry=entry,
+        out["bp%%d p%%d" %% (bp, p)] = dict(err=rel(prob.v.get_array_read(), ref), qd_err=qd_err, in_table=entry is not None, entry=entry,
                                          got=[got[k] for k in ("elems_per_group", "group_warps", "cta_warps", "min_blocks_per_sm", "qf_mode", "qf_unroll", "stage_mask")],
                                          num_elem=prob.num_elem)
 """ % ROOT
 
 
 def test_every_shipped_tuning_table_entry_generates_a_correct_kernel():
-    """BP1-BP6, p = 1..8 with the shipped tuning table active: the kernel each entry selects (layout, batch width, staging bits incl. the
+    """BP1-BP6, p = 1..8 with the shipped tuning table active, setup operator (quadrature data) and apply operator: the kernel each entry selects (layout, batch width, staging bits incl. the
     bulk-copy ones) is generated, emulated on the CPU and compared with the oracle; the resolved shape is the table's (the batch width is
     capped by the small mesh, the occupancy target by what shared memory allows)."""
     res = run(TABLE, shards=4, table=True)
     assert len(res) == 46
     hits = 0
     for key, v in res.items():
-        assert v["err"] < 1e-12, (key, v)
+        assert v["err"] < 1e-12 and v["qd_err"] < 1e-12, (key, v)
         if v["in_table"]:
             hits += 1
             e, g = v["entry"], v["got"]
