@@ -8,10 +8,12 @@ runs it against the argument block and performs the finalize pass in numpy -- so
 handling and scatter are checked against the oracle on a machine without a GPU.  cp.async is emulated as an immediate copy, cp.async.bulk +
 mbarrier by tests/emu/b200-tma.h (copy at once, byte-counted completion, phase parity), named barriers as pthread barriers; the in-kernel
 ordered completion / in-kernel finalize (acquire / release flags between CTAs) are not emulated.  Nothing of this is reachable from the product."""
+import atexit
 import ctypes as C
 import hashlib
 import os
 import re
+import shutil
 import subprocess
 import tempfile
 
@@ -48,6 +50,7 @@ def build(source):
         raise NotImplementedError("kernel uses inline PTX that is not emulated (acquire / release flags of the in-kernel ordered completion)")
     name = re.search(r"__global__ void\s+(?:__launch_bounds__\([^)]*\)\s*)?(b200_operator_\w+)\s*\(", source).group(1)
     d = tempfile.mkdtemp(prefix="b200emu_")
+    atexit.register(shutil.rmtree, d, ignore_errors=True)
     cu = os.path.join(d, "kernel.cpp")
     with open(cu, "w") as f:
         f.write(source + "\n#include \"emu_driver.inc\"\n")
