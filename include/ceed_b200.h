@@ -238,7 +238,7 @@ CEEDB200_EXPORT int ceedb200_operator_apply_streamed(B200Operator op, B200Vector
 /* Host-logic tests: description of the launch the fused apply would perform for (u, v) -- nothing is launched.  `args` is the kernel's
    argument block (the __constant__ B200OpArgs object of the generated source, see ceedb200_operator_kernel_source); the halo_* / v fields
    describe the second pass of the deterministic scatter (v[halo_node[i] + c comp_stride] += halo[j + c num_halo], j in
-   [halo_ptr[i], halo_ptr[i + 1]), ascending) for output field `fin_slot` (-1: none). */
+   [halo_ptr[i], halo_ptr[i + 1]), ascending) for output field `fin_slot` (-1: none); scatter_mode as ceedb200_set_scatter_mode. */
 typedef struct {
   unsigned char args[1024];
   int           args_size, grid, threads, smem_bytes, run_mode, kernel_add, zero_first, fin_slot, num_comp;
@@ -247,6 +247,12 @@ typedef struct {
   const double *halo;
   double       *v;
   const char   *source; /* generated source of the kernel variant (store / accumulate) this apply launches */
+  /* E-vector scatter mode: the kernel writes evec[e * elem_size + n + c * e_entries]; the transpose restriction that follows adds
+     evec entry i of component c to v[offsets[i] + c comp_stride] in ascending i */
+  int           scatter_mode;
+  long long     e_entries;
+  const int    *offsets;
+  const double *evec;
 } B200DebugLaunch;
 CEEDB200_EXPORT int ceedb200_operator_debug_launch(B200Operator op, B200Vector u, B200Vector v, int add, int part, B200DebugLaunch *desc);
 /* host-logic tests: the chunk tables of the streamed apply for num_chunks chunks -- element chunk ends, per chunk the number of leading

@@ -414,6 +414,9 @@ static int apply_fused(B200Operator op, B200Vector u, B200Vector v, int add, int
       if (f.rstr->is_strided || !is_writer) continue;
       B200_CHECK(!desc->v, ceed, B200_ERROR_UNSUPPORTED, "debug launch description holds one offset-restricted output");
       desc->v = args.out_ptr[i], desc->num_comp = f.rstr->num_comp, desc->comp_stride = f.rstr->comp_stride;
+      desc->scatter_mode = plan->scatter_mode;
+      if (plan->scatter_mode == B200_SCATTER_EVECTOR)
+        desc->e_entries = (long long)f.rstr->num_elem * f.rstr->elem_size, desc->offsets = f.rstr->d_offsets, desc->evec = plan->aux[i];
       if (!plan->aux[i] || run || fin_mode || plan->scatter_mode != B200_SCATTER_DETERMINISTIC) continue;
       int64_t first = 0, count = f.rstr->num_shared;
       if (part >= 1) first = f.rstr->shared_prefix[part - 1], count = f.rstr->shared_prefix[part] - first;

@@ -22,7 +22,7 @@ for case in range(n_cases):
     while True:
         nel = (rnd.randint(1, 5), rnd.randint(1, 4), rnd.randint(1, 3))
         if nel[0] * nel[1] * nel[2] <= budget: break
-    mode = rnd.choice([0, 0, 0, 1])  # (EVECTOR / ORDERED modes finish in kernels the emulation harness does not run)
+    mode = rnd.choice([0, 0, 0, 1, 2])  # (deterministic, atomic, E-vector; the in-kernel ORDERED completion is not emulated)
     interlaced = bp % 2 == 0 and rnd.random() < 0.4
     morton = rnd.random() < 0.3
     ceed = Ceed(); ceed.set_scatter_mode(mode)

@@ -6,8 +6,8 @@ element range, the generated source of the variant and the tables of the finaliz
 host with g++ (tests/emu/b200-jit.h maps the CUDA constructs: one OS thread per CUDA thread, barriers for __syncwarp / __syncthreads),
 runs it against the argument block and performs the finalize pass in numpy -- so the code generator's lane maps, table use, tail
 handling and scatter are checked against the oracle on a machine without a GPU.  cp.async is emulated as an immediate copy, cp.async.bulk +
-mbarrier by tests/emu/b200-tma.h (copy at once, byte-counted completion, phase parity), named barriers as pthread barriers; the in-kernel
-ordered completion / in-kernel finalize (acquire / release flags between CTAs) are not emulated.  Nothing of this is reachable from the product."""
+mbarrier by tests/emu/b200-tma.h (copy at once, byte-counted completion, phase parity), named barriers as pthread barriers, the E-vector mode's
+transpose restriction in numpy; the in-kernel ordered completion / in-kernel finalize (acquire / release flags between CTAs) are not emulated.  Nothing of this is reachable from the product."""
 import atexit
 import ctypes as C
 import hashlib
@@ -32,7 +32,8 @@ class DebugLaunch(C.Structure):
                 ("e_begin", C.c_longlong), ("e_end", C.c_longlong), ("comp_stride", C.c_longlong), ("num_shared", C.c_longlong),
                 ("num_halo", C.c_longlong),
                 ("halo_node", C.POINTER(C.c_int)), ("halo_ptr", C.POINTER(C.c_int)), ("halo", C.POINTER(C.c_double)),
-                ("v", C.POINTER(C.c_double)), ("source", C.c_char_p)]
+                ("v", C.POINTER(C.c_double)), ("source", C.c_char_p),
+                ("scatter_mode", C.c_int), ("e_entries", C.c_longlong), ("offsets", C.POINTER(C.c_int)), ("evec", C.POINTER(C.c_double))]
 
 
 def build(source):
@@ -93,4 +94,12 @@ def emulated_apply(op, u, v, add=False, part=0, grid=3):
             for k in range(int(cnt.max())):
                 m = cnt > k
                 out[node[m] + c * desc.comp_stride] += halo[ptr[:-1][m] + k + c * nh]
+    if desc.scatter_mode == 2 and desc.e_entries > 0:
+        # E-vector mode: the transpose restriction kernel that follows (k_offset_transpose, b200_restriction.cu) adds the E-vector into v in
+        # ascending E-index per node -- np.add.at accumulates in index order
+        ne = desc.e_entries
+        off = np.ctypeslib.as_array(desc.offsets, shape=(ne,)).astype(np.int64)
+        ev = np.ctypeslib.as_array(desc.evec, shape=(ne * desc.num_comp,))
+        for c in range(desc.num_comp):
+            np.add.at(out, off + c * desc.comp_stride, ev[c * ne:(c + 1) * ne])
     return desc
